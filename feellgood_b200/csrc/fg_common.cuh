@@ -1,0 +1,161 @@
+// fg_common.cuh — shared declarations of the B200 (sm_100a) LLG hot-path library.
+// FP64, HBM-bound kernels: no tensor cores anywhere (nothing here is a dense contraction).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/feellgood_b200.h"
+
+// physical constants and scheme parameters, reference src/config.h.in:31-32,52
+#define FG_MU0 1.25663706127e-6
+#define FG_GAMMA0 (1.76085962784e11 * FG_MU0)
+#define FG_THETA 0.5
+#define FG_EPSILON 1e-40
+
+namespace fg
+{
+void set_error(const char *fmt, ...);
+
+#define FG_CUDA(call)                                                                          \
+    do                                                                                         \
+        {                                                                                      \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            {                                                                                  \
+            fg::set_error("%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return FG_ERR_CUDA;                                                                \
+            }                                                                                  \
+        } while (0)
+
+#define FG_TRY(call)               \
+    do                             \
+        {                          \
+        int rc_ = (call);          \
+        if (rc_ != FG_OK) return rc_; \
+        } while (0)
+
+constexpr int NUM_SMS = 148;          // B200
+constexpr int BLOCK = 256;            // every kernel of the library uses 256-thread CTAs
+constexpr int CTAS_PER_SM = 8;        // 2048 resident threads per SM
+constexpr int MAX_GRID = NUM_SMS * CTAS_PER_SM;  // persistent grid-stride kernels: one full wave
+constexpr int RED_NV = 4;             // max simultaneous reductions per kernel
+
+// Node record = the reference's Nodes::dataNode {u, v, phi, phiv} (src/node.h:47-53): 64 B, so a
+// gather of one node by a tetrahedron is exactly two aligned 32-byte sectors.
+struct __align__(16) NodeRec
+    {
+    double u[3];
+    double v[3];
+    double phi;
+    double phiv;
+    };
+static_assert(sizeof(NodeRec) == 64, "NodeRec must be 64 bytes");
+
+// tangent-plane basis of a node (src/node.h:62-64): 48 B
+struct __align__(16) Basis
+    {
+    double ep[3];
+    double eq[3];
+    };
+static_assert(sizeof(Basis) == 48, "Basis must be 48 bytes");
+
+// per-region constants, pre-digested from fg_tet_prm (src/tetra.cpp:216-218,239,244)
+struct TetRegion
+    {
+    double alpha, Abis, Kbis, K3bis;
+    double uk[3], ex[3], ey[3], ez[3];
+    int has_K, has_K3;
+    };
+struct TriRegion
+    {
+    double Ks;
+    double uk[3];
+    };
+
+// iteration<T> (src/algebra/iter.h:37-179) + the Krylov scalars, resident on the device.
+struct KState
+    {
+    double rho1, rho2, alpha, beta, omega;
+    double res, rhsn, resmax;
+    double v2max, v_max;
+    int nit, maxiter, status;
+    int done;        // loop finished (any reason)
+    int final_half;  // converged on ||s||: x += alpha*phat still to apply (bicg.h:211-215)
+    int updated;     // node update applied for this solve
+    int failed;      // LinAlgebra::solve return value (src/solver.cpp:62-69)
+    int pad_;
+    };
+
+// buffers of the deterministic two-stage grid reduction
+struct RedBuf
+    {
+    double *partials;     // [RED_NV][MAX_GRID]
+    unsigned int *ticket; // one counter, self-resetting (atomicInc wrap)
+    };
+
+// The operator y = A x.
+//  OP_NODE2: the LLG matrix K (src/solver.h:75-104): rows 2a and 2a+1 share the column list
+//            {2b, 2b+1 : b in ncol[nptr[a]..nptr[a+1])}.  val is in the reference's CSR order
+//            (rowptr[2a] = 4 nptr[a], rowptr[2a+1] = 4 nptr[a] + 2 deg_a) but indexed through the
+//            node-level pattern: 4 B of index per 32 B of values.
+//  OP_CSR:   any algebra::SparseMatrix (src/algebra/sparseMat.h), plain CSR.
+enum { OP_NODE2 = 0, OP_CSR = 1 };
+struct Operator
+    {
+    int kind;
+    int n;       // rows
+    int lanes;   // lanes cooperating on one node (OP_NODE2) / one row (OP_CSR): 2..32
+    const int *ptr;     // nptr (NOD+1) | rowptr (n+1)
+    const int *col;     // ncol | col
+    const double *val;
+    // multi-GPU (fg_dist.cu): x vectors carry `n_ghost` extra entries after the n owned ones
+    };
+
+// optional CUDA-event pairs around every SpMV launch (fg_set_profiling(ctx, 2))
+struct SpmvProf
+    {
+    cudaEvent_t *ev;  // 2*cap events
+    int n, cap;       // pairs recorded / capacity
+    };
+
+// Krylov workspace (all device pointers, length n [+ ghosts for vectors that feed an SpMV])
+struct KrylovWork
+    {
+    int n;       // owned rows
+    int nx;      // length of vectors that are SpMV inputs (n + ghost entries)
+    double *x, *b, *r, *rt, *p, *v, *s, *t, *phat, *shat, *D;
+    const unsigned char *mask; // n : 1 = Dirichlet dof (lvd), may be NULL
+    KState *st;                // device
+    KState *h_st;              // pinned host mirror
+    RedBuf red;
+    cudaStream_t stream;
+    long long *launches;       // host counter of kernel launches
+    cudaEvent_t ev_poll;
+    int last_iters;            // iterations of the previous solve (sizes the first batch)
+    SpmvProf *prof;            // NULL unless SpMV profiling is on
+    // hooks for the row-block multi-GPU path (NULL on one GPU)
+    void *dist;
+    };
+
+
+// ---- fg_krylov.cu ----
+int krylov_alloc(KrylovWork &w, int n, int n_ghost, cudaStream_t stream, long long *launch_counter);
+void krylov_free(KrylovWork &w);
+int grid_for(long long work_items, int items_per_cta);
+// y = A x (optionally masked)
+int spmv(const Operator &op, const KrylovWork &w, const double *x, double *y, bool masked);
+// BiCGStab with Jacobi preconditioner and Dirichlet mask, reference src/algebra/bicg.h:163-234.
+// w.x holds the initial guess, w.b the (already masked) rhs, w.D the (masked) inverse diagonal.
+// post_batch, if not NULL, is called after each enqueued batch of iterations (same stream) so the
+// caller can append gated work (the node update) before the host polls the state.
+typedef int (*post_batch_fn)(void *user);
+int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, post_batch_fn post,
+                 void *user);
+// Jacobi-preconditioned CG, reference src/algebra/cg.h:15-58,68-121 (same conventions)
+int cg_run(const Operator &op, KrylovWork &w, double tol, int maxiter);
+// D = 1/diag(A) for a plain CSR operator (src/algebra/sparseMat.h:174-183), then masked
+int build_diag_precond_csr(const Operator &A, const KrylovWork &w);
+int vec_mask(const KrylovWork &w, double *x);                  // x[lvd] = 0
+int vec_axpy(const KrylovWork &w, double a, const double *x, double *y);  // y += a x
+
+}  // namespace fg

@@ -1,0 +1,645 @@
+// fg_krylov.cu — sparse algebra of the LLG hot path on B200: SpMV, fused BLAS-1, BiCGStab, CG.
+//
+// Replaces the reference's src/algebra/{sparseMat,algebra,algebraCore,bicg,cg,iter}.h.  Same
+// algorithm, same stopping rules and status codes, different execution model:
+//   * the Krylov scalars and the iteration monitor live on the device (KState); every kernel reads
+//     them at entry and the last CTA of each reducing kernel updates them, so a whole batch of
+//     iterations is enqueued without a host round trip;
+//   * every dot / norm is fused into the kernel that produces its operand and reduced with warp
+//     shuffles + a deterministic two-stage grid reduction (fixed grid => bitwise reproducible);
+//   * 5 kernels per BiCGStab iteration (reference: 2 parallel SpMV + 17 serial vector passes).
+// All kernels are HBM-bandwidth bound: persistent grids of 148 SMs x 8 CTAs, coalesced streams.
+#include <math.h>
+#include <stdio.h>
+
+#include "fg_common.cuh"
+#include "fg_reduce.cuh"
+
+namespace fg
+{
+// ------------------------------------------------------------------------------------------
+// iteration monitor, reference src/algebra/iter.h:113-157
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool it_finished(KState *st, double nr)
+    {
+    st->res = fabs(nr);
+    if (isnan(st->res))
+        {
+        st->status = FG_CANNOT_CONVERGE;
+        return false;
+        }
+    if (st->res <= st->rhsn * st->resmax)
+        {
+        st->status = FG_CONVERGED;
+        return true;
+        }
+    return false;
+    }
+
+// `while (!iter.finished(norm(r)))`, then rho_1 and the breakdown test (bicg.h:185-195)
+__device__ __forceinline__ void bicg_top_of_loop(KState *st, double rr, double rho1_new)
+    {
+    if (it_finished(st, sqrt(fabs(rr))))
+        {
+        st->done = 1;
+        return;
+        }
+    st->rho1 = rho1_new;
+    if (st->nit > 0 && (st->rho2 == 0.0 || st->omega == 0.0))
+        {
+        st->status = FG_CANNOT_CONVERGE;
+        st->done = 1;
+        }
+    }
+
+// ------------------------------------------------------------------------------------------
+// SpMV with fused epilogues
+// ------------------------------------------------------------------------------------------
+enum
+    {
+    ST_PLAIN = 0,    // y = A x
+    ST_BICG_SETUP,   // r = b - A x (masked); rt = p = r; ||b||^2, ||r||^2      (bicg.h:172-183)
+    ST_BICG_V,       // v = A phat (masked); (v, rt) -> alpha                    (bicg.h:203-206)
+    ST_BICG_T,       // t = A shat (masked); (t,s), (t,t) -> omega               (bicg.h:219-222)
+    ST_CG_SETUP,     // r = b - A x (masked); p = D r; ||b||^2, ||r||^2, (Dr,r)  (cg.h:24-34)
+    ST_CG_Q,         // q = A p (masked); (q,p) -> a                             (cg.h:45-52)
+    ST_RESID         // y = b - A x (masked)  [b -= A xd of the *_dir variants]
+    };
+
+struct SpmvArgs
+    {
+    const double *x;
+    double *y;
+    const double *a0;  // b | rt | s | p
+    const double *a1;  // D (CG_SETUP)
+    double *o0, *o1;   // rt, p (SETUP)
+    const unsigned char *mask;
+    KState *st;
+    RedBuf red;
+    };
+
+template <int KIND, int STAGE>
+__global__ void __launch_bounds__(BLOCK) k_spmv(const Operator op, const SpmvArgs a)
+    {
+    constexpr int ROWS = (KIND == OP_NODE2) ? 2 : 1;
+    if (STAGE != ST_PLAIN && STAGE != ST_RESID && STAGE != ST_BICG_SETUP && STAGE != ST_CG_SETUP)
+        if (a.st->done) return;
+    const int G = op.lanes;
+    const int lane_in_group = threadIdx.x & (G - 1);
+    const int groups_per_cta = BLOCK / G;
+    const int nunits = (KIND == OP_NODE2) ? op.n / 2 : op.n;
+    const long long total_groups = (long long)gridDim.x * groups_per_cta;
+    double acc[RED_NV] = {0.0, 0.0, 0.0, 0.0};
+
+    for (long long u0 = (long long)blockIdx.x * groups_per_cta + threadIdx.x / G;;
+         u0 += total_groups)
+        {
+        const bool active = u0 < nunits;
+        if (!__any_sync(0xffffffffu, active)) break;
+        const int u = (int)u0;
+        double y0 = 0.0, y1 = 0.0;
+        if (active)
+            {
+            const int beg = op.ptr[u], end = op.ptr[u + 1];
+            if (KIND == OP_NODE2)
+                {
+                const int deg = end - beg;
+                const double2 *row0 = reinterpret_cast<const double2 *>(op.val + 4 * (size_t)beg);
+                const double2 *row1 = row0 + deg;
+                const double2 *x2 = reinterpret_cast<const double2 *>(a.x);
+                for (int j = lane_in_group; j < deg; j += G)
+                    {
+                    const int bcol = __ldg(op.col + beg + j);
+                    const double2 k0 = __ldcs(row0 + j);
+                    const double2 k1 = __ldcs(row1 + j);
+                    const double2 xv = x2[bcol];
+                    y0 += k0.x * xv.x + k0.y * xv.y;
+                    y1 += k1.x * xv.x + k1.y * xv.y;
+                    }
+                }
+            else
+                {
+                for (int j = beg + lane_in_group; j < end; j += G)
+                    y0 += __ldcs(op.val + j) * a.x[__ldg(op.col + j)];
+                }
+            }
+        for (int o = G >> 1; o > 0; o >>= 1)
+            {
+            y0 += __shfl_xor_sync(0xffffffffu, y0, o);
+            if (ROWS == 2) y1 += __shfl_xor_sync(0xffffffffu, y1, o);
+            }
+        if (active && lane_in_group == 0)
+            {
+            const int i0 = ROWS * u;
+            double yv[2] = {y0, y1};
+#pragma unroll
+            for (int k = 0; k < ROWS; k++)
+                {
+                const int i = i0 + k;
+                const bool m = a.mask != nullptr && a.mask[i];
+                double y = yv[k];
+                if (STAGE == ST_PLAIN)
+                    a.y[i] = m ? 0.0 : y;
+                else if (STAGE == ST_RESID)
+                    a.y[i] = m ? 0.0 : a.a0[i] - y;
+                else if (STAGE == ST_BICG_SETUP)
+                    {
+                    const double b = a.a0[i];
+                    const double r = m ? 0.0 : b - y;
+                    a.y[i] = r;
+                    a.o0[i] = r;
+                    a.o1[i] = r;
+                    acc[0] += b * b;
+                    acc[1] += r * r;
+                    }
+                else if (STAGE == ST_CG_SETUP)
+                    {
+                    const double b = a.a0[i];
+                    const double r = m ? 0.0 : b - y;
+                    const double z = a.a1[i] * r;
+                    a.y[i] = r;
+                    a.o1[i] = z;
+                    acc[0] += b * b;
+                    acc[1] += r * r;
+                    acc[2] += z * r;
+                    }
+                else if (STAGE == ST_BICG_V || STAGE == ST_CG_Q)
+                    {
+                    y = m ? 0.0 : y;
+                    a.y[i] = y;
+                    acc[0] += y * a.a0[i];
+                    }
+                else if (STAGE == ST_BICG_T)
+                    {
+                    y = m ? 0.0 : y;
+                    a.y[i] = y;
+                    acc[0] += y * a.a0[i];
+                    acc[1] += y * y;
+                    }
+                }
+            }
+        }
+    if (STAGE == ST_PLAIN || STAGE == ST_RESID) return;
+    double tot[RED_NV];
+    if (!grid_reduce<RED_NV>(acc, a.red, tot)) return;
+    KState *st = a.st;
+    if (STAGE == ST_BICG_SETUP)
+        {
+        st->rhsn = sqrt(fabs(tot[0]));
+        bicg_top_of_loop(st, tot[1], tot[1]);  // rt == r: (rt, r) = ||r||^2
+        }
+    else if (STAGE == ST_BICG_V)
+        st->alpha = st->rho1 / tot[0];
+    else if (STAGE == ST_BICG_T)
+        st->omega = tot[0] / tot[1];
+    else if (STAGE == ST_CG_SETUP)
+        {
+        st->rhsn = sqrt(fabs(tot[0]));
+        st->rho1 = tot[2];  // rho
+        if (it_finished(st, sqrt(fabs(tot[1]))) || st->status == FG_CANNOT_CONVERGE) st->done = 1;
+        }
+    else if (STAGE == ST_CG_Q)
+        {
+        if (tot[0] == 0.0)
+            {
+            st->status = FG_CANNOT_CONVERGE;
+            st->done = 1;
+            }
+        else
+            st->alpha = st->rho1 / tot[0];
+        }
+    }
+
+int grid_for(long long work_items, int items_per_cta)
+    {
+    long long g = (work_items + items_per_cta - 1) / items_per_cta;
+    if (g < 1) g = 1;
+    if (g > MAX_GRID) g = MAX_GRID;
+    return (int)g;
+    }
+
+template <int STAGE>
+static int launch_spmv(const Operator &op, const KrylovWork &w, const SpmvArgs &a)
+    {
+    const int nunits = (op.kind == OP_NODE2) ? op.n / 2 : op.n;
+    const int grid = grid_for(nunits, BLOCK / op.lanes);
+    const bool prof = w.prof != nullptr && w.prof->n < w.prof->cap;
+    if (prof) cudaEventRecord(w.prof->ev[2 * w.prof->n], w.stream);
+    if (op.kind == OP_NODE2)
+        k_spmv<OP_NODE2, STAGE><<<grid, BLOCK, 0, w.stream>>>(op, a);
+    else
+        k_spmv<OP_CSR, STAGE><<<grid, BLOCK, 0, w.stream>>>(op, a);
+    if (prof) cudaEventRecord(w.prof->ev[2 * w.prof->n++ + 1], w.stream);
+    if (w.launches) ++*w.launches;
+    FG_CUDA(cudaGetLastError());
+    return FG_OK;
+    }
+
+int spmv(const Operator &op, const KrylovWork &w, const double *x, double *y, bool masked)
+    {
+    SpmvArgs a = {};
+    a.x = x;
+    a.y = y;
+    a.mask = masked ? w.mask : nullptr;
+    a.st = w.st;
+    a.red = w.red;
+    return launch_spmv<ST_PLAIN>(op, w, a);
+    }
+
+// ------------------------------------------------------------------------------------------
+// fused vector kernels of BiCGStab (reference src/algebra/bicg.h:185-232)
+// ------------------------------------------------------------------------------------------
+// p = r + beta (p - omega v) ; phat = D p                       (bicg.h:196-202)
+__global__ void __launch_bounds__(BLOCK)
+k_bicg_p(int n, const double *__restrict__ r, double *__restrict__ p, const double *__restrict__ v,
+         const double *__restrict__ D, double *__restrict__ phat, const KState *st)
+    {
+    if (st->done) return;
+    const bool first = st->nit == 0;
+    const double omega = st->omega;
+    const double beta = first ? 0.0 : (st->rho1 / st->rho2) * (st->alpha / omega);
+    const int stride = gridDim.x * BLOCK;
+    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += stride)
+        {
+        double pi;
+        if (first)
+            pi = r[i];  // p was set to r by the setup
+        else
+            pi = (p[i] - omega * v[i]) * beta + r[i];
+        p[i] = pi;
+        phat[i] = D[i] * pi;
+        }
+    }
+
+// s = r - alpha v ; shat = D s ; ||s||^2 -> mid-iteration exit test    (bicg.h:207-218)
+__global__ void __launch_bounds__(BLOCK)
+k_bicg_s(int n, const double *__restrict__ r, const double *__restrict__ v,
+         const double *__restrict__ D, double *__restrict__ s, double *__restrict__ shat, KState *st,
+         const RedBuf red)
+    {
+    if (st->done) return;
+    const double alpha = st->alpha;
+    double acc[1] = {0.0};
+    const int stride = gridDim.x * BLOCK;
+    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += stride)
+        {
+        const double si = r[i] - alpha * v[i];
+        s[i] = si;
+        shat[i] = D[i] * si;
+        acc[0] += si * si;
+        }
+    double tot[1];
+    if (!grid_reduce<1>(acc, red, tot)) return;
+    if (it_finished(st, sqrt(fabs(tot[0]))))
+        {
+        st->final_half = 1;  // x += alpha phat is applied by k_bicg_xr
+        st->done = 1;
+        }
+    else if (st->status == FG_ITER_OVERFLOW || st->status == FG_CANNOT_CONVERGE)
+        st->done = 1;
+    }
+
+// x += alpha phat + omega shat ; r = s - omega t ; ||r||^2, (rt,r) -> next loop test
+// (bicg.h:223-231 then :185-195).  When the loop ended on ||s|| only x += alpha phat is applied.
+__global__ void __launch_bounds__(BLOCK)
+k_bicg_xr(int n, double *__restrict__ x, const double *__restrict__ phat,
+          const double *__restrict__ shat, const double *__restrict__ s,
+          const double *__restrict__ t, const double *__restrict__ rt, double *__restrict__ r,
+          KState *st, const RedBuf red)
+    {
+    const int fh = st->final_half;
+    if (st->done && !fh) return;
+    const double alpha = st->alpha, omega = st->omega;
+    double acc[2] = {0.0, 0.0};
+    const int stride = gridDim.x * BLOCK;
+    if (fh)
+        {
+        for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += stride) x[i] += alpha * phat[i];
+        }
+    else
+        {
+        for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += stride)
+            {
+            x[i] = (x[i] + alpha * phat[i]) + omega * shat[i];
+            const double ri = s[i] - omega * t[i];
+            r[i] = ri;
+            acc[0] += ri * ri;
+            acc[1] += rt[i] * ri;
+            }
+        }
+    double tot[2];
+    if (!grid_reduce<2>(acc, red, tot)) return;
+    if (fh)
+        {
+        st->final_half = 0;
+        return;
+        }
+    st->rho2 = st->rho1;
+    st->nit++;
+    if (st->nit >= st->maxiter) st->status = FG_ITER_OVERFLOW;  // iter.h:119-124
+    bicg_top_of_loop(st, tot[0], tot[1]);
+    }
+
+// ------------------------------------------------------------------------------------------
+// fused vector kernels of CG (reference src/algebra/cg.h:36-56)
+// ------------------------------------------------------------------------------------------
+// p = (rho/rho_1) p + D r   (nit > 0)
+__global__ void __launch_bounds__(BLOCK)
+k_cg_p(int n, const double *__restrict__ r, const double *__restrict__ D, double *__restrict__ p,
+       const KState *st)
+    {
+    if (st->done || st->nit == 0) return;
+    const double f = st->rho1 / st->rho2;
+    const int stride = gridDim.x * BLOCK;
+    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += stride)
+        p[i] = p[i] * f + D[i] * r[i];
+    }
+
+// x += a p ; r -= a q ; ||r||^2, (Dr, r) -> loop test
+__global__ void __launch_bounds__(BLOCK)
+k_cg_xr(int n, double *__restrict__ x, const double *__restrict__ p, const double *__restrict__ q,
+        const double *__restrict__ D, double *__restrict__ r, KState *st, const RedBuf red)
+    {
+    if (st->done) return;
+    const double a = st->alpha;
+    double acc[2] = {0.0, 0.0};
+    const int stride = gridDim.x * BLOCK;
+    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += stride)
+        {
+        x[i] += a * p[i];
+        const double ri = r[i] - a * q[i];
+        r[i] = ri;
+        acc[0] += ri * ri;
+        acc[1] += (D[i] * ri) * ri;
+        }
+    double tot[2];
+    if (!grid_reduce<2>(acc, red, tot)) return;
+    st->rho2 = st->rho1;  // rho_1 = rho
+    st->rho1 = tot[1];
+    st->nit++;
+    if (st->nit >= st->maxiter) st->status = FG_ITER_OVERFLOW;
+    if (it_finished(st, sqrt(fabs(tot[0]))) || st->status == FG_ITER_OVERFLOW
+        || st->status == FG_CANNOT_CONVERGE)
+        st->done = 1;
+    }
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK)
+k_init_state(KState *st, double tol, int maxiter)
+    {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    st->rho1 = st->rho2 = st->alpha = st->beta = st->omega = 0.0;
+    st->res = 1.7976931348623157e308;  // iteration::reset, iter.h:92-98
+    st->rhsn = 1.0;
+    st->resmax = tol;
+    st->nit = 0;
+    st->maxiter = maxiter;
+    st->status = FG_UNDEFINED;
+    st->done = 0;
+    st->final_half = 0;
+    st->updated = 0;
+    st->failed = 0;
+    }
+
+__global__ void __launch_bounds__(BLOCK)
+k_mask(int n, const unsigned char *__restrict__ mask, double *__restrict__ x)
+    {
+    const int stride = gridDim.x * BLOCK;
+    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += stride)
+        if (mask[i]) x[i] = 0.0;
+    }
+
+__global__ void __launch_bounds__(BLOCK)
+k_axpy(int n, double a, const double *__restrict__ x, double *__restrict__ y)
+    {
+    const int stride = gridDim.x * BLOCK;
+    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += stride) y[i] += a * x[i];
+    }
+
+// D[i] = 1 / A(i,i) (0 when masked), src/algebra/sparseMat.h:174-183
+__global__ void __launch_bounds__(BLOCK)
+k_diag_precond(const Operator op, const unsigned char *__restrict__ mask, double *__restrict__ D)
+    {
+    const int stride = gridDim.x * BLOCK;
+    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < op.n; i += stride)
+        {
+        double c = 0.0;
+        int lo = op.ptr[i], hi = op.ptr[i + 1];
+        const int end = hi;
+        while (lo < hi)
+            {
+            const int mid = lo + (hi - lo) / 2;
+            if (op.col[mid] < i)
+                lo = mid + 1;
+            else
+                hi = mid;
+            }
+        if (lo < end && op.col[lo] == i) c = op.val[lo];
+        D[i] = (mask != nullptr && mask[i]) ? 0.0 : 1.0 / c;
+        }
+    }
+
+#define FG_LAUNCH(w, kernel, grid, ...)                            \
+    do                                                             \
+        {                                                          \
+        kernel<<<(grid), BLOCK, 0, (w).stream>>>(__VA_ARGS__);     \
+        if ((w).launches) ++*(w).launches;                         \
+        FG_CUDA(cudaGetLastError());                               \
+        } while (0)
+
+int vec_mask(const KrylovWork &w, double *x)
+    {
+    if (!w.mask) return FG_OK;
+    FG_LAUNCH(w, k_mask, grid_for(w.n, BLOCK * 4), w.n, w.mask, x);
+    return FG_OK;
+    }
+
+int vec_axpy(const KrylovWork &w, double a, const double *x, double *y)
+    {
+    FG_LAUNCH(w, k_axpy, grid_for(w.n, BLOCK * 4), w.n, a, x, y);
+    return FG_OK;
+    }
+
+int build_diag_precond_csr(const Operator &A, const KrylovWork &w)
+    {
+    FG_LAUNCH(w, k_diag_precond, grid_for(A.n, BLOCK), A, w.mask, w.D);
+    return FG_OK;
+    }
+
+int krylov_alloc(KrylovWork &w, int n, int n_ghost, cudaStream_t stream, long long *launch_counter)
+    {
+    w = KrylovWork();
+    w.n = n;
+    w.nx = n + n_ghost;
+    w.stream = stream;
+    w.launches = launch_counter;
+    const size_t nb = sizeof(double) * (size_t)(w.nx > 0 ? w.nx : 1);
+    double **vecs[] = {&w.x, &w.b, &w.r, &w.rt, &w.p, &w.v, &w.s, &w.t, &w.phat, &w.shat, &w.D};
+    for (double **v : vecs)
+        {
+        FG_CUDA(cudaMalloc(v, nb));
+        FG_CUDA(cudaMemsetAsync(*v, 0, nb, stream));
+        }
+    FG_CUDA(cudaMalloc(&w.st, sizeof(KState)));
+    FG_CUDA(cudaMemsetAsync(w.st, 0, sizeof(KState), stream));
+    FG_CUDA(cudaMallocHost(&w.h_st, sizeof(KState)));
+    memset(w.h_st, 0, sizeof(KState));
+    FG_CUDA(cudaMalloc(&w.red.partials, sizeof(double) * RED_NV * MAX_GRID));
+    FG_CUDA(cudaMalloc(&w.red.ticket, sizeof(unsigned int)));
+    FG_CUDA(cudaMemsetAsync(w.red.ticket, 0, sizeof(unsigned int), stream));
+    FG_CUDA(cudaEventCreateWithFlags(&w.ev_poll, cudaEventDisableTiming));
+    w.last_iters = 0;
+    return FG_OK;
+    }
+
+void krylov_free(KrylovWork &w)
+    {
+    double *vecs[] = {w.x, w.b, w.r, w.rt, w.p, w.v, w.s, w.t, w.phat, w.shat, w.D};
+    for (double *v : vecs)
+        if (v) cudaFree(v);
+    if (w.st) cudaFree(w.st);
+    if (w.h_st) cudaFreeHost(w.h_st);
+    if (w.red.partials) cudaFree(w.red.partials);
+    if (w.red.ticket) cudaFree(w.red.ticket);
+    if (w.ev_poll) cudaEventDestroy(w.ev_poll);
+    w = KrylovWork();
+    }
+
+static int poll_state(KrylovWork &w)
+    {
+    FG_CUDA(cudaMemcpyAsync(w.h_st, w.st, sizeof(KState), cudaMemcpyDeviceToHost, w.stream));
+    FG_CUDA(cudaEventRecord(w.ev_poll, w.stream));
+    FG_CUDA(cudaEventSynchronize(w.ev_poll));
+    return FG_OK;
+    }
+
+// ------------------------------------------------------------------------------------------
+// BiCGStab driver
+// ------------------------------------------------------------------------------------------
+int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, post_batch_fn post,
+                 void *user)
+    {
+    const int n = w.n;
+    const int gv = grid_for(n, BLOCK * 4);
+    FG_LAUNCH(w, k_init_state, 1, w.st, tol, maxiter);
+    // r = b - A x0 (masked); rt = p = r; rhsn, first loop test
+        {
+        SpmvArgs a = {};
+        a.x = w.x;
+        a.y = w.r;
+        a.a0 = w.b;
+        a.o0 = w.rt;
+        a.o1 = w.p;
+        a.mask = w.mask;
+        a.st = w.st;
+        a.red = w.red;
+        FG_TRY(launch_spmv<ST_BICG_SETUP>(op, w, a));
+        }
+    int enq = 0;
+    // first batch sized by the previous solve of this context, then short batches
+    int batch = w.last_iters > 0 ? w.last_iters + 1 : 8;
+    for (;;)
+        {
+        if (batch > maxiter + 1 - enq) batch = maxiter + 1 - enq;
+        if (batch < 1) batch = 1;
+        for (int k = 0; k < batch; k++)
+            {
+            FG_LAUNCH(w, k_bicg_p, gv, n, w.r, w.p, w.v, w.D, w.phat, w.st);
+            SpmvArgs a = {};
+            a.x = w.phat;
+            a.y = w.v;
+            a.a0 = w.rt;
+            a.mask = w.mask;
+            a.st = w.st;
+            a.red = w.red;
+            FG_TRY(launch_spmv<ST_BICG_V>(op, w, a));
+            FG_LAUNCH(w, k_bicg_s, gv, n, w.r, w.v, w.D, w.s, w.shat, w.st, w.red);
+            a.x = w.shat;
+            a.y = w.t;
+            a.a0 = w.s;
+            FG_TRY(launch_spmv<ST_BICG_T>(op, w, a));
+            FG_LAUNCH(w, k_bicg_xr, gv, n, w.x, w.phat, w.shat, w.s, w.t, w.rt, w.r, w.st, w.red);
+            }
+        enq += batch;
+        if (post) FG_TRY(post(user));
+        FG_TRY(poll_state(w));
+        if (w.h_st->done) break;
+        if (enq > maxiter + 1)
+            {
+            set_error("bicgstab_run: device loop did not terminate after %d iterations", enq);
+            return FG_ERR_STATE;
+            }
+        batch = 4;
+        }
+    w.last_iters = w.h_st->nit;
+    return FG_OK;
+    }
+
+// ------------------------------------------------------------------------------------------
+// CG driver
+// ------------------------------------------------------------------------------------------
+int cg_run(const Operator &op, KrylovWork &w, double tol, int maxiter)
+    {
+    const int n = w.n;
+    const int gv = grid_for(n, BLOCK * 4);
+    FG_LAUNCH(w, k_init_state, 1, w.st, tol, maxiter);
+        {
+        SpmvArgs a = {};
+        a.x = w.x;
+        a.y = w.r;
+        a.a0 = w.b;
+        a.a1 = w.D;
+        a.o1 = w.p;
+        a.mask = w.mask;
+        a.st = w.st;
+        a.red = w.red;
+        FG_TRY(launch_spmv<ST_CG_SETUP>(op, w, a));
+        }
+    int enq = 0;
+    int batch = 16;
+    for (;;)
+        {
+        if (batch > maxiter + 1 - enq) batch = maxiter + 1 - enq;
+        if (batch < 1) batch = 1;
+        for (int k = 0; k < batch; k++)
+            {
+            FG_LAUNCH(w, k_cg_p, gv, n, w.r, w.D, w.p, w.st);
+            SpmvArgs a = {};
+            a.x = w.p;
+            a.y = w.t;  // q
+            a.a0 = w.p;
+            a.mask = w.mask;
+            a.st = w.st;
+            a.red = w.red;
+            FG_TRY(launch_spmv<ST_CG_Q>(op, w, a));
+            FG_LAUNCH(w, k_cg_xr, gv, n, w.x, w.p, w.t, w.D, w.r, w.st, w.red);
+            }
+        enq += batch;
+        FG_TRY(poll_state(w));
+        if (w.h_st->done) break;
+        if (enq > maxiter + 1)
+            {
+            set_error("cg_run: device loop did not terminate after %d iterations", enq);
+            return FG_ERR_STATE;
+            }
+        }
+    return FG_OK;
+    }
+
+// b <- b - A xd (masked afterwards by the caller), the prelude of the *_dir(xd) variants
+int resid_into(const Operator &op, const KrylovWork &w, const double *xd, const double *b,
+               double *out)
+    {
+    SpmvArgs a = {};
+    a.x = xd;
+    a.y = out;
+    a.a0 = b;
+    a.mask = nullptr;
+    a.st = w.st;
+    a.red = w.red;
+    return launch_spmv<ST_RESID>(op, w, a);
+    }
+
+}  // namespace fg

@@ -1,0 +1,1031 @@
+// fg_llg.cu — the LLG step context and its C ABI (include/feellgood_b200.h).
+//
+// One fg_ctx = one LinAlgebra object of the reference (src/linear_algebra.h) bound to one B200 and
+// one CUDA stream.  All mesh tables, the node state (CURRENT and NEXT), the sparse system and the
+// Krylov workspace stay resident in HBM between steps; a step moves no bulk data across PCIe.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "fg_common.cuh"
+#include "fg_llg_kernels.cuh"
+#include "fg_setup.hpp"
+
+namespace fg
+{
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...)
+    {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    }
+int resid_into(const Operator &op, const KrylovWork &w, const double *xd, const double *b,
+               double *out);
+}  // namespace fg
+
+using namespace fg;
+
+struct fg_ctx
+    {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+    HostSetup h;
+    int NOD = 0, NTm = 0, NFa = 0, n = 0, nnzb = 0, lanes = 8;
+    double tol = 1e-6;
+    int maxiter = 700;
+    // node state
+    NodeRec *cur = nullptr, *next = nullptr;
+    Basis *basis = nullptr;
+    unsigned char *nonmag = nullptr, *dofmask = nullptr;
+    double *stage = nullptr;     // 8*NOD doubles, device
+    double *h_stage = nullptr;   // 8*NOD doubles, pinned host
+    // tets
+    int4 *tet_ind = nullptr;
+    double *tet_da = nullptr, *tet_detJ = nullptr, *ext_field = nullptr;
+    int *tet_reg = nullptr;
+    TetRegion *reg_tet = nullptr;
+    double4 *rec = nullptr;
+    // tris
+    int *tri_ind = nullptr, *tri_reg = nullptr;
+    double *tri_surf = nullptr, *tri_dMs = nullptr;
+    TriRegion *reg_tri = nullptr;
+    double2 *trec = nullptr;
+    std::vector<TriRegion> h_reg_tri;
+    // pattern and per-mesh constants
+    int *nptr = nullptr, *ncol = nullptr, *inc_ptr = nullptr, *inc = nullptr, *inc_tri_ptr = nullptr,
+        *inc_tri = nullptr;
+    double *S = nullptr, *Aw = nullptr, *val = nullptr;
+    KrylovWork kw;
+    Operator op;
+    // step bookkeeping
+    StepPrm sp = {};
+    bool have_basis = false, prepared = false, space_field = false, assembled = false;
+    double v_max = 0.0;
+    // profiling
+    int profiling = 0;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    SpmvProf prof = {nullptr, 0, 0};
+    };
+
+namespace
+{
+template <class T> int dev_upload(T **dst, const std::vector<T> &src, cudaStream_t s, size_t min_elems = 1)
+    {
+    const size_t nel = src.size() > min_elems ? src.size() : min_elems;
+    FG_CUDA(cudaMalloc(dst, sizeof(T) * nel));
+    if (!src.empty())
+        FG_CUDA(cudaMemcpyAsync(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice, s));
+    return FG_OK;
+    }
+
+#define CTX_LAUNCH(c, kernel, grid, ...)                           \
+    do                                                             \
+        {                                                          \
+        kernel<<<(grid), BLOCK, 0, (c)->stream>>>(__VA_ARGS__);    \
+        ++(c)->launches;                                           \
+        FG_CUDA(cudaGetLastError());                               \
+        } while (0)
+
+int check_ctx(const fg_ctx *c)
+    {
+    if (!c)
+        {
+        set_error("null context");
+        return FG_ERR_INVALID;
+        }
+    FG_CUDA(cudaSetDevice(c->device));
+    return FG_OK;
+    }
+
+TetArrays tet_arrays(const fg_ctx *c)
+    {
+    TetArrays A;
+    A.NTm = c->NTm;
+    A.ind = c->tet_ind;
+    A.da = c->tet_da;
+    A.detJ = c->tet_detJ;
+    A.reg = c->tet_reg;
+    A.regions = c->reg_tet;
+    A.ext_field = c->ext_field;
+    return A;
+    }
+
+int launch_basis(fg_ctx *c, double angle)
+    {
+    CTX_LAUNCH(c, k_basis, grid_for(c->NOD, BLOCK), c->NOD, c->cur, cos(angle), sin(angle), c->basis);
+    c->have_basis = true;
+    c->prepared = false;
+    c->assembled = false;
+    return FG_OK;
+    }
+
+int launch_elements(fg_ctx *c)
+    {
+    if (!c->have_basis)
+        {
+        set_error("prepareElements before base_projection");
+        return FG_ERR_STATE;
+        }
+    if (c->NTm > 0)
+        {
+        const TetArrays A = tet_arrays(c);
+        const int grid = grid_for(c->NTm, BLOCK);
+        if (c->h.npi_tet == 5)
+            {
+            if (c->space_field)
+                CTX_LAUNCH(c, (k_tet<5, true>), grid, A, c->cur, c->basis, c->sp, c->rec);
+            else
+                CTX_LAUNCH(c, (k_tet<5, false>), grid, A, c->cur, c->basis, c->sp, c->rec);
+            }
+        else
+            {
+            if (c->space_field)
+                CTX_LAUNCH(c, (k_tet<1, true>), grid, A, c->cur, c->basis, c->sp, c->rec);
+            else
+                CTX_LAUNCH(c, (k_tet<1, false>), grid, A, c->cur, c->basis, c->sp, c->rec);
+            }
+        }
+    if (c->NFa > 0)
+        {
+        TriArrays F;
+        F.NFa = c->NFa;
+        F.ind = c->tri_ind;
+        F.surf = c->tri_surf;
+        F.dMs = c->tri_dMs;
+        F.reg = c->tri_reg;
+        F.regions = c->reg_tri;
+        const int grid = grid_for(c->NFa, BLOCK);
+        if (c->h.npi_tri == 4)
+            CTX_LAUNCH(c, k_tri<4>, grid, F, c->cur, c->basis, c->trec);
+        else
+            CTX_LAUNCH(c, k_tri<1>, grid, F, c->cur, c->basis, c->trec);
+        }
+    c->prepared = true;
+    c->assembled = false;
+    return FG_OK;
+    }
+
+int launch_assemble(fg_ctx *c, double dt)
+    {
+    if (!c->prepared)
+        {
+        set_error("solve before prepareElements");
+        return FG_ERR_STATE;
+        }
+    if (dt != c->sp.dt)
+        {
+        set_error("solve(dt=%g) does not match prepareElements(dt=%g)", dt, c->sp.dt);
+        return FG_ERR_STATE;
+        }
+    RowArrays R;
+    R.NOD = c->NOD;
+    R.G = c->lanes;
+    R.nptr = c->nptr;
+    R.ncol = c->ncol;
+    R.S = c->S;
+    R.Aw = c->Aw;
+    R.inc_ptr = c->inc_ptr;
+    R.inc = c->inc;
+    R.inc_tri_ptr = c->inc_tri_ptr;
+    R.inc_tri = c->inc_tri;
+    R.nonmag = c->nonmag;
+    const double s_dt = FG_THETA * dt * FG_GAMMA0;
+    const double cS = c->sp.prefactor * s_dt;  // tetra.cpp:261: lumping(a_eff, prefactor*s_dt*Abis)
+    CTX_LAUNCH(c, k_assemble_rows, grid_for(c->NOD, BLOCK / c->lanes), R, c->cur, c->next, c->basis,
+               c->rec, c->trec, cS, c->val, c->kw.b, c->kw.x, c->kw.D);
+    c->assembled = true;
+    return FG_OK;
+    }
+
+int post_update(void *user)
+    {
+    fg_ctx *c = static_cast<fg_ctx *>(user);
+    CTX_LAUNCH(c, k_update, grid_for(c->NOD, BLOCK), c->NOD, c->nonmag, c->cur, c->next, c->basis,
+               c->kw.x, c->sp.dt, c->kw.st, c->kw.red);
+    return FG_OK;
+    }
+
+int run_solve(fg_ctx *c, double dt, fg_step_result *out)
+    {
+    if (c->profiling) FG_CUDA(cudaEventRecord(c->ev[2], c->stream));
+    FG_TRY(launch_assemble(c, dt));
+    if (c->profiling) FG_CUDA(cudaEventRecord(c->ev[3], c->stream));
+    FG_TRY(bicgstab_run(c->op, c->kw, c->tol, c->maxiter, post_update, c));
+    if (c->profiling)
+        {
+        FG_CUDA(cudaEventRecord(c->ev[4], c->stream));
+        FG_CUDA(cudaEventSynchronize(c->ev[4]));
+        float ms;
+        for (int k = 0; k < 4; k++)
+            {
+            FG_CUDA(cudaEventElapsedTime(&ms, c->ev[k], c->ev[k + 1]));
+            c->phase_ms[k] = ms;
+            }
+        }
+    const KState &st = *c->kw.h_st;
+    if (!st.updated)
+        {
+        set_error("solve: node update did not run (done=%d)", st.done);
+        return FG_ERR_STATE;
+        }
+    if (!st.failed) c->v_max = st.v_max;
+    c->prepared = false;  // Kp/Lp are consumed; the reference would reuse them, we require a new prepare
+    if (out)
+        {
+        out->failed = st.failed;
+        out->status = st.status;
+        out->iters = st.nit;
+        out->pad_ = 0;
+        out->res = st.res;
+        out->rhsnorm = st.rhsn;
+        out->v_max = c->v_max;
+        }
+    return FG_OK;
+    }
+
+// host array (pageable or pinned) -> staging -> NodeRec fields
+int push_fields(fg_ctx *c, NodeRec *dst, const double *u, const double *v, const double *phi,
+                const double *phiv, bool zero_missing)
+    {
+    const size_t N = (size_t)c->NOD;
+    int which = 0;
+    struct Part { const double *src; size_t off, len; int bit; };
+    const Part parts[4] = {{u, 0, 3 * N, 1}, {v, 3 * N, 3 * N, 2}, {phi, 6 * N, N, 4}, {phiv, 7 * N, N, 8}};
+    for (const Part &p : parts)
+        {
+        if (p.src)
+            FG_CUDA(cudaMemcpyAsync(c->stage + p.off, p.src, sizeof(double) * p.len,
+                                    cudaMemcpyHostToDevice, c->stream));
+        else if (zero_missing)
+            FG_CUDA(cudaMemsetAsync(c->stage + p.off, 0, sizeof(double) * p.len, c->stream));
+        else
+            continue;
+        which |= p.bit;
+        }
+    if (which) CTX_LAUNCH(c, k_pack, grid_for(c->NOD, BLOCK), c->NOD, dst, c->stage, which);
+    // the caller's buffer may be pageable and reused right away
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    return FG_OK;
+    }
+}  // namespace
+
+extern "C" {
+
+const char *fg_last_error(void) { return g_err; }
+int fg_version(void) { return 100; }
+
+int fg_create(const fg_mesh *mesh, const fg_params *prm, int device, fg_ctx **out)
+    {
+    if (!mesh || !prm || !out)
+        {
+        set_error("fg_create: null argument");
+        return FG_ERR_INVALID;
+        }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        {
+        set_error("fg_create: no CUDA device available (this library has no CPU fallback)");
+        return FG_ERR_CUDA;
+        }
+    if (device < 0 || device >= ndev)
+        {
+        set_error("fg_create: device %d out of range (%d devices)", device, ndev);
+        return FG_ERR_INVALID;
+        }
+    FG_CUDA(cudaSetDevice(device));
+    fg_ctx *c = new fg_ctx();
+    c->device = device;
+    std::string err;
+    int rc = host_setup(*mesh, *prm, c->h, err);
+    if (rc != FG_OK)
+        {
+        set_error("%s", err.c_str());
+        delete c;
+        return rc;
+        }
+    HostSetup &h = c->h;
+    c->NOD = h.NOD;
+    c->NTm = (int)h.magTet.size();
+    c->NFa = (int)h.actTri.size();
+    c->n = 2 * h.NOD;
+    c->nnzb = h.nptr[h.NOD];
+    c->tol = prm->tol;
+    c->maxiter = prm->maxiter;
+    const double mean_deg = (double)c->nnzb / (double)c->NOD;
+    c->lanes = mean_deg > 10.0 ? 16 : (mean_deg > 5.0 ? 8 : 4);
+
+#define CK(x)                      \
+    do                             \
+        {                          \
+        int rc_ = (x);             \
+        if (rc_ != FG_OK)          \
+            {                      \
+            fg_destroy(c);         \
+            return rc_;            \
+            }                      \
+        } while (0)
+#define CKCUDA(call)                                                                             \
+    do                                                                                           \
+        {                                                                                        \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            {                                                                                    \
+            set_error("%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));       \
+            fg_destroy(c);                                                                       \
+            return FG_ERR_CUDA;                                                                  \
+            }                                                                                    \
+        } while (0)
+
+    CKCUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    cudaStream_t s = c->stream;
+    // Gauss tables
+        {
+        double a[20], p[5];
+        tet_tables(5, a, p);
+        CKCUDA(cudaMemcpyToSymbol(c_tet_a5, a, sizeof(double) * 20));
+        CKCUDA(cudaMemcpyToSymbol(c_tet_pds5, p, sizeof(double) * 5));
+        tet_tables(1, a, p);
+        CKCUDA(cudaMemcpyToSymbol(c_tet_a1, a, sizeof(double) * 4));
+        CKCUDA(cudaMemcpyToSymbol(c_tet_pds1, p, sizeof(double) * 1));
+        tri_tables(4, a, p);
+        CKCUDA(cudaMemcpyToSymbol(c_tri_a4, a, sizeof(double) * 12));
+        CKCUDA(cudaMemcpyToSymbol(c_tri_pds4, p, sizeof(double) * 4));
+        tri_tables(1, a, p);
+        CKCUDA(cudaMemcpyToSymbol(c_tri_a1, a, sizeof(double) * 3));
+        CKCUDA(cudaMemcpyToSymbol(c_tri_pds1, p, sizeof(double) * 1));
+        }
+    const size_t N = (size_t)c->NOD;
+    CKCUDA(cudaMalloc(&c->cur, sizeof(NodeRec) * N));
+    CKCUDA(cudaMalloc(&c->next, sizeof(NodeRec) * N));
+    CKCUDA(cudaMalloc(&c->basis, sizeof(Basis) * N));
+    CKCUDA(cudaMemsetAsync(c->cur, 0, sizeof(NodeRec) * N, s));
+    CKCUDA(cudaMemsetAsync(c->next, 0, sizeof(NodeRec) * N, s));
+    CKCUDA(cudaMemsetAsync(c->basis, 0, sizeof(Basis) * N, s));
+    CKCUDA(cudaMalloc(&c->stage, sizeof(double) * 8 * N));
+    CKCUDA(cudaMallocHost(&c->h_stage, sizeof(double) * 8 * N));
+        {
+        std::vector<unsigned char> nonmag(N), dofmask(2 * N);
+        for (size_t a = 0; a < N; a++)
+            {
+            nonmag[a] = h.magNode[a] ? 0 : 1;
+            dofmask[2 * a] = dofmask[2 * a + 1] = nonmag[a];
+            }
+        CK(dev_upload(&c->nonmag, nonmag, s));
+        CK(dev_upload(&c->dofmask, dofmask, s));
+        CKCUDA(cudaStreamSynchronize(s));
+        }
+    // magnetic tets, SoA
+        {
+        const size_t M = (size_t)c->NTm;
+        std::vector<int4> ind(M);
+        std::vector<double> da(12 * M), dj(M);
+        std::vector<int> reg(M);
+        for (size_t tm = 0; tm < M; tm++)
+            {
+            const size_t t = (size_t)h.magTet[tm];
+            ind[tm] = make_int4(h.tet_ind[4 * t], h.tet_ind[4 * t + 1], h.tet_ind[4 * t + 2], h.tet_ind[4 * t + 3]);
+            for (int k = 0; k < 12; k++) da[(size_t)k * M + tm] = h.tet_da[12 * t + k];
+            dj[tm] = h.tet_detJ[t];
+            reg[tm] = h.tet_reg[t];
+            }
+        CK(dev_upload(&c->tet_ind, ind, s));
+        CK(dev_upload(&c->tet_da, da, s));
+        CK(dev_upload(&c->tet_detJ, dj, s));
+        CK(dev_upload(&c->tet_reg, reg, s));
+        std::vector<TetRegion> regs((size_t)prm->nreg_tet);
+        for (int r = 0; r < prm->nreg_tet; r++)
+            {
+            const fg_tet_prm &p = prm->prm_tet[r];
+            TetRegion &R = regs[r];
+            memset(&R, 0, sizeof R);
+            R.alpha = p.alpha_LLG;
+            if (p.Ms > 0)
+                {
+                R.Abis = 2.0 * p.A / (FG_MU0 * p.Ms);   // tetra.cpp:217
+                R.Kbis = 2.0 * p.K / (FG_MU0 * p.Ms);   // tetra.cpp:239
+                R.K3bis = 2.0 * p.K3 / (FG_MU0 * p.Ms); // tetra.cpp:244
+                }
+            R.has_K = p.K != 0;
+            R.has_K3 = p.K3 != 0;
+            for (int k = 0; k < 3; k++)
+                {
+                R.uk[k] = p.uk[k];
+                R.ex[k] = p.ex[k];
+                R.ey[k] = p.ey[k];
+                R.ez[k] = p.ez[k];
+                }
+            }
+        CK(dev_upload(&c->reg_tet, regs, s));
+        CKCUDA(cudaMalloc(&c->rec, sizeof(double4) * 4 * (M > 0 ? M : 1)));
+        CKCUDA(cudaStreamSynchronize(s));
+        }
+    // active triangles
+        {
+        const size_t M = (size_t)c->NFa;
+        std::vector<int> ind(3 * M), reg(M);
+        std::vector<double> surf(M), dMs(M);
+        for (size_t fa = 0; fa < M; fa++)
+            {
+            const size_t f = (size_t)h.actTri[fa];
+            for (int i = 0; i < 3; i++) ind[(size_t)i * M + fa] = h.tri_ind[3 * f + i];
+            reg[fa] = h.tri_reg[f];
+            surf[fa] = h.tri_surf[f];
+            dMs[fa] = h.tri_dMs[f];
+            }
+        CK(dev_upload(&c->tri_ind, ind, s));
+        CK(dev_upload(&c->tri_reg, reg, s));
+        CK(dev_upload(&c->tri_surf, surf, s));
+        CK(dev_upload(&c->tri_dMs, dMs, s));
+        c->h_reg_tri.resize((size_t)(prm->nreg_tri > 0 ? prm->nreg_tri : 1));
+        for (int r = 0; r < prm->nreg_tri; r++)
+            {
+            c->h_reg_tri[r].Ks = prm->prm_tri[r].Ks;
+            for (int k = 0; k < 3; k++) c->h_reg_tri[r].uk[k] = prm->prm_tri[r].uk[k];
+            }
+        CK(dev_upload(&c->reg_tri, c->h_reg_tri, s));
+        CKCUDA(cudaMalloc(&c->trec, sizeof(double2) * 3 * (M > 0 ? M : 1)));
+        CKCUDA(cudaStreamSynchronize(s));
+        }
+    CK(dev_upload(&c->nptr, h.nptr, s));
+    CK(dev_upload(&c->ncol, h.ncol, s));
+    CK(dev_upload(&c->S, h.S, s));
+    CK(dev_upload(&c->Aw, h.Aw, s));
+    CK(dev_upload(&c->inc_ptr, h.inc_ptr, s));
+    CK(dev_upload(&c->inc, h.inc, s));
+    CK(dev_upload(&c->inc_tri_ptr, h.inc_tri_ptr, s));
+    CK(dev_upload(&c->inc_tri, h.inc_tri, s));
+    CKCUDA(cudaMalloc(&c->val, sizeof(double) * 4 * (size_t)c->nnzb));
+    CKCUDA(cudaMemsetAsync(c->val, 0, sizeof(double) * 4 * (size_t)c->nnzb, s));
+    CK(krylov_alloc(c->kw, c->n, 0, s, &c->launches));
+    c->kw.mask = c->dofmask;
+    c->op.kind = OP_NODE2;
+    c->op.n = c->n;
+    c->op.lanes = c->lanes;
+    c->op.ptr = c->nptr;
+    c->op.col = c->ncol;
+    c->op.val = c->val;
+    for (int k = 0; k < 5; k++) CKCUDA(cudaEventCreate(&c->ev[k]));
+    CKCUDA(cudaStreamSynchronize(s));
+    // the per-mesh host tables no longer needed are released (S, incidences stay on the device)
+    std::vector<double>().swap(h.S);
+    std::vector<int>().swap(h.inc);
+    std::vector<int>().swap(h.inc_tri);
+    c->sp.idx_dir = FG_IDX_UNDEF;
+    *out = c;
+    return FG_OK;
+    }
+
+void fg_destroy(fg_ctx *c)
+    {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    void *ptrs[] = {c->cur, c->next, c->basis, c->nonmag, c->dofmask, c->stage, c->tet_ind, c->tet_da,
+                    c->tet_detJ, c->ext_field, c->tet_reg, c->reg_tet, c->rec, c->tri_ind,
+                    c->tri_reg, c->tri_surf, c->tri_dMs, c->reg_tri, c->trec, c->nptr, c->ncol,
+                    c->inc_ptr, c->inc, c->inc_tri_ptr, c->inc_tri, c->S, c->Aw, c->val};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->prof.ev)
+        {
+        for (int k = 0; k < 2 * c->prof.cap; k++) cudaEventDestroy(c->prof.ev[k]);
+        delete[] c->prof.ev;
+        }
+    krylov_free(c->kw);
+    for (int k = 0; k < 5; k++)
+        if (c->ev[k]) cudaEventDestroy(c->ev[k]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    }
+
+int fg_get_sizes(const fg_ctx *c, long long out[10])
+    {
+    if (!c || !out)
+        {
+        set_error("fg_get_sizes: null argument");
+        return FG_ERR_INVALID;
+        }
+    out[0] = c->h.NOD;
+    out[1] = c->h.NT;
+    out[2] = c->h.NF;
+    out[3] = (long long)c->h.magTet.size();
+    out[4] = (long long)c->h.magTri.size();
+    out[5] = c->h.n_edges;
+    out[6] = c->h.n_edges_mag;
+    out[7] = c->n;
+    out[8] = 4LL * c->nnzb;
+    out[9] = (long long)c->h.lvd.size();
+    return FG_OK;
+    }
+
+int fg_set_state(fg_ctx *c, const double *u, const double *v, const double *phi, const double *phiv)
+    {
+    FG_TRY(check_ctx(c));
+    if (!u)
+        {
+        set_error("fg_set_state: u is required");
+        return FG_ERR_INVALID;
+        }
+    FG_TRY(push_fields(c, c->cur, u, v, phi, phiv, true));
+    FG_CUDA(cudaMemcpyAsync(c->next, c->cur, sizeof(NodeRec) * (size_t)c->NOD, cudaMemcpyDeviceToDevice, c->stream));
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_basis = c->prepared = c->assembled = false;
+    return FG_OK;
+    }
+
+int fg_set_next_v(fg_ctx *c, const double *v)
+    {
+    FG_TRY(check_ctx(c));
+    if (!v)
+        {
+        set_error("fg_set_next_v: null v");
+        return FG_ERR_INVALID;
+        }
+    return push_fields(c, c->next, nullptr, v, nullptr, nullptr, false);
+    }
+
+int fg_set_potentials(fg_ctx *c, const double *phi, const double *phiv)
+    {
+    FG_TRY(check_ctx(c));
+    if (!phi || !phiv)
+        {
+        set_error("fg_set_potentials: null argument");
+        return FG_ERR_INVALID;
+        }
+    return push_fields(c, c->next, nullptr, nullptr, phi, phiv, false);
+    }
+
+int fg_get_state(fg_ctx *c, int step, double *u, double *v, double *phi, double *phiv)
+    {
+    FG_TRY(check_ctx(c));
+    if (step != 0 && step != 1)
+        {
+        set_error("fg_get_state: step must be 0 (CURRENT) or 1 (NEXT)");
+        return FG_ERR_INVALID;
+        }
+    const size_t N = (size_t)c->NOD;
+    const int which = (u ? 1 : 0) | (v ? 2 : 0) | (phi ? 4 : 0) | (phiv ? 8 : 0);
+    if (!which) return FG_OK;
+    CTX_LAUNCH(c, k_unpack, grid_for(c->NOD, BLOCK), c->NOD, step ? c->next : c->cur, c->stage, which);
+    struct Part { double *dst; size_t off, len; };
+    const Part parts[4] = {{u, 0, 3 * N}, {v, 3 * N, 3 * N}, {phi, 6 * N, N}, {phiv, 7 * N, N}};
+    for (const Part &p : parts)
+        if (p.dst)
+            FG_CUDA(cudaMemcpyAsync(p.dst, c->stage + p.off, sizeof(double) * p.len,
+                                    cudaMemcpyDeviceToHost, c->stream));
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    return FG_OK;
+    }
+
+int fg_commit(fg_ctx *c)
+    {
+    FG_TRY(check_ctx(c));
+    FG_CUDA(cudaMemcpyAsync(c->cur, c->next, sizeof(NodeRec) * (size_t)c->NOD, cudaMemcpyDeviceToDevice, c->stream));
+    c->have_basis = c->prepared = c->assembled = false;
+    return FG_OK;
+    }
+
+int fg_set_ext_space_field(fg_ctx *c, const double *field)
+    {
+    FG_TRY(check_ctx(c));
+    if (!field)
+        {
+        set_error("fg_set_ext_space_field: null field");
+        return FG_ERR_INVALID;
+        }
+    const int npi = c->h.npi_tet;
+    const size_t M = (size_t)c->NTm, K = 3 * (size_t)npi;
+    std::vector<double> soa(K * (M > 0 ? M : 1));
+    for (size_t tm = 0; tm < M; tm++)
+        for (size_t k = 0; k < K; k++) soa[k * M + tm] = field[K * (size_t)c->h.magTet[tm] + k];
+    if (!c->ext_field) FG_CUDA(cudaMalloc(&c->ext_field, sizeof(double) * soa.size()));
+    FG_CUDA(cudaMemcpyAsync(c->ext_field, soa.data(), sizeof(double) * soa.size(), cudaMemcpyHostToDevice, c->stream));
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    return FG_OK;
+    }
+
+int fg_base_projection(fg_ctx *c, double angle)
+    {
+    FG_TRY(check_ctx(c));
+    if (c->profiling) FG_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    return launch_basis(c, angle);
+    }
+
+static int set_step_prm(fg_ctx *c, const double Hext[3], double A_Hext, double dt, double prefactor,
+                        int idx_dir, double Vdrift, bool space)
+    {
+    if (!(dt > 0.0))
+        {
+        set_error("prepareElements: dt must be positive");
+        return FG_ERR_INVALID;
+        }
+    if (idx_dir < FG_IDX_UNDEF || idx_dir > FG_IDX_Z)
+        {
+        set_error("prepareElements: bad idx_dir %d", idx_dir);
+        return FG_ERR_INVALID;
+        }
+    if (space && !c->ext_field)
+        {
+        set_error("prepareElements(A_Hext): no space field set (fg_set_ext_space_field)");
+        return FG_ERR_STATE;
+        }
+    c->sp.dt = dt;
+    c->sp.prefactor = prefactor;
+    for (int k = 0; k < 3; k++) c->sp.Hext[k] = Hext ? Hext[k] : 0.0;
+    c->sp.A_Hext = A_Hext;
+    c->sp.idx_dir = idx_dir;
+    c->sp.Vdrift = Vdrift;
+    c->space_field = space;
+    return FG_OK;
+    }
+
+int fg_prepare_elements(fg_ctx *c, const double Hext[3], double dt, double prefactor, int idx_dir,
+                        double Vdrift)
+    {
+    FG_TRY(check_ctx(c));
+    if (!Hext)
+        {
+        set_error("fg_prepare_elements: null Hext");
+        return FG_ERR_INVALID;
+        }
+    FG_TRY(set_step_prm(c, Hext, 0.0, dt, prefactor, idx_dir, Vdrift, false));
+    if (c->profiling) FG_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    return launch_elements(c);
+    }
+
+int fg_prepare_elements_space(fg_ctx *c, double A_Hext, double dt, double prefactor, int idx_dir,
+                              double Vdrift)
+    {
+    FG_TRY(check_ctx(c));
+    FG_TRY(set_step_prm(c, nullptr, A_Hext, dt, prefactor, idx_dir, Vdrift, true));
+    if (c->profiling) FG_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    return launch_elements(c);
+    }
+
+int fg_solve(fg_ctx *c, double dt, fg_step_result *out)
+    {
+    FG_TRY(check_ctx(c));
+    return run_solve(c, dt, out);
+    }
+
+int fg_step(fg_ctx *c, double angle, const double Hext[3], double dt, double prefactor, int idx_dir,
+            double Vdrift, fg_step_result *out)
+    {
+    FG_TRY(check_ctx(c));
+    if (!Hext)
+        {
+        set_error("fg_step: null Hext");
+        return FG_ERR_INVALID;
+        }
+    FG_TRY(set_step_prm(c, Hext, 0.0, dt, prefactor, idx_dir, Vdrift, false));
+    if (c->profiling) FG_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    FG_TRY(launch_basis(c, angle));
+    if (c->profiling) FG_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    FG_TRY(launch_elements(c));
+    return run_solve(c, dt, out);
+    }
+
+// ---- taps ----
+int fg_get_basis(fg_ctx *c, double *ep, double *eq)
+    {
+    FG_TRY(check_ctx(c));
+    const size_t N = (size_t)c->NOD;
+    std::vector<Basis> b(N);
+    FG_CUDA(cudaMemcpyAsync(b.data(), c->basis, sizeof(Basis) * N, cudaMemcpyDeviceToHost, c->stream));
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    for (size_t a = 0; a < N; a++)
+        for (int k = 0; k < 3; k++)
+            {
+            if (ep) ep[3 * a + k] = b[a].ep[k];
+            if (eq) eq[3 * a + k] = b[a].eq[k];
+            }
+    return FG_OK;
+    }
+
+int fg_get_elements(fg_ctx *c, int first, int count, double *Kp, double *Lp)
+    {
+    FG_TRY(check_ctx(c));
+    if (first < 0 || count < 0 || first + count > c->h.NT || !Kp || !Lp)
+        {
+        set_error("fg_get_elements: bad range [%d,%d) of %d", first, first + count, c->h.NT);
+        return FG_ERR_INVALID;
+        }
+    if (!c->prepared && !c->assembled)
+        {
+        set_error("fg_get_elements: no prepareElements since the last state change");
+        return FG_ERR_STATE;
+        }
+    memset(Kp, 0, sizeof(double) * 64 * (size_t)count);
+    memset(Lp, 0, sizeof(double) * 8 * (size_t)count);
+    // magnetic tets in the range form a contiguous run of compact indices
+    int tm0 = -1, cnt = 0;
+    for (int t = first; t < first + count; t++)
+        if (c->h.tet_to_mag[t] >= 0)
+            {
+            if (tm0 < 0) tm0 = c->h.tet_to_mag[t];
+            cnt++;
+            }
+    if (cnt == 0) return FG_OK;
+    double *dK = nullptr, *dL = nullptr;
+    FG_CUDA(cudaMalloc(&dK, sizeof(double) * 64 * (size_t)cnt));
+    FG_CUDA(cudaMalloc(&dL, sizeof(double) * 8 * (size_t)cnt));
+    const TetArrays A = tet_arrays(c);
+    const int grid = (cnt + BLOCK - 1) / BLOCK;
+    if (c->h.npi_tet == 5)
+        {
+        if (c->space_field) k_tet_tap<5, true><<<grid, BLOCK, 0, c->stream>>>(A, c->cur, c->basis, c->sp, tm0, cnt, dK, dL);
+        else k_tet_tap<5, false><<<grid, BLOCK, 0, c->stream>>>(A, c->cur, c->basis, c->sp, tm0, cnt, dK, dL);
+        }
+    else
+        {
+        if (c->space_field) k_tet_tap<1, true><<<grid, BLOCK, 0, c->stream>>>(A, c->cur, c->basis, c->sp, tm0, cnt, dK, dL);
+        else k_tet_tap<1, false><<<grid, BLOCK, 0, c->stream>>>(A, c->cur, c->basis, c->sp, tm0, cnt, dK, dL);
+        }
+    ++c->launches;
+    std::vector<double> hK(64 * (size_t)cnt), hL(8 * (size_t)cnt);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hK.data(), dK, sizeof(double) * hK.size(), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hL.data(), dL, sizeof(double) * hL.size(), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(dK);
+    cudaFree(dL);
+    if (e != cudaSuccess)
+        {
+        set_error("fg_get_elements: %s", cudaGetErrorString(e));
+        return FG_ERR_CUDA;
+        }
+    for (int t = first; t < first + count; t++)
+        {
+        const int tm = c->h.tet_to_mag[t];
+        if (tm < 0) continue;
+        memcpy(Kp + 64 * (size_t)(t - first), &hK[64 * (size_t)(tm - tm0)], sizeof(double) * 64);
+        memcpy(Lp + 8 * (size_t)(t - first), &hL[8 * (size_t)(tm - tm0)], sizeof(double) * 8);
+        }
+    return FG_OK;
+    }
+
+int fg_get_tri_elements(fg_ctx *c, int first, int count, double *Lp)
+    {
+    FG_TRY(check_ctx(c));
+    if (first < 0 || count < 0 || first + count > c->h.NF || !Lp)
+        {
+        set_error("fg_get_tri_elements: bad range");
+        return FG_ERR_INVALID;
+        }
+    if (!c->have_basis)
+        {
+        set_error("fg_get_tri_elements: no basis");
+        return FG_ERR_STATE;
+        }
+    memset(Lp, 0, sizeof(double) * 6 * (size_t)count);
+    // Tri::integrales runs for magnetic triangles with Ks != 0 (src/linear_algebra.cpp:45-51),
+    // whether or not their Lp later reaches the rhs
+    std::vector<int> sel;
+    for (int f = first; f < first + count; f++)
+        {
+        const int *ind = &c->h.tri_ind[3 * (size_t)f];
+        const bool mag = c->h.magNode[ind[0]] && c->h.magNode[ind[1]] && c->h.magNode[ind[2]];
+        if (mag && c->h_reg_tri[c->h.tri_reg[f]].Ks != 0) sel.push_back(f);
+        }
+    if (sel.empty()) return FG_OK;
+    const size_t M = sel.size();
+    std::vector<int> ind(3 * M), reg(M);
+    std::vector<double> surf(M), dMs(M);
+    for (size_t k = 0; k < M; k++)
+        {
+        const size_t f = (size_t)sel[k];
+        for (int i = 0; i < 3; i++) ind[(size_t)i * M + k] = c->h.tri_ind[3 * f + i];
+        reg[k] = c->h.tri_reg[f];
+        surf[k] = c->h.tri_surf[f];
+        dMs[k] = c->h.tri_dMs[f];
+        }
+    int *d_ind = nullptr, *d_reg = nullptr;
+    double *d_surf = nullptr, *d_dMs = nullptr;
+    double2 *d_rec = nullptr;
+    int rc = FG_OK;
+    std::vector<double2> hrec(3 * M);
+    do
+        {
+        if ((rc = dev_upload(&d_ind, ind, c->stream)) != FG_OK) break;
+        if ((rc = dev_upload(&d_reg, reg, c->stream)) != FG_OK) break;
+        if ((rc = dev_upload(&d_surf, surf, c->stream)) != FG_OK) break;
+        if ((rc = dev_upload(&d_dMs, dMs, c->stream)) != FG_OK) break;
+        if (cudaMalloc(&d_rec, sizeof(double2) * 3 * M) != cudaSuccess) { rc = FG_ERR_CUDA; break; }
+        TriArrays F;
+        F.NFa = (int)M;
+        F.ind = d_ind;
+        F.surf = d_surf;
+        F.dMs = d_dMs;
+        F.reg = d_reg;
+        F.regions = c->reg_tri;
+        const int grid = grid_for((long long)M, BLOCK);
+        if (c->h.npi_tri == 4) k_tri<4><<<grid, BLOCK, 0, c->stream>>>(F, c->cur, c->basis, d_rec);
+        else k_tri<1><<<grid, BLOCK, 0, c->stream>>>(F, c->cur, c->basis, d_rec);
+        ++c->launches;
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hrec.data(), d_rec, sizeof(double2) * 3 * M, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess)
+            {
+            set_error("fg_get_tri_elements: %s", cudaGetErrorString(e));
+            rc = FG_ERR_CUDA;
+            }
+        } while (0);
+    cudaFree(d_ind);
+    cudaFree(d_reg);
+    cudaFree(d_surf);
+    cudaFree(d_dMs);
+    cudaFree(d_rec);
+    if (rc != FG_OK) return rc;
+    for (size_t k = 0; k < M; k++)
+        for (int i = 0; i < 3; i++)
+            {  // Perm = {3,4,5,0,1,2} (triangle.cpp:30-34): rows 0..2 eq-projections, 3..5 ep
+            Lp[6 * (size_t)(sel[k] - first) + i] = hrec[3 * k + i].x;
+            Lp[6 * (size_t)(sel[k] - first) + 3 + i] = hrec[3 * k + i].y;
+            }
+    return FG_OK;
+    }
+
+int fg_get_csr_pattern(const fg_ctx *c, int *rowptr, int *col)
+    {
+    if (!c || !rowptr || !col)
+        {
+        set_error("fg_get_csr_pattern: null argument");
+        return FG_ERR_INVALID;
+        }
+    const HostSetup &h = c->h;
+    rowptr[0] = 0;
+    for (int a = 0; a < h.NOD; a++)
+        {
+        const int beg = h.nptr[a], deg = h.nptr[a + 1] - beg;
+        for (int k = 0; k < 2; k++)
+            {
+            const int base = 4 * beg + 2 * deg * k;
+            for (int j = 0; j < deg; j++)
+                {
+                col[base + 2 * j] = 2 * h.ncol[beg + j];
+                col[base + 2 * j + 1] = 2 * h.ncol[beg + j] + 1;
+                }
+            rowptr[2 * a + k + 1] = base + 2 * deg;
+            }
+        }
+    return FG_OK;
+    }
+
+int fg_get_system(fg_ctx *c, double dt, double *val, double *rhs, double *x0)
+    {
+    FG_TRY(check_ctx(c));
+    // before the solve: assemble now; after it: K and L_rhs are still resident (x0 then holds Xw)
+    if (c->prepared || !c->assembled) FG_TRY(launch_assemble(c, dt));
+    if (val) FG_CUDA(cudaMemcpyAsync(val, c->val, sizeof(double) * 4 * (size_t)c->nnzb, cudaMemcpyDeviceToHost, c->stream));
+    if (rhs) FG_CUDA(cudaMemcpyAsync(rhs, c->kw.b, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+    if (x0) FG_CUDA(cudaMemcpyAsync(x0, c->kw.x, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    return FG_OK;
+    }
+
+int fg_apply_operator(fg_ctx *c, const double *x, double *y)
+    {
+    FG_TRY(check_ctx(c));
+    if (!x || !y)
+        {
+        set_error("fg_apply_operator: null argument");
+        return FG_ERR_INVALID;
+        }
+    if (!c->assembled)
+        {
+        set_error("fg_apply_operator: no assembled system");
+        return FG_ERR_STATE;
+        }
+    FG_CUDA(cudaMemcpyAsync(c->kw.phat, x, sizeof(double) * (size_t)c->n, cudaMemcpyHostToDevice, c->stream));
+    FG_TRY(spmv(c->op, c->kw, c->kw.phat, c->kw.v, false));
+    FG_CUDA(cudaMemcpyAsync(y, c->kw.v, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    return FG_OK;
+    }
+
+int fg_get_solution(fg_ctx *c, double *Xw)
+    {
+    FG_TRY(check_ctx(c));
+    if (!Xw)
+        {
+        set_error("fg_get_solution: null argument");
+        return FG_ERR_INVALID;
+        }
+    FG_CUDA(cudaMemcpyAsync(Xw, c->kw.x, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    return FG_OK;
+    }
+
+int fg_get_tet_tables(const fg_ctx *c, int *ind, double *da, double *weight)
+    {
+    if (!c)
+        {
+        set_error("fg_get_tet_tables: null context");
+        return FG_ERR_INVALID;
+        }
+    const HostSetup &h = c->h;
+    if (ind) memcpy(ind, h.tet_ind.data(), sizeof(int) * h.tet_ind.size());
+    if (da) memcpy(da, h.tet_da.data(), sizeof(double) * h.tet_da.size());
+    if (weight)
+        {
+        double a[20], p[5];
+        tet_tables(h.npi_tet, a, p);
+        for (size_t t = 0; t < (size_t)h.NT; t++)
+            for (int g = 0; g < h.npi_tet; g++) weight[(size_t)h.npi_tet * t + g] = h.tet_detJ[t] * p[g];
+        }
+    return FG_OK;
+    }
+
+// ---- instrumentation ----
+long long fg_kernel_launches(const fg_ctx *c) { return c ? c->launches : 0; }
+void *fg_stream(const fg_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int fg_set_profiling(fg_ctx *c, int on)
+    {
+    FG_TRY(check_ctx(c));
+    c->profiling = on == 1 ? 1 : 0;
+    if (on == 2)
+        {
+        if (!c->prof.ev)
+            {
+            c->prof.cap = 4096;
+            c->prof.ev = new cudaEvent_t[2 * c->prof.cap];
+            for (int k = 0; k < 2 * c->prof.cap; k++) FG_CUDA(cudaEventCreate(&c->prof.ev[k]));
+            }
+        c->prof.n = 0;
+        c->kw.prof = &c->prof;
+        }
+    else
+        c->kw.prof = nullptr;
+    return FG_OK;
+    }
+
+int fg_get_spmv_times(fg_ctx *c, double *total_ms, int *launches)
+    {
+    FG_TRY(check_ctx(c));
+    if (!total_ms || !launches)
+        {
+        set_error("fg_get_spmv_times: null argument");
+        return FG_ERR_INVALID;
+        }
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    double sum = 0.0;
+    for (int k = 0; k < c->prof.n; k++)
+        {
+        float ms = 0.f;
+        FG_CUDA(cudaEventElapsedTime(&ms, c->prof.ev[2 * k], c->prof.ev[2 * k + 1]));
+        sum += ms;
+        }
+    *total_ms = sum;
+    *launches = c->prof.n;
+    c->prof.n = 0;
+    return FG_OK;
+    }
+
+int fg_get_phase_times(const fg_ctx *c, double out[8])
+    {
+    if (!c || !out)
+        {
+        set_error("fg_get_phase_times: null argument");
+        return FG_ERR_INVALID;
+        }
+    for (int k = 0; k < 8; k++) out[k] = c->phase_ms[k];
+    return FG_OK;
+    }
+
+int fg_bench_spmv(fg_ctx *c, int reps, double *ms_per_launch)
+    {
+    FG_TRY(check_ctx(c));
+    if (reps <= 0 || !ms_per_launch)
+        {
+        set_error("fg_bench_spmv: bad argument");
+        return FG_ERR_INVALID;
+        }
+    if (!c->assembled)
+        {
+        set_error("fg_bench_spmv: no assembled system");
+        return FG_ERR_STATE;
+        }
+    for (int k = 0; k < 3; k++) FG_TRY(spmv(c->op, c->kw, c->kw.x, c->kw.t, true));
+    FG_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    for (int k = 0; k < reps; k++) FG_TRY(spmv(c->op, c->kw, c->kw.x, c->kw.t, true));
+    FG_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    FG_CUDA(cudaEventSynchronize(c->ev[1]));
+    float ms = 0.f;
+    FG_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+    *ms_per_launch = (double)ms / reps;
+    return FG_OK;
+    }
+
+}  // extern "C"

@@ -1,0 +1,740 @@
+// fg_llg_kernels.cuh — device code of the per-time-step LLG kernels (sm_100a, FP64).
+//
+//   k_basis          Node::setBasis                  reference src/node.h:73-102
+//   k_tet            Tet::integrales                 reference src/tetra.cpp:210-307
+//   k_tri            Tri::integrales                 reference src/triangle.cpp:6-36
+//   k_assemble_rows  solver::buildMat/buildVect + mask + buildInitGuess + build_diag_precond
+//                    reference src/solver.cpp:9-59, src/solver.h:110-143, sparseMat.h:174-183
+//   k_update         node update + v_max             reference src/solver.cpp:74-88, node.h:116-122
+//
+// Structure exploited.  With AE v = E v + a_w (m x v) (src/tetra.cpp:108-148) and
+// P depending on the node only, the projected element matrix is
+//     Kp[(r,a),(c,b)] = E_ab (e_r,a . e_c,b) + delta_ab a_w,a e_r,a . (m_a x e_c,a),
+//     E_ab = prefactor s_dt Abis wsum (grad a_a . grad a_b) + delta_ab sum_g a_a(g) w_g alpha_eff(g)
+// so the global K is the projection of a NODxNOD scalar matrix whose off-diagonal part is constant
+// per mesh (S, built once) and whose diagonal gains one state-dependent number per node per step
+// (Malpha).  The per-step element kernel therefore emits, per (tet, local node), one 32-byte
+// record {sum_g a w alpha_eff, eq.BE, ep.BE}; k_assemble_rows gathers the records of a node through
+// its incidence list (no atomics, fixed order => deterministic) and writes the node's two CSR rows.
+#pragma once
+#include "fg_common.cuh"
+#include "fg_reduce.cuh"
+
+namespace fg
+{
+// Gauss tables (src/tetra.h:29-81, src/triangle.h:21-65), filled by fg_create
+__constant__ double c_tet_a5[20], c_tet_pds5[5], c_tet_a1[4], c_tet_pds1[1];
+__constant__ double c_tri_a4[12], c_tri_pds4[4], c_tri_a1[3], c_tri_pds1[1];
+
+template <int NPI> __device__ __forceinline__ double tet_a(int i, int g)
+    { return NPI == 5 ? c_tet_a5[i * 5 + g] : c_tet_a1[i]; }
+template <int NPI> __device__ __forceinline__ double tet_pds(int g)
+    { return NPI == 5 ? c_tet_pds5[g] : c_tet_pds1[0]; }
+template <int NPI> __device__ __forceinline__ double tri_a(int i, int g)
+    { return NPI == 4 ? c_tri_a4[i * 4 + g] : c_tri_a1[i]; }
+template <int NPI> __device__ __forceinline__ double tri_pds(int g)
+    { return NPI == 4 ? c_tri_pds4[g] : c_tri_pds1[0]; }
+
+__device__ __forceinline__ double dot3(const double *a, const double *b)
+    { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__device__ __forceinline__ void cross3(const double *a, const double *b, double *r)
+    {
+    r[0] = a[1] * b[2] - a[2] * b[1];
+    r[1] = a[2] * b[0] - a[0] * b[2];
+    r[2] = a[0] * b[1] - a[1] * b[0];
+    }
+// Eigen normalize(): z = squaredNorm(); if (z > 0) v /= sqrt(z)
+__device__ __forceinline__ void normalize3(double *a)
+    {
+    const double z = dot3(a, a);
+    if (z > 0.0)
+        {
+        const double s = sqrt(z);
+        a[0] /= s;
+        a[1] /= s;
+        a[2] /= s;
+        }
+    }
+
+__device__ __forceinline__ void load_rec(const NodeRec *p, double u[3], double v[3], double &phi,
+                                         double &phiv)
+    {
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+    u[0] = a.x; u[1] = a.y; u[2] = b.x;
+    v[0] = b.y; v[1] = c.x; v[2] = c.y;
+    phi = d.x; phiv = d.y;
+    }
+__device__ __forceinline__ void load_basis(const Basis *p, double ep[3], double eq[3])
+    {
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    ep[0] = a.x; ep[1] = a.y; ep[2] = b.x;
+    eq[0] = b.y; eq[1] = c.x; eq[2] = c.y;
+    }
+
+// ------------------------------------------------------------------------------------------
+// Node::setBasis, src/node.h:73-102.  cr = cos(r), sr = sin(r) are evaluated by the host libm so
+// that the rotation uses the very numbers the reference would.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void node_set_basis(const double u[3], double cr, double sr,
+                                               double ep[3], double eq[3])
+    {
+    int k = 0;
+    double m = fabs(u[0]);
+    if (fabs(u[1]) < m) { m = fabs(u[1]); k = 1; }
+    if (fabs(u[2]) < m) { k = 2; }
+    double e[3] = {0.0, 0.0, 0.0};
+    e[k] = 1.0;
+    const double d = dot3(e, u);
+    e[0] -= d * u[0];
+    e[1] -= d * u[1];
+    e[2] -= d * u[2];
+    normalize3(e);
+    double f[3];
+    cross3(u, e, f);
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+        {
+        ep[c] = cr * e[c] - sr * f[c];
+        eq[c] = sr * e[c] + cr * f[c];
+        }
+    }
+
+__global__ void __launch_bounds__(BLOCK)
+k_basis(int NOD, const NodeRec *__restrict__ cur, double cr, double sr, Basis *__restrict__ basis)
+    {
+    const int stride = gridDim.x * BLOCK;
+    for (int a = blockIdx.x * BLOCK + threadIdx.x; a < NOD; a += stride)
+        {
+        double u[3], v[3], phi, phiv, ep[3], eq[3];
+        load_rec(cur + a, u, v, phi, phiv);
+        node_set_basis(u, cr, sr, ep, eq);
+        double2 *q = reinterpret_cast<double2 *>(basis + a);
+        q[0] = make_double2(ep[0], ep[1]);
+        q[1] = make_double2(ep[2], eq[0]);
+        q[2] = make_double2(eq[1], eq[2]);
+        }
+    }
+
+// ------------------------------------------------------------------------------------------
+// Tet::integrales, src/tetra.cpp:210-307
+// ------------------------------------------------------------------------------------------
+// src/tetra.cpp:47-75
+__device__ __forceinline__ double alpha_eff(double dt, double alpha, double h)
+    {
+    const double reduced_dt = FG_GAMMA0 * dt;
+    const double r = 0.1;
+    const double M = 2. * alpha * r / reduced_dt;
+    if (h > 0.)
+        return (h > M) ? alpha + reduced_dt / 2. * M : alpha + reduced_dt / 2. * h;
+    return (h < -M) ? alpha / (1. + reduced_dt / (2. * alpha) * M)
+                    : alpha / (1. - reduced_dt / (2. * alpha) * h);
+    }
+
+struct TetIn
+    {
+    double da[4][3];
+    double detJ;
+    double u[4][3], v[4][3], phi[4], phiv[4];
+    };
+
+struct StepPrm
+    {
+    double dt, prefactor, Hext[3], A_Hext, Vdrift;
+    int idx_dir;
+    };
+
+// Element core shared by the production kernel and the Kp/Lp tap.  Hext is [d][g].
+// Outputs: contrib[i] = sum_g a_i(g) w_g alpha_eff(g)   (the state-dependent diagonal of E)
+//          BE[d][i]                                      (src/tetra.cpp:277-303)
+template <int NPI>
+__device__ __forceinline__ void tet_core(const TetIn &T, const TetRegion &R, const StepPrm &sp,
+                                         const double (&Hext)[3][NPI], double contrib[4],
+                                         double BE[3][4])
+    {
+    const double alpha = R.alpha, Abis = R.Abis;
+    const double s_dt = FG_THETA * sp.dt * FG_GAMMA0;
+    const double th_dt = s_dt / FG_GAMMA0;  // what calc_aniso_* and Hv receive (tetra.cpp:240,292)
+    double w[NPI];
+#pragma unroll
+    for (int g = 0; g < NPI; g++) w[g] = T.detJ * tet_pds<NPI>(g);
+
+    // interpolation, src/tetra.h:183-218
+    double U[3][NPI], V[3][NPI], dU[3][3], Hd[3], Hv[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+        {
+#pragma unroll
+        for (int g = 0; g < NPI; g++)
+            {
+            double su = 0.0, sv = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                {
+                su += T.u[i][d] * tet_a<NPI>(i, g);
+                sv += T.v[i][d] * tet_a<NPI>(i, g);
+                }
+            U[d][g] = su;
+            V[d][g] = sv;
+            }
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            {
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) s += T.u[i][d] * T.da[i][k];
+            dU[d][k] = s;  // dUd{x,y,z}(d) for k = 0,1,2
+            }
+        double hd = 0.0, hv = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            {
+            hd -= T.phi[i] * T.da[i][d];
+            hv -= T.phiv[i] * T.da[i][d];
+            }
+        Hd[d] = hd;
+        Hv[d] = hv;
+        }
+
+    // tetra.cpp:232-233
+    double gsq = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        gsq += dU[0][k] * dU[0][k] + dU[1][k] * dU[1][k] + dU[2][k] * dU[2][k];
+    double uHeff[NPI], Han[3][NPI];
+#pragma unroll
+    for (int g = 0; g < NPI; g++)
+        {
+        uHeff[g] = -Abis * gsq;
+        Han[0][g] = Han[1][g] = Han[2][g] = 0.0;
+        }
+    if (R.has_K)  // calc_aniso_uniax, tetra.cpp:171-181
+        {
+#pragma unroll
+        for (int g = 0; g < NPI; g++)
+            {
+            const double t0 = U[0][g] + th_dt * V[0][g], t1 = U[1][g] + th_dt * V[1][g],
+                         t2 = U[2][g] + th_dt * V[2][g];
+            const double f = R.Kbis * (R.uk[0] * t0 + R.uk[1] * t1 + R.uk[2] * t2);
+            Han[0][g] += f * R.uk[0];
+            Han[1][g] += f * R.uk[1];
+            Han[2][g] += f * R.uk[2];
+            const double s = U[0][g] * R.uk[0] + U[1][g] * R.uk[1] + U[2][g] * R.uk[2];
+            uHeff[g] += R.Kbis * (s * s);
+            }
+        }
+    if (R.has_K3)  // calc_aniso_cub, tetra.cpp:183-208 (uk_v.cwiseProduct(ex) kept literally)
+        {
+#pragma unroll
+        for (int g = 0; g < NPI; g++)
+            {
+            const double Ug[3] = {U[0][g], U[1][g], U[2][g]}, Vg[3] = {V[0][g], V[1][g], V[2][g]};
+            const double uu[3] = {dot3(R.ex, Ug), dot3(R.ey, Ug), dot3(R.ez, Ug)};
+            const double uv[3] = {dot3(R.ex, Vg), dot3(R.ey, Vg), dot3(R.ez, Vg)};
+            double u3[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) u3[k] = uu[k] * (1.0 - uu[k] * uu[k]);
+#pragma unroll
+            for (int d = 0; d < 3; d++)
+                {
+                const double tmp = uv[d] * R.ex[d];
+                const double inner = u3[0] * R.ex[d] + u3[1] * R.ey[d] + u3[2] * R.ez[d]
+                                     + th_dt * (tmp * (1.0 - 3 * (uu[d] * uu[d])));
+                Han[d][g] += -R.K3bis * inner;
+                }
+            uHeff[g] += -R.K3bis * dot3(uu, u3);
+            }
+        }
+    // tetra.cpp:248-255 (Hst = 0: Tet::extraField is a no-op without spin accumulation)
+    double H[3][NPI];
+#pragma unroll
+    for (int g = 0; g < NPI; g++)
+        {
+        double s = 0.0;
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+            {
+            H[d][g] = Hd[d] + Hext[d][g];
+            s += U[d][g] * H[d][g];
+            }
+        uHeff[g] += s;
+        }
+    // tetra.cpp:257-261 + lumping :114 (the alpha_eff part of the diagonal block)
+    double wa[NPI];
+#pragma unroll
+    for (int g = 0; g < NPI; g++) wa[g] = w[g] * alpha_eff(sp.dt, alpha, uHeff[g]);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        {
+        double s = 0.0;
+#pragma unroll
+        for (int g = 0; g < NPI; g++) s += tet_a<NPI>(i, g) * wa[g];
+        contrib[i] = s;
+        }
+
+    // BE, tetra.cpp:277-303
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) BE[d][i] = 0.0;
+    if (sp.idx_dir != FG_IDX_UNDEF)  // add_drift_BE, tetra.cpp:150-169
+        {
+        const int k = sp.idx_dir;
+        double dUk[3], dVk[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+            {
+            dUk[d] = (k == 2) ? dU[d][2] : (k == 1 ? dU[d][1] : dU[d][0]);
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) s += T.v[i][d] * ((k == 2) ? T.da[i][2] : (k == 1 ? T.da[i][1] : T.da[i][0]));
+            dVk[d] = s;
+            }
+#pragma unroll
+        for (int g = 0; g < NPI; g++)
+            {
+            const double Ug[3] = {U[0][g], U[1][g], U[2][g]}, Vg[3] = {V[0][g], V[1][g], V[2][g]};
+            double c1[3], c2[3], c3[3];
+            cross3(Ug, dUk, c1);
+            cross3(Ug, dVk, c2);
+            cross3(Vg, dUk, c3);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int d = 0; d < 3; d++)
+                    {
+                    const double interim = tet_a<NPI>(i, g)
+                        * (alpha * dUk[d] + c1[d] + s_dt * (alpha * dVk[d] + c2[d] + c3[d]));
+                    BE[d][i] += sp.Vdrift * w[g] * interim;
+                    }
+            }
+        }
+#pragma unroll
+    for (int g = 0; g < NPI; g++)
+        {
+#pragma unroll
+        for (int d = 0; d < 3; d++) H[d][g] += Han[d][g] + th_dt * Hv[d];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            {
+            const double ai_w = w[g] * tet_a<NPI>(i, g);
+#pragma unroll
+            for (int d = 0; d < 3; d++)
+                {
+                BE[d][i] -= w[g] * Abis
+                            * (T.da[i][0] * dU[d][0] + T.da[i][1] * dU[d][1] + T.da[i][2] * dU[d][2]);
+                BE[d][i] += ai_w * H[d][g];
+                }
+            }
+        }
+    }
+
+// device-resident description of the magnetic tetrahedra (SoA, compact index tm)
+struct TetArrays
+    {
+    int NTm;
+    const int4 *ind;        // NTm
+    const double *da;       // [12][NTm]
+    const double *detJ;     // NTm
+    const int *reg;         // NTm
+    const TetRegion *regions;
+    const double *ext_field;  // [3*npi][NTm] or NULL
+    };
+
+template <int NPI>
+__device__ __forceinline__ void tet_load(const TetArrays &A, int tm, const NodeRec *cur, int4 &ind,
+                                         TetIn &T)
+    {
+    ind = __ldg(A.ind + tm);
+#pragma unroll
+    for (int k = 0; k < 12; k++) T.da[k / 3][k % 3] = __ldcs(A.da + (size_t)k * A.NTm + tm);
+    T.detJ = __ldcs(A.detJ + tm);
+    const int nd[4] = {ind.x, ind.y, ind.z, ind.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) load_rec(cur + nd[i], T.u[i], T.v[i], T.phi[i], T.phiv[i]);
+    }
+
+template <int NPI>
+__device__ __forceinline__ void tet_field(const TetArrays &A, int tm, const StepPrm &sp, bool space,
+                                          double (&Hext)[3][NPI])
+    {
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+#pragma unroll
+        for (int g = 0; g < NPI; g++)
+            Hext[d][g] = space ? sp.A_Hext * __ldcs(A.ext_field + (size_t)(d * NPI + g) * A.NTm + tm)
+                               : sp.Hext[d];
+    }
+
+// one thread per magnetic tetrahedron; emits 4 records {contrib, eq.BE, ep.BE, 0}
+template <int NPI, bool SPACE>
+__global__ void __launch_bounds__(BLOCK)
+k_tet(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__restrict__ basis,
+      const StepPrm sp, double4 *__restrict__ rec)
+    {
+    const int stride = gridDim.x * BLOCK;
+    for (int tm = blockIdx.x * BLOCK + threadIdx.x; tm < A.NTm; tm += stride)
+        {
+        TetIn T;
+        int4 ind;
+        tet_load<NPI>(A, tm, cur, ind, T);
+        double Hext[3][NPI];
+        tet_field<NPI>(A, tm, sp, SPACE, Hext);
+        const TetRegion R = A.regions[__ldg(A.reg + tm)];
+        double contrib[4], BE[3][4];
+        tet_core<NPI>(T, R, sp, Hext, contrib, BE);
+        const int nd[4] = {ind.x, ind.y, ind.z, ind.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            {
+            double ep[3], eq[3];
+            load_basis(basis + nd[i], ep, eq);
+            const double be[3] = {BE[0][i], BE[1][i], BE[2][i]};
+            // Lp = Perm P BE (tetra.cpp:306): rows 0..3 are the eq-projections, 4..7 the ep ones
+            double2 *r2 = reinterpret_cast<double2 *>(rec + 4 * (size_t)tm + i);
+            __stcs(r2, make_double2(contrib[i], dot3(eq, be)));
+            __stcs(r2 + 1, make_double2(dot3(ep, be), 0.0));
+            }
+        }
+    }
+
+// projection of one node pair: the 2x2 block of K / Kp (SURVEY.md §8a index facts)
+__device__ __forceinline__ void project_block(double E, const double ep_a[3], const double eq_a[3],
+                                              const double ep_b[3], const double eq_b[3],
+                                              double &k00, double &k01, double &k10, double &k11)
+    {
+    k00 = E * dot3(eq_a, ep_b);
+    k01 = E * dot3(eq_a, eq_b);
+    k10 = E * dot3(ep_a, ep_b);
+    k11 = E * dot3(ep_a, eq_b);
+    }
+// gyrotropic part of the diagonal block: a_w e_r . (m x e_c)
+__device__ __forceinline__ void gyro_block(double aw, const double m[3], const double ep[3],
+                                           const double eq[3], double &k00, double &k01,
+                                           double &k10, double &k11)
+    {
+    double mp[3], mq[3];
+    cross3(m, ep, mp);
+    cross3(m, eq, mq);
+    k00 += aw * dot3(eq, mp);
+    k01 += aw * dot3(eq, mq);
+    k10 += aw * dot3(ep, mp);
+    k11 += aw * dot3(ep, mq);
+    }
+
+// Tap: full element Kp (8x8 row-major) and Lp (8) of magnetic tets [first, first+count), computed
+// with the same device functions as the production path (element.h:62,65 layout).
+template <int NPI, bool SPACE>
+__global__ void __launch_bounds__(BLOCK)
+k_tet_tap(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__restrict__ basis,
+          const StepPrm sp, int first, int count, double *__restrict__ Kp, double *__restrict__ Lp)
+    {
+    const int q = blockIdx.x * BLOCK + threadIdx.x;
+    if (q >= count) return;
+    const int tm = first + q;
+    TetIn T;
+    int4 ind;
+    tet_load<NPI>(A, tm, cur, ind, T);
+    double Hext[3][NPI];
+    tet_field<NPI>(A, tm, sp, SPACE, Hext);
+    const TetRegion R = A.regions[A.reg[tm]];
+    double contrib[4], BE[3][4];
+    tet_core<NPI>(T, R, sp, Hext, contrib, BE);
+    const int nd[4] = {ind.x, ind.y, ind.z, ind.w};
+    double ep[4][3], eq[4][3];
+    for (int i = 0; i < 4; i++) load_basis(basis + nd[i], ep[i], eq[i]);
+    const double s_dt = FG_THETA * sp.dt * FG_GAMMA0;
+    double wsum = 0.0, aw[4] = {0, 0, 0, 0};
+    for (int g = 0; g < NPI; g++)
+        {
+        const double w = T.detJ * tet_pds<NPI>(g);
+        wsum += w;
+        for (int i = 0; i < 4; i++) aw[i] += tet_a<NPI>(i, g) * w;
+        }
+    const double cw = (sp.prefactor * s_dt) * (R.Abis * wsum);
+    double *K = Kp + 64 * (size_t)q, *L = Lp + 8 * (size_t)q;
+    for (int a = 0; a < 4; a++)
+        {
+        for (int b = 0; b < 4; b++)
+            {
+            double E = (T.da[a][0] * T.da[b][0] + T.da[a][1] * T.da[b][1] + T.da[a][2] * T.da[b][2]) * cw;
+            if (a == b) E += contrib[a];
+            double k00, k01, k10, k11;
+            project_block(E, ep[a], eq[a], ep[b], eq[b], k00, k01, k10, k11);
+            if (a == b) gyro_block(aw[a], T.u[a], ep[a], eq[a], k00, k01, k10, k11);
+            K[(0 * 4 + a) * 8 + (0 * 4 + b)] = k00;
+            K[(0 * 4 + a) * 8 + (1 * 4 + b)] = k01;
+            K[(1 * 4 + a) * 8 + (0 * 4 + b)] = k10;
+            K[(1 * 4 + a) * 8 + (1 * 4 + b)] = k11;
+            }
+        const double be[3] = {BE[0][a], BE[1][a], BE[2][a]};
+        L[a] = dot3(eq[a], be);
+        L[4 + a] = dot3(ep[a], be);
+        }
+    }
+
+// ------------------------------------------------------------------------------------------
+// Tri::integrales, src/triangle.cpp:6-36 : surface (Neel) anisotropy, rhs only
+// ------------------------------------------------------------------------------------------
+struct TriArrays
+    {
+    int NFa;
+    const int *ind;       // [3][NFa]
+    const double *surf;   // NFa
+    const double *dMs;    // NFa
+    const int *reg;       // NFa
+    const TriRegion *regions;
+    };
+
+template <int NPI>
+__device__ __forceinline__ void tri_core(const TriRegion &R, double surf, double dMs,
+                                         const double u[3][3], double BE[3][3])
+    {
+    const double Kbis = 2.0 * R.Ks / dMs;
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) BE[k][i] = 0.0;
+#pragma unroll
+    for (int g = 0; g < NPI; g++)
+        {
+        double ug[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+            {
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < 3; i++) s += u[i][d] * tri_a<NPI>(i, g);
+            ug[d] = s;
+            }
+        const double wg = 2.0 * surf * tri_pds<NPI>(g);  // triangle.h:121-122
+        const double pf = wg * Kbis * dot3(R.uk, ug);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) BE[k][i] += pf * tri_a<NPI>(i, g) * R.uk[k];
+        }
+    }
+
+// one thread per active triangle; emits 3 records {eq.BE, ep.BE}
+template <int NPI>
+__global__ void __launch_bounds__(BLOCK)
+k_tri(const TriArrays A, const NodeRec *__restrict__ cur, const Basis *__restrict__ basis,
+      double2 *__restrict__ trec)
+    {
+    const int stride = gridDim.x * BLOCK;
+    for (int fa = blockIdx.x * BLOCK + threadIdx.x; fa < A.NFa; fa += stride)
+        {
+        int nd[3];
+        double u[3][3], v[3], phi, phiv;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            {
+            nd[i] = A.ind[(size_t)i * A.NFa + fa];
+            load_rec(cur + nd[i], u[i], v, phi, phiv);
+            }
+        const TriRegion R = A.regions[A.reg[fa]];
+        double BE[3][3];
+        tri_core<NPI>(R, A.surf[fa], A.dMs[fa], u, BE);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            {
+            double ep[3], eq[3];
+            load_basis(basis + nd[i], ep, eq);
+            const double be[3] = {BE[0][i], BE[1][i], BE[2][i]};
+            trec[3 * (size_t)fa + i] = make_double2(dot3(eq, be), dot3(ep, be));
+            }
+        }
+    }
+
+// ------------------------------------------------------------------------------------------
+// Row assembly: G lanes per node gather the node's element records and write its two CSR rows,
+// the rhs, the initial guess and the Jacobi diagonal.
+// ------------------------------------------------------------------------------------------
+struct RowArrays
+    {
+    int NOD, G;
+    const int *nptr, *ncol;
+    const double *S, *Aw;
+    const int *inc_ptr, *inc, *inc_tri_ptr, *inc_tri;
+    const unsigned char *nonmag;  // NOD : 1 = node outside the magnetic material
+    };
+
+__global__ void __launch_bounds__(BLOCK)
+k_assemble_rows(const RowArrays A, const NodeRec *__restrict__ cur, const NodeRec *__restrict__ next,
+                const Basis *__restrict__ basis, const double4 *__restrict__ rec,
+                const double2 *__restrict__ trec, double cS, double *__restrict__ val,
+                double *__restrict__ rhs, double *__restrict__ x0, double *__restrict__ D)
+    {
+    const int G = A.G;
+    const int lig = threadIdx.x & (G - 1);
+    const int gpc = BLOCK / G;
+    const long long total = (long long)gridDim.x * gpc;
+    for (long long a0 = (long long)blockIdx.x * gpc + threadIdx.x / G;; a0 += total)
+        {
+        const bool active = a0 < A.NOD;
+        if (!__any_sync(0xffffffffu, active)) break;
+        const int a = (int)a0;
+        double Ma = 0.0, L0 = 0.0, L1 = 0.0;
+        if (active)
+            {
+            for (int q = A.inc_ptr[a] + lig; q < A.inc_ptr[a + 1]; q += G)
+                {
+                const double2 *r2 = reinterpret_cast<const double2 *>(rec + __ldg(A.inc + q));
+                const double2 r01 = __ldcs(r2), r23 = __ldcs(r2 + 1);
+                Ma += r01.x;
+                L0 += r01.y;
+                L1 += r23.x;
+                }
+            for (int q = A.inc_tri_ptr[a] + lig; q < A.inc_tri_ptr[a + 1]; q += G)
+                {
+                const double2 r = trec[A.inc_tri[q]];
+                L0 += r.x;
+                L1 += r.y;
+                }
+            }
+        for (int o = G >> 1; o > 0; o >>= 1)
+            {
+            Ma += __shfl_xor_sync(0xffffffffu, Ma, o);
+            L0 += __shfl_xor_sync(0xffffffffu, L0, o);
+            L1 += __shfl_xor_sync(0xffffffffu, L1, o);
+            }
+        if (!active) continue;
+        const int beg = A.nptr[a], deg = A.nptr[a + 1] - beg;
+        double2 *row0 = reinterpret_cast<double2 *>(val + 4 * (size_t)beg);
+        double2 *row1 = row0 + deg;
+        if (A.nonmag[a])
+            {  // identity rows, zero rhs and guess (src/solver.cpp:46-48, linear_algebra.cpp:13-24)
+            for (int j = lig; j < deg; j += G)
+                {
+                const bool dg = A.ncol[beg + j] == a;
+                row0[j] = make_double2(dg ? 1.0 : 0.0, 0.0);
+                row1[j] = make_double2(0.0, dg ? 1.0 : 0.0);
+                }
+            if (lig == 0)
+                {
+                reinterpret_cast<double2 *>(rhs)[a] = make_double2(0.0, 0.0);
+                reinterpret_cast<double2 *>(x0)[a] = make_double2(0.0, 0.0);
+                reinterpret_cast<double2 *>(D)[a] = make_double2(0.0, 0.0);
+                }
+            continue;
+            }
+        double m[3], vc[3], phi, phiv, ep_a[3], eq_a[3];
+        load_rec(cur + a, m, vc, phi, phiv);
+        load_basis(basis + a, ep_a, eq_a);
+        if (lig == 0)
+            {
+            double un[3], vn[3];
+            load_rec(next + a, un, vn, phi, phiv);
+            reinterpret_cast<double2 *>(rhs)[a] = make_double2(L0, L1);
+            reinterpret_cast<double2 *>(x0)[a] =
+                make_double2(dot3(vn, ep_a) / FG_GAMMA0, dot3(vn, eq_a) / FG_GAMMA0);
+            }
+        for (int j = lig; j < deg; j += G)
+            {
+            const int b = __ldg(A.ncol + beg + j);
+            double E = cS * __ldcs(A.S + beg + j);
+            double ep_b[3], eq_b[3];
+            load_basis(basis + b, ep_b, eq_b);
+            double k00, k01, k10, k11;
+            if (b == a)
+                {
+                E += Ma;
+                project_block(E, ep_a, eq_a, ep_a, eq_a, k00, k01, k10, k11);
+                gyro_block(A.Aw[a], m, ep_a, eq_a, k00, k01, k10, k11);
+                reinterpret_cast<double2 *>(D)[a] = make_double2(1.0 / k00, 1.0 / k11);
+                }
+            else
+                project_block(E, ep_a, eq_a, ep_b, eq_b, k00, k01, k10, k11);
+            __stcs(row0 + j, make_double2(k00, k01));
+            __stcs(row1 + j, make_double2(k10, k11));
+            }
+        }
+    }
+
+// ------------------------------------------------------------------------------------------
+// Node update (src/solver.cpp:62-88): gated on the device-side outcome of the solve.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK)
+k_update(int NOD, const unsigned char *__restrict__ nonmag, const NodeRec *__restrict__ cur,
+         NodeRec *__restrict__ next, const Basis *__restrict__ basis, const double *__restrict__ x,
+         double dt, KState *st, const RedBuf red)
+    {
+    if (!st->done || st->updated) return;
+    const bool failed = st->status == FG_ITER_OVERFLOW || st->status == FG_CANNOT_CONVERGE
+                        || st->res > st->resmax;
+    double v2max = 0.0;
+    if (!failed)
+        {
+        const int stride = gridDim.x * BLOCK;
+        for (int a = blockIdx.x * BLOCK + threadIdx.x; a < NOD; a += stride)
+            {
+            if (nonmag[a]) continue;
+            const double2 xv = reinterpret_cast<const double2 *>(x)[a];
+            const double v2 = xv.x * xv.x + xv.y * xv.y;
+            v2max = fmax(v2max, v2);
+            double u[3], vc[3], phi, phiv, ep[3], eq[3], vn[3], un[3];
+            load_rec(cur + a, u, vc, phi, phiv);
+            load_basis(basis + a, ep, eq);
+            const double vp = xv.x * FG_GAMMA0, vq = xv.y * FG_GAMMA0;  // mesh.h:185-186
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                {
+                vn[c] = vp * ep[c] + vq * eq[c];
+                un[c] = u[c] + dt * vn[c];
+                }
+            normalize3(un);
+            double2 *q = reinterpret_cast<double2 *>(next + a);
+            q[0] = make_double2(un[0], un[1]);
+            q[1] = make_double2(un[2], vn[0]);
+            q[2] = make_double2(vn[1], vn[2]);
+            }
+        }
+    double tot;
+    if (!grid_reduce_max(v2max, red, tot)) return;
+    st->failed = failed ? 1 : 0;
+    if (!failed)
+        {
+        st->v2max = tot;
+        st->v_max = FG_GAMMA0 * sqrt(tot);
+        }
+    st->updated = 1;
+    }
+
+// ------------------------------------------------------------------------------------------
+// state packing helpers (host <-> NodeRec)
+// ------------------------------------------------------------------------------------------
+// which: bit0 u, bit1 v, bit2 phi, bit3 phiv ; staging = [u(3N) | v(3N) | phi(N) | phiv(N)]
+__global__ void __launch_bounds__(BLOCK)
+k_pack(int NOD, NodeRec *__restrict__ dst, const double *__restrict__ stage, int which)
+    {
+    const int stride = gridDim.x * BLOCK;
+    const size_t N = (size_t)NOD;
+    for (int a = blockIdx.x * BLOCK + threadIdx.x; a < NOD; a += stride)
+        {
+        NodeRec r = dst[a];
+        if (which & 1) { r.u[0] = stage[3 * (size_t)a]; r.u[1] = stage[3 * (size_t)a + 1]; r.u[2] = stage[3 * (size_t)a + 2]; }
+        if (which & 2) { r.v[0] = stage[3 * N + 3 * (size_t)a]; r.v[1] = stage[3 * N + 3 * (size_t)a + 1]; r.v[2] = stage[3 * N + 3 * (size_t)a + 2]; }
+        if (which & 4) r.phi = stage[6 * N + a];
+        if (which & 8) r.phiv = stage[7 * N + a];
+        dst[a] = r;
+        }
+    }
+
+__global__ void __launch_bounds__(BLOCK)
+k_unpack(int NOD, const NodeRec *__restrict__ src, double *__restrict__ stage, int which)
+    {
+    const int stride = gridDim.x * BLOCK;
+    const size_t N = (size_t)NOD;
+    for (int a = blockIdx.x * BLOCK + threadIdx.x; a < NOD; a += stride)
+        {
+        const NodeRec r = src[a];
+        if (which & 1) { stage[3 * (size_t)a] = r.u[0]; stage[3 * (size_t)a + 1] = r.u[1]; stage[3 * (size_t)a + 2] = r.u[2]; }
+        if (which & 2) { stage[3 * N + 3 * (size_t)a] = r.v[0]; stage[3 * N + 3 * (size_t)a + 1] = r.v[1]; stage[3 * N + 3 * (size_t)a + 2] = r.v[2]; }
+        if (which & 4) stage[6 * N + a] = r.phi;
+        if (which & 8) stage[7 * N + a] = r.phiv;
+        }
+    }
+
+}  // namespace fg

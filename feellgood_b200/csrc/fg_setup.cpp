@@ -1,0 +1,349 @@
+// fg_setup.cpp — once-per-mesh host preprocessing (see fg_setup.hpp).
+#include "fg_setup.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <numeric>
+
+namespace fg
+{
+// Gauss tables, reference src/tetra.h:29-81.  The barycentric weights are evaluated with the same
+// expression as the reference (1 - u - v - w) so that they round identically.
+void tet_tables(int npi, double a[20], double pds[5])
+    {
+    if (npi == 1)
+        {
+        const double q = 1. / 4.;
+        a[0] = 1. - q - q - q;
+        a[1] = a[2] = a[3] = q;
+        pds[0] = 1. / 6.;
+        return;
+        }
+    const double A = 1. / 4., B = 1. / 6., C = 1. / 2., D = -2. / 15., E = 3. / 40.;
+    const double u[5] = {A, B, B, B, C}, v[5] = {A, B, B, C, B}, w[5] = {A, B, C, B, B};
+    const double p[5] = {D, E, E, E, E};
+    for (int g = 0; g < 5; g++)
+        {
+        a[0 * 5 + g] = 1. - u[g] - v[g] - w[g];
+        a[1 * 5 + g] = u[g];
+        a[2 * 5 + g] = v[g];
+        a[3 * 5 + g] = w[g];
+        pds[g] = p[g];
+        }
+    }
+
+// reference src/triangle.h:21-65
+void tri_tables(int npi, double a[12], double pds[4])
+    {
+    if (npi == 1)
+        {
+        a[0] = 1. - 1. / 3. - 1. / 3.;
+        a[1] = a[2] = 1. / 3.;
+        pds[0] = 1. / 2.;
+        return;
+        }
+    const double u[4] = {1 / 3., 1 / 5., 3 / 5., 1 / 5.}, v[4] = {1 / 3., 1 / 5., 1 / 5., 3 / 5.};
+    const double p[4] = {-27 / 96., 25 / 96., 25 / 96., 25 / 96.};
+    for (int g = 0; g < 4; g++)
+        {
+        a[0 * 4 + g] = 1. - u[g] - v[g];
+        a[1 * 4 + g] = u[g];
+        a[2 * 4 + g] = v[g];
+        pds[g] = p[g];
+        }
+    }
+
+namespace
+{
+struct V3
+    {
+    double x, y, z;
+    };
+inline V3 sub(const double *a, const double *b) { return {a[0] - b[0], a[1] - b[1], a[2] - b[2]}; }
+inline V3 cross(const V3 &a, const V3 &b)
+    { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline double dot(const V3 &a, const V3 &b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+// Tet ctor (src/tetra.h:140-163): orientate (src/tetra.cpp:410-424), Jacobian (:393-408),
+// da = dadu * J^-1 with Eigen's cofactor inverse.  Returns false on a singular element.
+bool tet_geometry(const double *P, int ind[4], double da[12], double &detJ)
+    {
+    const double *p0 = P + 3 * (size_t)ind[0];
+    V3 e1 = sub(P + 3 * (size_t)ind[1], p0), e2 = sub(P + 3 * (size_t)ind[2], p0),
+       e3 = sub(P + 3 * (size_t)ind[3], p0);
+    const double mixed = dot(e1, cross(e2, e3));
+    if (std::fabs(mixed) < 1e-40) return false;
+    if (mixed < 0.0)
+        {
+        std::swap(ind[2], ind[3]);
+        std::swap(e2, e3);
+        }
+    // J = [e1 e2 e3] (columns)
+    const double J[3][3] = {{e1.x, e2.x, e3.x}, {e1.y, e2.y, e3.y}, {e1.z, e2.z, e3.z}};
+    detJ = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1])
+           - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0])
+           + J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+    double cof[3][3];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++)
+            {
+            const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+            cof[i][j] = J[i1][j1] * J[i2][j2] - J[i1][j2] * J[i2][j1];
+            }
+    const double det = cof[0][0] * J[0][0] + cof[0][1] * J[0][1] + cof[0][2] * J[0][2];
+    const double inv = 1.0 / det;
+    double Ji[3][3];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) Ji[r][c] = cof[c][r] * inv;
+    for (int d = 0; d < 3; d++)
+        {
+        da[3 * 1 + d] = Ji[0][d];
+        da[3 * 2 + d] = Ji[1][d];
+        da[3 * 3 + d] = Ji[2][d];
+        da[3 * 0 + d] = (-1. * Ji[0][d] + -1. * Ji[1][d]) + -1. * Ji[2][d];
+        }
+    return true;
+    }
+}  // namespace
+
+int host_setup(const fg_mesh &m, const fg_params &prm, HostSetup &h, std::string &err)
+    {
+    char buf[256];
+    if (m.NOD <= 0 || m.NT < 0 || m.NF < 0 || !m.node_p || (m.NT > 0 && (!m.tet_ind || !m.tet_reg))
+        || (m.NF > 0 && (!m.tri_ind || !m.tri_reg || !m.tri_dMs)))
+        {
+        err = "fg_create: null or empty mesh arrays";
+        return FG_ERR_INVALID;
+        }
+    if ((prm.npi_tet != 5 && prm.npi_tet != 1) || (prm.npi_tri != 4 && prm.npi_tri != 1)
+        || prm.nreg_tet <= 0 || !prm.prm_tet || (prm.nreg_tri > 0 && !prm.prm_tri))
+        {
+        err = "fg_create: npi_tet must be 5|1, npi_tri 4|1, and region tables non-empty";
+        return FG_ERR_INVALID;
+        }
+    h.NOD = m.NOD;
+    h.NT = m.NT;
+    h.NF = m.NF;
+    h.npi_tet = prm.npi_tet;
+    h.npi_tri = prm.npi_tri;
+    const int NOD = m.NOD, NT = m.NT, NF = m.NF;
+
+    // ---- tets: connectivity checks, orientation, geometry -----------------------------------
+    h.tet_ind.assign(m.tet_ind, m.tet_ind + 4 * (size_t)NT);
+    h.tet_reg.assign(m.tet_reg, m.tet_reg + (size_t)NT);
+    h.tet_da.resize(12 * (size_t)NT);
+    h.tet_detJ.resize((size_t)NT);
+    int bad = -1, bad_kind = 0;
+#pragma omp parallel for schedule(static)
+    for (int t = 0; t < NT; t++)
+        {
+        int *ind = &h.tet_ind[4 * (size_t)t];
+        bool ok = h.tet_reg[t] >= 0 && h.tet_reg[t] < prm.nreg_tet;
+        for (int i = 0; i < 4; i++) ok = ok && ind[i] >= 0 && ind[i] < NOD;
+        if (!ok)
+            {
+#pragma omp critical
+                { bad = t; bad_kind = 1; }
+            continue;
+            }
+        if (!tet_geometry(m.node_p, ind, &h.tet_da[12 * (size_t)t], h.tet_detJ[t]))
+            {
+#pragma omp critical
+                { if (bad_kind == 0) { bad = t; bad_kind = 2; } }
+            }
+        }
+    if (bad >= 0)
+        {
+        snprintf(buf, sizeof buf, "fg_create: tetrahedron %d %s", bad,
+                 bad_kind == 1 ? "has an index out of range" : "is singular (Tet::orientate)");
+        err = buf;
+        return FG_ERR_MESH;
+        }
+
+    // ---- magnetic masks (src/mesh.h:115-131, :331-336) ---------------------------------------
+    h.magNode.assign((size_t)NOD, 0);
+    h.tet_to_mag.assign((size_t)NT, -1);
+    h.magTet.clear();
+    for (int t = 0; t < NT; t++)
+        if (prm.prm_tet[h.tet_reg[t]].Ms > 0)
+            {
+            h.tet_to_mag[t] = (int)h.magTet.size();
+            h.magTet.push_back(t);
+            for (int i = 0; i < 4; i++) h.magNode[h.tet_ind[4 * (size_t)t + i]] = 1;
+            }
+    const int NTm = (int)h.magTet.size();
+
+    // ---- triangles (src/triangle.h:113-127,227) ------------------------------------------------
+    h.tri_ind.assign(m.tri_ind, m.tri_ind + 3 * (size_t)NF);
+    h.tri_reg.assign(m.tri_reg, m.tri_reg + (size_t)NF);
+    h.tri_dMs.assign(m.tri_dMs, m.tri_dMs + (size_t)NF);
+    h.tri_surf.resize((size_t)NF);
+    h.magTri.clear();
+    h.actTri.clear();
+    for (int f = 0; f < NF; f++)
+        {
+        const int *ind = &h.tri_ind[3 * (size_t)f];
+        bool ok = h.tri_reg[f] >= 0 && h.tri_reg[f] < prm.nreg_tri;
+        for (int i = 0; i < 3; i++) ok = ok && ind[i] >= 0 && ind[i] < NOD;
+        if (!ok)
+            {
+            snprintf(buf, sizeof buf, "fg_create: triangle %d has an index out of range", f);
+            err = buf;
+            return FG_ERR_MESH;
+            }
+        const double *p0 = m.node_p + 3 * (size_t)ind[0];
+        const V3 nrm = cross(sub(m.node_p + 3 * (size_t)ind[1], p0),
+                             sub(m.node_p + 3 * (size_t)ind[2], p0));
+        h.tri_surf[f] = 0.5 * std::sqrt(dot(nrm, nrm));
+        const bool mag = h.magNode[ind[0]] && h.magNode[ind[1]] && h.magNode[ind[2]];
+        const fg_tri_prm &tp = prm.prm_tri[h.tri_reg[f]];
+        if (mag && !tp.suppress_charges)
+            {
+            h.magTri.push_back(f);
+            if (tp.Ks != 0) h.actTri.push_back(f);
+            }
+        }
+
+    // ---- node adjacency over ALL tets (src/mesh.h:100-114: sorted unique edge list) ----------
+    std::vector<int64_t> aptr((size_t)NOD + 1, 0);
+    for (int t = 0; t < NT; t++)
+        for (int i = 0; i < 4; i++) aptr[(size_t)h.tet_ind[4 * (size_t)t + i] + 1] += 3;
+    for (int a = 0; a < NOD; a++) aptr[a + 1] += aptr[a];
+    std::vector<int> adj((size_t)aptr[NOD]);
+        {
+        std::vector<int64_t> fill(aptr.begin(), aptr.end() - 1);
+        for (int t = 0; t < NT; t++)
+            {
+            const int *ind = &h.tet_ind[4 * (size_t)t];
+            for (int i = 0; i < 4; i++)
+                for (int j = 0; j < 4; j++)
+                    if (i != j) adj[(size_t)fill[ind[i]]++] = ind[j];
+            }
+        }
+    // sort + unique each row; count edges; keep magnetic neighbours (+ self) for the pattern
+    // (src/solver.h:75-104 with the filter of src/linear_algebra.h:43)
+    std::vector<int> deg_all((size_t)NOD), deg_mag((size_t)NOD);
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int a = 0; a < NOD; a++)
+        {
+        int *b = adj.data() + aptr[a], *e = adj.data() + aptr[a + 1];
+        std::sort(b, e);
+        e = std::unique(b, e);
+        deg_all[a] = (int)(e - b);
+        int k = 0;
+        if (h.magNode[a])
+            for (int *q = b; q < e; ++q)
+                if (h.magNode[*q]) b[k++] = *q;
+        deg_mag[a] = k;
+        }
+    h.n_edges = 0;
+    h.n_edges_mag = 0;
+    for (int a = 0; a < NOD; a++)
+        {
+        h.n_edges += deg_all[a];
+        h.n_edges_mag += deg_mag[a];
+        }
+    h.n_edges /= 2;
+    h.n_edges_mag /= 2;
+    h.nptr.assign((size_t)NOD + 1, 0);
+    for (int a = 0; a < NOD; a++)
+        {
+        const int64_t nx = (int64_t)h.nptr[a] + deg_mag[a] + 1;
+        if (4 * nx > INT32_MAX)
+            {
+            err = "fg_create: more than 2^31 matrix entries on one device; partition the mesh";
+            return FG_ERR_INVALID;
+            }
+        h.nptr[a + 1] = (int)nx;
+        }
+    h.ncol.resize((size_t)h.nptr[NOD]);
+#pragma omp parallel for schedule(static)
+    for (int a = 0; a < NOD; a++)
+        {
+        const int *b = adj.data() + aptr[a];
+        int *o = &h.ncol[(size_t)h.nptr[a]];
+        int k = 0, j = 0;
+        while (j < deg_mag[a] && b[j] < a) o[k++] = b[j++];
+        o[k++] = a;
+        while (j < deg_mag[a]) o[k++] = b[j++];
+        }
+    std::vector<int>().swap(adj);
+
+    // ---- incidence lists node -> (magnetic tet, local node) ------------------------------------
+    h.inc_ptr.assign((size_t)NOD + 1, 0);
+    for (int tm = 0; tm < NTm; tm++)
+        for (int i = 0; i < 4; i++) h.inc_ptr[(size_t)h.tet_ind[4 * (size_t)h.magTet[tm] + i] + 1]++;
+    for (int a = 0; a < NOD; a++) h.inc_ptr[a + 1] += h.inc_ptr[a];
+    h.inc.resize(4 * (size_t)NTm);
+        {
+        std::vector<int> fill(h.inc_ptr.begin(), h.inc_ptr.end() - 1);
+        for (int tm = 0; tm < NTm; tm++)  // ascending tm inside each node's list
+            for (int i = 0; i < 4; i++)
+                h.inc[(size_t)fill[h.tet_ind[4 * (size_t)h.magTet[tm] + i]]++] = 4 * tm + i;
+        }
+    const int NFa = (int)h.actTri.size();
+    h.inc_tri_ptr.assign((size_t)NOD + 1, 0);
+    for (int fa = 0; fa < NFa; fa++)
+        for (int i = 0; i < 3; i++) h.inc_tri_ptr[(size_t)h.tri_ind[3 * (size_t)h.actTri[fa] + i] + 1]++;
+    for (int a = 0; a < NOD; a++) h.inc_tri_ptr[a + 1] += h.inc_tri_ptr[a];
+    h.inc_tri.resize(3 * (size_t)NFa);
+        {
+        std::vector<int> fill(h.inc_tri_ptr.begin(), h.inc_tri_ptr.end() - 1);
+        for (int fa = 0; fa < NFa; fa++)
+            for (int i = 0; i < 3; i++)
+                h.inc_tri[(size_t)fill[h.tri_ind[3 * (size_t)h.actTri[fa] + i]]++] = 3 * fa + i;
+        }
+
+    // ---- per-mesh constants of the stiffness (src/tetra.cpp:108-140) -------------
+    // E_ab(step) = prefactor*s_dt * S_ab + delta_ab * Malpha_a(step);   a_w lumped into Aw_a.
+    double ta[20], tp[5];
+    tet_tables(prm.npi_tet, ta, tp);
+    const int npi = prm.npi_tet;
+    h.S.assign(h.ncol.size(), 0.0);
+    h.Aw.assign((size_t)NOD, 0.0);
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int a = 0; a < NOD; a++)
+        {
+        const int rb = h.nptr[a], re = h.nptr[a + 1];
+        double aw = 0.0;
+        for (int q = h.inc_ptr[a]; q < h.inc_ptr[a + 1]; q++)
+            {
+            const int tm = h.inc[q] >> 2, i = h.inc[q] & 3, t = h.magTet[tm];
+            const fg_tet_prm &rp = prm.prm_tet[h.tet_reg[t]];
+            const double Abis = 2.0 * rp.A / (FG_MU0_HOST * rp.Ms);
+            const double detJ = h.tet_detJ[t];
+            double wsum = 0.0, a_w = 0.0;
+            for (int g = 0; g < npi; g++)
+                {
+                const double w = detJ * tp[g];
+                wsum += w;
+                a_w += ta[i * npi + g] * w;
+                }
+            aw += a_w;
+            const double *da = &h.tet_da[12 * (size_t)t];
+            const int *ind = &h.tet_ind[4 * (size_t)t];
+            for (int j = 0; j < 4; j++)
+                {
+                const double dd = da[3 * i] * da[3 * j] + da[3 * i + 1] * da[3 * j + 1]
+                                  + da[3 * i + 2] * da[3 * j + 2];
+                const int pos = (int)(std::lower_bound(&h.ncol[rb], &h.ncol[rb] + (re - rb), ind[j])
+                                      - &h.ncol[0]);
+                h.S[pos] += dd * (Abis * wsum);
+                }
+            }
+        h.Aw[a] = aw;
+        }
+
+    // ---- masked dofs (src/linear_algebra.h:55-63) ---------------------------------------------
+    h.lvd.clear();
+    for (int a = 0; a < NOD; a++)
+        if (!h.magNode[a])
+            {
+            h.lvd.push_back(2 * a);
+            h.lvd.push_back(2 * a + 1);
+            }
+    return FG_OK;
+    }
+
+}  // namespace fg

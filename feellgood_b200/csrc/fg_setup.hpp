@@ -1,0 +1,56 @@
+// fg_setup.hpp — once-per-mesh host preprocessing for the B200 LLG path (pure C++17, OpenMP).
+//
+// Builds, from what Mesh::mesh hands to LinAlgebra, everything the per-step kernels read:
+// oriented connectivity and geometry tables (Tet ctor), magnetic masks (mesh ctor), the node-level
+// sparsity of K (solver<2>::build_shape with the LinAlgebra edge filter), the node->element
+// incidence lists that make the per-step assembly a race-free gather, and the two per-mesh
+// constants of the factorised stiffness: S_ab = sum_T Abis_T vol_T (grad a_a . grad a_b) and the
+// lumped mass Aw_a.  References are cited at each step in fg_setup.cpp.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/feellgood_b200.h"
+
+namespace fg
+{
+constexpr double FG_MU0_HOST = 1.25663706127e-6;  // src/config.h.in:31
+
+struct HostSetup
+    {
+    int NOD = 0, NT = 0, NF = 0;
+    int npi_tet = 5, npi_tri = 4;
+    // all tets, in caller order (taps + energies)
+    std::vector<int> tet_ind;      // NT x 4, oriented
+    std::vector<double> tet_da;    // NT x 12
+    std::vector<double> tet_detJ;  // NT
+    std::vector<int> tet_reg;      // NT
+    std::vector<int> magTet;       // indices of magnetic tets (Ms > 0)
+    std::vector<int> tet_to_mag;   // NT: compact index or -1
+    std::vector<unsigned char> magNode;  // NOD
+    // triangles
+    std::vector<int> tri_ind;      // NF x 3
+    std::vector<int> tri_reg;      // NF
+    std::vector<double> tri_dMs, tri_surf;  // NF
+    std::vector<int> magTri;       // magnetic && !suppress_charges (rhs contributors)
+    std::vector<int> actTri;       // magTri with Ks != 0 : the only ones whose Lp reaches the rhs
+    // node-level pattern of K
+    std::vector<int> nptr, ncol;   // NOD+1, nnzb
+    std::vector<double> S;         // nnzb
+    std::vector<double> Aw;        // NOD
+    long long n_edges = 0, n_edges_mag = 0;
+    // incidences: entry = 4*tm + i (tm = compact magnetic tet index) / 3*fa + i
+    std::vector<int> inc_ptr, inc;          // NOD+1, 4*n_magTet
+    std::vector<int> inc_tri_ptr, inc_tri;  // NOD+1, 3*n_actTri
+    std::vector<int> lvd;          // masked dofs (src/linear_algebra.h:55-63)
+    };
+
+// returns FG_OK or FG_ERR_*; message in err
+int host_setup(const fg_mesh &mesh, const fg_params &prm, HostSetup &out, std::string &err);
+
+// Gauss tables (src/tetra.h:29-81, src/triangle.h:21-65): a[i*npi+g], pds[g]
+void tet_tables(int npi, double a[20], double pds[5]);
+void tri_tables(int npi, double a[12], double pds[4]);
+
+}  // namespace fg

@@ -1,0 +1,320 @@
+"""Host-side mirror of the reference's call surface for the LLG hot path, on top of the C ABI.
+
+Same names, argument meaning and error behaviour as the reference classes the time-integration
+loop drives (reference src/time_integration.cpp:193-206):
+
+    timing       src/time_integration.h:6-59
+    LinAlgebra   src/linear_algebra.h:40-118  (base_projection, prepareElements x2, solve,
+                                               get_v_max, set_DW_vz, buildInitGuess)
+
+The C++17 drop-in (feellgood_b200/host/feellgood_b200.hpp) exposes the same surface to C++
+callers; this module is what tests/ and bench.py drive.  All compute runs in
+libfeellgood_b200.so on the GPU; nothing here has a CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import capi
+from .capi import check, dp, f64, i32, ip
+
+MU0 = 1.25663706127e-6                 # src/config.h.in:31
+GAMMA0 = 1.76085962784e11 * MU0        # src/config.h.in:32
+M_2_PI = 0.63661977236758134308        # <cmath>: 2/pi (sic — what the reference multiplies by)
+
+_libc = None
+
+
+def _c_rand():
+    """glibc rand(): the stream `--seed N` / srand(N) controls (reference src/main.cpp:211)."""
+    global _libc
+    if _libc is None:
+        _libc = C.CDLL("libc.so.6")
+        _libc.rand.restype = C.c_int
+    return _libc.rand()
+
+
+def c_srand(seed):
+    global _libc
+    if _libc is None:
+        _c_rand()
+    _libc.srand(C.c_uint(seed))
+
+
+def mt19937_uniform01(seed):
+    """First draw of std::uniform_real_distribution<>(0,1) from std::mt19937(seed)
+    (libstdc++ generate_canonical<double,53>: two 32-bit outputs)."""
+    bg = np.random.MT19937()
+    bg._legacy_seeding(int(seed) & 0xFFFFFFFF)
+    x0, x1 = (int(v) for v in bg.random_raw(2))
+    r = (x0 + x1 * 4294967296.0) / 18446744073709551616.0
+    if r >= 1.0:
+        r = math.nextafter(1.0, 0.0)
+    return r
+
+
+class timing:
+    """reference src/time_integration.h:6-59 (prefactor kept in sync with dt)."""
+
+    def __init__(self, tf, dtmin, dtmax):
+        self.tf, self.DTMIN, self.DTMAX = tf, dtmin, dtmax
+        self.TAUR = 100. * dtmax
+        self._t = 0.0
+        self.set_dt(math.sqrt(dtmin * dtmax))
+
+    def get_dt(self):
+        return self._dt
+
+    def set_dt(self, dt):
+        self._dt = dt
+        t_tilde = dt / self.TAUR
+        self.prefactor = 1. + t_tilde * abs(math.log(t_tilde))
+
+    def is_dt_TooSmall(self):
+        return self._dt < self.DTMIN
+
+    def inc_t(self):
+        self._t += self._dt
+
+    def get_t(self):
+        return self._t
+
+    def set_t(self, t):
+        self._t = t
+
+
+class Settings:
+    """The Settings fields LinAlgebra reads (reference src/settings.h): paramTetra, paramTriangle,
+    TOL, MAXITER, verbose, recenter, recentering_direction, plus the NPI compile-time switch."""
+
+    def __init__(self, paramTetra, paramTriangle=(), TOL=1e-6, MAXITER=700, verbose=False,
+                 recenter=False, recentering_direction=capi.FG_IDX_Z, npi_tet=5, npi_tri=4):
+        self.paramTetra = list(paramTetra)
+        self.paramTriangle = list(paramTriangle)
+        self.TOL, self.MAXITER, self.verbose = TOL, MAXITER, verbose
+        self.recenter, self.recentering_direction = recenter, recentering_direction
+        self.npi_tet, self.npi_tri = npi_tet, npi_tri
+
+
+class LinAlgebra:
+    """reference src/linear_algebra.h:40-118 on one B200.
+
+    `mesh` is a feellgood_b200.meshgen.Mesh (what Mesh::mesh hands over: sorted, scaled nodes,
+    zero-based connectivity, region ids, dMs).  The node state the reference keeps inside
+    Mesh::mesh (u, v, phi, phiv CURRENT/NEXT) lives in the device context; `set_state`,
+    `set_potentials`, `evolution`, `get_state` are the mesh-side accessors the loop needs.
+    """
+
+    def __init__(self, settings, mesh, device=0):
+        L = capi.lib()
+        self._L = L
+        self.settings = settings
+        self.verbose = settings.verbose
+        self.NOD = mesh.NOD
+        self._keep = (f64(mesh.node_p), i32(mesh.tet_ind), i32(mesh.tet_reg), i32(mesh.tri_ind),
+                      i32(mesh.tri_reg), f64(mesh.tri_dMs))
+        p, ti, tr, fi, fr, fd = self._keep
+        cm = capi.CMesh(mesh.NOD, dp(p), mesh.NT, ip(ti), ip(tr), mesh.NF, ip(fi), ip(fr), dp(fd))
+        pt = (capi.TetPrm * len(settings.paramTetra))(*settings.paramTetra)
+        ntri = len(settings.paramTriangle)
+        pf = (capi.TriPrm * max(1, ntri))(*settings.paramTriangle)
+        cp = capi.CParams(len(settings.paramTetra), pt, ntri, pf, settings.npi_tet,
+                          settings.npi_tri, settings.TOL, settings.MAXITER)
+        h = C.c_void_p()
+        check(L.fg_create(C.byref(cm), C.byref(cp), C.c_int(device), C.byref(h)))
+        self._h = h
+        out = (C.c_longlong * 10)()
+        check(L.fg_get_sizes(h, out))
+        (_, self.NT, self.NF, self.n_magTet, self.n_magTri, self.E, self.E_mag, self.n, self.nnz,
+         self.nlvd) = list(out)
+        self.npi = settings.npi_tet
+        # linear_algebra.h:50-53
+        self.idx_dir = settings.recentering_direction if settings.recenter else capi.FG_IDX_UNDEF
+        self.DW_vz = 0.0   # never initialised in the reference: explicit here
+        self.v_max = 0.0
+        self.iter = dict(status=capi.FG_UNDEFINED, nit=0, res=0.0, rhsn=0.0)
+        self.last_angle = None
+
+    # ---- lifetime ----
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.fg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- mesh-side state accessors (Mesh::mesh in the reference) ----
+    def set_state(self, u, v=None, phi=None, phiv=None):
+        """mesh::init_distrib + first evolution: CURRENT = NEXT = (u, v, phi, phiv)."""
+        u = f64(u)
+        v = f64(v) if v is not None else None
+        phi = f64(phi) if phi is not None else None
+        phiv = f64(phiv) if phiv is not None else None
+        check(self._L.fg_set_state(self._h, dp(u), dp(v), dp(phi), dp(phiv)))
+
+    def set_next_v(self, v):
+        v = f64(v)
+        check(self._L.fg_set_next_v(self._h, dp(v)))
+
+    def set_potentials(self, phi, phiv):
+        """Nodes::set_phi / set_phiv on NEXT (what the demag solver writes each step)."""
+        phi, phiv = f64(phi), f64(phiv)
+        check(self._L.fg_set_potentials(self._h, dp(phi), dp(phiv)))
+
+    def get_state(self, step=1, what="uvpq"):
+        """(u, v, phi, phiv) of step 0 = CURRENT | 1 = NEXT; `what` selects the arrays."""
+        N = self.NOD
+        u = np.empty((N, 3)) if "u" in what else None
+        v = np.empty((N, 3)) if "v" in what else None
+        phi = np.empty(N) if "p" in what else None
+        phiv = np.empty(N) if "q" in what else None
+        check(self._L.fg_get_state(self._h, C.c_int(step), dp(u), dp(v), dp(phi), dp(phiv)))
+        return u, v, phi, phiv
+
+    def get_state_into(self, step, u=None, v=None, phi=None, phiv=None):
+        """Same, into caller-owned (e.g. pinned) float64 buffers."""
+        check(self._L.fg_get_state(self._h, C.c_int(step), dp(u), dp(v), dp(phi), dp(phiv)))
+
+    def evolution(self):
+        """mesh::evolution (src/mesh.h:189-193): NEXT -> CURRENT."""
+        check(self._L.fg_commit(self._h))
+
+    def set_ext_space_field(self, field):
+        field = f64(field)
+        assert field.shape == (self.NT, 3, self.npi)
+        check(self._L.fg_set_ext_space_field(self._h, dp(field)))
+
+    # ---- the reference's LinAlgebra surface ----
+    def base_projection(self, angle=None):
+        """src/linear_algebra.cpp:3-11.  With angle=None the angle is drawn exactly like the
+        reference does: mt19937 seeded by rand(), one uniform draw, times M_2_PI."""
+        if angle is None:
+            angle = M_2_PI * mt19937_uniform01(_c_rand())
+        self.last_angle = angle
+        check(self._L.fg_base_projection(self._h, C.c_double(angle)))
+
+    def prepareElements(self, Hext, t_prm):
+        """Both overloads (src/linear_algebra.cpp:26-52 and :54-81): a 3-vector is the uniform
+        applied field, a scalar is the amplitude multiplying mesh.extSpaceField."""
+        if np.ndim(Hext) == 0:
+            check(self._L.fg_prepare_elements_space(
+                self._h, C.c_double(float(Hext)), C.c_double(t_prm.get_dt()),
+                C.c_double(t_prm.prefactor), C.c_int(self.idx_dir), C.c_double(self.DW_vz)))
+        else:
+            H = f64(Hext)
+            assert H.shape == (3,)
+            check(self._L.fg_prepare_elements(
+                self._h, dp(H), C.c_double(t_prm.get_dt()), C.c_double(t_prm.prefactor),
+                C.c_int(self.idx_dir), C.c_double(self.DW_vz)))
+
+    def _store(self, r):
+        self.iter = dict(status=r.status, nit=r.iters, res=r.res, rhsn=r.rhsnorm)
+        self.v_max = r.v_max
+        return bool(r.failed)
+
+    def solve(self, t_prm):
+        """src/solver.cpp:6-90.  Returns True on FAILURE, like the reference."""
+        r = capi.StepResult()
+        check(self._L.fg_solve(self._h, C.c_double(t_prm.get_dt()), C.byref(r)))
+        return self._store(r)
+
+    def step(self, Hext, t_prm, angle=None):
+        """base_projection + prepareElements(Hext) + solve in one enqueue (one host sync)."""
+        if angle is None:
+            angle = M_2_PI * mt19937_uniform01(_c_rand())
+        self.last_angle = angle
+        H = f64(Hext)
+        r = capi.StepResult()
+        check(self._L.fg_step(self._h, C.c_double(angle), dp(H), C.c_double(t_prm.get_dt()),
+                              C.c_double(t_prm.prefactor), C.c_int(self.idx_dir),
+                              C.c_double(self.DW_vz), C.byref(r)))
+        return self._store(r)
+
+    def get_v_max(self):
+        return self.v_max
+
+    def set_DW_vz(self, vz):
+        self.DW_vz = vz
+
+    def buildInitGuess(self, t_prm):
+        """src/linear_algebra.cpp:13-24 (as assembled for the system of the last prepareElements)."""
+        return self.system(t_prm)[2]
+
+    # ---- taps for the parity tests ----
+    def basis(self):
+        ep, eq = np.empty((self.NOD, 3)), np.empty((self.NOD, 3))
+        check(self._L.fg_get_basis(self._h, dp(ep), dp(eq)))
+        return ep, eq
+
+    def elements(self, first=0, count=None):
+        count = self.NT - first if count is None else count
+        Kp, Lp = np.empty((count, 8, 8)), np.empty((count, 8))
+        check(self._L.fg_get_elements(self._h, C.c_int(first), C.c_int(count), dp(Kp), dp(Lp)))
+        return Kp, Lp
+
+    def tri_elements(self, first=0, count=None):
+        count = self.NF - first if count is None else count
+        Lp = np.empty((max(count, 1), 6))
+        check(self._L.fg_get_tri_elements(self._h, C.c_int(first), C.c_int(count), dp(Lp)))
+        return Lp[:count]
+
+    def csr(self):
+        rowptr, col = np.empty(self.n + 1, dtype=np.int32), np.empty(self.nnz, dtype=np.int32)
+        check(self._L.fg_get_csr_pattern(self._h, ip(rowptr), ip(col)))
+        return rowptr, col
+
+    def system(self, t_prm):
+        val, rhs, x0 = np.empty(self.nnz), np.empty(self.n), np.empty(self.n)
+        check(self._L.fg_get_system(self._h, C.c_double(t_prm.get_dt()), dp(val), dp(rhs), dp(x0)))
+        return val, rhs, x0
+
+    def apply_operator(self, x):
+        x = f64(x)
+        y = np.empty(self.n)
+        check(self._L.fg_apply_operator(self._h, dp(x), dp(y)))
+        return y
+
+    def solution(self):
+        x = np.empty(self.n)
+        check(self._L.fg_get_solution(self._h, dp(x)))
+        return x
+
+    def tet_tables(self):
+        ind = np.empty((self.NT, 4), dtype=np.int32)
+        da, w = np.empty((self.NT, 4, 3)), np.empty((self.NT, self.npi))
+        check(self._L.fg_get_tet_tables(self._h, ip(ind), dp(da), dp(w)))
+        return ind, da, w
+
+    # ---- instrumentation ----
+    def kernel_launches(self):
+        return int(self._L.fg_kernel_launches(self._h))
+
+    def stream(self):
+        return self._L.fg_stream(self._h)
+
+    def set_profiling(self, on=1):
+        """0 off, 1 phase timers (adds syncs), 2 CUDA-event pairs around every SpMV launch."""
+        check(self._L.fg_set_profiling(self._h, C.c_int(int(on))))
+
+    def spmv_times(self):
+        """(total device ms, launches) of the SpMV kernels since profiling mode 2 was set."""
+        ms, cnt = C.c_double(), C.c_int()
+        check(self._L.fg_get_spmv_times(self._h, C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value
+
+    def phase_times(self):
+        out = (C.c_double * 8)()
+        check(self._L.fg_get_phase_times(self._h, out))
+        return dict(basis=out[0], elements=out[1], assemble=out[2], solve=out[3])
+
+    def bench_spmv(self, reps=20):
+        ms = C.c_double()
+        check(self._L.fg_bench_spmv(self._h, C.c_int(reps), C.byref(ms)))
+        return ms.value

@@ -1,0 +1,260 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes -> libfeellgood_b200.so),
+against the CPU oracle on the same seeded inputs.  Tolerances (BASELINE.json north_star):
+element matrices / vectors and assembled system 1e-12 relative (norm-wise per element / per
+system); per-step solution within the solver tolerance; averages after N steps 1e-6 relative.
+"""
+import numpy as np
+import pytest
+
+import cases
+from cases import FixedTiming, rel_max
+
+pytestmark = pytest.mark.gpu
+
+TOL_ELEM = 1e-12
+
+
+def _pair(case):
+    oc = cases.oracle_ctx(case)
+    la = cases.gpu_linalg(case)
+    oc.set_state(case.u, case.v, case.phi, case.phiv)
+    la.set_state(case.u, case.v, case.phi, case.phiv)
+    return oc, la
+
+
+def _prepare(case, oc, la):
+    t = FixedTiming(case)
+    oc.base_projection(case.angle)
+    la.base_projection(case.angle)
+    oc.prepare_elements(case.Hext, case.dt, case.prefactor)
+    la.prepareElements(case.Hext, t)
+    return t
+
+
+@pytest.fixture(scope="module", params=["small_cuboid", "small_cuboid_npi1", "ellipsoid"])
+def prepared(request, oracle, gpu_lib):
+    case = {"small_cuboid": lambda: cases.small_cuboid(),
+            "small_cuboid_npi1": lambda: cases.small_cuboid(npi=1),
+            "ellipsoid": lambda: cases.ellipsoid()}[request.param]()
+    oc, la = _pair(case)
+    t = _prepare(case, oc, la)
+    yield case, oc, la, t
+    la.close()
+    oc.close()
+
+
+def test_sizes_and_pattern(prepared):
+    case, oc, la, _ = prepared
+    assert (la.NT, la.NF, la.n_magTet, la.n_magTri, la.E, la.E_mag, la.n, la.nnz, la.nlvd) == \
+        (oc.NT, oc.NF, oc.n_magTet, oc.n_magTri, oc.E, oc.E_mag, oc.n, oc.nnz, oc.nlvd)
+    rp_o, col_o = oc.csr()
+    rp_g, col_g = la.csr()
+    assert np.array_equal(rp_o, rp_g) and np.array_equal(col_o, col_g)   # bit-exact index work
+
+
+def test_tet_tables(prepared):
+    case, oc, la, _ = prepared
+    ind, da, w = la.tet_tables()
+    assert np.array_equal(ind, oc.tet_ind())                             # Tet::orientate
+    da_o, w_o = oc.tet_geom()
+    assert rel_max(da, da_o) < 1e-15 and rel_max(w, w_o) < 1e-15
+
+
+def test_basis(prepared):
+    case, oc, la, _ = prepared
+    ep, eq = la.basis()
+    ep_o, eq_o = oc.get_basis()
+    assert np.max(np.abs(ep - ep_o)) < 5e-15 and np.max(np.abs(eq - eq_o)) < 5e-15
+    # node_setBasis properties (unit-tests/ut_node.cpp:58-121): orthonormal to 5e-15
+    u = case.u
+    assert np.max(np.abs(np.einsum("ij,ij->i", ep, u))) < 5e-15
+    assert np.max(np.abs(np.einsum("ij,ij->i", ep, eq))) < 5e-15
+    assert np.max(np.abs(np.linalg.norm(eq, axis=1) - 1)) < 5e-15
+
+
+def test_element_matrices(prepared):
+    case, oc, la, _ = prepared
+    Kp, Lp = la.elements()
+    worstK = worstL = 0.0
+    for t in range(oc.NT):
+        Ko, Lo = oc.element(t)
+        worstK = max(worstK, rel_max(Kp[t], Ko))
+        worstL = max(worstL, rel_max(Lp[t], Lo))
+    assert worstK < TOL_ELEM, worstK
+    assert worstL < TOL_ELEM, worstL
+
+
+def test_tri_vectors(prepared):
+    case, oc, la, _ = prepared
+    Lp = la.tri_elements()
+    nz = 0
+    for f in range(oc.NF):
+        Lo = oc.tri_element(f)
+        nz += bool(np.any(Lo != 0))
+        assert rel_max(Lp[f], Lo) < TOL_ELEM
+    if case.name == "small_cuboid":
+        assert nz > 0
+
+
+def test_assembled_system(prepared):
+    case, oc, la, t = prepared
+    oc.assemble()
+    val_o, rhs_o, x0_o = oc.system()
+    val, rhs, x0 = la.system(t)
+    assert rel_max(val, val_o) < TOL_ELEM
+    assert rel_max(rhs, rhs_o) < TOL_ELEM
+    assert rel_max(x0, x0_o) < TOL_ELEM
+    # masked dofs: identity rows and zero rhs, bit-exact
+    _, lvd = oc.masks()
+    rp, col = la.csr()
+    for i in lvd:
+        row = val[rp[i]:rp[i + 1]]
+        assert rhs[i] == 0.0 and np.all(row[col[rp[i]:rp[i + 1]] != i] == 0.0)
+        assert row[col[rp[i]:rp[i + 1]] == i][0] == 1.0
+    # the device SpMV on that K (SparseMatrix::mult)
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(la.n)
+    y = la.apply_operator(x)
+    assert rel_max(y, oracle_spmv(rp, col, val_o, x)) < 1e-13
+
+
+def oracle_spmv(rp, col, val, x):
+    from oracle import fg_oracle_py as fo
+    return fo.spmv(rp, col, val, x)
+
+
+def test_solve_and_update(prepared):
+    case, oc, la, t = prepared
+    failed_o = oc.solve(case.dt)
+    failed_g = la.solve(t)
+    io = oc.iter_info()
+    assert failed_g == failed_o and la.iter["status"] == io["status"] == 0
+    assert abs(la.iter["nit"] - io["nit"]) <= 3
+    assert abs(la.iter["rhsn"] - io["rhsn"]) <= 1e-12 * io["rhsn"]
+    # per-step solution within the solver tolerance: the GPU solution satisfies the ORACLE's system
+    val_o, rhs_o, x_o = oc.system()
+    rp, col = oc.csr()
+    x_g = la.solution()
+    r = rhs_o - oracle_spmv(rp, col, val_o, x_g)
+    assert np.linalg.norm(r) <= 1.01 * case.tol * np.linalg.norm(rhs_o)
+    assert np.linalg.norm(x_g - x_o) <= 1e-4 * np.linalg.norm(x_o)
+    u_o, v_o, _, _ = oc.get_state(1)
+    u_g, v_g, phi_g, phiv_g = la.get_state(1)
+    assert np.max(np.abs(u_g - u_o)) < 1e-7
+    assert rel_max(v_g, v_o) < 1e-4
+    assert abs(la.get_v_max() - oc.v_max()) <= 1e-4 * oc.v_max()
+    assert np.array_equal(phi_g, case.phi) and np.array_equal(phiv_g, case.phiv)
+    mag, _ = oc.masks()
+    assert np.max(np.abs(np.linalg.norm(u_g[mag], axis=1) - 1)) < 1e-15
+    assert np.array_equal(u_g[~mag], case.u[~mag])            # non-magnetic nodes untouched
+
+
+def test_golden_llg_system(oracle, gpu_lib):
+    """Committed fixture produced with the REFERENCE's own SparseMatrix::add + bicg_dir."""
+    z = np.load(cases.GOLDEN + "/llg_system.npz")
+    case = cases.small_cuboid()
+    la = cases.gpu_linalg(case)
+    la.set_state(case.u, case.v, case.phi, case.phiv)
+    t = FixedTiming(case)
+    la.base_projection(case.angle)
+    la.prepareElements(case.Hext, t)
+    Kp, Lp = la.elements(0, 1)
+    assert rel_max(Kp[0], z["Kp0"]) < TOL_ELEM and rel_max(Lp[0], z["Lp0"]) < TOL_ELEM
+    val, rhs, _ = la.system(t)
+    assert rel_max(val, z["val"]) < TOL_ELEM and rel_max(rhs, z["rhs"]) < TOL_ELEM
+    assert la.solve(t) == bool(z["failed"])
+    assert abs(la.iter["nit"] - int(z["info"][1])) <= 3
+    u1, v1, _, _ = la.get_state(1)
+    assert np.max(np.abs(u1 - z["u1"])) < 1e-7 and rel_max(v1, z["v1"]) < 1e-4
+    assert abs(la.get_v_max() - float(z["v_max"])) <= 1e-4 * float(z["v_max"])
+    la.close()
+
+
+def test_space_field_and_drift(oracle, gpu_lib):
+    """prepareElements(A_Hext) overload (linear_algebra.cpp:54-81) and the recentring drift term
+    (tetra.cpp:150-169, 279-288)."""
+    case = cases.small_cuboid(seed=7)
+    oc, la = _pair(case)
+    rng = np.random.default_rng(3)
+    fieldv = rng.standard_normal((case.mesh.NT, 3, case.npi)) * 2e4
+    oc.set_ext_space_field(fieldv)
+    la.set_ext_space_field(fieldv)
+    t = FixedTiming(case)
+    oc.base_projection(case.angle)
+    la.base_projection(case.angle)
+    la.idx_dir, la.DW_vz = 2, 37.5
+    oc.prepare_elements_space(1.7, case.dt, case.prefactor, idx_dir=2, Vdrift=37.5)
+    la.prepareElements(1.7, t)
+    Kp, Lp = la.elements()
+    for tt in range(oc.NT):
+        Ko, Lo = oc.element(tt)
+        assert rel_max(Kp[tt], Ko) < TOL_ELEM and rel_max(Lp[tt], Lo) < TOL_ELEM
+    la.close()
+    oc.close()
+
+
+def test_trajectory_averages(oracle, gpu_lib):
+    """N accepted steps with NEXT->CURRENT commits: <m> and v_max agree to 1e-6 relative."""
+    case = cases.ellipsoid()
+    oc, la = _pair(case)
+    t = FixedTiming(case)
+    from feellgood_b200.linear_algebra import M_2_PI, mt19937_uniform01
+    for step in range(12):
+        ang = M_2_PI * mt19937_uniform01(1000 + step)
+        oc.base_projection(ang)
+        oc.prepare_elements(case.Hext, case.dt, case.prefactor)
+        fo_ = oc.solve(case.dt)
+        fg_ = la.step(case.Hext, t, angle=ang)
+        assert fg_ == fo_ is False
+        oc.evolution()
+        la.evolution()
+    u_o = oc.get_state(0)[0]
+    u_g = la.get_state(0, "u")[0]
+    assert rel_max(u_g.mean(axis=0), u_o.mean(axis=0)) < 1e-6
+    assert np.max(np.abs(u_g - u_o)) < 1e-6
+    assert abs(la.get_v_max() - oc.v_max()) <= 1e-6 * oc.v_max() * 100
+    la.close()
+    oc.close()
+
+
+def test_failure_semantics(oracle, gpu_lib):
+    """solve() returns True (failure) on ITER_OVERFLOW and leaves NEXT and v_max untouched
+    (src/solver.cpp:62-69)."""
+    case = cases.small_cuboid()
+    case.maxiter = 2
+    oc, la = _pair(case)
+    t = _prepare(case, oc, la)
+    fo_ = oc.solve(case.dt)
+    fg_ = la.solve(t)
+    assert fo_ and fg_
+    assert la.iter["status"] == oc.iter_info()["status"] == 1
+    assert la.iter["nit"] == oc.iter_info()["nit"] == 2
+    u_g, v_g, _, _ = la.get_state(1)
+    assert np.array_equal(u_g, case.u) and np.array_equal(v_g, case.v)
+    assert la.get_v_max() == 0.0
+    la.close()
+    oc.close()
+
+
+def test_error_paths(gpu_lib):
+    """C-ABI error behaviour: bad meshes and call-sequence errors return codes, never exit()."""
+    import ctypes as C
+    from feellgood_b200 import capi, meshgen, LinAlgebra, Settings
+    case = cases.small_cuboid()
+    s = Settings([capi.tet_prm(**r) for r in case.tet_regions],
+                 [capi.tri_prm(**r) for r in case.tri_regions])
+    bad = meshgen.Mesh(case.mesh.node_p, case.mesh.tet_ind.copy(), case.mesh.tet_reg,
+                       case.mesh.tri_ind, case.mesh.tri_reg, case.mesh.tri_dMs)
+    bad.tet_ind[3] = [0, 0, 1, 2]                           # degenerate (Tet::orientate exits in the ref)
+    with pytest.raises(capi.FgError) as e:
+        LinAlgebra(s, bad)
+    assert e.value.code == -3
+    bad.tet_ind[3] = [0, 1, 2, case.mesh.NOD + 5]
+    with pytest.raises(capi.FgError):
+        LinAlgebra(s, bad)
+    la = LinAlgebra(s, case.mesh)
+    la.set_state(case.u)
+    with pytest.raises(capi.FgError) as e:
+        la.solve(FixedTiming(case))                         # solve before prepareElements
+    assert e.value.code == -4
+    la.close()
