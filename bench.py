@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py — LLG steps/s of the B200 hot path (base_projection + prepareElements + solve) on a
+BASELINE.json configuration, with the SpMV roofline, an end-to-end leg through the public API with
+host buffers, and the CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+One JSON line on stdout (rank 0).  For N > 1 launch with torch.distributed.run, one rank per GPU:
+the unknowns are row-block (slab) partitioned over the ranks, same mesh at every N (strong
+scaling).  `--impl reference` times the CPU implementation (oracle port driving the reference's
+algorithm with all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "LLG steps/s (assembly+BiCGStab)"
+UNIT = "steps/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak_gbs():
+    """HBM copy bandwidth measured by the driver on this pool (MEASURED_PEAKS.json), else the
+    fallback of /opt/skills/guides/B200_PROFILING.md."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            for k in ("hbm_gbs", "hbm_gbs_sustained"):
+                if k in d and d[k]:
+                    return float(d[k]), "measured (MEASURED_PEAKS.json %s)" % k
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return out
+        time.sleep(0.12)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+                power.append(float(c[3]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if c[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out = dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)),
+                       reasons=sorted(reasons), power_w=float(np.median(power)), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU leg: the oracle port on a bounded sample of the workload
+# ---------------------------------------------------------------------------------------------
+def cpu_leg(workload_name, steps, warmup, budget_s=25.0):
+    """Times base_projection + prepareElements + solve (+ evolution) of the CPU implementation on
+    a reduced-extent sample of the workload (same cell size, materials, dt) with all host threads
+    the implementation can use (the loops the reference runs under std::execution::par: basis,
+    element integrals, matrix scatter, SpMV; BLAS-1 serial, as in the reference), and scales the
+    result to the full workload by the tetrahedron count (the work per step is linear in the
+    mesh size at fixed cell size: same sparsity per row and the same BiCGStab iteration count)."""
+    from feellgood_b200 import workloads
+    from oracle import fg_oracle_py as fo
+    fo.build()
+    full = dict(ellipsoid=(167, 499), sp4=(47439, 186000), disk1m=(0, 0), tube5m=(0, 0),
+                film20m=(5000043, 19969200)).get(workload_name, (0, 0))
+    scale = dict(ellipsoid=1.0, sp4=1.0, disk1m=0.45, tube5m=0.2, film20m=0.25)[workload_name]
+    w = workloads.build(workload_name, scale=scale)
+    NT_full = full[1]
+    if NT_full == 0:
+        # closed-form full size of the generators (no need to build the full mesh on the host)
+        NT_full = dict(disk1m=942000, tube5m=8 * 152 * 690 * 6)[workload_name]
+    ncores = os.cpu_count() or 1
+    pt = [fo.tet_prm(**r) for r in w.tet_regions]
+    pf = [fo.tri_prm(**r) for r in w.tri_regions]
+    oc = fo.OracleCtx(w.mesh, pt, pf, npi=w.npi, npi_tri=4 if w.npi == 5 else 1, tol=w.tol,
+                      maxiter=w.maxiter)
+    oc.set_num_threads(ncores)
+    oc.set_state(w.u)
+    t = w.timing()
+    from feellgood_b200.linear_algebra import M_2_PI, mt19937_uniform01
+
+    def one(k):
+        oc.base_projection(M_2_PI * mt19937_uniform01(1000 + k))
+        oc.prepare_elements(w.Hext, t.get_dt(), t.prefactor)
+        failed = oc.solve(t.get_dt())
+        oc.evolution()
+        return failed, oc.iter_info()["nit"]
+
+    for k in range(warmup):
+        one(k)
+    its, t0 = [], time.perf_counter()
+    done = 0
+    for k in range(steps):
+        f, nit = one(warmup + k)
+        its.append(nit)
+        done += 1
+        if time.perf_counter() - t0 > budget_s and done >= 2:
+            break
+    el = time.perf_counter() - t0
+    sps_sample = done / el
+    ratio = w.mesh.NT / float(NT_full)
+    value = sps_sample * ratio
+    oc.close()
+    return dict(value=value, unit=UNIT, cores=ncores, kind="port",
+                sample=("%s: %d tets / %d nodes (%.4g of the %d-tet workload, same cell size and "
+                        "dt), %d steps in %.1f s = %.3f steps/s on the sample, scaled by the "
+                        "tet ratio; mean %.1f BiCGStab iterations; oracle port with OpenMP on the "
+                        "reference's parallel loops, serial BLAS-1 as in the reference"
+                        % (w.name, w.mesh.NT, w.mesh.NOD, ratio, NT_full, done, el, sps_sample,
+                           float(np.mean(its)))),
+                ms_per_step_sample=1e3 * el / done, steps=done)
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="film20m")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.warmup < 3:
+        args.warmup = 3
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cb = cpu_leg(args.workload, max(2, min(args.steps, 12)), 1)
+        line = dict(metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=args.gpus, steps=cb["steps"],
+                    warmup=1, ms_per_step=1e3 / cb["value"], higher_is_better=True,
+                    scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
+                    impl="reference", config=dict(workload=args.workload),
+                    cpu_baseline=cb,
+                    e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0,
+                             d2h_bytes_per_step=0))
+        print(json.dumps(line), flush=True)
+        return 0
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this framework has no CPU fallback; "
+                         "use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from feellgood_b200 import LinAlgebra, workloads
+    from feellgood_b200.linear_algebra import M_2_PI, mt19937_uniform01
+
+    t_build = time.perf_counter()
+    w = workloads.build(args.workload, scale=args.scale)
+    if world > 1:
+        from feellgood_b200.dist import DistLinAlgebra
+        la = DistLinAlgebra(w.settings(), w.mesh, rank=rank, world=world, device=local_rank)
+    else:
+        la = LinAlgebra(w.settings(), w.mesh, device=local_rank)
+    la.set_state(w.u)
+    tm = w.timing()
+    if rank == 0:
+        log("bench: %s NOD=%d NT=%d n=%d nnz=%d  (setup %.1f s)"
+            % (w.name, w.mesh.NOD, w.mesh.NT, la.n, la.nnz, time.perf_counter() - t_build))
+    stream = torch.cuda.ExternalStream(la.stream(), device=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    iters = []
+
+    def one_step(k):
+        ang = M_2_PI * mt19937_uniform01(1000 + k)      # same angle stream on every rank
+        failed = la.step(w.Hext, tm, angle=ang)
+        la.evolution()
+        iters.append(la.iter["nit"])
+        return failed
+
+    def timed(fn, nsteps, k0):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        nfail = 0
+        for k in range(nsteps):
+            nfail += bool(fn(k0 + k))
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms, nfail
+
+    # ---- device-resident leg --------------------------------------------------------------
+    for k in range(args.warmup):
+        one_step(k)
+    iters.clear()
+    la.set_profiling(2)                       # CUDA-event pair around every SpMV launch
+    l0 = la.kernel_launches()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms, nfail = timed(one_step, args.steps, args.warmup)
+    clk = clocks.stop() if rank == 0 else {}
+    launches = la.kernel_launches() - l0
+    spmv_ms, spmv_n = la.spmv_times()
+    la.set_profiling(0)
+    mean_it = float(np.mean(iters)) if iters else 0.0
+    value = args.steps / (ms * 1e-3)
+
+    # ---- end-to-end leg: host buffers in and out every step -----------------------------------
+    e2e = None
+    if not args.no_e2e:
+        NODl = la.NOD_local if hasattr(la, "NOD_local") else la.NOD
+        pin = lambda *s: torch.empty(*s, dtype=torch.float64, pin_memory=True).numpy()
+        h_phi, h_phiv = pin(NODl), pin(NODl)
+        h_phi[:] = 0.0
+        h_phiv[:] = 0.0
+        h_u, h_v = pin(NODl, 3), pin(NODl, 3)
+
+        def e2e_step(k):
+            # what the reference's loop moves around one hot-path call: the demag solver's
+            # potentials in (Nodes::set_phi/set_phiv), the new u and v out (its next input)
+            la.set_potentials(h_phi, h_phiv)
+            la.evolution()
+            ang = M_2_PI * mt19937_uniform01(1000 + k)
+            failed = la.step(w.Hext, tm, angle=ang)
+            la.get_state_into(1, u=h_u, v=h_v)
+            return failed
+
+        for k in range(2):
+            e2e_step(args.warmup + args.steps + k)
+        ms_e, _ = timed(e2e_step, args.steps, args.warmup + args.steps + 2)
+        e2e = dict(value=args.steps / (ms_e * 1e-3), unit=UNIT,
+                   h2d_bytes_per_step=int(2 * 8 * w.mesh.NOD), d2h_bytes_per_step=int(48 * w.mesh.NOD),
+                   ms_per_step=ms_e / args.steps,
+                   api="LinAlgebra.set_potentials + evolution + step + get_state (pinned host)")
+
+    # ---- roofline of the dominant kernel (SpMV) --------------------------------------------------
+    peak, peak_src = measured_peak_gbs()
+    n_loc = la.n_local if hasattr(la, "n_local") else la.n
+    nnz_loc = la.nnz_local if hasattr(la, "nnz_local") else la.nnz
+    roof = None
+    if spmv_n > 0:
+        b_spmv = workloads.spmv_bytes(n_loc, nnz_loc)
+        ach = b_spmv / (spmv_ms * 1e-3 / spmv_n) / 1e9
+        roof = dict(bound="hbm", kernel="k_spmv<OP_NODE2,*>", achieved=ach, peak=peak, unit="GB/s",
+                    frac=ach / peak, traffic=None, peak_source=peak_src,
+                    bytes_per_launch=b_spmv, launches=spmv_n, us_per_launch=1e3 * spmv_ms / spmv_n,
+                    share_of_step=spmv_ms / ms,
+                    csr_equiv_gbs=workloads.spmv_bytes_csr(n_loc, nnz_loc)
+                    / (spmv_ms * 1e-3 / spmv_n) / 1e9)
+        tfile = os.path.join(ROOT, "profiles", "spmv_traffic.json")
+        if os.path.exists(tfile):
+            try:
+                tj = json.load(open(tfile))
+                if tj.get("workload") == w.name and world == 1:
+                    roof["traffic"] = tj.get("dram_bytes_per_launch")
+            except Exception:
+                pass
+    b_step = workloads.step_bytes(w.mesh.NOD, w.mesh.NT, la.n, la.nnz, mean_it)
+    step_roof = dict(bytes_per_step=b_step, achieved=b_step / (ms * 1e-3 / args.steps) / 1e9 / world,
+                     unit="GB/s per GPU", frac=b_step / (ms * 1e-3 / args.steps) / 1e9 / world / peak)
+
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cb = cpu_leg(args.workload, 6, 1, budget_s=15.0)
+        except Exception as e:  # the checker is optional for the measurement itself
+            cb = dict(error=str(e))
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True,
+                    scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
+                    config=dict(workload=w.name, baseline_config=w.config, NOD=w.mesh.NOD,
+                                NT=w.mesh.NT, n=la.n, nnz=la.nnz, dt=w.dt, tol=w.tol, npi=w.npi,
+                                mean_bicgstab_iters=mean_it, failed_steps=nfail,
+                                l2="inputs exceed L2 (matrix %.0f MB >> 126 MB), no flush"
+                                   % (8e-6 * la.nnz),
+                                parallelism="row-block slabs x%d" % world if world > 1 else "1 GPU"),
+                    roofline=roof, step_roofline=step_roof, cpu_baseline=cb, e2e=e2e,
+                    gpu_launches=int(launches), clocks=clk)
+        print(json.dumps(line), flush=True)
+    la.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
