@@ -1,0 +1,125 @@
+"""Host-side logic that needs no GPU: timing, the basis-angle random stream, mesh builders and
+readers, workload builders and the algorithmic-byte model."""
+import math
+import os
+
+import numpy as np
+
+import cases
+from feellgood_b200 import meshgen, workloads
+from feellgood_b200.linear_algebra import M_2_PI, c_srand, mt19937_uniform01, timing, _c_rand
+
+
+def test_timing_matches_reference_header():
+    # src/time_integration.h:11-15,37-42 ; unit-tests/ut_time_int.cpp:19-43 (dt0 = sqrt(a b))
+    t = timing(2e-11, 1e-16, 5e-13)
+    assert t.get_dt() == math.sqrt(1e-16 * 5e-13) and t.TAUR == 100 * 5e-13
+    tt = t.get_dt() / t.TAUR
+    assert t.prefactor == 1.0 + tt * abs(math.log(tt))
+    t.set_dt(1e-13)
+    assert not t.is_dt_TooSmall()
+    t.set_dt(1e-17)
+    assert t.is_dt_TooSmall()
+    t.inc_t()
+    assert t.get_t() == 1e-17
+
+
+def test_mt19937_first_uniform_draw():
+    # libstdc++ generate_canonical<double,53> of mt19937(5489): first two outputs 3499211612, 581869302
+    r = mt19937_uniform01(5489)
+    assert r == (3499211612 + 581869302 * 4294967296.0) / 18446744073709551616.0
+    assert 0.0 <= r < 1.0 and M_2_PI == 2.0 / math.pi
+    c_srand(2)
+    a = [_c_rand() for _ in range(3)]
+    c_srand(2)
+    assert a == [_c_rand() for _ in range(3)]            # --seed N reproducibility (src/main.cpp:211)
+
+
+def test_cuboid_counts_and_orientation():
+    m = meshgen.cuboid([0, 0, 0], [4, 3, 2], 4, 3, 2, scale=1e-9)
+    assert m.NOD == 5 * 4 * 3 and m.NT == 4 * 3 * 2 * 6
+    assert m.NF == 2 * 2 * (4 * 3 + 4 * 2 + 3 * 2)       # two triangles per boundary quad
+    p = m.node_p[m.tet_ind]
+    vol = np.einsum("ij,ij->i", p[:, 1] - p[:, 0], np.cross(p[:, 2] - p[:, 0], p[:, 3] - p[:, 0])) / 6
+    assert abs(np.abs(vol).sum() - 24e-27) < 1e-36
+    # boundary triangles point outwards: sum of area vectors vanishes, divergence theorem gives V
+    q = m.node_p[m.tri_ind]
+    nrm = 0.5 * np.cross(q[:, 1] - q[:, 0], q[:, 2] - q[:, 0])
+    assert np.max(np.abs(nrm.sum(axis=0))) < 1e-30
+    assert abs(np.einsum("ij,ij->", q.mean(axis=1), nrm) / 3 - 24e-27) < 1e-36
+
+
+def test_sort_nodes_is_a_consistent_renumbering():
+    m = meshgen.cuboid([0, 0, 0], [2, 7, 3], 2, 5, 3, scale=1e-9)
+    p0, t0 = m.node_p.copy(), m.tet_ind.copy()
+    meshgen.sort_nodes(m)
+    assert np.all(np.diff(m.node_p[:, 1]) >= 0)          # longest axis = y
+    assert np.array_equal(m.node_p[m.node_index[t0]], p0[t0])
+    assert np.array_equal(m.node_p[m.tet_ind], p0[t0])
+
+
+def test_dMs_of_closed_surface():
+    m = meshgen.cuboid([0, 0, 0], [2, 2, 2], 2, 2, 2, scale=1e-9)
+    d = meshgen.compute_dMs(m, [0.0, 8e5])
+    assert np.all(d == 8e5)                              # outward surface of a single region
+    m.tri_ind = m.tri_ind[:, [0, 2, 1]].copy()
+    assert np.all(meshgen.compute_dMs(m, [0.0, 8e5]) == -8e5)
+
+
+def test_read_msh_v2_and_v4(tmp_path):
+    v2 = """$MeshFormat
+2.2 0 8
+$EndMeshFormat
+$PhysicalNames
+2
+2 200 "surf"
+3 300 "vol"
+$EndPhysicalNames
+$Nodes
+5
+1 0 0 0
+2 1 0 0
+3 0 1 0
+4 0 0 1
+5 1 1 1
+$EndNodes
+$Elements
+4
+1 2 2 200 1 1 3 2
+2 4 2 300 1 1 2 3 4
+3 4 2 300 1 2 3 4 5
+4 15 2 1 1 1
+$EndElements
+"""
+    f = tmp_path / "a.msh"
+    f.write_text(v2)
+    m = meshgen.read_msh(str(f), ["vol"], ["surf"], scale=1e-9)
+    assert (m.NOD, m.NT, m.NF) == (5, 2, 1)
+    assert np.array_equal(m.tet_ind, [[0, 1, 2, 3], [1, 2, 3, 4]]) and np.all(m.tet_reg == 1)
+    assert np.array_equal(m.tri_ind, [[0, 2, 1]]) and m.node_p[4, 2] == 1e-9
+    assert meshgen.read_msh(str(f), ["other"], [], scale=1.0).NT == 0     # unknown region dropped
+    z = np.load(os.path.join(cases.GOLDEN, "ellipsoid_mesh.npz"))
+    assert (z["node_p"].shape[0], z["tet_ind"].shape[0], z["tri_ind"].shape[0]) == (167, 499, 274)
+
+
+def test_workload_builders_small():
+    for name, scale, nt in (("film20m", 0.02, 26 * 26 * 2 * 6), ("sp4", 0.1, 25 * 6 * 2 * 6),
+                            ("tube5m", 0.01, 8 * 152 * 7 * 6), ("ellipsoid", 1.0, 499)):
+        w = workloads.build(name, scale=scale)
+        assert w.mesh.NT == nt, name
+        assert np.max(np.abs(np.linalg.norm(w.u, axis=1) - 1)) < 1e-14
+        assert w.mesh.tet_ind.min() == 0 and w.mesh.tet_ind.max() == w.mesh.NOD - 1
+        t = w.timing()
+        assert t.get_dt() == w.dt and t.prefactor > 1.0
+    d = workloads.build("disk1m", scale=0.1)
+    r = np.hypot(d.mesh.node_p[:, 0], d.mesh.node_p[:, 1])
+    assert r.max() < 250e-9 * 1.1 and d.mesh.NT % 6 == 0
+
+
+def test_algorithmic_byte_model():
+    n, nnz = 2000, 60000
+    assert workloads.spmv_bytes_csr(n, nnz) == 12 * nnz + 20 * n
+    assert workloads.spmv_bytes(n, nnz) == 9 * nnz + 4 * (n // 2) + 16 * n
+    assert workloads.iter_bytes(n, nnz) == 2 * workloads.spmv_bytes(n, nnz) + 144 * n
+    b0 = workloads.step_bytes(1000, 6000, n, nnz, 0)
+    assert workloads.step_bytes(1000, 6000, n, nnz, 10) - b0 == 10 * workloads.iter_bytes(n, nnz)
