@@ -1,0 +1,188 @@
+// host_shim_test.cpp — drives the C++17 drop-in (feellgood_b200/host/feellgood_b200.hpp) the way
+// the reference's Fem::time_integration drives LinAlgebra (src/time_integration.cpp:193-206), and
+// runs ports of the reference's algebra unit tests (unit-tests/ut_algebra.cpp:160-330) through the
+// algebra:: surface.  Needs a GPU; with `--compile-only` semantics the CPU suite just builds it.
+#include <cstdio>
+#include <cstring>
+
+#include "../../feellgood_b200/host/feellgood_b200.hpp"
+
+static int n_fail = 0;
+#define CHECK(c)                                                   \
+    do                                                             \
+        {                                                          \
+        if (!(c))                                                  \
+            {                                                      \
+            n_fail++;                                              \
+            std::printf("FAIL %s:%d: %s\n", __FILE__, __LINE__, #c); \
+            }                                                      \
+        } while (0)
+
+// the gmsh-free Cuboid scheme of python-modules/meshMaker.py:440-519
+static fgb200::MeshView cuboid(int nx, int ny, int nz, double h)
+    {
+    fgb200::MeshView m;
+    auto nid = [&](int i, int j, int k) { return (nz + 1) * (ny + 1) * i + (nz + 1) * j + k; };
+    for (int i = 0; i <= nx; i++)
+        for (int j = 0; j <= ny; j++)
+            for (int k = 0; k <= nz; k++)
+                for (double c : {i * h, j * h, k * h}) m.node_p.push_back(c);
+    static const int T[6][4][3] = {
+        {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 1, 1}}, {{0, 0, 0}, {1, 0, 0}, {0, 0, 1}, {0, 1, 1}},
+        {{0, 0, 1}, {1, 0, 1}, {0, 1, 1}, {1, 0, 0}}, {{1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 1, 1}},
+        {{1, 0, 0}, {1, 1, 0}, {1, 1, 1}, {0, 1, 1}}, {{1, 0, 1}, {1, 0, 0}, {1, 1, 1}, {0, 1, 1}}};
+    for (int i = 0; i < nx; i++)
+        for (int j = 0; j < ny; j++)
+            for (int k = 0; k < nz; k++)
+                for (auto &t : T)
+                    {
+                    for (auto &c : t) m.tet_ind.push_back(nid(i + c[0], j + c[1], k + c[2]));
+                    m.tet_reg.push_back(1);
+                    }
+    return m;
+    }
+
+static void test_llg_loop()
+    {
+    fgb200::MeshView msh = cuboid(8, 4, 3, 2e-9);
+    fgb200::Settings s;
+    fg_tet_prm def{};
+    fg_tet_prm py{};
+    py.alpha_LLG = 0.02; py.A = 1.3e-11; py.Ms = 8e5; py.K = 0; py.K3 = 0;
+    py.uk[2] = 1; py.ex[0] = 1; py.ey[1] = 1; py.ez[2] = 1;
+    def = py; def.Ms = 795774.7;
+    s.paramTetra = {def, py};
+    s.paramTriangle = {fg_tri_prm{}};
+    srand(2);                                       // --seed 2 (ci-tests/full_test.py:54)
+    LinAlgebra linAlg(s, msh);
+    const int NOD = msh.NOD();
+    std::vector<double> u(3 * (size_t)NOD), un(3 * (size_t)NOD), vn(3 * (size_t)NOD), phi(NOD, 0.0);
+    for (int a = 0; a < NOD; a++)
+        {
+        const double x = msh.node_p[3 * a] * 1e8;
+        const double c[3] = {std::cos(x), std::sin(x), 0.2};
+        const double nn = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+        for (int k = 0; k < 3; k++) u[3 * a + k] = c[k] / nn;
+        }
+    linAlg.set_state(u.data(), nullptr, nullptr, nullptr);
+    timing t_prm(2e-11, 1e-16, 5e-13);
+    t_prm.set_dt(1e-13);
+    const fgb200::Vec3 Hext{{0.0, 8000.0, 0.0}};
+    for (int step = 0; step < 5; step++)
+        {
+        linAlg.base_projection();
+        linAlg.prepareElements(Hext, t_prm);
+        std::vector<double> G;
+        if (step == 1)
+            {
+            linAlg.buildInitGuess(G);
+            CHECK(G.size() == 2 * (size_t)NOD);
+            }
+        const bool err = linAlg.solve(t_prm);
+        CHECK(!err);
+        CHECK(linAlg.iter.status == algebra::CONVERGED);
+        CHECK(linAlg.iter.get_res() <= linAlg.iter.get_rhsnorm() * linAlg.iter.resmax);
+        CHECK(linAlg.get_v_max() > 0.0);
+        linAlg.get_state(1, un.data(), vn.data(), nullptr, nullptr);
+        linAlg.set_potentials(phi.data(), phi.data());  // what the demag solver would write
+        linAlg.evolution();
+        t_prm.inc_t();
+        }
+    double worst = 0.0, moved = 0.0;
+    for (int a = 0; a < NOD; a++)
+        {
+        double nn = 0.0, d = 0.0;
+        for (int k = 0; k < 3; k++)
+            {
+            nn += un[3 * a + k] * un[3 * a + k];
+            d += std::fabs(un[3 * a + k] - u[3 * a + k]);
+            }
+        worst = std::max(worst, std::fabs(std::sqrt(nn) - 1.0));
+        moved = std::max(moved, d);
+        }
+    CHECK(worst < 1e-15);
+    CHECK(moved > 1e-6);
+    std::printf("llg loop: %s v_max=%.6g\n", linAlg.iter.infos().c_str(), linAlg.get_v_max());
+    }
+
+// unit-tests/ut_algebra.cpp:160-190 (test_cg) and :245-275 (test_bicg): identity solves in 0 iterations
+static void test_identity_solves()
+    {
+    const int N = 1000;
+    algebra::MatrixShape shape(N);
+    for (int i = 0; i < N; i++) shape[i].insert(i);
+    algebra::SparseMatrix A(shape);
+    for (int i = 0; i < N; i++) A.set(i, i, 1.0);
+    std::vector<double> x(N, 0.0), b(N);
+    for (int i = 0; i < N; i++) b[i] = 1.0 + i;
+    algebra::iteration<double> it("cg", 1e-6, false, 100);
+    x = b;
+    algebra::cg(it, A, x, b);
+    CHECK(it.status == algebra::CONVERGED && it.get_iteration() == 0);
+    algebra::iteration<double> it2("bicg", 1e-6, false, 100);
+    algebra::bicg(it2, A, x, b);
+    CHECK(it2.status == algebra::CONVERGED && it2.get_iteration() == 0);
+    }
+
+// unit-tests/ut_algebra.cpp:192-243 (test_cg_dir) / :277-330 (test_bicg_dir): 1-D Laplacian with
+// Dirichlet values 0 and 1 at the ends -> linear ramp
+static void test_laplacian_dirichlet()
+    {
+    const int NOD = 1001;
+    algebra::MatrixShape shape(NOD);
+    for (int i = 0; i < NOD; i++)
+        for (int j : {i - 1, i, i + 1})
+            if (j >= 0 && j < NOD) shape[i].insert(j);
+    algebra::SparseMatrix A(shape);
+    for (int i = 0; i < NOD; i++)
+        {
+        A.set(i, i, 2.0);
+        if (i > 0) A.set(i, i - 1, -1.0);
+        if (i < NOD - 1) A.set(i, i + 1, -1.0);
+        }
+    CHECK(A(3, 4) == -1.0 && A(3, 7) == 0.0);
+    std::vector<double> x(NOD, 0.0), rhs(NOD, 0.0), xd(NOD, 0.0);
+    std::vector<int> ld = {0, NOD - 1};
+    xd[NOD - 1] = 1.0;
+    algebra::iteration<double> it("cg_dir", 1e-10, false, 5000);
+    algebra::cg_dir(it, A, x, rhs, xd, ld);
+    CHECK(it.status == algebra::CONVERGED);
+    double worst = 0.0;
+    for (int i = 0; i < NOD; i++) worst = std::max(worst, std::fabs(x[i] - (double)i / (NOD - 1)));
+    CHECK(worst < 1e-6);
+    std::fill(x.begin(), x.end(), 0.0);
+    algebra::iteration<double> it2("bicg_dir", 1e-10, false, 5000);
+    algebra::bicg_dir(it2, A, x, rhs, xd, ld);
+    CHECK(it2.status == algebra::CONVERGED);
+    worst = 0.0;
+    for (int i = 0; i < NOD; i++) worst = std::max(worst, std::fabs(x[i] - (double)i / (NOD - 1)));
+    CHECK(worst < 1e-6);
+    // SparseMatrix::mult
+    std::vector<double> y(NOD);
+    algebra::mult(A, x, y);
+    double r2 = 0.0;
+    for (int i = 1; i < NOD - 1; i++) r2 += y[i] * y[i];
+    CHECK(std::sqrt(r2) < 1e-8);
+    }
+
+int main(int argc, char **argv)
+    {
+    if (argc > 1 && !std::strcmp(argv[1], "--link-check"))
+        {
+        std::printf("fg_version %d\n", fg_version());
+        return fg_version() >= 100 ? 0 : 1;
+        }
+    try
+        {
+        test_identity_solves();
+        test_laplacian_dirichlet();
+        test_llg_loop();
+        }
+    catch (const std::exception &e)
+        {
+        std::printf("exception: %s\n", e.what());
+        return 2;
+        }
+    std::printf("%s (%d failures)\n", n_fail ? "FAILED" : "ok", n_fail);
+    return n_fail ? 1 : 0;
+    }
