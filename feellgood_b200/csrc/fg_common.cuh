@@ -39,6 +39,7 @@ constexpr int BLOCK = 256;            // every kernel of the library uses 256-th
 constexpr int CTAS_PER_SM = 8;        // 2048 resident threads per SM
 constexpr int MAX_GRID = NUM_SMS * CTAS_PER_SM;  // persistent grid-stride kernels: one full wave
 constexpr int RED_NV = 4;             // max simultaneous reductions per kernel
+constexpr int SLICE = 32;             // SELL slice height = warp size
 
 // Node record = the reference's Nodes::dataNode {u, v, phi, phiv} (src/node.h:47-53): 64 B, so a
 // gather of one node by a tetrahedron is exactly two aligned 32-byte sectors.
@@ -94,21 +95,25 @@ struct RedBuf
     };
 
 // The operator y = A x.
-//  OP_NODE2: the LLG matrix K (src/solver.h:75-104): rows 2a and 2a+1 share the column list
-//            {2b, 2b+1 : b in ncol[nptr[a]..nptr[a+1])}.  val is in the reference's CSR order
-//            (rowptr[2a] = 4 nptr[a], rowptr[2a+1] = 4 nptr[a] + 2 deg_a) but indexed through the
-//            node-level pattern: 4 B of index per 32 B of values.
+//  OP_SELL2: the LLG matrix K (src/solver.h:75-104) in SELL-32-sigma with 2x2 blocks, device row
+//            order.  Slice s holds 32 node rows and sptr[s+1]-sptr[s] block-columns;
+//            block-column j of the slice stores, for lane l = row s*32+l,
+//              scol[(sptr[s]+j)*32 + l]                  device row of the column node
+//              val2[((sptr[s]+j)*2 + 0)*32 + l]          (K[2r,2c], K[2r,2c+1])     as double2
+//              val2[((sptr[s]+j)*2 + 1)*32 + l]          (K[2r+1,2c], K[2r+1,2c+1]) as double2
+//            so one warp streams a slice with fully coalesced 128 B / 512 B requests and every
+//            lane folds its own row left to right (no shuffles).  4 B of index per 32 B of values.
 //  OP_CSR:   any algebra::SparseMatrix (src/algebra/sparseMat.h), plain CSR.
-enum { OP_NODE2 = 0, OP_CSR = 1 };
+enum { OP_SELL2 = 0, OP_CSR = 1 };
 struct Operator
     {
     int kind;
-    int n;       // rows
-    int lanes;   // lanes cooperating on one node (OP_NODE2) / one row (OP_CSR): 2..32
-    const int *ptr;     // nptr (NOD+1) | rowptr (n+1)
-    const int *col;     // ncol | col
+    int n;       // rows (OP_SELL2: 2 * padded node count)
+    int lanes;   // OP_CSR: lanes cooperating on one row: 2..32
+    const int *ptr;     // OP_CSR rowptr (n+1) | OP_SELL2 sptr (nslice+1)
+    const int *col;     // OP_CSR col | OP_SELL2 scol
     const double *val;
-    // multi-GPU (fg_dist.cu): x vectors carry `n_ghost` extra entries after the n owned ones
+    int nslice;         // OP_SELL2
     };
 
 // optional CUDA-event pairs around every SpMV launch (fg_set_profiling(ctx, 2))

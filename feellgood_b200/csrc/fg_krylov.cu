@@ -78,111 +78,9 @@ struct SpmvArgs
     RedBuf red;
     };
 
-template <int KIND, int STAGE>
-__global__ void __launch_bounds__(BLOCK) k_spmv(const Operator op, const SpmvArgs a)
+// finalisation of a reducing SpMV stage by the last CTA (the scalars of bicg.h / cg.h)
+template <int STAGE> __device__ __forceinline__ void spmv_finalize(KState *st, const double (&tot)[RED_NV])
     {
-    constexpr int ROWS = (KIND == OP_NODE2) ? 2 : 1;
-    if (STAGE != ST_PLAIN && STAGE != ST_RESID && STAGE != ST_BICG_SETUP && STAGE != ST_CG_SETUP)
-        if (a.st->done) return;
-    const int G = op.lanes;
-    const int lane_in_group = threadIdx.x & (G - 1);
-    const int groups_per_cta = BLOCK / G;
-    const int nunits = (KIND == OP_NODE2) ? op.n / 2 : op.n;
-    const long long total_groups = (long long)gridDim.x * groups_per_cta;
-    double acc[RED_NV] = {0.0, 0.0, 0.0, 0.0};
-
-    for (long long u0 = (long long)blockIdx.x * groups_per_cta + threadIdx.x / G;;
-         u0 += total_groups)
-        {
-        const bool active = u0 < nunits;
-        if (!__any_sync(0xffffffffu, active)) break;
-        const int u = (int)u0;
-        double y0 = 0.0, y1 = 0.0;
-        if (active)
-            {
-            const int beg = op.ptr[u], end = op.ptr[u + 1];
-            if (KIND == OP_NODE2)
-                {
-                const int deg = end - beg;
-                const double2 *row0 = reinterpret_cast<const double2 *>(op.val + 4 * (size_t)beg);
-                const double2 *row1 = row0 + deg;
-                const double2 *x2 = reinterpret_cast<const double2 *>(a.x);
-                for (int j = lane_in_group; j < deg; j += G)
-                    {
-                    const int bcol = __ldg(op.col + beg + j);
-                    const double2 k0 = __ldcs(row0 + j);
-                    const double2 k1 = __ldcs(row1 + j);
-                    const double2 xv = x2[bcol];
-                    y0 += k0.x * xv.x + k0.y * xv.y;
-                    y1 += k1.x * xv.x + k1.y * xv.y;
-                    }
-                }
-            else
-                {
-                for (int j = beg + lane_in_group; j < end; j += G)
-                    y0 += __ldcs(op.val + j) * a.x[__ldg(op.col + j)];
-                }
-            }
-        for (int o = G >> 1; o > 0; o >>= 1)
-            {
-            y0 += __shfl_xor_sync(0xffffffffu, y0, o);
-            if (ROWS == 2) y1 += __shfl_xor_sync(0xffffffffu, y1, o);
-            }
-        if (active && lane_in_group == 0)
-            {
-            const int i0 = ROWS * u;
-            double yv[2] = {y0, y1};
-#pragma unroll
-            for (int k = 0; k < ROWS; k++)
-                {
-                const int i = i0 + k;
-                const bool m = a.mask != nullptr && a.mask[i];
-                double y = yv[k];
-                if (STAGE == ST_PLAIN)
-                    a.y[i] = m ? 0.0 : y;
-                else if (STAGE == ST_RESID)
-                    a.y[i] = m ? 0.0 : a.a0[i] - y;
-                else if (STAGE == ST_BICG_SETUP)
-                    {
-                    const double b = a.a0[i];
-                    const double r = m ? 0.0 : b - y;
-                    a.y[i] = r;
-                    a.o0[i] = r;
-                    a.o1[i] = r;
-                    acc[0] += b * b;
-                    acc[1] += r * r;
-                    }
-                else if (STAGE == ST_CG_SETUP)
-                    {
-                    const double b = a.a0[i];
-                    const double r = m ? 0.0 : b - y;
-                    const double z = a.a1[i] * r;
-                    a.y[i] = r;
-                    a.o1[i] = z;
-                    acc[0] += b * b;
-                    acc[1] += r * r;
-                    acc[2] += z * r;
-                    }
-                else if (STAGE == ST_BICG_V || STAGE == ST_CG_Q)
-                    {
-                    y = m ? 0.0 : y;
-                    a.y[i] = y;
-                    acc[0] += y * a.a0[i];
-                    }
-                else if (STAGE == ST_BICG_T)
-                    {
-                    y = m ? 0.0 : y;
-                    a.y[i] = y;
-                    acc[0] += y * a.a0[i];
-                    acc[1] += y * y;
-                    }
-                }
-            }
-        }
-    if (STAGE == ST_PLAIN || STAGE == ST_RESID) return;
-    double tot[RED_NV];
-    if (!grid_reduce<RED_NV>(acc, a.red, tot)) return;
-    KState *st = a.st;
     if (STAGE == ST_BICG_SETUP)
         {
         st->rhsn = sqrt(fabs(tot[0]));
@@ -210,6 +108,199 @@ __global__ void __launch_bounds__(BLOCK) k_spmv(const Operator op, const SpmvArg
         }
     }
 
+// per-row epilogue shared by both layouts: applies the mask, writes y (and the fused outputs) and
+// accumulates the fused dot products.
+template <int STAGE>
+__device__ __forceinline__ void spmv_row(const SpmvArgs &a, int i, double y, double (&acc)[RED_NV])
+    {
+    const bool m = a.mask != nullptr && a.mask[i];
+    if (STAGE == ST_PLAIN)
+        a.y[i] = m ? 0.0 : y;
+    else if (STAGE == ST_RESID)
+        a.y[i] = m ? 0.0 : a.a0[i] - y;
+    else if (STAGE == ST_BICG_SETUP)
+        {
+        const double b = a.a0[i];
+        const double r = m ? 0.0 : b - y;
+        a.y[i] = r;
+        a.o0[i] = r;
+        a.o1[i] = r;
+        acc[0] += b * b;
+        acc[1] += r * r;
+        }
+    else if (STAGE == ST_CG_SETUP)
+        {
+        const double b = a.a0[i];
+        const double r = m ? 0.0 : b - y;
+        const double z = a.a1[i] * r;
+        a.y[i] = r;
+        a.o1[i] = z;
+        acc[0] += b * b;
+        acc[1] += r * r;
+        acc[2] += z * r;
+        }
+    else if (STAGE == ST_BICG_V || STAGE == ST_CG_Q)
+        {
+        y = m ? 0.0 : y;
+        a.y[i] = y;
+        acc[0] += y * a.a0[i];
+        }
+    else if (STAGE == ST_BICG_T)
+        {
+        y = m ? 0.0 : y;
+        a.y[i] = y;
+        acc[0] += y * a.a0[i];
+        acc[1] += y * y;
+        }
+    }
+
+// same, for the two rows of a node at once (16-byte accesses)
+template <int STAGE>
+__device__ __forceinline__ void spmv_row2(const SpmvArgs &a, int row, double y0, double y1,
+                                          double (&acc)[RED_NV])
+    {
+    bool m0 = false, m1 = false;
+    if (a.mask != nullptr)
+        {
+        const uchar2 mm = reinterpret_cast<const uchar2 *>(a.mask)[row];
+        m0 = mm.x != 0;
+        m1 = mm.y != 0;
+        }
+    double2 *Y = reinterpret_cast<double2 *>(a.y) + row;
+    if (STAGE == ST_PLAIN)
+        *Y = make_double2(m0 ? 0.0 : y0, m1 ? 0.0 : y1);
+    else if (STAGE == ST_RESID)
+        {
+        const double2 b = reinterpret_cast<const double2 *>(a.a0)[row];
+        *Y = make_double2(m0 ? 0.0 : b.x - y0, m1 ? 0.0 : b.y - y1);
+        }
+    else if (STAGE == ST_BICG_SETUP || STAGE == ST_CG_SETUP)
+        {
+        const double2 b = reinterpret_cast<const double2 *>(a.a0)[row];
+        const double2 r = make_double2(m0 ? 0.0 : b.x - y0, m1 ? 0.0 : b.y - y1);
+        *Y = r;
+        acc[0] += b.x * b.x + b.y * b.y;
+        acc[1] += r.x * r.x + r.y * r.y;
+        if (STAGE == ST_BICG_SETUP)
+            {
+            reinterpret_cast<double2 *>(a.o0)[row] = r;
+            reinterpret_cast<double2 *>(a.o1)[row] = r;
+            }
+        else
+            {
+            const double2 d = reinterpret_cast<const double2 *>(a.a1)[row];
+            const double2 z = make_double2(d.x * r.x, d.y * r.y);
+            reinterpret_cast<double2 *>(a.o1)[row] = z;
+            acc[2] += z.x * r.x + z.y * r.y;
+            }
+        }
+    else
+        {
+        y0 = m0 ? 0.0 : y0;
+        y1 = m1 ? 0.0 : y1;
+        *Y = make_double2(y0, y1);
+        const double2 q = reinterpret_cast<const double2 *>(a.a0)[row];
+        acc[0] += y0 * q.x + y1 * q.y;
+        if (STAGE == ST_BICG_T) acc[1] += y0 * y0 + y1 * y1;
+        }
+    }
+
+__host__ __device__ constexpr bool stage_gated(int STAGE)
+    { return STAGE == ST_BICG_V || STAGE == ST_BICG_T || STAGE == ST_CG_Q; }
+__host__ __device__ constexpr bool stage_reduces(int STAGE) { return STAGE != ST_PLAIN && STAGE != ST_RESID; }
+
+// ---- SELL-32 2x2-block SpMV: one warp per slice, one lane per node row -------------------------
+// Every request of the streaming part is a full-warp coalesced access (128 B of indices, 512 B of
+// values); the only gather is x (16 B per block, L2-resident: the rows of a slice are neighbours
+// in the mesh).  UNROLL independent block-columns are in flight per lane.
+constexpr int SPMV_UNROLL = 4;
+constexpr int SPMV_CTAS_PER_SM = 4;
+template <int STAGE>
+__global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_sell(const Operator op, const SpmvArgs a)
+    {
+    if (stage_gated(STAGE))
+        if (a.st->done) return;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * (BLOCK / 32);
+    const double2 *x2 = reinterpret_cast<const double2 *>(a.x);
+    const double2 *val2 = reinterpret_cast<const double2 *>(op.val);
+    double acc[RED_NV] = {0.0, 0.0, 0.0, 0.0};
+    int s = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
+    int p0 = 0, p1 = 0;
+    if (s < op.nslice)
+        {
+        p0 = __ldg(op.ptr + s);
+        p1 = __ldg(op.ptr + s + 1);
+        }
+    while (s < op.nslice)
+        {
+        const int sn = s + nwarps;
+        int q0 = 0, q1 = 0;
+        if (sn < op.nslice)
+            {  // next slice's extent, fetched under the shadow of this slice's stream
+            q0 = __ldg(op.ptr + sn);
+            q1 = __ldg(op.ptr + sn + 1);
+            }
+        const int *cp = op.col + (size_t)p0 * SLICE + lane;
+        const double2 *vp = val2 + (size_t)p0 * (2 * SLICE) + lane;
+        double y0 = 0.0, y1 = 0.0;
+#pragma unroll SPMV_UNROLL
+        for (int j = p0; j < p1; ++j)
+            {
+            const int c = __ldcs(cp);
+            const double2 k0 = __ldcs(vp);
+            const double2 k1 = __ldcs(vp + SLICE);
+            const double2 xv = x2[c];
+            y0 += k0.x * xv.x;
+            y0 += k0.y * xv.y;
+            y1 += k1.x * xv.x;
+            y1 += k1.y * xv.y;
+            cp += SLICE;
+            vp += 2 * SLICE;
+            }
+        spmv_row2<STAGE>(a, s * SLICE + lane, y0, y1, acc);
+        s = sn;
+        p0 = q0;
+        p1 = q1;
+        }
+    if (!stage_reduces(STAGE)) return;
+    double tot[RED_NV];
+    if (!grid_reduce<RED_NV>(acc, a.red, tot)) return;
+    spmv_finalize<STAGE>(a.st, tot);
+    }
+
+// ---- plain CSR (algebra::SparseMatrix of the side solvers): G lanes per row ---------------------
+template <int STAGE>
+__global__ void __launch_bounds__(BLOCK) k_spmv_csr(const Operator op, const SpmvArgs a)
+    {
+    if (stage_gated(STAGE))
+        if (a.st->done) return;
+    const int G = op.lanes;
+    const int lane_in_group = threadIdx.x & (G - 1);
+    const int groups_per_cta = BLOCK / G;
+    const long long total_groups = (long long)gridDim.x * groups_per_cta;
+    double acc[RED_NV] = {0.0, 0.0, 0.0, 0.0};
+    for (long long u0 = (long long)blockIdx.x * groups_per_cta + threadIdx.x / G;; u0 += total_groups)
+        {
+        const bool active = u0 < op.n;
+        if (!__any_sync(0xffffffffu, active)) break;
+        const int u = (int)u0;
+        double y0 = 0.0;
+        if (active)
+            {
+            const int beg = op.ptr[u], end = op.ptr[u + 1];
+            for (int j = beg + lane_in_group; j < end; j += G)
+                y0 += __ldcs(op.val + j) * a.x[__ldg(op.col + j)];
+            }
+        for (int o = G >> 1; o > 0; o >>= 1) y0 += __shfl_xor_sync(0xffffffffu, y0, o);
+        if (active && lane_in_group == 0) spmv_row<STAGE>(a, u, y0, acc);
+        }
+    if (!stage_reduces(STAGE)) return;
+    double tot[RED_NV];
+    if (!grid_reduce<RED_NV>(acc, a.red, tot)) return;
+    spmv_finalize<STAGE>(a.st, tot);
+    }
+
 int grid_for(long long work_items, int items_per_cta)
     {
     long long g = (work_items + items_per_cta - 1) / items_per_cta;
@@ -218,17 +309,40 @@ int grid_for(long long work_items, int items_per_cta)
     return (int)g;
     }
 
+// persistent grids are sized from the occupancy the compiled kernel really gets (a grid larger
+// than one resident wave would serialise a second, mostly idle wave)
+template <class K> static int resident_grid(K kernel)
+    {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BLOCK, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    int dev = 0, sms = NUM_SMS;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int g = per_sm * sms;
+    return g > MAX_GRID ? MAX_GRID : g;
+    }
+
 template <int STAGE>
 static int launch_spmv(const Operator &op, const KrylovWork &w, const SpmvArgs &a)
     {
-    const int nunits = (op.kind == OP_NODE2) ? op.n / 2 : op.n;
-    const int grid = grid_for(nunits, BLOCK / op.lanes);
     const bool prof = w.prof != nullptr && w.prof->n < w.prof->cap;
     if (prof) cudaEventRecord(w.prof->ev[2 * w.prof->n], w.stream);
-    if (op.kind == OP_NODE2)
-        k_spmv<OP_NODE2, STAGE><<<grid, BLOCK, 0, w.stream>>>(op, a);
+    if (op.kind == OP_SELL2)
+        {
+        static int wave = 0;
+        if (!wave) wave = resident_grid(k_spmv_sell<STAGE>);
+        const int need = (op.nslice + BLOCK / 32 - 1) / (BLOCK / 32);
+        const int grid = need < wave ? (need > 0 ? need : 1) : wave;
+        k_spmv_sell<STAGE><<<grid, BLOCK, 0, w.stream>>>(op, a);
+        }
     else
-        k_spmv<OP_CSR, STAGE><<<grid, BLOCK, 0, w.stream>>>(op, a);
+        {
+        static int wave = 0;
+        if (!wave) wave = resident_grid(k_spmv_csr<STAGE>);
+        int grid = grid_for(op.n, BLOCK / op.lanes);
+        if (grid > wave) grid = wave;
+        k_spmv_csr<STAGE><<<grid, BLOCK, 0, w.stream>>>(op, a);
+        }
     if (prof) cudaEventRecord(w.prof->ev[2 * w.prof->n++ + 1], w.stream);
     if (w.launches) ++*w.launches;
     FG_CUDA(cudaGetLastError());

@@ -37,7 +37,8 @@ struct fg_ctx
     cudaStream_t stream = nullptr;
     long long launches = 0;
     HostSetup h;
-    int NOD = 0, NTm = 0, NFa = 0, n = 0, nnzb = 0, lanes = 8;
+    int NOD = 0, NODp = 0, NTm = 0, NFa = 0, n = 0, np = 0, nnzb = 0;
+    long long nblk = 0;          // stored blocks incl. SELL padding
     double tol = 1e-6;
     int maxiter = 700;
     // node state
@@ -59,9 +60,9 @@ struct fg_ctx
     double2 *trec = nullptr;
     std::vector<TriRegion> h_reg_tri;
     // pattern and per-mesh constants
-    int *nptr = nullptr, *ncol = nullptr, *inc_ptr = nullptr, *inc = nullptr, *inc_tri_ptr = nullptr,
-        *inc_tri = nullptr;
-    double *S = nullptr, *Aw = nullptr, *val = nullptr;
+    int *perm = nullptr, *sptr = nullptr, *scol = nullptr, *sdeg = nullptr, *iptr = nullptr,
+        *sinc = nullptr, *itptr = nullptr, *sinct = nullptr;
+    double *sS = nullptr, *Aw = nullptr, *val = nullptr;
     KrylovWork kw;
     Operator op;
     // step bookkeeping
@@ -120,7 +121,7 @@ TetArrays tet_arrays(const fg_ctx *c)
 
 int launch_basis(fg_ctx *c, double angle)
     {
-    CTX_LAUNCH(c, k_basis, grid_for(c->NOD, BLOCK), c->NOD, c->cur, cos(angle), sin(angle), c->basis);
+    CTX_LAUNCH(c, k_basis, grid_for(c->NODp, BLOCK), c->NODp, c->cur, cos(angle), sin(angle), c->basis);
     c->have_basis = true;
     c->prepared = false;
     c->assembled = false;
@@ -186,21 +187,32 @@ int launch_assemble(fg_ctx *c, double dt)
         return FG_ERR_STATE;
         }
     RowArrays R;
-    R.NOD = c->NOD;
-    R.G = c->lanes;
-    R.nptr = c->nptr;
-    R.ncol = c->ncol;
-    R.S = c->S;
+    R.nslice = c->h.nslice;
+    R.sptr = c->sptr;
+    R.scol = c->scol;
+    R.sdeg = c->sdeg;
+    R.sS = c->sS;
     R.Aw = c->Aw;
-    R.inc_ptr = c->inc_ptr;
-    R.inc = c->inc;
-    R.inc_tri_ptr = c->inc_tri_ptr;
-    R.inc_tri = c->inc_tri;
+    R.iptr = c->iptr;
+    R.sinc = c->sinc;
+    R.itptr = c->itptr;
+    R.sinct = c->sinct;
     R.nonmag = c->nonmag;
     const double s_dt = FG_THETA * dt * FG_GAMMA0;
     const double cS = c->sp.prefactor * s_dt;  // tetra.cpp:261: lumping(a_eff, prefactor*s_dt*Abis)
-    CTX_LAUNCH(c, k_assemble_rows, grid_for(c->NOD, BLOCK / c->lanes), R, c->cur, c->next, c->basis,
-               c->rec, c->trec, cS, c->val, c->kw.b, c->kw.x, c->kw.D);
+    static int wave = 0;
+    if (!wave)
+        {
+        int per_sm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_sell, BLOCK, 0) != cudaSuccess || per_sm < 1)
+            per_sm = 1;
+        wave = per_sm * NUM_SMS;
+        }
+    int grid = (c->h.nslice + BLOCK / 32 - 1) / (BLOCK / 32);
+    if (grid > wave) grid = wave;
+    if (grid < 1) grid = 1;
+    CTX_LAUNCH(c, k_assemble_sell, grid, R, c->cur, c->next, c->basis, c->rec, c->trec, cS, c->val,
+               c->kw.b, c->kw.x, c->kw.D);
     c->assembled = true;
     return FG_OK;
     }
@@ -208,7 +220,7 @@ int launch_assemble(fg_ctx *c, double dt)
 int post_update(void *user)
     {
     fg_ctx *c = static_cast<fg_ctx *>(user);
-    CTX_LAUNCH(c, k_update, grid_for(c->NOD, BLOCK), c->NOD, c->nonmag, c->cur, c->next, c->basis,
+    CTX_LAUNCH(c, k_update, grid_for(c->NODp, BLOCK), c->NODp, c->nonmag, c->cur, c->next, c->basis,
                c->kw.x, c->sp.dt, c->kw.st, c->kw.red);
     return FG_OK;
     }
@@ -270,10 +282,31 @@ int push_fields(fg_ctx *c, NodeRec *dst, const double *u, const double *v, const
             continue;
         which |= p.bit;
         }
-    if (which) CTX_LAUNCH(c, k_pack, grid_for(c->NOD, BLOCK), c->NOD, dst, c->stage, which);
+    if (which) CTX_LAUNCH(c, k_pack, grid_for(c->NODp, BLOCK), c->NODp, c->NOD, c->perm, dst, c->stage, which);
     // the caller's buffer may be pageable and reused right away
     FG_CUDA(cudaStreamSynchronize(c->stream));
     return FG_OK;
+    }
+
+// device row order <-> caller's dof order, for the taps (host side)
+void dofs_to_caller(const fg_ctx *c, const std::vector<double> &dev, double *out)
+    {
+    for (int a = 0; a < c->NOD; a++)
+        {
+        const size_t r = (size_t)c->h.iperm[a];
+        out[2 * (size_t)a] = dev[2 * r];
+        out[2 * (size_t)a + 1] = dev[2 * r + 1];
+        }
+    }
+void dofs_to_device(const fg_ctx *c, const double *in, std::vector<double> &dev)
+    {
+    dev.assign((size_t)c->np, 0.0);
+    for (int a = 0; a < c->NOD; a++)
+        {
+        const size_t r = (size_t)c->h.iperm[a];
+        dev[2 * r] = in[2 * (size_t)a];
+        dev[2 * r + 1] = in[2 * (size_t)a + 1];
+        }
     }
 }  // namespace
 
@@ -314,14 +347,15 @@ int fg_create(const fg_mesh *mesh, const fg_params *prm, int device, fg_ctx **ou
         }
     HostSetup &h = c->h;
     c->NOD = h.NOD;
+    c->NODp = h.NODp;
     c->NTm = (int)h.magTet.size();
     c->NFa = (int)h.actTri.size();
     c->n = 2 * h.NOD;
+    c->np = 2 * h.NODp;
     c->nnzb = h.nptr[h.NOD];
+    c->nblk = (long long)h.sptr[h.nslice] * SLICE;
     c->tol = prm->tol;
     c->maxiter = prm->maxiter;
-    const double mean_deg = (double)c->nnzb / (double)c->NOD;
-    c->lanes = mean_deg > 10.0 ? 16 : (mean_deg > 5.0 ? 8 : 4);
 
 #define CK(x)                      \
     do                             \
@@ -363,7 +397,7 @@ int fg_create(const fg_mesh *mesh, const fg_params *prm, int device, fg_ctx **ou
         CKCUDA(cudaMemcpyToSymbol(c_tri_a1, a, sizeof(double) * 3));
         CKCUDA(cudaMemcpyToSymbol(c_tri_pds1, p, sizeof(double) * 1));
         }
-    const size_t N = (size_t)c->NOD;
+    const size_t N = (size_t)c->NODp;   // node arrays are in device row order, padded to 32
     CKCUDA(cudaMalloc(&c->cur, sizeof(NodeRec) * N));
     CKCUDA(cudaMalloc(&c->next, sizeof(NodeRec) * N));
     CKCUDA(cudaMalloc(&c->basis, sizeof(Basis) * N));
@@ -373,14 +407,20 @@ int fg_create(const fg_mesh *mesh, const fg_params *prm, int device, fg_ctx **ou
     CKCUDA(cudaMalloc(&c->stage, sizeof(double) * 8 * N));
     CKCUDA(cudaMallocHost(&c->h_stage, sizeof(double) * 8 * N));
         {
-        std::vector<unsigned char> nonmag(N), dofmask(2 * N);
-        for (size_t a = 0; a < N; a++)
+        std::vector<unsigned char> nonmag(N, 1), dofmask(2 * N, 1);
+        std::vector<double> aw(N, 0.0);
+        for (size_t r = 0; r < N; r++)
             {
-            nonmag[a] = h.magNode[a] ? 0 : 1;
-            dofmask[2 * a] = dofmask[2 * a + 1] = nonmag[a];
+            const int a = h.perm[r];
+            if (a < 0) continue;
+            nonmag[r] = h.magNode[a] ? 0 : 1;
+            dofmask[2 * r] = dofmask[2 * r + 1] = nonmag[r];
+            aw[r] = h.Aw[a];
             }
         CK(dev_upload(&c->nonmag, nonmag, s));
         CK(dev_upload(&c->dofmask, dofmask, s));
+        CK(dev_upload(&c->Aw, aw, s));
+        CK(dev_upload(&c->perm, h.perm, s));
         CKCUDA(cudaStreamSynchronize(s));
         }
     // magnetic tets, SoA
@@ -392,7 +432,7 @@ int fg_create(const fg_mesh *mesh, const fg_params *prm, int device, fg_ctx **ou
         for (size_t tm = 0; tm < M; tm++)
             {
             const size_t t = (size_t)h.magTet[tm];
-            ind[tm] = make_int4(h.tet_ind[4 * t], h.tet_ind[4 * t + 1], h.tet_ind[4 * t + 2], h.tet_ind[4 * t + 3]);
+            ind[tm] = make_int4(h.tet_dev_ind[4 * tm], h.tet_dev_ind[4 * tm + 1], h.tet_dev_ind[4 * tm + 2], h.tet_dev_ind[4 * tm + 3]);
             for (int k = 0; k < 12; k++) da[(size_t)k * M + tm] = h.tet_da[12 * t + k];
             dj[tm] = h.tet_detJ[t];
             reg[tm] = h.tet_reg[t];
@@ -436,7 +476,7 @@ int fg_create(const fg_mesh *mesh, const fg_params *prm, int device, fg_ctx **ou
         for (size_t fa = 0; fa < M; fa++)
             {
             const size_t f = (size_t)h.actTri[fa];
-            for (int i = 0; i < 3; i++) ind[(size_t)i * M + fa] = h.tri_ind[3 * f + i];
+            for (int i = 0; i < 3; i++) ind[(size_t)i * M + fa] = h.iperm[h.tri_ind[3 * f + i]];
             reg[fa] = h.tri_reg[f];
             surf[fa] = h.tri_surf[f];
             dMs[fa] = h.tri_dMs[f];
@@ -455,30 +495,36 @@ int fg_create(const fg_mesh *mesh, const fg_params *prm, int device, fg_ctx **ou
         CKCUDA(cudaMalloc(&c->trec, sizeof(double2) * 3 * (M > 0 ? M : 1)));
         CKCUDA(cudaStreamSynchronize(s));
         }
-    CK(dev_upload(&c->nptr, h.nptr, s));
-    CK(dev_upload(&c->ncol, h.ncol, s));
-    CK(dev_upload(&c->S, h.S, s));
-    CK(dev_upload(&c->Aw, h.Aw, s));
-    CK(dev_upload(&c->inc_ptr, h.inc_ptr, s));
-    CK(dev_upload(&c->inc, h.inc, s));
-    CK(dev_upload(&c->inc_tri_ptr, h.inc_tri_ptr, s));
-    CK(dev_upload(&c->inc_tri, h.inc_tri, s));
-    CKCUDA(cudaMalloc(&c->val, sizeof(double) * 4 * (size_t)c->nnzb));
-    CKCUDA(cudaMemsetAsync(c->val, 0, sizeof(double) * 4 * (size_t)c->nnzb, s));
-    CK(krylov_alloc(c->kw, c->n, 0, s, &c->launches));
+    CK(dev_upload(&c->sptr, h.sptr, s));
+    CK(dev_upload(&c->scol, h.scol, s));
+    CK(dev_upload(&c->sdeg, h.sdeg, s));
+    CK(dev_upload(&c->sS, h.sS, s));
+    CK(dev_upload(&c->iptr, h.iptr, s));
+    CK(dev_upload(&c->sinc, h.sinc, s));
+    CK(dev_upload(&c->itptr, h.itptr, s));
+    CK(dev_upload(&c->sinct, h.sinct, s));
+    const size_t nval = 4 * (size_t)(c->nblk > 0 ? c->nblk : 1);
+    CKCUDA(cudaMalloc(&c->val, sizeof(double) * nval));
+    CKCUDA(cudaMemsetAsync(c->val, 0, sizeof(double) * nval, s));
+    CK(krylov_alloc(c->kw, c->np, 0, s, &c->launches));
     c->kw.mask = c->dofmask;
-    c->op.kind = OP_NODE2;
-    c->op.n = c->n;
-    c->op.lanes = c->lanes;
-    c->op.ptr = c->nptr;
-    c->op.col = c->ncol;
+    c->op.kind = OP_SELL2;
+    c->op.n = c->np;
+    c->op.lanes = 32;
+    c->op.ptr = c->sptr;
+    c->op.col = c->scol;
     c->op.val = c->val;
+    c->op.nslice = h.nslice;
     for (int k = 0; k < 5; k++) CKCUDA(cudaEventCreate(&c->ev[k]));
     CKCUDA(cudaStreamSynchronize(s));
-    // the per-mesh host tables no longer needed are released (S, incidences stay on the device)
+    // the per-mesh host tables no longer needed are released (their SELL images are on the device)
     std::vector<double>().swap(h.S);
+    std::vector<double>().swap(h.sS);
     std::vector<int>().swap(h.inc);
     std::vector<int>().swap(h.inc_tri);
+    std::vector<int>().swap(h.sinc);
+    std::vector<int>().swap(h.sinct);
+    std::vector<int>().swap(h.scol);
     c->sp.idx_dir = FG_IDX_UNDEF;
     *out = c;
     return FG_OK;
@@ -491,8 +537,8 @@ void fg_destroy(fg_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->cur, c->next, c->basis, c->nonmag, c->dofmask, c->stage, c->tet_ind, c->tet_da,
                     c->tet_detJ, c->ext_field, c->tet_reg, c->reg_tet, c->rec, c->tri_ind,
-                    c->tri_reg, c->tri_surf, c->tri_dMs, c->reg_tri, c->trec, c->nptr, c->ncol,
-                    c->inc_ptr, c->inc, c->inc_tri_ptr, c->inc_tri, c->S, c->Aw, c->val};
+                    c->tri_reg, c->tri_surf, c->tri_dMs, c->reg_tri, c->trec, c->perm, c->sptr,
+                    c->scol, c->sdeg, c->iptr, c->sinc, c->itptr, c->sinct, c->sS, c->Aw, c->val};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -537,7 +583,7 @@ int fg_set_state(fg_ctx *c, const double *u, const double *v, const double *phi,
         return FG_ERR_INVALID;
         }
     FG_TRY(push_fields(c, c->cur, u, v, phi, phiv, true));
-    FG_CUDA(cudaMemcpyAsync(c->next, c->cur, sizeof(NodeRec) * (size_t)c->NOD, cudaMemcpyDeviceToDevice, c->stream));
+    FG_CUDA(cudaMemcpyAsync(c->next, c->cur, sizeof(NodeRec) * (size_t)c->NODp, cudaMemcpyDeviceToDevice, c->stream));
     FG_CUDA(cudaStreamSynchronize(c->stream));
     c->have_basis = c->prepared = c->assembled = false;
     return FG_OK;
@@ -576,7 +622,7 @@ int fg_get_state(fg_ctx *c, int step, double *u, double *v, double *phi, double 
     const size_t N = (size_t)c->NOD;
     const int which = (u ? 1 : 0) | (v ? 2 : 0) | (phi ? 4 : 0) | (phiv ? 8 : 0);
     if (!which) return FG_OK;
-    CTX_LAUNCH(c, k_unpack, grid_for(c->NOD, BLOCK), c->NOD, step ? c->next : c->cur, c->stage, which);
+    CTX_LAUNCH(c, k_unpack, grid_for(c->NODp, BLOCK), c->NODp, c->NOD, c->perm, step ? c->next : c->cur, c->stage, which);
     struct Part { double *dst; size_t off, len; };
     const Part parts[4] = {{u, 0, 3 * N}, {v, 3 * N, 3 * N}, {phi, 6 * N, N}, {phiv, 7 * N, N}};
     for (const Part &p : parts)
@@ -590,7 +636,7 @@ int fg_get_state(fg_ctx *c, int step, double *u, double *v, double *phi, double 
 int fg_commit(fg_ctx *c)
     {
     FG_TRY(check_ctx(c));
-    FG_CUDA(cudaMemcpyAsync(c->cur, c->next, sizeof(NodeRec) * (size_t)c->NOD, cudaMemcpyDeviceToDevice, c->stream));
+    FG_CUDA(cudaMemcpyAsync(c->cur, c->next, sizeof(NodeRec) * (size_t)c->NODp, cudaMemcpyDeviceToDevice, c->stream));
     c->have_basis = c->prepared = c->assembled = false;
     return FG_OK;
     }
@@ -699,16 +745,19 @@ int fg_step(fg_ctx *c, double angle, const double Hext[3], double dt, double pre
 int fg_get_basis(fg_ctx *c, double *ep, double *eq)
     {
     FG_TRY(check_ctx(c));
-    const size_t N = (size_t)c->NOD;
+    const size_t N = (size_t)c->NODp;
     std::vector<Basis> b(N);
     FG_CUDA(cudaMemcpyAsync(b.data(), c->basis, sizeof(Basis) * N, cudaMemcpyDeviceToHost, c->stream));
     FG_CUDA(cudaStreamSynchronize(c->stream));
-    for (size_t a = 0; a < N; a++)
+    for (int a = 0; a < c->NOD; a++)
+        {
+        const Basis &q = b[(size_t)c->h.iperm[a]];
         for (int k = 0; k < 3; k++)
             {
-            if (ep) ep[3 * a + k] = b[a].ep[k];
-            if (eq) eq[3 * a + k] = b[a].eq[k];
+            if (ep) ep[3 * (size_t)a + k] = q.ep[k];
+            if (eq) eq[3 * (size_t)a + k] = q.eq[k];
             }
+        }
     return FG_OK;
     }
 
@@ -727,29 +776,32 @@ int fg_get_elements(fg_ctx *c, int first, int count, double *Kp, double *Lp)
         }
     memset(Kp, 0, sizeof(double) * 64 * (size_t)count);
     memset(Lp, 0, sizeof(double) * 8 * (size_t)count);
-    // magnetic tets in the range form a contiguous run of compact indices
-    int tm0 = -1, cnt = 0;
+    std::vector<int> list, where;
     for (int t = first; t < first + count; t++)
         if (c->h.tet_to_mag[t] >= 0)
             {
-            if (tm0 < 0) tm0 = c->h.tet_to_mag[t];
-            cnt++;
+            list.push_back(c->h.tet_to_mag[t]);
+            where.push_back(t - first);
             }
+    const int cnt = (int)list.size();
     if (cnt == 0) return FG_OK;
     double *dK = nullptr, *dL = nullptr;
+    int *dlist = nullptr;
     FG_CUDA(cudaMalloc(&dK, sizeof(double) * 64 * (size_t)cnt));
     FG_CUDA(cudaMalloc(&dL, sizeof(double) * 8 * (size_t)cnt));
+    FG_CUDA(cudaMalloc(&dlist, sizeof(int) * (size_t)cnt));
+    FG_CUDA(cudaMemcpyAsync(dlist, list.data(), sizeof(int) * (size_t)cnt, cudaMemcpyHostToDevice, c->stream));
     const TetArrays A = tet_arrays(c);
     const int grid = (cnt + BLOCK - 1) / BLOCK;
     if (c->h.npi_tet == 5)
         {
-        if (c->space_field) k_tet_tap<5, true><<<grid, BLOCK, 0, c->stream>>>(A, c->cur, c->basis, c->sp, tm0, cnt, dK, dL);
-        else k_tet_tap<5, false><<<grid, BLOCK, 0, c->stream>>>(A, c->cur, c->basis, c->sp, tm0, cnt, dK, dL);
+        if (c->space_field) k_tet_tap<5, true><<<grid, BLOCK, 0, c->stream>>>(A, c->cur, c->basis, c->sp, dlist, cnt, dK, dL);
+        else k_tet_tap<5, false><<<grid, BLOCK, 0, c->stream>>>(A, c->cur, c->basis, c->sp, dlist, cnt, dK, dL);
         }
     else
         {
-        if (c->space_field) k_tet_tap<1, true><<<grid, BLOCK, 0, c->stream>>>(A, c->cur, c->basis, c->sp, tm0, cnt, dK, dL);
-        else k_tet_tap<1, false><<<grid, BLOCK, 0, c->stream>>>(A, c->cur, c->basis, c->sp, tm0, cnt, dK, dL);
+        if (c->space_field) k_tet_tap<1, true><<<grid, BLOCK, 0, c->stream>>>(A, c->cur, c->basis, c->sp, dlist, cnt, dK, dL);
+        else k_tet_tap<1, false><<<grid, BLOCK, 0, c->stream>>>(A, c->cur, c->basis, c->sp, dlist, cnt, dK, dL);
         }
     ++c->launches;
     std::vector<double> hK(64 * (size_t)cnt), hL(8 * (size_t)cnt);
@@ -759,17 +811,16 @@ int fg_get_elements(fg_ctx *c, int first, int count, double *Kp, double *Lp)
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     cudaFree(dK);
     cudaFree(dL);
+    cudaFree(dlist);
     if (e != cudaSuccess)
         {
         set_error("fg_get_elements: %s", cudaGetErrorString(e));
         return FG_ERR_CUDA;
         }
-    for (int t = first; t < first + count; t++)
+    for (int q = 0; q < cnt; q++)
         {
-        const int tm = c->h.tet_to_mag[t];
-        if (tm < 0) continue;
-        memcpy(Kp + 64 * (size_t)(t - first), &hK[64 * (size_t)(tm - tm0)], sizeof(double) * 64);
-        memcpy(Lp + 8 * (size_t)(t - first), &hL[8 * (size_t)(tm - tm0)], sizeof(double) * 8);
+        memcpy(Kp + 64 * (size_t)where[q], &hK[64 * (size_t)q], sizeof(double) * 64);
+        memcpy(Lp + 8 * (size_t)where[q], &hL[8 * (size_t)q], sizeof(double) * 8);
         }
     return FG_OK;
     }
@@ -804,7 +855,7 @@ int fg_get_tri_elements(fg_ctx *c, int first, int count, double *Lp)
     for (size_t k = 0; k < M; k++)
         {
         const size_t f = (size_t)sel[k];
-        for (int i = 0; i < 3; i++) ind[(size_t)i * M + k] = c->h.tri_ind[3 * f + i];
+        for (int i = 0; i < 3; i++) ind[(size_t)i * M + k] = c->h.iperm[c->h.tri_ind[3 * f + i]];
         reg[k] = c->h.tri_reg[f];
         surf[k] = c->h.tri_surf[f];
         dMs[k] = c->h.tri_dMs[f];
@@ -887,10 +938,40 @@ int fg_get_system(fg_ctx *c, double dt, double *val, double *rhs, double *x0)
     FG_TRY(check_ctx(c));
     // before the solve: assemble now; after it: K and L_rhs are still resident (x0 then holds Xw)
     if (c->prepared || !c->assembled) FG_TRY(launch_assemble(c, dt));
-    if (val) FG_CUDA(cudaMemcpyAsync(val, c->val, sizeof(double) * 4 * (size_t)c->nnzb, cudaMemcpyDeviceToHost, c->stream));
-    if (rhs) FG_CUDA(cudaMemcpyAsync(rhs, c->kw.b, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
-    if (x0) FG_CUDA(cudaMemcpyAsync(x0, c->kw.x, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
-    FG_CUDA(cudaStreamSynchronize(c->stream));
+    const HostSetup &h = c->h;
+    if (val)
+        {  // SELL-32 2x2 blocks -> the reference's CSR order (rows 2a, 2a+1 of node a, sorted columns)
+        std::vector<double> sv(4 * (size_t)c->nblk);
+        FG_CUDA(cudaMemcpyAsync(sv.data(), c->val, sizeof(double) * sv.size(), cudaMemcpyDeviceToHost, c->stream));
+        FG_CUDA(cudaStreamSynchronize(c->stream));
+        for (int a = 0; a < h.NOD; a++)
+            {
+            const int r = h.iperm[a], sl = r / SLICE, lane = r % SLICE;
+            const int beg = h.nptr[a], deg = h.nptr[a + 1] - beg;
+            double *row0 = val + 4 * (size_t)beg, *row1 = row0 + 2 * (size_t)deg;
+            for (int j = 0; j < deg; j++)
+                {
+                const size_t p0 = (((size_t)h.sptr[sl] + j) * 2) * SLICE + lane;  // double2 index
+                row0[2 * j] = sv[2 * p0];
+                row0[2 * j + 1] = sv[2 * p0 + 1];
+                row1[2 * j] = sv[2 * (p0 + SLICE)];
+                row1[2 * j + 1] = sv[2 * (p0 + SLICE) + 1];
+                }
+            }
+        }
+    std::vector<double> tmp((size_t)c->np);
+    if (rhs)
+        {
+        FG_CUDA(cudaMemcpyAsync(tmp.data(), c->kw.b, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, c->stream));
+        FG_CUDA(cudaStreamSynchronize(c->stream));
+        dofs_to_caller(c, tmp, rhs);
+        }
+    if (x0)
+        {
+        FG_CUDA(cudaMemcpyAsync(tmp.data(), c->kw.x, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, c->stream));
+        FG_CUDA(cudaStreamSynchronize(c->stream));
+        dofs_to_caller(c, tmp, x0);
+        }
     return FG_OK;
     }
 
@@ -907,10 +988,13 @@ int fg_apply_operator(fg_ctx *c, const double *x, double *y)
         set_error("fg_apply_operator: no assembled system");
         return FG_ERR_STATE;
         }
-    FG_CUDA(cudaMemcpyAsync(c->kw.phat, x, sizeof(double) * (size_t)c->n, cudaMemcpyHostToDevice, c->stream));
+    std::vector<double> tmp;
+    dofs_to_device(c, x, tmp);
+    FG_CUDA(cudaMemcpyAsync(c->kw.phat, tmp.data(), sizeof(double) * tmp.size(), cudaMemcpyHostToDevice, c->stream));
     FG_TRY(spmv(c->op, c->kw, c->kw.phat, c->kw.v, false));
-    FG_CUDA(cudaMemcpyAsync(y, c->kw.v, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+    FG_CUDA(cudaMemcpyAsync(tmp.data(), c->kw.v, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, c->stream));
     FG_CUDA(cudaStreamSynchronize(c->stream));
+    dofs_to_caller(c, tmp, y);
     return FG_OK;
     }
 
@@ -922,8 +1006,10 @@ int fg_get_solution(fg_ctx *c, double *Xw)
         set_error("fg_get_solution: null argument");
         return FG_ERR_INVALID;
         }
-    FG_CUDA(cudaMemcpyAsync(Xw, c->kw.x, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<double> tmp((size_t)c->np);
+    FG_CUDA(cudaMemcpyAsync(tmp.data(), c->kw.x, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, c->stream));
     FG_CUDA(cudaStreamSynchronize(c->stream));
+    dofs_to_caller(c, tmp, Xw);
     return FG_OK;
     }
 
@@ -944,6 +1030,87 @@ int fg_get_tet_tables(const fg_ctx *c, int *ind, double *da, double *weight)
         for (size_t t = 0; t < (size_t)h.NT; t++)
             for (int g = 0; g < h.npi_tet; g++) weight[(size_t)h.npi_tet * t + g] = h.tet_detJ[t] * p[g];
         }
+    return FG_OK;
+    }
+
+int fg_host_plan(const fg_mesh *mesh, const fg_params *prm, long long out[12])
+    {
+    if (!mesh || !prm || !out)
+        {
+        set_error("fg_host_plan: null argument");
+        return FG_ERR_INVALID;
+        }
+    HostSetup h;
+    std::string err;
+    const int rc = host_setup(*mesh, *prm, h, err);
+    if (rc != FG_OK)
+        {
+        set_error("%s", err.c_str());
+        return rc;
+        }
+    // the device layout must be a faithful image of the reference pattern
+    long long bad = 0;
+    std::vector<char> seen((size_t)h.NODp, 0);
+    for (int r = 0; r < h.NODp; r++)
+        {
+        const int a = h.perm[r];
+        if (a < 0) continue;
+        if (a >= h.NOD || h.iperm[a] != r || seen[a]) bad++;
+        else seen[a] = 1;
+        if (r / SELL_WINDOW != a / SELL_WINDOW) bad++;  // rows only move inside their window
+        }
+    for (int a = 0; a < h.NOD; a++)
+        if (!seen[a]) bad++;
+    int wmax = 0;
+    for (int s = 0; s < h.nslice; s++)
+        {
+        const int w = h.sptr[s + 1] - h.sptr[s];
+        wmax = w > wmax ? w : wmax;
+        for (int l = 0; l < SELL_C; l++)
+            {
+            const int r = s * SELL_C + l, a = h.perm[r];
+            const int deg = a < 0 ? 0 : h.nptr[a + 1] - h.nptr[a];
+            if (deg > w || h.sdeg[r] != deg) bad++;
+            for (int j = 0; j < w; j++)
+                {
+                const size_t pos = ((size_t)h.sptr[s] + j) * SELL_C + l;
+                if (j < deg)
+                    {
+                    if (h.perm[h.scol[pos]] != h.ncol[(size_t)h.nptr[a] + j]) bad++;
+                    if (h.sS[pos] != h.S[(size_t)h.nptr[a] + j]) bad++;
+                    }
+                else if (h.scol[pos] != r || h.sS[pos] != 0.0)
+                    bad++;
+                }
+            const int wi = h.iptr[s + 1] - h.iptr[s];
+            const int ni = a < 0 ? 0 : h.inc_ptr[a + 1] - h.inc_ptr[a];
+            for (int q = 0; q < wi; q++)
+                {
+                const int v = h.sinc[((size_t)h.iptr[s] + q) * SELL_C + l];
+                if (q < ni ? v != h.inc[(size_t)h.inc_ptr[a] + q] : v != -1) bad++;
+                }
+            }
+        }
+    for (size_t tm = 0; tm < h.magTet.size(); tm++)
+        for (int i = 0; i < 4; i++)
+            if (h.perm[h.tet_dev_ind[4 * tm + i]] != h.tet_ind[4 * (size_t)h.magTet[tm] + i]) bad++;
+    if (bad)
+        {
+        set_error("fg_host_plan: device layout inconsistent with the reference pattern (%lld defects)", bad);
+        return FG_ERR_STATE;
+        }
+    out[0] = h.NOD;
+    out[1] = h.NODp;
+    out[2] = h.nslice;
+    out[3] = h.nptr[h.NOD];
+    out[4] = (long long)h.sptr[h.nslice] * SELL_C;
+    out[5] = (long long)h.magTet.size();
+    out[6] = wmax;
+    out[7] = (long long)h.iptr[h.nslice] * SELL_C;
+    out[8] = 4LL * (long long)h.magTet.size();
+    out[9] = (long long)h.lvd.size();
+    out[10] = h.n_edges;
+    out[11] = h.n_edges_mag;
     return FG_OK;
     }
 

@@ -3,7 +3,7 @@
 //   k_basis          Node::setBasis                  reference src/node.h:73-102
 //   k_tet            Tet::integrales                 reference src/tetra.cpp:210-307
 //   k_tri            Tri::integrales                 reference src/triangle.cpp:6-36
-//   k_assemble_rows  solver::buildMat/buildVect + mask + buildInitGuess + build_diag_precond
+//   k_assemble_sell  solver::buildMat/buildVect + mask + buildInitGuess + build_diag_precond
 //                    reference src/solver.cpp:9-59, src/solver.h:110-143, sparseMat.h:174-183
 //   k_update         node update + v_max             reference src/solver.cpp:74-88, node.h:116-122
 //
@@ -14,8 +14,8 @@
 // so the global K is the projection of a NODxNOD scalar matrix whose off-diagonal part is constant
 // per mesh (S, built once) and whose diagonal gains one state-dependent number per node per step
 // (Malpha).  The per-step element kernel therefore emits, per (tet, local node), one 32-byte
-// record {sum_g a w alpha_eff, eq.BE, ep.BE}; k_assemble_rows gathers the records of a node through
-// its incidence list (no atomics, fixed order => deterministic) and writes the node's two CSR rows.
+// record {sum_g a w alpha_eff, eq.BE, ep.BE}; k_assemble_sell gathers the records of a node through
+// its incidence list (no atomics, fixed order => deterministic) and writes the node's two matrix rows.
 #pragma once
 #include "fg_common.cuh"
 #include "fg_reduce.cuh"
@@ -148,6 +148,10 @@ struct StepPrm
 // Element core shared by the production kernel and the Kp/Lp tap.  Hext is [d][g].
 // Outputs: contrib[i] = sum_g a_i(g) w_g alpha_eff(g)   (the state-dependent diagonal of E)
 //          BE[d][i]                                      (src/tetra.cpp:277-303)
+// Organised Gauss-point-outermost so that only the accumulators (contrib, BE), the node values and
+// the per-element constants (grad U, Hd, Hv, the exchange products Ex) stay live: the reference's
+// per-point tables U, V, H, H_aniso (4 x 3 x NPI doubles) never exist.  Every sum keeps the
+// reference's order of accumulation.
 template <int NPI>
 __device__ __forceinline__ void tet_core(const TetIn &T, const TetRegion &R, const StepPrm &sp,
                                          const double (&Hext)[3][NPI], double contrib[4],
@@ -156,28 +160,12 @@ __device__ __forceinline__ void tet_core(const TetIn &T, const TetRegion &R, con
     const double alpha = R.alpha, Abis = R.Abis;
     const double s_dt = FG_THETA * sp.dt * FG_GAMMA0;
     const double th_dt = s_dt / FG_GAMMA0;  // what calc_aniso_* and Hv receive (tetra.cpp:240,292)
-    double w[NPI];
-#pragma unroll
-    for (int g = 0; g < NPI; g++) w[g] = T.detJ * tet_pds<NPI>(g);
 
-    // interpolation, src/tetra.h:183-218
-    double U[3][NPI], V[3][NPI], dU[3][3], Hd[3], Hv[3];
+    // interpolation of the element-wise constants, src/tetra.h:183-218
+    double dU[3][3], Hd[3], Hv[3];
 #pragma unroll
     for (int d = 0; d < 3; d++)
         {
-#pragma unroll
-        for (int g = 0; g < NPI; g++)
-            {
-            double su = 0.0, sv = 0.0;
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                {
-                su += T.u[i][d] * tet_a<NPI>(i, g);
-                sv += T.v[i][d] * tet_a<NPI>(i, g);
-                }
-            U[d][g] = su;
-            V[d][g] = sv;
-            }
 #pragma unroll
         for (int k = 0; k < 3; k++)
             {
@@ -196,92 +184,31 @@ __device__ __forceinline__ void tet_core(const TetIn &T, const TetRegion &R, con
         Hd[d] = hd;
         Hv[d] = hv;
         }
-
     // tetra.cpp:232-233
     double gsq = 0.0;
 #pragma unroll
     for (int k = 0; k < 3; k++)
         gsq += dU[0][k] * dU[0][k] + dU[1][k] * dU[1][k] + dU[2][k] * dU[2][k];
-    double uHeff[NPI], Han[3][NPI];
+    // exchange products da_i . grad U_d of tetra.cpp:296-297
+    double Ex[3][4];
 #pragma unroll
-    for (int g = 0; g < NPI; g++)
-        {
-        uHeff[g] = -Abis * gsq;
-        Han[0][g] = Han[1][g] = Han[2][g] = 0.0;
-        }
-    if (R.has_K)  // calc_aniso_uniax, tetra.cpp:171-181
-        {
+    for (int d = 0; d < 3; d++)
 #pragma unroll
-        for (int g = 0; g < NPI; g++)
-            {
-            const double t0 = U[0][g] + th_dt * V[0][g], t1 = U[1][g] + th_dt * V[1][g],
-                         t2 = U[2][g] + th_dt * V[2][g];
-            const double f = R.Kbis * (R.uk[0] * t0 + R.uk[1] * t1 + R.uk[2] * t2);
-            Han[0][g] += f * R.uk[0];
-            Han[1][g] += f * R.uk[1];
-            Han[2][g] += f * R.uk[2];
-            const double s = U[0][g] * R.uk[0] + U[1][g] * R.uk[1] + U[2][g] * R.uk[2];
-            uHeff[g] += R.Kbis * (s * s);
-            }
-        }
-    if (R.has_K3)  // calc_aniso_cub, tetra.cpp:183-208 (uk_v.cwiseProduct(ex) kept literally)
-        {
-#pragma unroll
-        for (int g = 0; g < NPI; g++)
-            {
-            const double Ug[3] = {U[0][g], U[1][g], U[2][g]}, Vg[3] = {V[0][g], V[1][g], V[2][g]};
-            const double uu[3] = {dot3(R.ex, Ug), dot3(R.ey, Ug), dot3(R.ez, Ug)};
-            const double uv[3] = {dot3(R.ex, Vg), dot3(R.ey, Vg), dot3(R.ez, Vg)};
-            double u3[3];
-#pragma unroll
-            for (int k = 0; k < 3; k++) u3[k] = uu[k] * (1.0 - uu[k] * uu[k]);
-#pragma unroll
-            for (int d = 0; d < 3; d++)
-                {
-                const double tmp = uv[d] * R.ex[d];
-                const double inner = u3[0] * R.ex[d] + u3[1] * R.ey[d] + u3[2] * R.ez[d]
-                                     + th_dt * (tmp * (1.0 - 3 * (uu[d] * uu[d])));
-                Han[d][g] += -R.K3bis * inner;
-                }
-            uHeff[g] += -R.K3bis * dot3(uu, u3);
-            }
-        }
-    // tetra.cpp:248-255 (Hst = 0: Tet::extraField is a no-op without spin accumulation)
-    double H[3][NPI];
-#pragma unroll
-    for (int g = 0; g < NPI; g++)
-        {
-        double s = 0.0;
-#pragma unroll
-        for (int d = 0; d < 3; d++)
-            {
-            H[d][g] = Hd[d] + Hext[d][g];
-            s += U[d][g] * H[d][g];
-            }
-        uHeff[g] += s;
-        }
-    // tetra.cpp:257-261 + lumping :114 (the alpha_eff part of the diagonal block)
-    double wa[NPI];
-#pragma unroll
-    for (int g = 0; g < NPI; g++) wa[g] = w[g] * alpha_eff(sp.dt, alpha, uHeff[g]);
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-        {
-        double s = 0.0;
-#pragma unroll
-        for (int g = 0; g < NPI; g++) s += tet_a<NPI>(i, g) * wa[g];
-        contrib[i] = s;
-        }
+        for (int i = 0; i < 4; i++)
+            Ex[d][i] = T.da[i][0] * dU[d][0] + T.da[i][1] * dU[d][1] + T.da[i][2] * dU[d][2];
 
-    // BE, tetra.cpp:277-303
+#pragma unroll
+    for (int i = 0; i < 4; i++) contrib[i] = 0.0;
 #pragma unroll
     for (int d = 0; d < 3; d++)
 #pragma unroll
         for (int i = 0; i < 4; i++) BE[d][i] = 0.0;
-    if (sp.idx_dir != FG_IDX_UNDEF)  // add_drift_BE, tetra.cpp:150-169
+
+    const bool drift = sp.idx_dir != FG_IDX_UNDEF;
+    double dUk[3] = {0, 0, 0}, dVk[3] = {0, 0, 0};
+    if (drift)  // add_drift_BE, tetra.cpp:150-169 (accumulated for all points before the fields)
         {
         const int k = sp.idx_dir;
-        double dUk[3], dVk[3];
 #pragma unroll
         for (int d = 0; d < 3; d++)
             {
@@ -294,7 +221,21 @@ __device__ __forceinline__ void tet_core(const TetIn &T, const TetRegion &R, con
 #pragma unroll
         for (int g = 0; g < NPI; g++)
             {
-            const double Ug[3] = {U[0][g], U[1][g], U[2][g]}, Vg[3] = {V[0][g], V[1][g], V[2][g]};
+            const double w = T.detJ * tet_pds<NPI>(g);
+            double Ug[3], Vg[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++)
+                {
+                double su = 0.0, sv = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    {
+                    su += T.u[i][d] * tet_a<NPI>(i, g);
+                    sv += T.v[i][d] * tet_a<NPI>(i, g);
+                    }
+                Ug[d] = su;
+                Vg[d] = sv;
+                }
             double c1[3], c2[3], c3[3];
             cross3(Ug, dUk, c1);
             cross3(Ug, dVk, c2);
@@ -306,25 +247,90 @@ __device__ __forceinline__ void tet_core(const TetIn &T, const TetRegion &R, con
                     {
                     const double interim = tet_a<NPI>(i, g)
                         * (alpha * dUk[d] + c1[d] + s_dt * (alpha * dVk[d] + c2[d] + c3[d]));
-                    BE[d][i] += sp.Vdrift * w[g] * interim;
+                    BE[d][i] += sp.Vdrift * w * interim;
                     }
             }
         }
+
 #pragma unroll
     for (int g = 0; g < NPI; g++)
         {
+        const double w = T.detJ * tet_pds<NPI>(g);
+        double Ug[3], Vg[3] = {0, 0, 0};
 #pragma unroll
-        for (int d = 0; d < 3; d++) H[d][g] += Han[d][g] + th_dt * Hv[d];
-#pragma unroll
-        for (int i = 0; i < 4; i++)
+        for (int d = 0; d < 3; d++)
             {
-            const double ai_w = w[g] * tet_a<NPI>(i, g);
+            double su = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) su += T.u[i][d] * tet_a<NPI>(i, g);
+            Ug[d] = su;
+            }
+        if (R.has_K || R.has_K3)
+            {
 #pragma unroll
             for (int d = 0; d < 3; d++)
                 {
-                BE[d][i] -= w[g] * Abis
-                            * (T.da[i][0] * dU[d][0] + T.da[i][1] * dU[d][1] + T.da[i][2] * dU[d][2]);
-                BE[d][i] += ai_w * H[d][g];
+                double sv = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) sv += T.v[i][d] * tet_a<NPI>(i, g);
+                Vg[d] = sv;
+                }
+            }
+        double uH = -Abis * gsq;
+        double Han[3] = {0.0, 0.0, 0.0};
+        if (R.has_K)  // calc_aniso_uniax, tetra.cpp:171-181
+            {
+            const double t0 = Ug[0] + th_dt * Vg[0], t1 = Ug[1] + th_dt * Vg[1], t2 = Ug[2] + th_dt * Vg[2];
+            const double f = R.Kbis * (R.uk[0] * t0 + R.uk[1] * t1 + R.uk[2] * t2);
+            Han[0] += f * R.uk[0];
+            Han[1] += f * R.uk[1];
+            Han[2] += f * R.uk[2];
+            const double s = Ug[0] * R.uk[0] + Ug[1] * R.uk[1] + Ug[2] * R.uk[2];
+            uH += R.Kbis * (s * s);
+            }
+        if (R.has_K3)  // calc_aniso_cub, tetra.cpp:183-208 (uk_v.cwiseProduct(ex) kept literally)
+            {
+            const double uu[3] = {dot3(R.ex, Ug), dot3(R.ey, Ug), dot3(R.ez, Ug)};
+            const double uv[3] = {dot3(R.ex, Vg), dot3(R.ey, Vg), dot3(R.ez, Vg)};
+            double u3[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) u3[k] = uu[k] * (1.0 - uu[k] * uu[k]);
+#pragma unroll
+            for (int d = 0; d < 3; d++)
+                {
+                const double tmp = uv[d] * R.ex[d];
+                const double inner = u3[0] * R.ex[d] + u3[1] * R.ey[d] + u3[2] * R.ez[d]
+                                     + th_dt * (tmp * (1.0 - 3 * (uu[d] * uu[d])));
+                Han[d] += -R.K3bis * inner;
+                }
+            uH += -R.K3bis * dot3(uu, u3);
+            }
+        // tetra.cpp:248-255 (Hst = 0: Tet::extraField is a no-op without spin accumulation)
+        double H[3];
+            {
+            double s = 0.0;
+#pragma unroll
+            for (int d = 0; d < 3; d++)
+                {
+                H[d] = Hd[d] + Hext[d][g];
+                s += Ug[d] * H[d];
+                }
+            uH += s;
+            }
+        // tetra.cpp:257-261 + lumping :114 (the alpha_eff part of the diagonal block)
+        const double wa = w * alpha_eff(sp.dt, alpha, uH);
+#pragma unroll
+        for (int d = 0; d < 3; d++) H[d] += Han[d] + th_dt * Hv[d];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            {
+            contrib[i] += tet_a<NPI>(i, g) * wa;
+            const double ai_w = w * tet_a<NPI>(i, g);
+#pragma unroll
+            for (int d = 0; d < 3; d++)
+                {
+                BE[d][i] -= w * Abis * Ex[d][i];
+                BE[d][i] += ai_w * H[d];
                 }
             }
         }
@@ -367,9 +373,10 @@ __device__ __forceinline__ void tet_field(const TetArrays &A, int tm, const Step
                                : sp.Hext[d];
     }
 
+constexpr int TET_CTAS_PER_SM = 1;
 // one thread per magnetic tetrahedron; emits 4 records {contrib, eq.BE, ep.BE, 0}
 template <int NPI, bool SPACE>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, TET_CTAS_PER_SM)
 k_tet(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__restrict__ basis,
       const StepPrm sp, double4 *__restrict__ rec)
     {
@@ -423,16 +430,17 @@ __device__ __forceinline__ void gyro_block(double aw, const double m[3], const d
     k11 += aw * dot3(ep, mq);
     }
 
-// Tap: full element Kp (8x8 row-major) and Lp (8) of magnetic tets [first, first+count), computed
+// Tap: full element Kp (8x8 row-major) and Lp (8) of the magnetic tets list[0..count), computed
 // with the same device functions as the production path (element.h:62,65 layout).
 template <int NPI, bool SPACE>
 __global__ void __launch_bounds__(BLOCK)
 k_tet_tap(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__restrict__ basis,
-          const StepPrm sp, int first, int count, double *__restrict__ Kp, double *__restrict__ Lp)
+          const StepPrm sp, const int *__restrict__ list, int count, double *__restrict__ Kp,
+          double *__restrict__ Lp)
     {
     const int q = blockIdx.x * BLOCK + threadIdx.x;
     if (q >= count) return;
-    const int tm = first + q;
+    const int tm = list[q];
     TetIn T;
     int4 ind;
     tet_load<NPI>(A, tm, cur, ind, T);
@@ -549,106 +557,125 @@ k_tri(const TriArrays A, const NodeRec *__restrict__ cur, const Basis *__restric
     }
 
 // ------------------------------------------------------------------------------------------
-// Row assembly: G lanes per node gather the node's element records and write its two CSR rows,
-// the rhs, the initial guess and the Jacobi diagonal.
+// Row assembly in SELL-32 order: one warp per slice, one lane per node row.  The lane gathers the
+// node's element records through its (SELL-stored, coalesced) incidence list in a fixed order — no
+// atomics, bitwise reproducible — then streams its blocks: S and the column index are coalesced
+// reads, the neighbour's basis a 48-byte gather, the 2x2 block two coalesced 16-byte stores.  The
+// rhs, the initial guess and the Jacobi diagonal leave in the same pass.
 // ------------------------------------------------------------------------------------------
 struct RowArrays
     {
-    int NOD, G;
-    const int *nptr, *ncol;
-    const double *S, *Aw;
-    const int *inc_ptr, *inc, *inc_tri_ptr, *inc_tri;
-    const unsigned char *nonmag;  // NOD : 1 = node outside the magnetic material
+    int nslice;
+    const int *sptr, *scol, *sdeg;     // SELL pattern (fg_common.cuh Operator) + blocks per row
+    const double *sS;                  // S in SELL order
+    const double *Aw;                  // NODp lumped mass
+    const int *iptr, *sinc;            // SELL incidence lists (record index, -1 = none)
+    const int *itptr, *sinct;          // same for the active triangles
+    const unsigned char *nonmag;       // NODp : 1 = node outside the magnetic material (or pad row)
     };
 
-__global__ void __launch_bounds__(BLOCK)
-k_assemble_rows(const RowArrays A, const NodeRec *__restrict__ cur, const NodeRec *__restrict__ next,
+constexpr int ASM_CTAS_PER_SM = 3;
+__global__ void __launch_bounds__(BLOCK, ASM_CTAS_PER_SM)
+k_assemble_sell(const RowArrays A, const NodeRec *__restrict__ cur, const NodeRec *__restrict__ next,
                 const Basis *__restrict__ basis, const double4 *__restrict__ rec,
                 const double2 *__restrict__ trec, double cS, double *__restrict__ val,
                 double *__restrict__ rhs, double *__restrict__ x0, double *__restrict__ D)
     {
-    const int G = A.G;
-    const int lig = threadIdx.x & (G - 1);
-    const int gpc = BLOCK / G;
-    const long long total = (long long)gridDim.x * gpc;
-    for (long long a0 = (long long)blockIdx.x * gpc + threadIdx.x / G;; a0 += total)
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * (BLOCK / 32);
+    double2 *val2 = reinterpret_cast<double2 *>(val);
+    for (int s = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); s < A.nslice; s += nwarps)
         {
-        const bool active = a0 < A.NOD;
-        if (!__any_sync(0xffffffffu, active)) break;
-        const int a = (int)a0;
+        const int row = s * SLICE + lane;
+        // ---- gather of the element records -------------------------------------------------
         double Ma = 0.0, L0 = 0.0, L1 = 0.0;
-        if (active)
             {
-            for (int q = A.inc_ptr[a] + lig; q < A.inc_ptr[a + 1]; q += G)
+            const int i0 = __ldg(A.iptr + s), i1 = __ldg(A.iptr + s + 1);
+            const int *ip = A.sinc + (size_t)i0 * SLICE + lane;
+#pragma unroll 4
+            for (int q = i0; q < i1; ++q, ip += SLICE)
                 {
-                const double2 *r2 = reinterpret_cast<const double2 *>(rec + __ldg(A.inc + q));
-                const double2 r01 = __ldcs(r2), r23 = __ldcs(r2 + 1);
-                Ma += r01.x;
-                L0 += r01.y;
-                L1 += r23.x;
+                const int idx = __ldcs(ip);
+                if (idx >= 0)
+                    {
+                    const double2 *r2 = reinterpret_cast<const double2 *>(rec + idx);
+                    const double2 r01 = __ldcs(r2), r23 = __ldcs(r2 + 1);
+                    Ma += r01.x;
+                    L0 += r01.y;
+                    L1 += r23.x;
+                    }
                 }
-            for (int q = A.inc_tri_ptr[a] + lig; q < A.inc_tri_ptr[a + 1]; q += G)
+            const int t0 = __ldg(A.itptr + s), t1 = __ldg(A.itptr + s + 1);
+            const int *tp = A.sinct + (size_t)t0 * SLICE + lane;
+            for (int q = t0; q < t1; ++q, tp += SLICE)
                 {
-                const double2 r = trec[A.inc_tri[q]];
-                L0 += r.x;
-                L1 += r.y;
+                const int idx = __ldcs(tp);
+                if (idx >= 0)
+                    {
+                    const double2 r = trec[idx];
+                    L0 += r.x;
+                    L1 += r.y;
+                    }
                 }
             }
-        for (int o = G >> 1; o > 0; o >>= 1)
-            {
-            Ma += __shfl_xor_sync(0xffffffffu, Ma, o);
-            L0 += __shfl_xor_sync(0xffffffffu, L0, o);
-            L1 += __shfl_xor_sync(0xffffffffu, L1, o);
-            }
-        if (!active) continue;
-        const int beg = A.nptr[a], deg = A.nptr[a + 1] - beg;
-        double2 *row0 = reinterpret_cast<double2 *>(val + 4 * (size_t)beg);
-        double2 *row1 = row0 + deg;
-        if (A.nonmag[a])
+        const int p0 = __ldg(A.sptr + s), p1 = __ldg(A.sptr + s + 1);
+        const int deg = A.sdeg[row];
+        const bool nonmag = A.nonmag[row] != 0;
+        const int *cp = A.scol + (size_t)p0 * SLICE + lane;
+        const double *sp = A.sS + (size_t)p0 * SLICE + lane;
+        double2 *vp = val2 + (size_t)p0 * (2 * SLICE) + lane;
+        double m[3] = {0, 0, 0}, vc[3], phi, phiv, ep_a[3] = {0, 0, 0}, eq_a[3] = {0, 0, 0};
+        double2 *rhs2 = reinterpret_cast<double2 *>(rhs) + row, *x02 = reinterpret_cast<double2 *>(x0) + row,
+                *D2 = reinterpret_cast<double2 *>(D) + row;
+        if (nonmag)
             {  // identity rows, zero rhs and guess (src/solver.cpp:46-48, linear_algebra.cpp:13-24)
-            for (int j = lig; j < deg; j += G)
-                {
-                const bool dg = A.ncol[beg + j] == a;
-                row0[j] = make_double2(dg ? 1.0 : 0.0, 0.0);
-                row1[j] = make_double2(0.0, dg ? 1.0 : 0.0);
-                }
-            if (lig == 0)
-                {
-                reinterpret_cast<double2 *>(rhs)[a] = make_double2(0.0, 0.0);
-                reinterpret_cast<double2 *>(x0)[a] = make_double2(0.0, 0.0);
-                reinterpret_cast<double2 *>(D)[a] = make_double2(0.0, 0.0);
-                }
-            continue;
+            *rhs2 = make_double2(0.0, 0.0);
+            *x02 = make_double2(0.0, 0.0);
+            *D2 = make_double2(0.0, 0.0);
             }
-        double m[3], vc[3], phi, phiv, ep_a[3], eq_a[3];
-        load_rec(cur + a, m, vc, phi, phiv);
-        load_basis(basis + a, ep_a, eq_a);
-        if (lig == 0)
+        else
             {
+            load_rec(cur + row, m, vc, phi, phiv);
+            load_basis(basis + row, ep_a, eq_a);
             double un[3], vn[3];
-            load_rec(next + a, un, vn, phi, phiv);
-            reinterpret_cast<double2 *>(rhs)[a] = make_double2(L0, L1);
-            reinterpret_cast<double2 *>(x0)[a] =
-                make_double2(dot3(vn, ep_a) / FG_GAMMA0, dot3(vn, eq_a) / FG_GAMMA0);
+            load_rec(next + row, un, vn, phi, phiv);
+            *rhs2 = make_double2(L0, L1);
+            *x02 = make_double2(dot3(vn, ep_a) / FG_GAMMA0, dot3(vn, eq_a) / FG_GAMMA0);
             }
-        for (int j = lig; j < deg; j += G)
+        const double aw = nonmag ? 0.0 : A.Aw[row];
+#pragma unroll 2
+        for (int j = 0; j < p1 - p0; ++j, cp += SLICE, sp += SLICE, vp += 2 * SLICE)
             {
-            const int b = __ldg(A.ncol + beg + j);
-            double E = cS * __ldcs(A.S + beg + j);
-            double ep_b[3], eq_b[3];
-            load_basis(basis + b, ep_b, eq_b);
-            double k00, k01, k10, k11;
-            if (b == a)
+            const int b = __ldcs(cp);
+            const double Sv = __ldcs(sp);
+            double k00 = 0.0, k01 = 0.0, k10 = 0.0, k11 = 0.0;
+            if (j < deg)
                 {
-                E += Ma;
-                project_block(E, ep_a, eq_a, ep_a, eq_a, k00, k01, k10, k11);
-                gyro_block(A.Aw[a], m, ep_a, eq_a, k00, k01, k10, k11);
-                reinterpret_cast<double2 *>(D)[a] = make_double2(1.0 / k00, 1.0 / k11);
+                if (nonmag)
+                    {
+                    k00 = (b == row) ? 1.0 : 0.0;
+                    k11 = k00;
+                    }
+                else
+                    {
+                    double E = cS * Sv;
+                    if (b == row)
+                        {
+                        E += Ma;
+                        project_block(E, ep_a, eq_a, ep_a, eq_a, k00, k01, k10, k11);
+                        gyro_block(aw, m, ep_a, eq_a, k00, k01, k10, k11);
+                        *D2 = make_double2(1.0 / k00, 1.0 / k11);
+                        }
+                    else
+                        {
+                        double ep_b[3], eq_b[3];
+                        load_basis(basis + b, ep_b, eq_b);
+                        project_block(E, ep_a, eq_a, ep_b, eq_b, k00, k01, k10, k11);
+                        }
+                    }
                 }
-            else
-                project_block(E, ep_a, eq_a, ep_b, eq_b, k00, k01, k10, k11);
-            __stcs(row0 + j, make_double2(k00, k01));
-            __stcs(row1 + j, make_double2(k10, k11));
+            __stcs(vp, make_double2(k00, k01));
+            __stcs(vp + SLICE, make_double2(k10, k11));
             }
         }
     }
@@ -705,31 +732,38 @@ k_update(int NOD, const unsigned char *__restrict__ nonmag, const NodeRec *__res
 // ------------------------------------------------------------------------------------------
 // state packing helpers (host <-> NodeRec)
 // ------------------------------------------------------------------------------------------
-// which: bit0 u, bit1 v, bit2 phi, bit3 phiv ; staging = [u(3N) | v(3N) | phi(N) | phiv(N)]
+// which: bit0 u, bit1 v, bit2 phi, bit3 phiv ; staging = [u(3N) | v(3N) | phi(N) | phiv(N)] in the
+// caller's node order; the records are in device row order (perm[row] = node, -1 = pad row).
 __global__ void __launch_bounds__(BLOCK)
-k_pack(int NOD, NodeRec *__restrict__ dst, const double *__restrict__ stage, int which)
+k_pack(int NODp, int NOD, const int *__restrict__ perm, NodeRec *__restrict__ dst,
+       const double *__restrict__ stage, int which)
     {
     const int stride = gridDim.x * BLOCK;
     const size_t N = (size_t)NOD;
-    for (int a = blockIdx.x * BLOCK + threadIdx.x; a < NOD; a += stride)
+    for (int row = blockIdx.x * BLOCK + threadIdx.x; row < NODp; row += stride)
         {
-        NodeRec r = dst[a];
+        const int a = perm[row];
+        if (a < 0) continue;
+        NodeRec r = dst[row];
         if (which & 1) { r.u[0] = stage[3 * (size_t)a]; r.u[1] = stage[3 * (size_t)a + 1]; r.u[2] = stage[3 * (size_t)a + 2]; }
         if (which & 2) { r.v[0] = stage[3 * N + 3 * (size_t)a]; r.v[1] = stage[3 * N + 3 * (size_t)a + 1]; r.v[2] = stage[3 * N + 3 * (size_t)a + 2]; }
         if (which & 4) r.phi = stage[6 * N + a];
         if (which & 8) r.phiv = stage[7 * N + a];
-        dst[a] = r;
+        dst[row] = r;
         }
     }
 
 __global__ void __launch_bounds__(BLOCK)
-k_unpack(int NOD, const NodeRec *__restrict__ src, double *__restrict__ stage, int which)
+k_unpack(int NODp, int NOD, const int *__restrict__ perm, const NodeRec *__restrict__ src,
+         double *__restrict__ stage, int which)
     {
     const int stride = gridDim.x * BLOCK;
     const size_t N = (size_t)NOD;
-    for (int a = blockIdx.x * BLOCK + threadIdx.x; a < NOD; a += stride)
+    for (int row = blockIdx.x * BLOCK + threadIdx.x; row < NODp; row += stride)
         {
-        const NodeRec r = src[a];
+        const int a = perm[row];
+        if (a < 0) continue;
+        const NodeRec r = src[row];
         if (which & 1) { stage[3 * (size_t)a] = r.u[0]; stage[3 * (size_t)a + 1] = r.u[1]; stage[3 * (size_t)a + 2] = r.u[2]; }
         if (which & 2) { stage[3 * N + 3 * (size_t)a] = r.v[0]; stage[3 * N + 3 * (size_t)a + 1] = r.v[1]; stage[3 * N + 3 * (size_t)a + 2] = r.v[2]; }
         if (which & 4) stage[6 * N + a] = r.phi;

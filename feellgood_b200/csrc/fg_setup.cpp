@@ -270,6 +270,48 @@ int host_setup(const fg_mesh &m, const fg_params &prm, HostSetup &h, std::string
         }
     std::vector<int>().swap(adj);
 
+    // ---- device ordering: window-local stable sort by descending block count, slices of 32 -----
+    const int NODp = ((NOD + SELL_C - 1) / SELL_C) * SELL_C;
+    h.NODp = NODp;
+    h.nslice = NODp / SELL_C;
+    h.perm.assign((size_t)NODp, -1);
+    h.iperm.assign((size_t)NOD, -1);
+        {
+        const int nwin = (NOD + SELL_WINDOW - 1) / SELL_WINDOW;
+#pragma omp parallel for schedule(static)
+        for (int wdx = 0; wdx < nwin; wdx++)
+            {
+            const int b = wdx * SELL_WINDOW, e = std::min(NOD, b + SELL_WINDOW);
+            int *q = &h.perm[(size_t)b];
+            std::iota(q, q + (e - b), b);
+            std::stable_sort(q, q + (e - b), [&](int x, int y)
+                { return h.nptr[x + 1] - h.nptr[x] > h.nptr[y + 1] - h.nptr[y]; });
+            for (int r = b; r < e; r++) h.iperm[(size_t)h.perm[(size_t)r]] = r;
+            }
+        }
+    // magnetic tets follow the node order (sorted by their smallest device row) so that
+    // neighbouring threads of the element kernel gather neighbouring node records
+        {
+        std::vector<int> key((size_t)NTm);
+        for (int tm = 0; tm < NTm; tm++)
+            {
+            const int *ind = &h.tet_ind[4 * (size_t)h.magTet[tm]];
+            key[tm] = std::min(std::min(h.iperm[ind[0]], h.iperm[ind[1]]),
+                               std::min(h.iperm[ind[2]], h.iperm[ind[3]]));
+            }
+        std::vector<int> order((size_t)NTm);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return key[x] < key[y]; });
+        std::vector<int> mt((size_t)NTm);
+        for (int k = 0; k < NTm; k++) mt[k] = h.magTet[order[k]];
+        h.magTet.swap(mt);
+        for (int tm = 0; tm < NTm; tm++) h.tet_to_mag[h.magTet[tm]] = tm;
+        h.tet_dev_ind.resize(4 * (size_t)NTm);
+        for (int tm = 0; tm < NTm; tm++)
+            for (int i = 0; i < 4; i++)
+                h.tet_dev_ind[4 * (size_t)tm + i] = h.iperm[h.tet_ind[4 * (size_t)h.magTet[tm] + i]];
+        }
+
     // ---- incidence lists node -> (magnetic tet, local node) ------------------------------------
     h.inc_ptr.assign((size_t)NOD + 1, 0);
     for (int tm = 0; tm < NTm; tm++)
@@ -333,6 +375,66 @@ int host_setup(const fg_mesh &m, const fg_params &prm, HostSetup &h, std::string
                 }
             }
         h.Aw[a] = aw;
+        }
+
+    // ---- SELL-32 images of the pattern, of S and of the incidence lists ------------------------
+        {
+        const int ns = h.nslice;
+        h.sdeg.assign((size_t)NODp, 0);
+        h.sptr.assign((size_t)ns + 1, 0);
+        h.iptr.assign((size_t)ns + 1, 0);
+        h.itptr.assign((size_t)ns + 1, 0);
+        for (int s = 0; s < ns; s++)
+            {
+            int wk = 0, wi = 0, wt = 0;
+            for (int l = 0; l < SELL_C; l++)
+                {
+                const int a = h.perm[(size_t)s * SELL_C + l];
+                if (a < 0) continue;
+                h.sdeg[(size_t)s * SELL_C + l] = h.nptr[a + 1] - h.nptr[a];
+                wk = std::max(wk, h.nptr[a + 1] - h.nptr[a]);
+                wi = std::max(wi, h.inc_ptr[a + 1] - h.inc_ptr[a]);
+                wt = std::max(wt, h.inc_tri_ptr[a + 1] - h.inc_tri_ptr[a]);
+                }
+            const int64_t nk = (int64_t)h.sptr[s] + wk;
+            if (nk * SELL_C * 4 > INT32_MAX)
+                {
+                err = "fg_create: more than 2^31 matrix entries on one device; partition the mesh";
+                return FG_ERR_INVALID;
+                }
+            h.sptr[s + 1] = (int)nk;
+            h.iptr[s + 1] = h.iptr[s] + wi;
+            h.itptr[s + 1] = h.itptr[s] + wt;
+            }
+        h.scol.assign((size_t)h.sptr[ns] * SELL_C, 0);
+        h.sS.assign((size_t)h.sptr[ns] * SELL_C, 0.0);
+        h.sinc.assign((size_t)h.iptr[ns] * SELL_C, -1);
+        h.sinct.assign((size_t)h.itptr[ns] * SELL_C, -1);
+#pragma omp parallel for schedule(static)
+        for (int s = 0; s < ns; s++)
+            for (int l = 0; l < SELL_C; l++)
+                {
+                const int r = s * SELL_C + l;
+                const int a = h.perm[(size_t)r];
+                const int wk = h.sptr[s + 1] - h.sptr[s];
+                const int deg = a < 0 ? 0 : h.nptr[a + 1] - h.nptr[a];
+                for (int j = 0; j < wk; j++)
+                    {
+                    const size_t pos = ((size_t)h.sptr[s] + j) * SELL_C + l;
+                    if (j < deg)
+                        {
+                        h.scol[pos] = h.iperm[(size_t)h.ncol[(size_t)h.nptr[a] + j]];
+                        h.sS[pos] = h.S[(size_t)h.nptr[a] + j];
+                        }
+                    else
+                        h.scol[pos] = r;
+                    }
+                if (a < 0) continue;
+                for (int q = h.inc_ptr[a]; q < h.inc_ptr[a + 1]; q++)
+                    h.sinc[((size_t)h.iptr[s] + (q - h.inc_ptr[a])) * SELL_C + l] = h.inc[q];
+                for (int q = h.inc_tri_ptr[a]; q < h.inc_tri_ptr[a + 1]; q++)
+                    h.sinct[((size_t)h.itptr[s] + (q - h.inc_tri_ptr[a])) * SELL_C + l] = h.inc_tri[q];
+                }
         }
 
     // ---- masked dofs (src/linear_algebra.h:55-63) ---------------------------------------------

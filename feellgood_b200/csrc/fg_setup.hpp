@@ -44,7 +44,24 @@ struct HostSetup
     std::vector<int> inc_ptr, inc;          // NOD+1, 4*n_magTet
     std::vector<int> inc_tri_ptr, inc_tri;  // NOD+1, 3*n_actTri
     std::vector<int> lvd;          // masked dofs (src/linear_algebra.h:55-63)
+
+    // ---- device ordering ------------------------------------------------------
+    // Rows are permuted inside windows of SELL_WINDOW nodes by descending block count (stable, so
+    // locality survives) and cut into slices of 32 rows: SELL-32-sigma with 2x2 blocks.  All
+    // device arrays indexed by node use the device row number.
+    int NODp = 0;                  // NOD rounded up to a multiple of 32 (pad rows: perm = -1)
+    std::vector<int> perm, iperm;  // device row -> node | node -> device row
+    int nslice = 0;
+    std::vector<int> sptr;         // nslice+1 : first block-column of each slice
+    std::vector<int> sdeg;         // NODp : blocks in the row (0 for pad rows)
+    std::vector<int> scol;         // sptr[nslice]*32 : device row of the column node (pad: own row)
+    std::vector<double> sS;        // sptr[nslice]*32 : S in SELL order (pad: 0)
+    std::vector<int> iptr, sinc;   // SELL incidence lists: nslice+1 | iptr[nslice]*32 (record index, -1 pad)
+    std::vector<int> itptr, sinct; // same for the active triangles
+    std::vector<int> tet_dev_ind;  // 4*n_magTet : device rows of the magnetic tets, device tet order
     };
+constexpr int SELL_C = 32;
+constexpr int SELL_WINDOW = 1024;
 
 // returns FG_OK or FG_ERR_*; message in err
 int host_setup(const fg_mesh &mesh, const fg_params &prm, HostSetup &out, std::string &err);

@@ -192,6 +192,15 @@ int fg_cg(fg_matrix *m, double *x, const double *rhs, double tol, int maxiter,
 int fg_cg_dir(fg_matrix *m, double *x, const double *rhs, const double *xd, const int *ld, int nld,
               double tol, int maxiter, fg_iter_result *out);
 
+/* ---- host-side planning (no GPU needed) ---- */
+/* Runs the once-per-mesh preprocessing of fg_create (orientation, geometry tables, sparsity of
+ * solver<2>::build_shape, device row ordering and the SELL-32 layout, incidence lists) on the host
+ * only, verifies that the device layout is a faithful image of the reference's CSR pattern, and
+ * reports its sizes: out[0..11] = NOD, padded NOD, slices, 2x2 blocks of the pattern (nnz/4),
+ * stored blocks incl. SELL padding, magnetic tets, widest slice, stored incidence slots,
+ * incidences (4 x magnetic tets), masked dofs, E, E_mag. */
+int fg_host_plan(const fg_mesh *mesh, const fg_params *prm, long long out[12]);
+
 /* ---- instrumentation ---- */
 /* number of kernels this library launched on the context's stream since creation */
 long long fg_kernel_launches(const fg_ctx *ctx);
