@@ -298,6 +298,7 @@ def main():
         ms_e, _ = timed(e2e_step, args.steps, args.warmup + args.steps + 2)
         e2e = dict(value=args.steps / (ms_e * 1e-3), unit=UNIT,
                    h2d_bytes_per_step=int(2 * 8 * w.mesh.NOD), d2h_bytes_per_step=int(48 * w.mesh.NOD),
+                   note="per rank: potentials of its owned+ghost nodes in, u and v of its nodes out" if world > 1 else None,
                    ms_per_step=ms_e / args.steps,
                    api="LinAlgebra.set_potentials + evolution + step + get_state (pinned host)")
 

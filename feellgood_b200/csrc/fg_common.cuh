@@ -88,10 +88,12 @@ struct KState
     };
 
 // buffers of the deterministic two-stage grid reduction
+struct DistDev;
 struct RedBuf
     {
     double *partials;     // [RED_NV][MAX_GRID]
     unsigned int *ticket; // one counter, self-resetting (atomicInc wrap)
+    DistDev *dist;        // multi-GPU: the grid totals are all-reduced over the ranks (fg_dist.cuh)
     };
 
 // The operator y = A x.
@@ -138,13 +140,17 @@ struct KrylovWork
     cudaEvent_t ev_poll;
     int last_iters;            // iterations of the previous solve (sizes the first batch)
     SpmvProf *prof;            // NULL unless SpMV profiling is on
-    // hooks for the row-block multi-GPU path (NULL on one GPU)
-    void *dist;
+    // row-block multi-GPU path (NULL on one GPU): x, phat, shat then live in the IPC arena
+    DistDev *dist;
+    void *arena;
+    int halo_grid;
     };
 
 
 // ---- fg_krylov.cu ----
-int krylov_alloc(KrylovWork &w, int n, int n_ghost, cudaStream_t stream, long long *launch_counter);
+// ext (optional): externally owned storage for x, phat, shat (the multi-GPU exchange arena)
+int krylov_alloc(KrylovWork &w, int n, int n_ghost, cudaStream_t stream, long long *launch_counter,
+                 double *const ext[3] = nullptr);
 void krylov_free(KrylovWork &w);
 int grid_for(long long work_items, int items_per_cta);
 // y = A x (optionally masked)
@@ -162,5 +168,8 @@ int cg_run(const Operator &op, KrylovWork &w, double tol, int maxiter);
 int build_diag_precond_csr(const Operator &A, const KrylovWork &w);
 int vec_mask(const KrylovWork &w, double *x);                  // x[lvd] = 0
 int vec_axpy(const KrylovWork &w, double a, const double *x, double *y);  // y += a x
+// multi-GPU halo exchange of one of the arena vectors (fg_dist.cuh): which = 0 x | 1 phat | 2 shat;
+// gate = 1: skipped once the solve is done | 2: only when done and the node update is pending
+int halo_exchange(const KrylovWork &w, int which, int gate);
 
 }  // namespace fg

@@ -582,7 +582,8 @@ int build_diag_precond_csr(const Operator &A, const KrylovWork &w)
     return FG_OK;
     }
 
-int krylov_alloc(KrylovWork &w, int n, int n_ghost, cudaStream_t stream, long long *launch_counter)
+int krylov_alloc(KrylovWork &w, int n, int n_ghost, cudaStream_t stream, long long *launch_counter,
+                 double *const ext[3])
     {
     w = KrylovWork();
     w.n = n;
@@ -591,9 +592,16 @@ int krylov_alloc(KrylovWork &w, int n, int n_ghost, cudaStream_t stream, long lo
     w.launches = launch_counter;
     const size_t nb = sizeof(double) * (size_t)(w.nx > 0 ? w.nx : 1);
     double **vecs[] = {&w.x, &w.b, &w.r, &w.rt, &w.p, &w.v, &w.s, &w.t, &w.phat, &w.shat, &w.D};
+    if (ext)
+        {
+        w.x = ext[0];
+        w.phat = ext[1];
+        w.shat = ext[2];
+        w.arena = ext[0];
+        }
     for (double **v : vecs)
         {
-        FG_CUDA(cudaMalloc(v, nb));
+        if (!*v) FG_CUDA(cudaMalloc(v, nb));
         FG_CUDA(cudaMemsetAsync(*v, 0, nb, stream));
         }
     FG_CUDA(cudaMalloc(&w.st, sizeof(KState)));
@@ -603,6 +611,7 @@ int krylov_alloc(KrylovWork &w, int n, int n_ghost, cudaStream_t stream, long lo
     FG_CUDA(cudaMalloc(&w.red.partials, sizeof(double) * RED_NV * MAX_GRID));
     FG_CUDA(cudaMalloc(&w.red.ticket, sizeof(unsigned int)));
     FG_CUDA(cudaMemsetAsync(w.red.ticket, 0, sizeof(unsigned int), stream));
+    w.red.dist = nullptr;
     FG_CUDA(cudaEventCreateWithFlags(&w.ev_poll, cudaEventDisableTiming));
     w.last_iters = 0;
     return FG_OK;
@@ -610,6 +619,7 @@ int krylov_alloc(KrylovWork &w, int n, int n_ghost, cudaStream_t stream, long lo
 
 void krylov_free(KrylovWork &w)
     {
+    if (w.arena) w.x = w.phat = w.shat = nullptr;  // owned by the exchange arena
     double *vecs[] = {w.x, w.b, w.r, w.rt, w.p, w.v, w.s, w.t, w.phat, w.shat, w.D};
     for (double *v : vecs)
         if (v) cudaFree(v);
@@ -619,6 +629,62 @@ void krylov_free(KrylovWork &w)
     if (w.red.ticket) cudaFree(w.red.ticket);
     if (w.ev_poll) cudaEventDestroy(w.ev_poll);
     w = KrylovWork();
+    }
+
+// ------------------------------------------------------------------------------------------
+// multi-GPU halo exchange (fg_dist.cuh): push my boundary entries into the neighbours' ghost tails
+// over NVLink peer memory, raise the halo epoch flag, wait for my own sources.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK)
+k_halo(DistDev *d, const double *__restrict__ vec, int which, int gate, const KState *st,
+       unsigned int *ticket)
+    {
+    if (gate == 1 && st->done) return;
+    if (gate == 2 && (!st->done || st->updated)) return;
+    __shared__ int is_last;
+    const double2 *v2 = reinterpret_cast<const double2 *>(vec);
+    const int nsend = d->send_ptr[d->world];
+    const int stride = gridDim.x * BLOCK;
+    for (int idx = blockIdx.x * BLOCK + threadIdx.x; idx < nsend; idx += stride)
+        {
+        int q = 0;
+        while (idx >= d->send_ptr[q + 1]) q++;
+        const double2 val = v2[d->send_rows[idx]];
+        double2 *dst = d->tail[which][q] + d->send_dst[q] + (idx - d->send_ptr[q]);
+        *dst = val;
+        }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+        {
+        const unsigned int t = atomicInc(ticket, gridDim.x - 1);
+        is_last = (t == gridDim.x - 1);
+        }
+    __syncthreads();
+    if (!is_last || threadIdx.x != 0) return;
+    __threadfence_system();
+    const unsigned long long e = ++d->hepoch;
+    for (int q = 0; q < d->world; q++)
+        if (d->send_ptr[q + 1] > d->send_ptr[q]) st_sys(&d->ctrl[q]->hflag[d->rank], e);
+    if (d->error) return;
+    DistCtrl *me = d->ctrl[d->rank];
+    for (int src = 0; src < d->world; src++)
+        if (d->recv_from[src] && !wait_flag(&me->hflag[src], e))
+            {
+            d->error = 1;
+            break;
+            }
+    __threadfence_system();
+    }
+
+int halo_exchange(const KrylovWork &w, int which, int gate)
+    {
+    if (!w.dist) return FG_OK;
+    const double *vec = which == 0 ? w.x : (which == 1 ? w.phat : w.shat);
+    k_halo<<<w.halo_grid, BLOCK, 0, w.stream>>>(w.dist, vec, which, gate, w.st, w.red.ticket);
+    if (w.launches) ++*w.launches;
+    FG_CUDA(cudaGetLastError());
+    return FG_OK;
     }
 
 static int poll_state(KrylovWork &w)
@@ -661,6 +727,7 @@ int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, pos
         for (int k = 0; k < batch; k++)
             {
             FG_LAUNCH(w, k_bicg_p, gv, n, w.r, w.p, w.v, w.D, w.phat, w.st);
+            FG_TRY(halo_exchange(w, 1, 1));
             SpmvArgs a = {};
             a.x = w.phat;
             a.y = w.v;
@@ -670,6 +737,7 @@ int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, pos
             a.red = w.red;
             FG_TRY(launch_spmv<ST_BICG_V>(op, w, a));
             FG_LAUNCH(w, k_bicg_s, gv, n, w.r, w.v, w.D, w.s, w.shat, w.st, w.red);
+            FG_TRY(halo_exchange(w, 2, 1));
             a.x = w.shat;
             a.y = w.t;
             a.a0 = w.s;

@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stddef.h>
 #include <string.h>
 
 #include <string>
@@ -37,7 +38,16 @@ struct fg_ctx
     cudaStream_t stream = nullptr;
     long long launches = 0;
     HostSetup h;
-    int NOD = 0, NODp = 0, NTm = 0, NFa = 0, n = 0, np = 0, nnzb = 0;
+    int NOD = 0, NODp = 0, NODt = 0, NTm = 0, NFa = 0, n = 0, np = 0, nnzb = 0;
+    // multi-GPU (fg_dist_*): world == 1 on a single device
+    int rank = 0, world = 1;
+    void *arena = nullptr;
+    size_t arena_bytes = 0, tail_off[3] = {0, 0, 0};
+    DistDev h_dist = {};
+    DistDev *d_dist = nullptr;
+    int *send_rows = nullptr;
+    void *peer_base[DIST_MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool connected = false;
     long long nblk = 0;          // stored blocks incl. SELL padding
     double tol = 1e-6;
     int maxiter = 700;
@@ -48,7 +58,7 @@ struct fg_ctx
     double *stage = nullptr;     // 8*NOD doubles, device
     double *h_stage = nullptr;   // 8*NOD doubles, pinned host
     // tets
-    int4 *tet_ind = nullptr;
+    int4 *tet_ind = nullptr, *tet_slot = nullptr;
     double *tet_da = nullptr, *tet_detJ = nullptr, *ext_field = nullptr;
     int *tet_reg = nullptr;
     TetRegion *reg_tet = nullptr;
@@ -61,7 +71,7 @@ struct fg_ctx
     std::vector<TriRegion> h_reg_tri;
     // pattern and per-mesh constants
     int *perm = nullptr, *sptr = nullptr, *scol = nullptr, *sdeg = nullptr, *iptr = nullptr,
-        *sinc = nullptr, *itptr = nullptr, *sinct = nullptr;
+        *itptr = nullptr, *sinct = nullptr;
     double *sS = nullptr, *Aw = nullptr, *val = nullptr;
     KrylovWork kw;
     Operator op;
@@ -116,12 +126,13 @@ TetArrays tet_arrays(const fg_ctx *c)
     A.reg = c->tet_reg;
     A.regions = c->reg_tet;
     A.ext_field = c->ext_field;
+    A.slot = c->tet_slot;
     return A;
     }
 
 int launch_basis(fg_ctx *c, double angle)
     {
-    CTX_LAUNCH(c, k_basis, grid_for(c->NODp, BLOCK), c->NODp, c->cur, cos(angle), sin(angle), c->basis);
+    CTX_LAUNCH(c, k_basis, grid_for(c->NODt, BLOCK), c->NODt, c->cur, cos(angle), sin(angle), c->basis);
     c->have_basis = true;
     c->prepared = false;
     c->assembled = false;
@@ -194,7 +205,6 @@ int launch_assemble(fg_ctx *c, double dt)
     R.sS = c->sS;
     R.Aw = c->Aw;
     R.iptr = c->iptr;
-    R.sinc = c->sinc;
     R.itptr = c->itptr;
     R.sinct = c->sinct;
     R.nonmag = c->nonmag;
@@ -213,6 +223,9 @@ int launch_assemble(fg_ctx *c, double dt)
     if (grid < 1) grid = 1;
     CTX_LAUNCH(c, k_assemble_sell, grid, R, c->cur, c->next, c->basis, c->rec, c->trec, cS, c->val,
                c->kw.b, c->kw.x, c->kw.D);
+    if (c->NODt > c->NODp)
+        CTX_LAUNCH(c, k_ghost_guess, (c->NODt - c->NODp + BLOCK - 1) / BLOCK, c->NODp, c->NODt, c->nonmag,
+                   c->next, c->basis, c->kw.x);
     c->assembled = true;
     return FG_OK;
     }
@@ -220,13 +233,19 @@ int launch_assemble(fg_ctx *c, double dt)
 int post_update(void *user)
     {
     fg_ctx *c = static_cast<fg_ctx *>(user);
-    CTX_LAUNCH(c, k_update, grid_for(c->NODp, BLOCK), c->NODp, c->nonmag, c->cur, c->next, c->basis,
+    FG_TRY(halo_exchange(c->kw, 0, 2));  // multi-GPU: the solution of the ghost rows
+    CTX_LAUNCH(c, k_update, grid_for(c->NODt, BLOCK), c->NODt, c->NODp, c->nonmag, c->cur, c->next, c->basis,
                c->kw.x, c->sp.dt, c->kw.st, c->kw.red);
     return FG_OK;
     }
 
 int run_solve(fg_ctx *c, double dt, fg_step_result *out)
     {
+    if (c->arena && !c->connected)
+        {
+        set_error("solve: distributed context not connected (fg_dist_connect)");
+        return FG_ERR_DIST;
+        }
     if (c->profiling) FG_CUDA(cudaEventRecord(c->ev[2], c->stream));
     FG_TRY(launch_assemble(c, dt));
     if (c->profiling) FG_CUDA(cudaEventRecord(c->ev[3], c->stream));
@@ -243,6 +262,18 @@ int run_solve(fg_ctx *c, double dt, fg_step_result *out)
             }
         }
     const KState &st = *c->kw.h_st;
+    if (c->d_dist && st.status == FG_CANNOT_CONVERGE)
+        {
+        int derr = 0;
+        FG_CUDA(cudaMemcpy(&derr, reinterpret_cast<char *>(c->d_dist) + offsetof(DistDev, error), sizeof(int),
+                           cudaMemcpyDeviceToHost));
+        if (derr)
+            {
+            set_error("solve: a peer did not answer within %g s (multi-GPU exchange timed out)",
+                      (double)DIST_TIMEOUT_NS * 1e-9);
+            return FG_ERR_DIST;
+            }
+        }
     if (!st.updated)
         {
         set_error("solve: node update did not run (done=%d)", st.done);
@@ -282,7 +313,7 @@ int push_fields(fg_ctx *c, NodeRec *dst, const double *u, const double *v, const
             continue;
         which |= p.bit;
         }
-    if (which) CTX_LAUNCH(c, k_pack, grid_for(c->NODp, BLOCK), c->NODp, c->NOD, c->perm, dst, c->stage, which);
+    if (which) CTX_LAUNCH(c, k_pack, grid_for(c->NODt, BLOCK), c->NODt, c->NOD, c->perm, dst, c->stage, which);
     // the caller's buffer may be pageable and reused right away
     FG_CUDA(cudaStreamSynchronize(c->stream));
     return FG_OK;
@@ -300,7 +331,7 @@ void dofs_to_caller(const fg_ctx *c, const std::vector<double> &dev, double *out
     }
 void dofs_to_device(const fg_ctx *c, const double *in, std::vector<double> &dev)
     {
-    dev.assign((size_t)c->np, 0.0);
+    dev.assign(2 * (size_t)c->NODt, 0.0);
     for (int a = 0; a < c->NOD; a++)
         {
         const size_t r = (size_t)c->h.iperm[a];
@@ -315,7 +346,8 @@ extern "C" {
 const char *fg_last_error(void) { return g_err; }
 int fg_version(void) { return 100; }
 
-int fg_create(const fg_mesh *mesh, const fg_params *prm, int device, fg_ctx **out)
+static int create_ctx(const fg_mesh *mesh, const fg_params *prm, int device, const fg_dist_desc *dd,
+                      fg_ctx **out)
     {
     if (!mesh || !prm || !out)
         {
@@ -338,7 +370,7 @@ int fg_create(const fg_mesh *mesh, const fg_params *prm, int device, fg_ctx **ou
     fg_ctx *c = new fg_ctx();
     c->device = device;
     std::string err;
-    int rc = host_setup(*mesh, *prm, c->h, err);
+    int rc = host_setup(*mesh, *prm, dd ? dd->n_owned : -1, c->h, err);
     if (rc != FG_OK)
         {
         set_error("%s", err.c_str());
@@ -348,6 +380,12 @@ int fg_create(const fg_mesh *mesh, const fg_params *prm, int device, fg_ctx **ou
     HostSetup &h = c->h;
     c->NOD = h.NOD;
     c->NODp = h.NODp;
+    c->NODt = h.NODt;
+    if (dd)
+        {
+        c->rank = dd->rank;
+        c->world = dd->world;
+        }
     c->NTm = (int)h.magTet.size();
     c->NFa = (int)h.actTri.size();
     c->n = 2 * h.NOD;
@@ -397,7 +435,7 @@ int fg_create(const fg_mesh *mesh, const fg_params *prm, int device, fg_ctx **ou
         CKCUDA(cudaMemcpyToSymbol(c_tri_a1, a, sizeof(double) * 3));
         CKCUDA(cudaMemcpyToSymbol(c_tri_pds1, p, sizeof(double) * 1));
         }
-    const size_t N = (size_t)c->NODp;   // node arrays are in device row order, padded to 32
+    const size_t N = (size_t)c->NODt;   // node arrays are in device row order, padded to 32 (+ ghosts)
     CKCUDA(cudaMalloc(&c->cur, sizeof(NodeRec) * N));
     CKCUDA(cudaMalloc(&c->next, sizeof(NodeRec) * N));
     CKCUDA(cudaMalloc(&c->basis, sizeof(Basis) * N));
@@ -438,6 +476,13 @@ int fg_create(const fg_mesh *mesh, const fg_params *prm, int device, fg_ctx **ou
             reg[tm] = h.tet_reg[t];
             }
         CK(dev_upload(&c->tet_ind, ind, s));
+            {
+            std::vector<int4> slot(M);
+            for (size_t tm = 0; tm < M; tm++)
+                slot[tm] = make_int4(h.tet_slot[4 * tm], h.tet_slot[4 * tm + 1], h.tet_slot[4 * tm + 2], h.tet_slot[4 * tm + 3]);
+            CK(dev_upload(&c->tet_slot, slot, s));
+            CKCUDA(cudaStreamSynchronize(s));
+            }
         CK(dev_upload(&c->tet_da, da, s));
         CK(dev_upload(&c->tet_detJ, dj, s));
         CK(dev_upload(&c->tet_reg, reg, s));
@@ -465,7 +510,10 @@ int fg_create(const fg_mesh *mesh, const fg_params *prm, int device, fg_ctx **ou
                 }
             }
         CK(dev_upload(&c->reg_tet, regs, s));
-        CKCUDA(cudaMalloc(&c->rec, sizeof(double4) * 4 * (M > 0 ? M : 1)));
+        // records live in the SELL incidence layout (slots without a tet stay zero for ever)
+        const size_t nrec = (size_t)h.iptr[h.nslice] * SLICE;
+        CKCUDA(cudaMalloc(&c->rec, sizeof(double4) * (nrec > 0 ? nrec : 1)));
+        CKCUDA(cudaMemsetAsync(c->rec, 0, sizeof(double4) * (nrec > 0 ? nrec : 1), s));
         CKCUDA(cudaStreamSynchronize(s));
         }
     // active triangles
@@ -500,13 +548,57 @@ int fg_create(const fg_mesh *mesh, const fg_params *prm, int device, fg_ctx **ou
     CK(dev_upload(&c->sdeg, h.sdeg, s));
     CK(dev_upload(&c->sS, h.sS, s));
     CK(dev_upload(&c->iptr, h.iptr, s));
-    CK(dev_upload(&c->sinc, h.sinc, s));
     CK(dev_upload(&c->itptr, h.itptr, s));
     CK(dev_upload(&c->sinct, h.sinct, s));
     const size_t nval = 4 * (size_t)(c->nblk > 0 ? c->nblk : 1);
     CKCUDA(cudaMalloc(&c->val, sizeof(double) * nval));
     CKCUDA(cudaMemsetAsync(c->val, 0, sizeof(double) * nval, s));
-    CK(krylov_alloc(c->kw, c->np, 0, s, &c->launches));
+    if (dd)
+        {  // exchange arena: control block + the three halo-exchanged vectors, one IPC-exportable block
+        const size_t vb = ((sizeof(double) * 2 * (size_t)c->NODt + 255) / 256) * 256;
+        const size_t cb = ((sizeof(DistCtrl) + 255) / 256) * 256;
+        c->arena_bytes = cb + 3 * vb;
+        CKCUDA(cudaMalloc(&c->arena, c->arena_bytes));
+        CKCUDA(cudaMemsetAsync(c->arena, 0, c->arena_bytes, s));
+        char *base = static_cast<char *>(c->arena);
+        double *ext[3];
+        for (int k = 0; k < 3; k++)
+            {
+            ext[k] = reinterpret_cast<double *>(base + cb + k * vb);
+            c->tail_off[k] = cb + k * vb + sizeof(double) * 2 * (size_t)c->NODp;
+            }
+        CK(krylov_alloc(c->kw, c->np, 2 * (c->NODt - c->NODp), s, &c->launches, ext));
+        c->kw.arena = c->arena;
+        // halo plan: boundary rows in device order, grouped by destination rank
+        DistDev &D = c->h_dist;
+        D.rank = dd->rank;
+        D.world = dd->world;
+        std::vector<int> rows((size_t)dd->send_ptr[dd->world]);
+        for (int q = 0; q <= dd->world; q++) D.send_ptr[q] = dd->send_ptr[q];
+        for (int q = 0; q < dd->world; q++)
+            {
+            D.send_dst[q] = dd->send_dst[q];
+            D.recv_from[q] = dd->recv_from[q];
+            }
+        for (size_t k = 0; k < rows.size(); k++)
+            {
+            const int a = dd->send_nodes[k];
+            if (a < 0 || a >= h.n_owned)
+                {
+                set_error("fg_dist_create: send node %d is not an owned node", a);
+                fg_destroy(c);
+                return FG_ERR_DIST;
+                }
+            rows[k] = h.iperm[a];
+            }
+        CK(dev_upload(&c->send_rows, rows, s));
+        D.send_rows = c->send_rows;
+        CKCUDA(cudaMalloc(&c->d_dist, sizeof(DistDev)));
+        int ng = ((int)rows.size() + BLOCK - 1) / BLOCK;
+        c->kw.halo_grid = ng < 1 ? 1 : (ng > 64 ? 64 : ng);
+        }
+    else
+        CK(krylov_alloc(c->kw, c->np, 0, s, &c->launches));
     c->kw.mask = c->dofmask;
     c->op.kind = OP_SELL2;
     c->op.n = c->np;
@@ -523,10 +615,104 @@ int fg_create(const fg_mesh *mesh, const fg_params *prm, int device, fg_ctx **ou
     std::vector<int>().swap(h.inc);
     std::vector<int>().swap(h.inc_tri);
     std::vector<int>().swap(h.sinc);
+    std::vector<int>().swap(h.tet_slot);
     std::vector<int>().swap(h.sinct);
     std::vector<int>().swap(h.scol);
     c->sp.idx_dir = FG_IDX_UNDEF;
     *out = c;
+    return FG_OK;
+    }
+
+int fg_create(const fg_mesh *mesh, const fg_params *prm, int device, fg_ctx **out)
+    { return create_ctx(mesh, prm, device, nullptr, out); }
+
+// ---- multi-GPU: one rank of the slab-partitioned solve (fg_dist.cuh) ----
+int fg_dist_create(const fg_mesh *local_mesh, const fg_params *prm, int device, const fg_dist_desc *dd,
+                   fg_ctx **out)
+    {
+    if (!dd || dd->world < 1 || dd->world > DIST_MAX_RANKS || dd->rank < 0 || dd->rank >= dd->world
+        || !dd->send_ptr || !dd->send_dst || !dd->recv_from || (dd->send_ptr[dd->world] > 0 && !dd->send_nodes)
+        || !local_mesh || dd->n_owned < 0 || dd->n_owned > local_mesh->NOD)
+        {
+        set_error("fg_dist_create: bad distribution descriptor (world 1..%d)", DIST_MAX_RANKS);
+        return FG_ERR_DIST;
+        }
+    return create_ctx(local_mesh, prm, device, dd, out);
+    }
+
+namespace
+{
+struct DistBlob  // FG_DIST_BLOB_BYTES
+    {
+    cudaIpcMemHandle_t handle;       // 64 B
+    unsigned long long tail_off[3];  // byte offsets of the ghost tails of x, phat, shat in the arena
+    int rank, n_ghost;
+    char pad_[FG_DIST_BLOB_BYTES - 64 - 24 - 8];
+    };
+static_assert(sizeof(DistBlob) == FG_DIST_BLOB_BYTES, "blob size");
+}  // namespace
+
+int fg_dist_export(fg_ctx *c, void *blob)
+    {
+    FG_TRY(check_ctx(c));
+    if (!c->arena || !blob)
+        {
+        set_error("fg_dist_export: not a distributed context");
+        return FG_ERR_DIST;
+        }
+    DistBlob b;
+    memset(&b, 0, sizeof b);
+    FG_CUDA(cudaIpcGetMemHandle(&b.handle, c->arena));
+    for (int k = 0; k < 3; k++) b.tail_off[k] = c->tail_off[k];
+    b.rank = c->rank;
+    b.n_ghost = c->NODt - c->NODp;
+    memcpy(blob, &b, sizeof b);
+    return FG_OK;
+    }
+
+int fg_dist_connect(fg_ctx *c, const void *blobs)
+    {
+    FG_TRY(check_ctx(c));
+    if (!c->arena || !blobs)
+        {
+        set_error("fg_dist_connect: not a distributed context");
+        return FG_ERR_DIST;
+        }
+    const DistBlob *B = static_cast<const DistBlob *>(blobs);
+    DistDev &D = c->h_dist;
+    for (int q = 0; q < c->world; q++)
+        {
+        if (B[q].rank != q)
+            {
+            set_error("fg_dist_connect: blob %d belongs to rank %d", q, B[q].rank);
+            return FG_ERR_DIST;
+            }
+        void *base = c->arena;
+        if (q != c->rank)
+            {
+            const bool needed = D.send_ptr[q + 1] > D.send_ptr[q] || true;  // mailboxes: every peer
+            if (needed && !c->peer_base[q])
+                FG_CUDA(cudaIpcOpenMemHandle(&c->peer_base[q], B[q].handle, cudaIpcMemLazyEnablePeerAccess));
+            base = c->peer_base[q];
+            }
+        else
+            c->peer_base[q] = c->arena;
+        D.ctrl[q] = static_cast<DistCtrl *>(base);
+        for (int k = 0; k < 3; k++)
+            D.tail[k][q] = reinterpret_cast<double2 *>(static_cast<char *>(base) + B[q].tail_off[k]);
+        if (D.send_ptr[q + 1] - D.send_ptr[q] + D.send_dst[q] > B[q].n_ghost)
+            {
+            set_error("fg_dist_connect: segment for rank %d exceeds its ghost range", q);
+            return FG_ERR_DIST;
+            }
+        }
+    D.epoch = D.hepoch = 0;
+    D.error = 0;
+    FG_CUDA(cudaMemcpyAsync(c->d_dist, &D, sizeof(DistDev), cudaMemcpyHostToDevice, c->stream));
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    c->kw.dist = c->d_dist;
+    c->kw.red.dist = c->d_dist;
+    c->connected = true;
     return FG_OK;
     }
 
@@ -538,9 +724,13 @@ void fg_destroy(fg_ctx *c)
     void *ptrs[] = {c->cur, c->next, c->basis, c->nonmag, c->dofmask, c->stage, c->tet_ind, c->tet_da,
                     c->tet_detJ, c->ext_field, c->tet_reg, c->reg_tet, c->rec, c->tri_ind,
                     c->tri_reg, c->tri_surf, c->tri_dMs, c->reg_tri, c->trec, c->perm, c->sptr,
-                    c->scol, c->sdeg, c->iptr, c->sinc, c->itptr, c->sinct, c->sS, c->Aw, c->val};
+                    c->scol, c->sdeg, c->iptr, c->tet_slot, c->itptr, c->sinct, c->sS, c->Aw, c->val};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    for (int q = 0; q < DIST_MAX_RANKS; q++)
+        if (c->peer_base[q] && q != c->rank) cudaIpcCloseMemHandle(c->peer_base[q]);
+    if (c->d_dist) cudaFree(c->d_dist);
+    if (c->send_rows) cudaFree(c->send_rows);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->prof.ev)
         {
@@ -548,6 +738,7 @@ void fg_destroy(fg_ctx *c)
         delete[] c->prof.ev;
         }
     krylov_free(c->kw);
+    if (c->arena) cudaFree(c->arena);
     for (int k = 0; k < 5; k++)
         if (c->ev[k]) cudaEventDestroy(c->ev[k]);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -583,7 +774,7 @@ int fg_set_state(fg_ctx *c, const double *u, const double *v, const double *phi,
         return FG_ERR_INVALID;
         }
     FG_TRY(push_fields(c, c->cur, u, v, phi, phiv, true));
-    FG_CUDA(cudaMemcpyAsync(c->next, c->cur, sizeof(NodeRec) * (size_t)c->NODp, cudaMemcpyDeviceToDevice, c->stream));
+    FG_CUDA(cudaMemcpyAsync(c->next, c->cur, sizeof(NodeRec) * (size_t)c->NODt, cudaMemcpyDeviceToDevice, c->stream));
     FG_CUDA(cudaStreamSynchronize(c->stream));
     c->have_basis = c->prepared = c->assembled = false;
     return FG_OK;
@@ -622,7 +813,7 @@ int fg_get_state(fg_ctx *c, int step, double *u, double *v, double *phi, double 
     const size_t N = (size_t)c->NOD;
     const int which = (u ? 1 : 0) | (v ? 2 : 0) | (phi ? 4 : 0) | (phiv ? 8 : 0);
     if (!which) return FG_OK;
-    CTX_LAUNCH(c, k_unpack, grid_for(c->NODp, BLOCK), c->NODp, c->NOD, c->perm, step ? c->next : c->cur, c->stage, which);
+    CTX_LAUNCH(c, k_unpack, grid_for(c->NODt, BLOCK), c->NODt, c->NOD, c->perm, step ? c->next : c->cur, c->stage, which);
     struct Part { double *dst; size_t off, len; };
     const Part parts[4] = {{u, 0, 3 * N}, {v, 3 * N, 3 * N}, {phi, 6 * N, N}, {phiv, 7 * N, N}};
     for (const Part &p : parts)
@@ -636,7 +827,7 @@ int fg_get_state(fg_ctx *c, int step, double *u, double *v, double *phi, double 
 int fg_commit(fg_ctx *c)
     {
     FG_TRY(check_ctx(c));
-    FG_CUDA(cudaMemcpyAsync(c->cur, c->next, sizeof(NodeRec) * (size_t)c->NODp, cudaMemcpyDeviceToDevice, c->stream));
+    FG_CUDA(cudaMemcpyAsync(c->cur, c->next, sizeof(NodeRec) * (size_t)c->NODt, cudaMemcpyDeviceToDevice, c->stream));
     c->have_basis = c->prepared = c->assembled = false;
     return FG_OK;
     }
@@ -936,6 +1127,11 @@ int fg_get_csr_pattern(const fg_ctx *c, int *rowptr, int *col)
 int fg_get_system(fg_ctx *c, double dt, double *val, double *rhs, double *x0)
     {
     FG_TRY(check_ctx(c));
+    if (c->arena)
+        {
+        set_error("fg_get_system: not available on a distributed context");
+        return FG_ERR_STATE;
+        }
     // before the solve: assemble now; after it: K and L_rhs are still resident (x0 then holds Xw)
     if (c->prepared || !c->assembled) FG_TRY(launch_assemble(c, dt));
     const HostSetup &h = c->h;
@@ -959,7 +1155,7 @@ int fg_get_system(fg_ctx *c, double dt, double *val, double *rhs, double *x0)
                 }
             }
         }
-    std::vector<double> tmp((size_t)c->np);
+    std::vector<double> tmp(2 * (size_t)c->NODt);
     if (rhs)
         {
         FG_CUDA(cudaMemcpyAsync(tmp.data(), c->kw.b, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, c->stream));
@@ -983,9 +1179,9 @@ int fg_apply_operator(fg_ctx *c, const double *x, double *y)
         set_error("fg_apply_operator: null argument");
         return FG_ERR_INVALID;
         }
-    if (!c->assembled)
+    if (!c->assembled || c->arena)
         {
-        set_error("fg_apply_operator: no assembled system");
+        set_error("fg_apply_operator: no assembled system (or distributed context)");
         return FG_ERR_STATE;
         }
     std::vector<double> tmp;
@@ -1006,7 +1202,7 @@ int fg_get_solution(fg_ctx *c, double *Xw)
         set_error("fg_get_solution: null argument");
         return FG_ERR_INVALID;
         }
-    std::vector<double> tmp((size_t)c->np);
+    std::vector<double> tmp(2 * (size_t)c->NODt);
     FG_CUDA(cudaMemcpyAsync(tmp.data(), c->kw.x, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, c->stream));
     FG_CUDA(cudaStreamSynchronize(c->stream));
     dofs_to_caller(c, tmp, Xw);
@@ -1042,7 +1238,7 @@ int fg_host_plan(const fg_mesh *mesh, const fg_params *prm, long long out[12])
         }
     HostSetup h;
     std::string err;
-    const int rc = host_setup(*mesh, *prm, h, err);
+    const int rc = host_setup(*mesh, *prm, -1, h, err);
     if (rc != FG_OK)
         {
         set_error("%s", err.c_str());
@@ -1093,7 +1289,12 @@ int fg_host_plan(const fg_mesh *mesh, const fg_params *prm, long long out[12])
         }
     for (size_t tm = 0; tm < h.magTet.size(); tm++)
         for (int i = 0; i < 4; i++)
+            {
             if (h.perm[h.tet_dev_ind[4 * tm + i]] != h.tet_ind[4 * (size_t)h.magTet[tm] + i]) bad++;
+            const int sl = h.tet_slot[4 * tm + i];
+            if (sl < 0 || h.sinc[(size_t)sl] != (int)(4 * tm + i)) bad++;
+            else if (sl % SELL_C != h.tet_dev_ind[4 * tm + i] % SELL_C) bad++;
+            }
     if (bad)
         {
         set_error("fg_host_plan: device layout inconsistent with the reference pattern (%lld defects)", bad);

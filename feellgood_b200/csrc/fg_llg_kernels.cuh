@@ -346,6 +346,7 @@ struct TetArrays
     const int *reg;         // NTm
     const TetRegion *regions;
     const double *ext_field;  // [3*npi][NTm] or NULL
+    const int4 *slot;       // NTm : record slots of the 4 local nodes (incidence order of the row)
     };
 
 template <int NPI>
@@ -374,7 +375,8 @@ __device__ __forceinline__ void tet_field(const TetArrays &A, int tm, const Step
     }
 
 constexpr int TET_CTAS_PER_SM = 1;
-// one thread per magnetic tetrahedron; emits 4 records {contrib, eq.BE, ep.BE, 0}
+// one thread per magnetic tetrahedron; emits 4 records {contrib, eq.BE, ep.BE, 0}, each stored at
+// the slot of its node's incidence list so that the row assembly reads them as a stream
 template <int NPI, bool SPACE>
 __global__ void __launch_bounds__(BLOCK, TET_CTAS_PER_SM)
 k_tet(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__restrict__ basis,
@@ -392,6 +394,8 @@ k_tet(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__restric
         double contrib[4], BE[3][4];
         tet_core<NPI>(T, R, sp, Hext, contrib, BE);
         const int nd[4] = {ind.x, ind.y, ind.z, ind.w};
+        const int4 s4 = __ldcs(A.slot + tm);
+        const int sl[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
         for (int i = 0; i < 4; i++)
             {
@@ -399,9 +403,11 @@ k_tet(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__restric
             load_basis(basis + nd[i], ep, eq);
             const double be[3] = {BE[0][i], BE[1][i], BE[2][i]};
             // Lp = Perm P BE (tetra.cpp:306): rows 0..3 are the eq-projections, 4..7 the ep ones
-            double2 *r2 = reinterpret_cast<double2 *>(rec + 4 * (size_t)tm + i);
-            __stcs(r2, make_double2(contrib[i], dot3(eq, be)));
-            __stcs(r2 + 1, make_double2(dot3(ep, be), 0.0));
+            // the record goes where the node's row will stream it from (its incidence slot)
+            if (sl[i] < 0) continue;
+            double2 *r2 = reinterpret_cast<double2 *>(rec + sl[i]);
+            r2[0] = make_double2(contrib[i], dot3(eq, be));
+            r2[1] = make_double2(dot3(ep, be), 0.0);
             }
         }
     }
@@ -569,7 +575,7 @@ struct RowArrays
     const int *sptr, *scol, *sdeg;     // SELL pattern (fg_common.cuh Operator) + blocks per row
     const double *sS;                  // S in SELL order
     const double *Aw;                  // NODp lumped mass
-    const int *iptr, *sinc;            // SELL incidence lists (record index, -1 = none)
+    const int *iptr;                   // SELL incidence lists: slice extents of the record stream
     const int *itptr, *sinct;          // same for the active triangles
     const unsigned char *nonmag;       // NODp : 1 = node outside the magnetic material (or pad row)
     };
@@ -590,20 +596,17 @@ k_assemble_sell(const RowArrays A, const NodeRec *__restrict__ cur, const NodeRe
         // ---- gather of the element records -------------------------------------------------
         double Ma = 0.0, L0 = 0.0, L1 = 0.0;
             {
+            // the records were written in incidence order: a pure coalesced stream (1 KB per warp
+            // request), empty slots hold zeros
             const int i0 = __ldg(A.iptr + s), i1 = __ldg(A.iptr + s + 1);
-            const int *ip = A.sinc + (size_t)i0 * SLICE + lane;
+            const double2 *rp = reinterpret_cast<const double2 *>(rec + (size_t)i0 * SLICE + lane);
 #pragma unroll 4
-            for (int q = i0; q < i1; ++q, ip += SLICE)
+            for (int q = i0; q < i1; ++q, rp += 2 * SLICE)
                 {
-                const int idx = __ldcs(ip);
-                if (idx >= 0)
-                    {
-                    const double2 *r2 = reinterpret_cast<const double2 *>(rec + idx);
-                    const double2 r01 = __ldcs(r2), r23 = __ldcs(r2 + 1);
-                    Ma += r01.x;
-                    L0 += r01.y;
-                    L1 += r23.x;
-                    }
+                const double2 r01 = __ldcs(rp), r23 = __ldcs(rp + 1);
+                Ma += r01.x;
+                L0 += r01.y;
+                L1 += r23.x;
                 }
             const int t0 = __ldg(A.itptr + s), t1 = __ldg(A.itptr + s + 1);
             const int *tp = A.sinct + (size_t)t0 * SLICE + lane;
@@ -684,7 +687,7 @@ k_assemble_sell(const RowArrays A, const NodeRec *__restrict__ cur, const NodeRe
 // Node update (src/solver.cpp:62-88): gated on the device-side outcome of the solve.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BLOCK)
-k_update(int NOD, const unsigned char *__restrict__ nonmag, const NodeRec *__restrict__ cur,
+k_update(int NOD, int NOWN, const unsigned char *__restrict__ nonmag, const NodeRec *__restrict__ cur,
          NodeRec *__restrict__ next, const Basis *__restrict__ basis, const double *__restrict__ x,
          double dt, KState *st, const RedBuf red)
     {
@@ -700,7 +703,7 @@ k_update(int NOD, const unsigned char *__restrict__ nonmag, const NodeRec *__res
             if (nonmag[a]) continue;
             const double2 xv = reinterpret_cast<const double2 *>(x)[a];
             const double v2 = xv.x * xv.x + xv.y * xv.y;
-            v2max = fmax(v2max, v2);
+            if (a < NOWN) v2max = fmax(v2max, v2);  // ghost rows (multi-GPU) belong to another rank
             double u[3], vc[3], phi, phiv, ep[3], eq[3], vn[3], un[3];
             load_rec(cur + a, u, vc, phi, phiv);
             load_basis(basis + a, ep, eq);
@@ -727,6 +730,24 @@ k_update(int NOD, const unsigned char *__restrict__ nonmag, const NodeRec *__res
         st->v_max = FG_GAMMA0 * sqrt(tot);
         }
     st->updated = 1;
+    }
+
+// multi-GPU: initial guess of the ghost rows (their owner's assembly writes the same numbers there)
+__global__ void __launch_bounds__(BLOCK)
+k_ghost_guess(int first, int last, const unsigned char *__restrict__ nonmag,
+              const NodeRec *__restrict__ next, const Basis *__restrict__ basis, double *__restrict__ x0)
+    {
+    const int row = first + blockIdx.x * BLOCK + threadIdx.x;
+    if (row >= last) return;
+    double2 g = make_double2(0.0, 0.0);
+    if (!nonmag[row])
+        {
+        double un[3], vn[3], phi, phiv, ep[3], eq[3];
+        load_rec(next + row, un, vn, phi, phiv);
+        load_basis(basis + row, ep, eq);
+        g = make_double2(dot3(vn, ep) / FG_GAMMA0, dot3(vn, eq) / FG_GAMMA0);
+        }
+    reinterpret_cast<double2 *>(x0)[row] = g;
     }
 
 // ------------------------------------------------------------------------------------------

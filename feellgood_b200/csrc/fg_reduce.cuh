@@ -2,6 +2,7 @@
 // Replaces the serial std::inner_product folds of the reference (src/algebra/algebraCore.h:10-17).
 #pragma once
 #include "fg_common.cuh"
+#include "fg_dist.cuh"
 
 namespace fg
 {
@@ -64,6 +65,7 @@ __device__ bool grid_reduce(double (&v)[NV], const RedBuf red, double (&out)[NV]
         for (int w = 0; w < BLOCK / 32; w++) s += sm[k][w];
         out[k] = s;
         }
+    if (red.dist != nullptr) dist_allreduce(red.dist, out, NV, false);
     return true;
     }
 
@@ -103,6 +105,7 @@ __device__ __forceinline__ bool grid_reduce_max(double v, const RedBuf red, doub
 #pragma unroll
     for (int w = 1; w < BLOCK / 32; w++) s = fmax(s, smx[w]);
     out = s;
+    if (red.dist != nullptr) dist_allreduce(red.dist, &out, 1, true);
     return true;
     }
 

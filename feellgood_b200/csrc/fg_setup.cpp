@@ -107,7 +107,7 @@ bool tet_geometry(const double *P, int ind[4], double da[12], double &detJ)
     }
 }  // namespace
 
-int host_setup(const fg_mesh &m, const fg_params &prm, HostSetup &h, std::string &err)
+int host_setup(const fg_mesh &m, const fg_params &prm, int n_owned, HostSetup &h, std::string &err)
     {
     char buf[256];
     if (m.NOD <= 0 || m.NT < 0 || m.NF < 0 || !m.node_p || (m.NT > 0 && (!m.tet_ind || !m.tet_reg))
@@ -123,6 +123,8 @@ int host_setup(const fg_mesh &m, const fg_params &prm, HostSetup &h, std::string
         return FG_ERR_INVALID;
         }
     h.NOD = m.NOD;
+    if (n_owned < 0 || n_owned > m.NOD) n_owned = m.NOD;
+    h.n_owned = n_owned;
     h.NT = m.NT;
     h.NF = m.NF;
     h.npi_tet = prm.npi_tet;
@@ -271,17 +273,24 @@ int host_setup(const fg_mesh &m, const fg_params &prm, HostSetup &h, std::string
     std::vector<int>().swap(adj);
 
     // ---- device ordering: window-local stable sort by descending block count, slices of 32 -----
-    const int NODp = ((NOD + SELL_C - 1) / SELL_C) * SELL_C;
+    const int NOW = h.n_owned;   // rows exist for the owned nodes only; ghosts follow the padded rows
+    const int NODp = ((NOW + SELL_C - 1) / SELL_C) * SELL_C;
     h.NODp = NODp;
+    h.NODt = NODp + (NOD - NOW);
     h.nslice = NODp / SELL_C;
-    h.perm.assign((size_t)NODp, -1);
+    h.perm.assign((size_t)h.NODt, -1);
     h.iperm.assign((size_t)NOD, -1);
+    for (int a = NOW; a < NOD; a++)
         {
-        const int nwin = (NOD + SELL_WINDOW - 1) / SELL_WINDOW;
+        h.perm[(size_t)NODp + (a - NOW)] = a;
+        h.iperm[a] = NODp + (a - NOW);
+        }
+        {
+        const int nwin = (NOW + SELL_WINDOW - 1) / SELL_WINDOW;
 #pragma omp parallel for schedule(static)
         for (int wdx = 0; wdx < nwin; wdx++)
             {
-            const int b = wdx * SELL_WINDOW, e = std::min(NOD, b + SELL_WINDOW);
+            const int b = wdx * SELL_WINDOW, e = std::min(NOW, b + SELL_WINDOW);
             int *q = &h.perm[(size_t)b];
             std::iota(q, q + (e - b), b);
             std::stable_sort(q, q + (e - b), [&](int x, int y)
@@ -410,6 +419,7 @@ int host_setup(const fg_mesh &m, const fg_params &prm, HostSetup &h, std::string
         h.sS.assign((size_t)h.sptr[ns] * SELL_C, 0.0);
         h.sinc.assign((size_t)h.iptr[ns] * SELL_C, -1);
         h.sinct.assign((size_t)h.itptr[ns] * SELL_C, -1);
+        h.tet_slot.assign(4 * (size_t)NTm, -1);
 #pragma omp parallel for schedule(static)
         for (int s = 0; s < ns; s++)
             for (int l = 0; l < SELL_C; l++)
@@ -431,7 +441,11 @@ int host_setup(const fg_mesh &m, const fg_params &prm, HostSetup &h, std::string
                     }
                 if (a < 0) continue;
                 for (int q = h.inc_ptr[a]; q < h.inc_ptr[a + 1]; q++)
-                    h.sinc[((size_t)h.iptr[s] + (q - h.inc_ptr[a])) * SELL_C + l] = h.inc[q];
+                    {
+                    const size_t slot = ((size_t)h.iptr[s] + (q - h.inc_ptr[a])) * SELL_C + l;
+                    h.sinc[slot] = h.inc[q];
+                    h.tet_slot[(size_t)h.inc[q]] = (int)slot;  // each (tet, local node) occurs once
+                    }
                 for (int q = h.inc_tri_ptr[a]; q < h.inc_tri_ptr[a + 1]; q++)
                     h.sinct[((size_t)h.itptr[s] + (q - h.inc_tri_ptr[a])) * SELL_C + l] = h.inc_tri[q];
                 }

@@ -49,7 +49,9 @@ struct HostSetup
     // Rows are permuted inside windows of SELL_WINDOW nodes by descending block count (stable, so
     // locality survives) and cut into slices of 32 rows: SELL-32-sigma with 2x2 blocks.  All
     // device arrays indexed by node use the device row number.
-    int NODp = 0;                  // NOD rounded up to a multiple of 32 (pad rows: perm = -1)
+    int n_owned = 0;               // nodes [0, n_owned) have rows here; the rest are ghosts (multi-GPU)
+    int NODp = 0;                  // n_owned rounded up to a multiple of 32 (pad rows: perm = -1)
+    int NODt = 0;                  // NODp + ghosts: length of every device node array
     std::vector<int> perm, iperm;  // device row -> node | node -> device row
     int nslice = 0;
     std::vector<int> sptr;         // nslice+1 : first block-column of each slice
@@ -59,12 +61,15 @@ struct HostSetup
     std::vector<int> iptr, sinc;   // SELL incidence lists: nslice+1 | iptr[nslice]*32 (record index, -1 pad)
     std::vector<int> itptr, sinct; // same for the active triangles
     std::vector<int> tet_dev_ind;  // 4*n_magTet : device rows of the magnetic tets, device tet order
+    std::vector<int> tet_slot;     // 4*n_magTet : where (tet, local node) writes its record = its
+                                   // position in the node's SELL incidence list (-1: no row)
     };
 constexpr int SELL_C = 32;
 constexpr int SELL_WINDOW = 1024;
 
 // returns FG_OK or FG_ERR_*; message in err
-int host_setup(const fg_mesh &mesh, const fg_params &prm, HostSetup &out, std::string &err);
+// n_owned < 0: all nodes are owned (single GPU)
+int host_setup(const fg_mesh &mesh, const fg_params &prm, int n_owned, HostSetup &out, std::string &err);
 
 // Gauss tables (src/tetra.h:29-81, src/triangle.h:21-65): a[i*npi+g], pds[g]
 void tet_tables(int npi, double a[20], double pds[5]);

@@ -1,0 +1,178 @@
+"""Row-block (slab) partition of the LLG solve over the GPUs of one box.
+
+The reference is a single-process code; there is nothing to mirror here.  What this module does:
+
+* ``Partition``       — owner ranges over the reference's sorted node order (src/mesh.cpp:334-367:
+                        contiguous row blocks are slabs along the longest axis), balanced by the
+                        number of matrix blocks; per-rank local meshes (owned nodes first, then the
+                        ghost nodes of the tetrahedra touching an owned node) and the halo plan
+                        (who pushes which boundary rows into whose ghost tail).  Pure numpy and
+                        deterministic, so every rank computes the same plan without talking.
+* ``DistLinAlgebra``  — the ``LinAlgebra`` surface on one rank: builds the local context with
+                        ``fg_dist_create``, swaps the IPC blobs through ``torch.distributed``
+                        (plumbing only) and connects the peers (``fg_dist_connect``).  From then on
+                        every per-step call is collective; the data path (halo pushes, all-reduces
+                        of the Krylov scalars) runs inside the CUDA kernels over NVLink peer memory.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi, meshgen
+from .capi import check, dp, f64, i32, ip
+from .linear_algebra import LinAlgebra
+
+
+class DistDesc(C.Structure):
+    """fg_dist_desc (include/feellgood_b200.h)."""
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("n_owned", C.c_int),
+                ("send_ptr", capi.c_int_p), ("send_nodes", capi.c_int_p),
+                ("send_dst", capi.c_int_p), ("recv_from", capi.c_int_p)]
+
+
+class LocalProblem:
+    """What one rank hands to fg_dist_create, plus the maps back to global numbering."""
+
+    def __init__(self, rank, world, mesh, n_owned, l2g, send_ptr, send_nodes, send_dst, recv_from):
+        self.rank, self.world, self.mesh, self.n_owned = rank, world, mesh, n_owned
+        self.l2g = l2g                          # local node -> global node
+        self.send_ptr, self.send_nodes = i32(send_ptr), i32(send_nodes)
+        self.send_dst, self.recv_from = i32(send_dst), i32(recv_from)
+
+    @property
+    def n_ghost(self):
+        return self.mesh.NOD - self.n_owned
+
+
+class Partition:
+    def __init__(self, mesh, world, align=32):
+        """Owner ranges [cuts[r], cuts[r+1]) balanced by 1 + (tets incident to the node), which is
+        proportional to the matrix blocks of the row; cuts are aligned to the SELL slice height."""
+        self.mesh, self.world = mesh, int(world)
+        NOD = mesh.NOD
+        w = 1.0 + np.bincount(mesh.tet_ind.ravel(), minlength=NOD)
+        cum = np.cumsum(w)
+        cuts = [0]
+        for k in range(1, self.world):
+            c = int(np.searchsorted(cum, cum[-1] * k / self.world))
+            c = min(NOD, max(cuts[-1], (c + align // 2) // align * align))
+            cuts.append(c)
+        cuts.append(NOD)
+        self.cuts = np.asarray(cuts, dtype=np.int64)
+        self._ghosts = {}
+
+    def owner_of(self, nodes):
+        return np.searchsorted(self.cuts, nodes, side="right") - 1
+
+    def _local_tets(self, rank):
+        lo, hi = self.cuts[rank], self.cuts[rank + 1]
+        t = self.mesh.tet_ind
+        return ((t >= lo) & (t < hi)).any(axis=1)
+
+    def ghosts(self, rank):
+        """Global ids (sorted) of the ghost nodes of a rank."""
+        if rank not in self._ghosts:
+            lo, hi = self.cuts[rank], self.cuts[rank + 1]
+            used = np.unique(self.mesh.tet_ind[self._local_tets(rank)])
+            self._ghosts[rank] = used[(used < lo) | (used >= hi)].astype(np.int64)
+        return self._ghosts[rank]
+
+    def local(self, rank):
+        m = self.mesh
+        lo, hi = int(self.cuts[rank]), int(self.cuts[rank + 1])
+        n_owned = hi - lo
+        gh = self.ghosts(rank)
+        l2g = np.concatenate([np.arange(lo, hi, dtype=np.int64), gh])
+        g2l = np.full(m.NOD, -1, dtype=np.int64)
+        g2l[l2g] = np.arange(l2g.size)
+        tmask = self._local_tets(rank)
+        ltet = g2l[m.tet_ind[tmask]].astype(np.int32)
+        if m.NF:
+            fl = g2l[m.tri_ind]
+            fmask = (fl >= 0).all(axis=1) & (fl < n_owned).any(axis=1)
+            ltri, ltreg, ldms = fl[fmask].astype(np.int32), m.tri_reg[fmask], m.tri_dMs[fmask]
+        else:
+            ltri = np.zeros((0, 3), dtype=np.int32)
+            ltreg, ldms = np.zeros(0, dtype=np.int32), np.zeros(0)
+        lm = meshgen.Mesh(node_p=np.ascontiguousarray(m.node_p[l2g]), tet_ind=np.ascontiguousarray(ltet),
+                          tet_reg=np.ascontiguousarray(m.tet_reg[tmask]), tri_ind=np.ascontiguousarray(ltri),
+                          tri_reg=np.ascontiguousarray(ltreg), tri_dMs=np.ascontiguousarray(ldms))
+        # halo plan: my owned nodes that are ghosts of q, in q's ghost order (sorted global id)
+        send_ptr, send_nodes, send_dst = [0], [], []
+        recv_from = np.zeros(self.world, dtype=np.int32)
+        own = self.owner_of(gh) if gh.size else np.zeros(0, dtype=np.int64)
+        for q in range(self.world):
+            if q == rank:
+                send_ptr.append(send_ptr[-1])
+                send_dst.append(0)
+                continue
+            gq = self.ghosts(q)
+            a, b = np.searchsorted(gq, lo), np.searchsorted(gq, hi)
+            send_nodes.append(gq[a:b] - lo)
+            send_ptr.append(send_ptr[-1] + int(b - a))
+            send_dst.append(int(a))
+            recv_from[q] = int(np.any(own == q))
+        send_nodes = np.concatenate(send_nodes) if send_nodes else np.zeros(0, dtype=np.int64)
+        return LocalProblem(rank, self.world, lm, n_owned, l2g, send_ptr, send_nodes, send_dst, recv_from)
+
+
+class DistLinAlgebra(LinAlgebra):
+    """LinAlgebra on one rank of a slab-partitioned mesh.  `mesh` is the GLOBAL mesh (every rank
+    builds it identically); state setters take global arrays and keep the local part, getters
+    return local arrays (`l2g` maps them back; `gather_state` assembles the global array)."""
+
+    def __init__(self, settings, mesh, rank, world, device=0, connect=True):
+        self.part = Partition(mesh, world)
+        self.lp = lp = self.part.local(rank)
+        self.rank, self.world = rank, world
+        self.l2g, self.NOD_global = lp.l2g, mesh.NOD
+        self.NOD_local, self.n_owned = lp.mesh.NOD, lp.n_owned
+        desc = DistDesc(rank, world, lp.n_owned, ip(lp.send_ptr), ip(lp.send_nodes), ip(lp.send_dst),
+                        ip(lp.recv_from))
+        self._desc_keep = desc
+
+        def create(L, cm, cp, dev, h):
+            return L.fg_dist_create(cm, cp, dev, C.byref(desc), h)
+        self._init_ctx(settings, lp.mesh, device, create)
+        # owned part of the global sizes (the taps of K are not available on a distributed context)
+        self.n_local, self.nnz_local = 2 * lp.n_owned, self.nnz
+        if connect:
+            self.connect()
+
+    def connect(self):
+        import torch.distributed as dist
+        blob = (C.c_char * 128)()
+        check(self._L.fg_dist_export(self._h, blob))
+        blobs = [None] * self.world
+        dist.all_gather_object(blobs, bytes(blob))
+        allb = b"".join(blobs)
+        check(self._L.fg_dist_connect(self._h, allb))
+        tot = [None] * self.world
+        dist.all_gather_object(tot, (self.n_local, self.nnz_local))
+        self.n = int(sum(t[0] for t in tot))
+        self.nnz = int(sum(t[1] for t in tot))
+        dist.barrier()
+
+    # ---- state in global numbering ----
+    def _loc(self, a):
+        return None if a is None else np.ascontiguousarray(np.asarray(a, dtype=np.float64)[self.l2g])
+
+    def set_state(self, u, v=None, phi=None, phiv=None):
+        if np.shape(u)[0] == self.NOD_global and self.NOD_global != self.NOD_local:
+            u, v, phi, phiv = self._loc(u), self._loc(v), self._loc(phi), self._loc(phiv)
+        super().set_state(u, v, phi, phiv)
+
+    def set_potentials(self, phi, phiv):
+        if np.shape(phi)[0] == self.NOD_global and self.NOD_global != self.NOD_local:
+            phi, phiv = self._loc(phi), self._loc(phiv)
+        super().set_potentials(phi, phiv)
+
+    def gather_state(self, step=1, what="u"):
+        """Global (NOD, 3) array of u or v from the owned rows of every rank (tests)."""
+        import torch.distributed as dist
+        loc = self.get_state(step, what)[0 if what == "u" else 1][:self.n_owned]
+        parts = [None] * self.world
+        dist.all_gather_object(parts, loc)
+        return np.concatenate(parts, axis=0)

@@ -109,6 +109,10 @@ class LinAlgebra:
     """
 
     def __init__(self, settings, mesh, device=0):
+        self._init_ctx(settings, mesh, device,
+                       lambda L, cm, cp, dev, h: L.fg_create(cm, cp, dev, h))
+
+    def _init_ctx(self, settings, mesh, device, create):
         L = capi.lib()
         self._L = L
         self.settings = settings
@@ -124,7 +128,7 @@ class LinAlgebra:
         cp = capi.CParams(len(settings.paramTetra), pt, ntri, pf, settings.npi_tet,
                           settings.npi_tri, settings.TOL, settings.MAXITER)
         h = C.c_void_p()
-        check(L.fg_create(C.byref(cm), C.byref(cp), C.c_int(device), C.byref(h)))
+        check(create(L, C.byref(cm), C.byref(cp), C.c_int(device), C.byref(h)))
         self._h = h
         out = (C.c_longlong * 10)()
         check(L.fg_get_sizes(h, out))

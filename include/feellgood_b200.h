@@ -192,6 +192,31 @@ int fg_cg(fg_matrix *m, double *x, const double *rhs, double tol, int maxiter,
 int fg_cg_dir(fg_matrix *m, double *x, const double *rhs, const double *xd, const int *ld, int nld,
               double tol, int maxiter, fg_iter_result *out);
 
+/* ---- multi-GPU: row-block (slab) partition over the GPUs of one box ----
+ * No reference equivalent (the reference is single-process); SURVEY.md §8(e), DESIGN.md §8.  One
+ * process per GPU.  Each rank passes its LOCAL mesh: nodes [0, n_owned) are the rows it owns (a
+ * contiguous range of the reference's sorted node order), nodes [n_owned, NOD) are ghosts (the
+ * other nodes of the tetrahedra touching an owned node), tets/tris in local numbering.  The
+ * ranks exchange the opaque blobs of fg_dist_export out of band (torch.distributed / MPI / files)
+ * and hand all of them to fg_dist_connect, which maps the peers' exchange arenas (CUDA IPC over
+ * NVLink).  After that every per-step call of this header works unchanged and must be made by
+ * all ranks; fg_step_result is identical on every rank.  State arrays are local (owned + ghosts);
+ * the taps that return K / L / solution vectors are not available on a distributed context. */
+#define FG_DIST_BLOB_BYTES 128
+typedef struct fg_dist_desc
+    {
+    int rank, world;        /* world <= 8 */
+    int n_owned;            /* local nodes [0, n_owned) are owned, the rest are ghosts */
+    const int *send_ptr;    /* world+1 : send_nodes grouped by destination rank */
+    const int *send_nodes;  /* local ids of owned nodes, in the order the destination stores its ghosts */
+    const int *send_dst;    /* world : offset (in nodes) of my segment inside the destination's ghost range */
+    const int *recv_from;   /* world : 1 if that rank sends ghosts to me */
+    } fg_dist_desc;
+int fg_dist_create(const fg_mesh *local_mesh, const fg_params *prm, int device,
+                   const fg_dist_desc *dist, fg_ctx **out);
+int fg_dist_export(fg_ctx *ctx, void *blob /* FG_DIST_BLOB_BYTES */);
+int fg_dist_connect(fg_ctx *ctx, const void *blobs /* world x FG_DIST_BLOB_BYTES, rank order */);
+
 /* ---- host-side planning (no GPU needed) ---- */
 /* Runs the once-per-mesh preprocessing of fg_create (orientation, geometry tables, sparsity of
  * solver<2>::build_shape, device row ordering and the SELL-32 layout, incidence lists) on the host

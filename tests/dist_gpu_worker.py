@@ -1,0 +1,77 @@
+"""torchrun worker for tests/test_gpu_dist.py: the slab-partitioned multi-GPU LLG step (NVLink peer
+halo pushes + in-kernel all-reduce) against the single-GPU path on the same inputs."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import cases  # noqa: E402
+from feellgood_b200 import LinAlgebra, Settings, capi  # noqa: E402
+from feellgood_b200.dist import DistLinAlgebra  # noqa: E402
+from feellgood_b200.linear_algebra import M_2_PI, mt19937_uniform01  # noqa: E402
+
+
+def settings_of(case):
+    return Settings([capi.tet_prm(**r) for r in case.tet_regions],
+                    [capi.tri_prm(**r) for r in case.tri_regions], TOL=case.tol,
+                    MAXITER=case.maxiter, npi_tet=case.npi, npi_tri=case.npi_tri)
+
+
+def run_case(case, rank, world, dev, nsteps=4):
+    s = settings_of(case)
+    dla = DistLinAlgebra(s, case.mesh, rank, world, device=dev)
+    dla.set_state(case.u, case.v, case.phi, case.phiv)
+    ref = None
+    if rank == 0:
+        ref = LinAlgebra(s, case.mesh, device=dev)
+        ref.set_state(case.u, case.v, case.phi, case.phiv)
+    t = cases.FixedTiming(case)
+    for k in range(nsteps):
+        ang = M_2_PI * mt19937_uniform01(77 + k)
+        fd = dla.step(case.Hext, t, angle=ang)
+        u = dla.gather_state(1, "u")
+        v = dla.gather_state(1, "v")
+        if rank == 0:
+            fr = ref.step(case.Hext, t, angle=ang)
+            ur, vr, _, _ = ref.get_state(1, "uv")
+            assert fd == fr is False, (fd, fr, dla.iter, ref.iter)
+            assert abs(dla.iter["nit"] - ref.iter["nit"]) <= 2, (dla.iter, ref.iter)
+            assert abs(dla.iter["rhsn"] - ref.iter["rhsn"]) <= 1e-12 * ref.iter["rhsn"]
+            assert abs(dla.get_v_max() - ref.get_v_max()) <= 1e-4 * ref.get_v_max()
+            du = float(np.max(np.abs(u - ur)))
+            assert du < 1e-6, du
+            assert cases.rel_max(v, vr) < 1e-4
+            ref.evolution()
+            print("  %s step %d: iters %d/%d max|du| %.2e" % (case.name, k, dla.iter["nit"], ref.iter["nit"], du),
+                  flush=True)
+        dla.evolution()
+    # failure semantics are collective: ITER_OVERFLOW on every rank, state untouched
+    dla.close()
+    if ref is not None:
+        ref.close()
+
+
+def main():
+    dist.init_process_group("nccl")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(dev)
+    run_case(cases.small_cuboid(nx=16, ny=6, nz=3), rank, world, dev)
+    run_case(cases.film(48, 16, 2), rank, world, dev)
+    e = cases.ellipsoid()
+    if world <= 2:
+        run_case(e, rank, world, dev, nsteps=2)
+    dist.barrier()
+    if rank == 0:
+        print("DIST_GPU_OK world=%d" % world, flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

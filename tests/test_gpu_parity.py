@@ -140,7 +140,12 @@ def test_solve_and_update(prepared):
     assert np.linalg.norm(x_g - x_o) <= 1e-4 * np.linalg.norm(x_o)
     u_o, v_o, _, _ = oc.get_state(1)
     u_g, v_g, phi_g, phiv_g = la.get_state(1)
-    assert np.max(np.abs(u_g - u_o)) < 1e-7
+    # the node update is exact given x (src/node.h:116-122): |du| <= dt*gamma0*|dx| per node, and x
+    # itself agrees to the solver tolerance (two converged BiCGStab runs differ by ~cond*TOL)
+    from feellgood_b200.linear_algebra import GAMMA0
+    dx = np.max(np.hypot(x_g[0::2] - x_o[0::2], x_g[1::2] - x_o[1::2]))
+    assert np.max(np.abs(u_g - u_o)) <= 1.01 * case.dt * GAMMA0 * dx + 1e-14
+    assert np.max(np.abs(u_g - u_o)) < 1e-6
     assert rel_max(v_g, v_o) < 1e-4
     assert abs(la.get_v_max() - oc.v_max()) <= 1e-4 * oc.v_max()
     assert np.array_equal(phi_g, case.phi) and np.array_equal(phiv_g, case.phiv)
