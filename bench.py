@@ -310,7 +310,7 @@ def main():
     if spmv_n > 0:
         b_spmv = workloads.spmv_bytes(n_loc, nnz_loc)
         ach = b_spmv / (spmv_ms * 1e-3 / spmv_n) / 1e9
-        roof = dict(bound="hbm", kernel="k_spmv<OP_NODE2,*>", achieved=ach, peak=peak, unit="GB/s",
+        roof = dict(bound="hbm", kernel="k_spmv_sell<STAGE>", achieved=ach, peak=peak, unit="GB/s",
                     frac=ach / peak, traffic=None, peak_source=peak_src,
                     bytes_per_launch=b_spmv, launches=spmv_n, us_per_launch=1e3 * spmv_ms / spmv_n,
                     share_of_step=spmv_ms / ms,

@@ -42,7 +42,8 @@ def run_case(case, rank, world, dev, nsteps=4):
             ur, vr, _, _ = ref.get_state(1, "uv")
             assert fd == fr is False, (fd, fr, dla.iter, ref.iter)
             assert abs(dla.iter["nit"] - ref.iter["nit"]) <= 2, (dla.iter, ref.iter)
-            assert abs(dla.iter["rhsn"] - ref.iter["rhsn"]) <= 1e-12 * ref.iter["rhsn"]
+            # step 0 starts from identical states; later steps inherit solver-tolerance differences
+            assert abs(dla.iter["rhsn"] - ref.iter["rhsn"]) <= (1e-12 if k == 0 else 1e-5) * ref.iter["rhsn"]
             assert abs(dla.get_v_max() - ref.get_v_max()) <= 1e-4 * ref.get_v_max()
             du = float(np.max(np.abs(u - ur)))
             assert du < 1e-6, du
