@@ -12,8 +12,10 @@
 //     the mailbox IN RANK ORDER — every rank obtains bit-identical scalars, hence takes identical
 //     convergence decisions without any further agreement protocol;
 //   * halo exchange: the owner pushes its boundary entries of a vector into the ghost tail of the
-//     neighbour's copy of that vector (same peer mapping) and raises a halo epoch flag; the
-//     receiver spins on the flags of its (at most two, for slabs) sources.
+//     neighbour's copy of that vector (same peer mapping).  D.p: pushed by the last CTA of the kernel
+//     whose reduction fixes beta (setup SpMV, k_bicg_xr) right after that reduction, followed by a
+//     halo epoch flag on which the consuming SpMV spins; D.s: pushed at the start of k_bicg_s, whose
+//     own all-reduce (|s|^2) is the barrier that publishes it; x: one k_halo launch per solve.
 //
 // Why single-buffered ghost tails and double-buffered mailboxes are race-free: an all-reduce is a
 // barrier (no rank leaves epoch e before every rank has entered it).  Between two successive
@@ -128,6 +130,50 @@ __device__ inline void dist_allreduce(DistDev *d, double *v, int nv, bool op_max
             }
         v[k] = s;
         }
+    }
+
+// Push f(row) for every boundary row of this rank into the neighbours' ghost tails of vector
+// `which`; executed by `nthreads` cooperating threads (thread index tid).  Each thread fences its
+// own stores at system scope, so a later flag / all-reduce by any thread of the grid that is
+// ordered after them (block barrier + device-scope ticket) publishes them to the peers.
+template <class F>
+__device__ __forceinline__ void dist_push(const DistDev *d, int which, int tid, int nthreads, F f)
+    {
+    const int nsend = d->send_ptr[d->world];
+    bool any = false;
+    for (int idx = tid; idx < nsend; idx += nthreads)
+        {
+        int q = 0;
+        while (idx >= d->send_ptr[q + 1]) q++;
+        const double2 val = f(d->send_rows[idx]);
+        *(d->tail[which][q] + d->send_dst[q] + (idx - d->send_ptr[q])) = val;
+        any = true;
+        }
+    if (any) __threadfence_system();
+    }
+
+// After a dist_push by a whole CTA: one thread raises the halo epoch flag on every destination.
+__device__ inline void dist_raise(DistDev *d)
+    {
+    __threadfence_system();
+    const unsigned long long e = ++d->hepoch;
+    for (int q = 0; q < d->world; q++)
+        if (d->send_ptr[q + 1] > d->send_ptr[q]) st_sys(&d->ctrl[q]->hflag[d->rank], e);
+    }
+
+// Consumer side: wait until every source rank has raised the current halo epoch (one thread).
+__device__ inline void dist_wait(DistDev *d)
+    {
+    if (d->error) return;
+    const unsigned long long e = d->hepoch;
+    DistCtrl *me = d->ctrl[d->rank];
+    for (int src = 0; src < d->world; src++)
+        if (d->recv_from[src] && !wait_flag(&me->hflag[src], e))
+            {
+            d->error = 1;
+            return;
+            }
+    __threadfence_system();
     }
 
 }  // namespace fg

@@ -76,7 +76,19 @@ struct SpmvArgs
     const unsigned char *mask;
     KState *st;
     RedBuf red;
+    DistDev *dist;     // multi-GPU: halo protocol of the SpMV input (fg_dist.cuh)
+    const double *D;   // multi-GPU setup stage: preconditioner, to push phat = D r
     };
+
+// The two vector updates whose results cross GPUs are written with explicit roundings so that the
+// owner's value and the copy it pushes to a neighbour are bit-identical whatever the compiler
+// contracts elsewhere.   p = r + beta (p - omega v)  (bicg.h:196-201);   s = r - alpha v  (:207-208)
+__device__ __forceinline__ double bicg_p_value(double p, double v, double r, double omega, double beta)
+    { return __fma_rn(__fma_rn(-omega, v, p), beta, r); }
+__device__ __forceinline__ double bicg_s_value(double r, double v, double alpha)
+    { return __fma_rn(-alpha, v, r); }
+__device__ __forceinline__ double bicg_beta(const KState *st)
+    { return (st->rho1 / st->rho2) * (st->alpha / st->omega); }
 
 // finalisation of a reducing SpMV stage by the last CTA (the scalars of bicg.h / cg.h)
 template <int STAGE> __device__ __forceinline__ void spmv_finalize(KState *st, const double (&tot)[RED_NV])
@@ -220,6 +232,11 @@ __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_sell(const Ope
     {
     if (stage_gated(STAGE))
         if (a.st->done) return;
+    if (STAGE == ST_BICG_V && a.dist != nullptr)
+        {  // the ghost entries of D.p were pushed by the neighbours' previous kernel: wait for them
+        if (threadIdx.x == 0) dist_wait(a.dist);
+        __syncthreads();
+        }
     const int lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * (BLOCK / 32);
     const double2 *x2 = reinterpret_cast<const double2 *>(a.x);
@@ -265,8 +282,25 @@ __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_sell(const Ope
         }
     if (!stage_reduces(STAGE)) return;
     double tot[RED_NV];
-    if (!grid_reduce<RED_NV>(acc, a.red, tot)) return;
-    spmv_finalize<STAGE>(a.st, tot);
+    const int role = grid_reduce<RED_NV>(acc, a.red, tot);
+    if (role == 0) return;
+    if (role == 1) spmv_finalize<STAGE>(a.st, tot);
+    if (STAGE == ST_BICG_SETUP && a.dist != nullptr)
+        {  // first iteration: p = r, phat = D r — push the boundary rows now (last CTA only)
+        __syncthreads();
+        if (!a.st->done)
+            {
+            const double2 *r2 = reinterpret_cast<const double2 *>(a.y);
+            const double2 *D2 = reinterpret_cast<const double2 *>(a.D);
+            dist_push(a.dist, 1, threadIdx.x, BLOCK, [&](int row)
+                {
+                const double2 r = __ldcg(r2 + row), d = D2[row];
+                return make_double2(d.x * r.x, d.y * r.y);
+                });
+            __syncthreads();
+            if (threadIdx.x == 0) dist_raise(a.dist);
+            }
+        }
     }
 
 // ---- plain CSR (algebra::SparseMatrix of the side solvers): G lanes per row ---------------------
@@ -297,7 +331,7 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_csr(const Operator op, const Spm
         }
     if (!stage_reduces(STAGE)) return;
     double tot[RED_NV];
-    if (!grid_reduce<RED_NV>(acc, a.red, tot)) return;
+    if (grid_reduce<RED_NV>(acc, a.red, tot) != 1) return;
     spmv_finalize<STAGE>(a.st, tot);
     }
 
@@ -371,7 +405,7 @@ k_bicg_p(int n, const double *__restrict__ r, double *__restrict__ p, const doub
     if (st->done) return;
     const bool first = st->nit == 0;
     const double omega = st->omega;
-    const double beta = first ? 0.0 : (st->rho1 / st->rho2) * (st->alpha / omega);
+    const double beta = first ? 0.0 : bicg_beta(st);
     const int stride = gridDim.x * BLOCK;
     for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += stride)
         {
@@ -379,7 +413,7 @@ k_bicg_p(int n, const double *__restrict__ r, double *__restrict__ p, const doub
         if (first)
             pi = r[i];  // p was set to r by the setup
         else
-            pi = (p[i] - omega * v[i]) * beta + r[i];
+            pi = bicg_p_value(p[i], v[i], r[i], omega, beta);
         p[i] = pi;
         phat[i] = D[i] * pi;
         }
@@ -395,15 +429,26 @@ k_bicg_s(int n, const double *__restrict__ r, const double *__restrict__ v,
     const double alpha = st->alpha;
     double acc[1] = {0.0};
     const int stride = gridDim.x * BLOCK;
+    if (red.dist != nullptr)
+        {  // multi-GPU: D.s of the boundary rows goes to the neighbours first; the all-reduce of
+           // |s|^2 below is the barrier that publishes it (fg_dist.cuh)
+        const double2 *r2 = reinterpret_cast<const double2 *>(r), *v2 = reinterpret_cast<const double2 *>(v),
+                      *D2 = reinterpret_cast<const double2 *>(D);
+        dist_push(red.dist, 2, blockIdx.x * BLOCK + threadIdx.x, stride, [&](int row)
+            {
+            const double2 rr = r2[row], vv = v2[row], d = D2[row];
+            return make_double2(d.x * bicg_s_value(rr.x, vv.x, alpha), d.y * bicg_s_value(rr.y, vv.y, alpha));
+            });
+        }
     for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += stride)
         {
-        const double si = r[i] - alpha * v[i];
+        const double si = bicg_s_value(r[i], v[i], alpha);
         s[i] = si;
         shat[i] = D[i] * si;
         acc[0] += si * si;
         }
     double tot[1];
-    if (!grid_reduce<1>(acc, red, tot)) return;
+    if (grid_reduce<1>(acc, red, tot) != 1) return;
     if (it_finished(st, sqrt(fabs(tot[0]))))
         {
         st->final_half = 1;  // x += alpha phat is applied by k_bicg_xr
@@ -419,6 +464,7 @@ __global__ void __launch_bounds__(BLOCK)
 k_bicg_xr(int n, double *__restrict__ x, const double *__restrict__ phat,
           const double *__restrict__ shat, const double *__restrict__ s,
           const double *__restrict__ t, const double *__restrict__ rt, double *__restrict__ r,
+          const double *__restrict__ p, const double *__restrict__ v, const double *__restrict__ D,
           KState *st, const RedBuf red)
     {
     const int fh = st->final_half;
@@ -442,16 +488,38 @@ k_bicg_xr(int n, double *__restrict__ x, const double *__restrict__ phat,
             }
         }
     double tot[2];
-    if (!grid_reduce<2>(acc, red, tot)) return;
-    if (fh)
+    const int role = grid_reduce<2>(acc, red, tot);
+    if (role == 0) return;
+    if (role == 1)
         {
-        st->final_half = 0;
-        return;
+        if (fh)
+            st->final_half = 0;
+        else
+            {
+            st->rho2 = st->rho1;
+            st->nit++;
+            if (st->nit >= st->maxiter) st->status = FG_ITER_OVERFLOW;  // iter.h:119-124
+            bicg_top_of_loop(st, tot[0], tot[1]);
+            }
         }
-    st->rho2 = st->rho1;
-    st->nit++;
-    if (st->nit >= st->maxiter) st->status = FG_ITER_OVERFLOW;  // iter.h:119-124
-    bicg_top_of_loop(st, tot[0], tot[1]);
+    if (red.dist != nullptr)
+        {  // multi-GPU: beta is known now — push D.p of the boundary rows for the next SpMV (last CTA)
+        __syncthreads();
+        if (!fh && !st->done)
+            {
+            const double omega = st->omega, beta = bicg_beta(st);
+            const double2 *p2 = reinterpret_cast<const double2 *>(p), *v2 = reinterpret_cast<const double2 *>(v),
+                          *r2 = reinterpret_cast<const double2 *>(r), *D2 = reinterpret_cast<const double2 *>(D);
+            dist_push(red.dist, 1, threadIdx.x, BLOCK, [&](int row)
+                {
+                const double2 pp = p2[row], vv = v2[row], rr = __ldcg(r2 + row), d = D2[row];
+                return make_double2(d.x * bicg_p_value(pp.x, vv.x, rr.x, omega, beta),
+                                    d.y * bicg_p_value(pp.y, vv.y, rr.y, omega, beta));
+                });
+            __syncthreads();
+            if (threadIdx.x == 0) dist_raise(red.dist);
+            }
+        }
     }
 
 // ------------------------------------------------------------------------------------------
@@ -487,7 +555,7 @@ k_cg_xr(int n, double *__restrict__ x, const double *__restrict__ p, const doubl
         acc[1] += (D[i] * ri) * ri;
         }
     double tot[2];
-    if (!grid_reduce<2>(acc, red, tot)) return;
+    if (grid_reduce<2>(acc, red, tot) != 1) return;
     st->rho2 = st->rho1;  // rho_1 = rho
     st->rho1 = tot[1];
     st->nit++;
@@ -702,7 +770,17 @@ int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, pos
                  void *user)
     {
     const int n = w.n;
-    const int gv = grid_for(n, BLOCK * 4);
+    // one resident wave per vector kernel (their register counts differ)
+    static int wave_p = 0, wave_s = 0, wave_xr = 0;
+    if (!wave_p)
+        {
+        wave_p = resident_grid(k_bicg_p);
+        wave_s = resident_grid(k_bicg_s);
+        wave_xr = resident_grid(k_bicg_xr);
+        }
+    const int gneed = grid_for(n, BLOCK * 2);
+    const int gp = gneed < wave_p ? gneed : wave_p, gs = gneed < wave_s ? gneed : wave_s,
+              gxr = gneed < wave_xr ? gneed : wave_xr;
     FG_LAUNCH(w, k_init_state, 1, w.st, tol, maxiter);
     // r = b - A x0 (masked); rt = p = r; rhsn, first loop test
         {
@@ -715,6 +793,8 @@ int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, pos
         a.mask = w.mask;
         a.st = w.st;
         a.red = w.red;
+        a.dist = w.dist;
+        a.D = w.D;
         FG_TRY(launch_spmv<ST_BICG_SETUP>(op, w, a));
         }
     int enq = 0;
@@ -726,9 +806,9 @@ int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, pos
         if (batch < 1) batch = 1;
         for (int k = 0; k < batch; k++)
             {
-            FG_LAUNCH(w, k_bicg_p, gv, n, w.r, w.p, w.v, w.D, w.phat, w.st);
-            FG_TRY(halo_exchange(w, 1, 1));
+            FG_LAUNCH(w, k_bicg_p, gp, n, w.r, w.p, w.v, w.D, w.phat, w.st);
             SpmvArgs a = {};
+            a.dist = w.dist;
             a.x = w.phat;
             a.y = w.v;
             a.a0 = w.rt;
@@ -736,13 +816,12 @@ int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, pos
             a.st = w.st;
             a.red = w.red;
             FG_TRY(launch_spmv<ST_BICG_V>(op, w, a));
-            FG_LAUNCH(w, k_bicg_s, gv, n, w.r, w.v, w.D, w.s, w.shat, w.st, w.red);
-            FG_TRY(halo_exchange(w, 2, 1));
+            FG_LAUNCH(w, k_bicg_s, gs, n, w.r, w.v, w.D, w.s, w.shat, w.st, w.red);
             a.x = w.shat;
             a.y = w.t;
             a.a0 = w.s;
             FG_TRY(launch_spmv<ST_BICG_T>(op, w, a));
-            FG_LAUNCH(w, k_bicg_xr, gv, n, w.x, w.phat, w.shat, w.s, w.t, w.rt, w.r, w.st, w.red);
+            FG_LAUNCH(w, k_bicg_xr, gxr, n, w.x, w.phat, w.shat, w.s, w.t, w.rt, w.r, w.p, w.v, w.D, w.st, w.red);
             }
         enq += batch;
         if (post) FG_TRY(post(user));

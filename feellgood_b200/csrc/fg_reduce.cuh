@@ -13,10 +13,11 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
     }
 
-// Sum NV per-thread values over the whole grid.  Returns true on thread 0 of the last CTA to
-// finish, with the totals in out[].  Deterministic: CTA partials are summed in index order.
+// Sum NV per-thread values over the whole grid.  Returns 1 on thread 0 of the last CTA to finish,
+// with the totals in out[] (all-reduced over the ranks on a distributed context), 2 on the other
+// threads of that CTA, 0 elsewhere.  Deterministic: CTA partials are summed in index order.
 template <int NV>
-__device__ bool grid_reduce(double (&v)[NV], const RedBuf red, double (&out)[NV])
+__device__ int grid_reduce(double (&v)[NV], const RedBuf red, double (&out)[NV])
     {
     __shared__ double sm[NV][BLOCK / 32];
     __shared__ int is_last;
@@ -43,7 +44,7 @@ __device__ bool grid_reduce(double (&v)[NV], const RedBuf red, double (&out)[NV]
         is_last = (t == gridDim.x - 1);
         }
     __syncthreads();
-    if (!is_last) return false;
+    if (!is_last) return 0;
     __threadfence();
 #pragma unroll
     for (int k = 0; k < NV; k++)
@@ -56,7 +57,7 @@ __device__ bool grid_reduce(double (&v)[NV], const RedBuf red, double (&out)[NV]
         if (lane == 0) sm[k][wid] = s;
         }
     __syncthreads();
-    if (threadIdx.x != 0) return false;
+    if (threadIdx.x != 0) return 2;
 #pragma unroll
     for (int k = 0; k < NV; k++)
         {
@@ -66,7 +67,7 @@ __device__ bool grid_reduce(double (&v)[NV], const RedBuf red, double (&out)[NV]
         out[k] = s;
         }
     if (red.dist != nullptr) dist_allreduce(red.dist, out, NV, false);
-    return true;
+    return 1;
     }
 
 
