@@ -170,6 +170,15 @@ def cpu_leg(workload_name, steps, warmup, budget_s=25.0):
 
 # ---------------------------------------------------------------------------------------------
 def main():
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner)
+    # are sent to stderr for the whole run, and the line is written to the saved descriptor
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(saved_stdout, (json.dumps(line) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -197,7 +206,7 @@ def main():
                     cpu_baseline=cb,
                     e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0,
                              d2h_bytes_per_step=0))
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     import torch
@@ -347,7 +356,7 @@ def main():
                                 parallelism="row-block slabs x%d" % world if world > 1 else "1 GPU"),
                     roofline=roof, step_roofline=step_roof, cpu_baseline=cb, e2e=e2e,
                     gpu_launches=int(launches), clocks=clk)
-        print(json.dumps(line), flush=True)
+        emit(line)
     la.close()
     if dist is not None:
         dist.destroy_process_group()
