@@ -188,6 +188,8 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--kernel-times", action="store_true",
+                    help="bracket every kernel with CUDA events and print the per-class table (stderr)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -269,7 +271,7 @@ def main():
     for k in range(args.warmup):
         one_step(k)
     iters.clear()
-    la.set_profiling(2)                       # CUDA-event pair around every SpMV launch
+    la.set_profiling(3 if args.kernel_times else 2)   # CUDA-event pair around every SpMV launch
     l0 = la.kernel_launches()
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -277,6 +279,15 @@ def main():
     ms, nfail = timed(one_step, args.steps, args.warmup)
     clk = clocks.stop() if rank == 0 else {}
     launches = la.kernel_launches() - l0
+    if args.kernel_times:
+        kt = la.kernel_times()
+        tot = sum(v[0] for v in kt.values())
+        log("rank %d kernel classes over %d steps (%.3f ms/step timed, %.3f ms/step in kernels+gaps):"
+            % (rank, args.steps, ms / args.steps, tot / args.steps))
+        for k, (t, cnt) in kt.items():
+            if cnt:
+                log("  rank %d %-10s %5d launches  %8.3f ms/step  %8.1f us/launch"
+                    % (rank, k, cnt, t / args.steps, 1e3 * t / cnt))
     spmv_ms, spmv_n = la.spmv_times()
     la.set_profiling(0)
     mean_it = float(np.mean(iters)) if iters else 0.0

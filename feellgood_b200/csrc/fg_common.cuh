@@ -64,6 +64,7 @@ static_assert(sizeof(Basis) == 48, "Basis must be 48 bytes");
 struct TetRegion
     {
     double alpha, Abis, Kbis, K3bis;
+    double A, K, K3, Ms;  // raw constants, read by the energy kernels (src/tetra.cpp:309-391)
     double uk[3], ex[3], ey[3], ez[3];
     int has_K, has_K3;
     };
@@ -118,19 +119,40 @@ struct Operator
     int nslice;         // OP_SELL2
     };
 
-// optional CUDA-event pairs around every SpMV launch (fg_set_profiling(ctx, 2))
+// optional CUDA-event pairs around kernel launches: fg_set_profiling(ctx, 2) brackets every SpMV
+// launch, fg_set_profiling(ctx, 3) every kernel of the step (classes below)
+enum
+    {
+    KC_BASIS = 0, KC_TET, KC_TRI, KC_ASSEMBLE, KC_SPMV_SETUP, KC_BICG_P, KC_SPMV_V, KC_BICG_S,
+    KC_SPMV_T, KC_BICG_XR, KC_HALO, KC_UPDATE, KC_OTHER, KC_COUNT
+    };
 struct SpmvProf
     {
     cudaEvent_t *ev;  // 2*cap events
     int n, cap;       // pairs recorded / capacity
+    int *cls;         // kernel class of each pair
+    int mode;         // 2: SpMV launches only | 3: every kernel
     };
+inline bool prof_is_spmv(int cls) { return cls == KC_SPMV_SETUP || cls == KC_SPMV_V || cls == KC_SPMV_T; }
+inline bool prof_begin(SpmvProf *p, cudaStream_t s, int cls)
+    {
+    if (!p || p->n >= p->cap || (p->mode == 2 && !prof_is_spmv(cls))) return false;
+    p->cls[p->n] = cls;
+    cudaEventRecord(p->ev[2 * p->n], s);
+    return true;
+    }
+inline void prof_end(SpmvProf *p, cudaStream_t s)
+    {
+    cudaEventRecord(p->ev[2 * p->n + 1], s);
+    p->n++;
+    }
 
 // Krylov workspace (all device pointers, length n [+ ghosts for vectors that feed an SpMV])
 struct KrylovWork
     {
     int n;       // owned rows
     int nx;      // length of vectors that are SpMV inputs (n + ghost entries)
-    double *x, *b, *r, *rt, *p, *v, *s, *t, *phat, *shat, *D;
+    double *x, *b, *r, *rt, *p, *p2, *v, *s, *t, *phat, *shat, *D;  // p2: ping-pong partner of p
     const unsigned char *mask; // n : 1 = Dirichlet dof (lvd), may be NULL
     KState *st;                // device
     KState *h_st;              // pinned host mirror
@@ -144,6 +166,7 @@ struct KrylovWork
     DistDev *dist;
     void *arena;
     int halo_grid;
+    int nsend;                 // boundary rows this rank pushes to its neighbours
     };
 
 

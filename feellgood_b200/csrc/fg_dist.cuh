@@ -6,16 +6,18 @@
 // is the B200 execution model of SURVEY.md §8(e).
 //
 // Communication never leaves the kernels that produce or consume the data:
-//   * all-reduce of the Krylov scalars: the last CTA of a reducing kernel stores its partial sums
-//     into EVERY rank's mailbox through CUDA-IPC-mapped peer memory (NVLink P2P stores), fences at
-//     system scope, raises a per-source epoch flag, then waits for the flags of all ranks and sums
-//     the mailbox IN RANK ORDER — every rank obtains bit-identical scalars, hence takes identical
-//     convergence decisions without any further agreement protocol;
+//   * all-reduce of the Krylov scalars: warp 0 of the last CTA of a reducing kernel stores its
+//     partial sums into EVERY rank's mailbox through CUDA-IPC-mapped peer memory (NVLink P2P
+//     stores) as self-validating 8-byte words {32 data bits, 32-bit epoch tag} — an aligned 8-byte
+//     store is one NVLink transaction, so no fence / flag round trip is needed (the "LL" idea) —
+//     then spins on its own mailbox until every word carries the current tag and sums IN RANK
+//     ORDER: every rank obtains bit-identical scalars, hence takes identical convergence decisions
+//     without any further agreement protocol.  One-way NVLink latency per all-reduce;
 //   * halo exchange: the owner pushes its boundary entries of a vector into the ghost tail of the
-//     neighbour's copy of that vector (same peer mapping).  D.p: pushed by the last CTA of the kernel
-//     whose reduction fixes beta (setup SpMV, k_bicg_xr) right after that reduction, followed by a
-//     halo epoch flag on which the consuming SpMV spins; D.s: pushed at the start of k_bicg_s, whose
-//     own all-reduce (|s|^2) is the barrier that publishes it; x: one k_halo launch per solve.
+//     neighbour's copy of that vector (same peer mapping).  D.p: pushed grid-wide by the first CTAs
+//     of k_bicg_p (beta is known when it starts); the last pusher CTA raises a halo epoch flag on
+//     which the consuming SpMV spins; D.s: pushed at the start of k_bicg_s, whose own all-reduce
+//     (|s|^2) is the barrier that publishes it; x: one k_halo launch per solve.
 //
 // Why single-buffered ghost tails and double-buffered mailboxes are race-free: an all-reduce is a
 // barrier (no rank leaves epoch e before every rank has entered it).  Between two successive
@@ -40,8 +42,8 @@ constexpr unsigned long long DIST_TIMEOUT_NS = 10000000000ull;  // 10 s before a
 // Control block at the start of every rank's exchange arena (one cudaMalloc, IPC-exported).
 struct DistCtrl
     {
-    double mailbox[2][DIST_MAX_RANKS][DIST_NV];          // [epoch parity][source rank][value]
-    unsigned long long mflag[2][DIST_MAX_RANKS];         // epoch of the mailbox entry
+    // [epoch parity][source rank][32-bit half of value k]: low 32 bits data, high 32 bits epoch tag
+    unsigned long long ll[2][DIST_MAX_RANKS][2 * DIST_NV];
     unsigned long long hflag[DIST_MAX_RANKS];            // halo epoch written by each source rank
     };
 
@@ -95,41 +97,73 @@ __device__ __forceinline__ double ld_sys_f64(const double *p)
     return v;
     }
 
-// All-reduce of nv <= DIST_NV doubles over the ranks; called by ONE thread per rank (thread 0 of the
-// last CTA of a reducing kernel).  op_max = false: sum in rank order; true: maximum.
-__device__ inline void dist_allreduce(DistDev *d, double *v, int nv, bool op_max)
+// All-reduce of nv <= DIST_NV doubles over the ranks, executed by ONE FULL WARP per rank (warp 0 of
+// the last CTA of a reducing kernel).  v points to shared memory holding this rank's values on
+// entry and the rank-ordered result on exit.  op_max = false: sum in rank order; true: maximum.
+__device__ inline void dist_allreduce_warp(DistDev *d, double *v, int nv, bool op_max)
     {
-    const unsigned long long e = ++d->epoch;
-    const int par = (int)(e & 1ull);
+    __shared__ unsigned int rx[DIST_MAX_RANKS][2 * DIST_NV];
+    const int lane = threadIdx.x & 31;
+    unsigned long long e = 0;
+    if (lane == 0) e = ++d->epoch;
+    e = __shfl_sync(0xffffffffu, e, 0);
     if (d->error)
         {  // a previous spin timed out: do not wait again, poison the scalars
-        for (int k = 0; k < nv; k++) v[k] = nan("");
+        if (lane == 0)
+            for (int k = 0; k < nv; k++) v[k] = nan("");
+        __syncwarp();
         return;
         }
-    for (int q = 0; q < d->world; q++)
-        for (int k = 0; k < nv; k++) st_sys_f64(&d->ctrl[q]->mailbox[par][d->rank][k], v[k]);
-    __threadfence_system();
-    for (int q = 0; q < d->world; q++) st_sys(&d->ctrl[q]->mflag[par][d->rank], e);
-    DistCtrl *me = d->ctrl[d->rank];
+    const int par = (int)(e & 1ull), nw = 2 * nv, world = d->world, rank = d->rank;
+    const unsigned long long tag = (e & 0xffffffffull) << 32;
+    const unsigned int *v32 = reinterpret_cast<const unsigned int *>(v);
+    for (int idx = lane; idx < world * nw; idx += 32)
+        {
+        const int q = idx / nw, w = idx - q * nw;
+        st_sys(&d->ctrl[q]->ll[par][rank][w], tag | (unsigned long long)v32[w]);
+        }
+    DistCtrl *me = d->ctrl[rank];
     bool ok = true;
-    for (int src = 0; src < d->world && ok; src++) ok = wait_flag(&me->mflag[par][src], e);
-    __threadfence_system();
-    if (!ok)
+    for (int idx = lane; idx < world * nw; idx += 32)
         {
-        d->error = 1;
-        for (int k = 0; k < nv; k++) v[k] = nan("");  // NaN residual => CANNOT_CONVERGE (iter.h:147)
-        return;
-        }
-    for (int k = 0; k < nv; k++)
-        {
-        double s = ld_sys_f64(&me->mailbox[par][0][k]);
-        for (int src = 1; src < d->world; src++)
+        const int src = idx / nw, w = idx - src * nw;
+        const unsigned long long *p = &me->ll[par][src][w];
+        unsigned long long x = ld_sys(p);
+        if ((x & 0xffffffff00000000ull) != tag)
             {
-            const double t = ld_sys_f64(&me->mailbox[par][src][k]);
-            s = op_max ? fmax(s, t) : s + t;
+            const unsigned long long t0 = now_ns();
+            unsigned int k = 0;
+            while (((x = ld_sys(p)) & 0xffffffff00000000ull) != tag)
+                if ((++k & 1023u) == 0 && now_ns() - t0 > DIST_TIMEOUT_NS)
+                    {
+                    ok = false;
+                    break;
+                    }
             }
-        v[k] = s;
+        rx[src][w] = (unsigned int)x;
         }
+    ok = __all_sync(0xffffffffu, ok);
+    __syncwarp();
+    if (lane == 0)
+        {
+        if (!ok)
+            {
+            d->error = 1;
+            for (int k = 0; k < nv; k++) v[k] = nan("");  // NaN residual => CANNOT_CONVERGE (iter.h:147)
+            }
+        else
+            for (int k = 0; k < nv; k++)
+                {
+                double s = __hiloint2double((int)rx[0][2 * k + 1], (int)rx[0][2 * k]);
+                for (int src = 1; src < world; src++)
+                    {
+                    const double t = __hiloint2double((int)rx[src][2 * k + 1], (int)rx[src][2 * k]);
+                    s = op_max ? fmax(s, t) : s + t;
+                    }
+                v[k] = s;
+                }
+        }
+    __syncwarp();
     }
 
 // Push f(row) for every boundary row of this rank into the neighbours' ghost tails of vector

@@ -58,7 +58,7 @@ __device__ __forceinline__ void bicg_top_of_loop(KState *st, double rr, double r
 enum
     {
     ST_PLAIN = 0,    // y = A x
-    ST_BICG_SETUP,   // r = b - A x (masked); rt = p = r; ||b||^2, ||r||^2      (bicg.h:172-183)
+    ST_BICG_SETUP,   // r = b - A x (masked); rt = r (p = r implicit); ||b||^2, ||r||^2 (bicg.h:172-183)
     ST_BICG_V,       // v = A phat (masked); (v, rt) -> alpha                    (bicg.h:203-206)
     ST_BICG_T,       // t = A shat (masked); (t,s), (t,t) -> omega               (bicg.h:219-222)
     ST_CG_SETUP,     // r = b - A x (masked); p = D r; ||b||^2, ||r||^2, (Dr,r)  (cg.h:24-34)
@@ -72,12 +72,11 @@ struct SpmvArgs
     double *y;
     const double *a0;  // b | rt | s | p
     const double *a1;  // D (CG_SETUP)
-    double *o0, *o1;   // rt, p (SETUP)
+    double *o0, *o1;   // rt (BICG_SETUP) ; p (CG_SETUP)
     const unsigned char *mask;
     KState *st;
     RedBuf red;
     DistDev *dist;     // multi-GPU: halo protocol of the SpMV input (fg_dist.cuh)
-    const double *D;   // multi-GPU setup stage: preconditioner, to push phat = D r
     };
 
 // The two vector updates whose results cross GPUs are written with explicit roundings so that the
@@ -136,7 +135,6 @@ __device__ __forceinline__ void spmv_row(const SpmvArgs &a, int i, double y, dou
         const double r = m ? 0.0 : b - y;
         a.y[i] = r;
         a.o0[i] = r;
-        a.o1[i] = r;
         acc[0] += b * b;
         acc[1] += r * r;
         }
@@ -194,10 +192,7 @@ __device__ __forceinline__ void spmv_row2(const SpmvArgs &a, int row, double y0,
         acc[0] += b.x * b.x + b.y * b.y;
         acc[1] += r.x * r.x + r.y * r.y;
         if (STAGE == ST_BICG_SETUP)
-            {
-            reinterpret_cast<double2 *>(a.o0)[row] = r;
-            reinterpret_cast<double2 *>(a.o1)[row] = r;
-            }
+            reinterpret_cast<double2 *>(a.o0)[row] = r;  // rt = r; p = r is implicit (k_bicg_p, nit == 0)
         else
             {
             const double2 d = reinterpret_cast<const double2 *>(a.a1)[row];
@@ -285,22 +280,6 @@ __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_sell(const Ope
     const int role = grid_reduce<RED_NV>(acc, a.red, tot);
     if (role == 0) return;
     if (role == 1) spmv_finalize<STAGE>(a.st, tot);
-    if (STAGE == ST_BICG_SETUP && a.dist != nullptr)
-        {  // first iteration: p = r, phat = D r — push the boundary rows now (last CTA only)
-        __syncthreads();
-        if (!a.st->done)
-            {
-            const double2 *r2 = reinterpret_cast<const double2 *>(a.y);
-            const double2 *D2 = reinterpret_cast<const double2 *>(a.D);
-            dist_push(a.dist, 1, threadIdx.x, BLOCK, [&](int row)
-                {
-                const double2 r = __ldcg(r2 + row), d = D2[row];
-                return make_double2(d.x * r.x, d.y * r.y);
-                });
-            __syncthreads();
-            if (threadIdx.x == 0) dist_raise(a.dist);
-            }
-        }
     }
 
 // ---- plain CSR (algebra::SparseMatrix of the side solvers): G lanes per row ---------------------
@@ -359,8 +338,8 @@ template <class K> static int resident_grid(K kernel)
 template <int STAGE>
 static int launch_spmv(const Operator &op, const KrylovWork &w, const SpmvArgs &a)
     {
-    const bool prof = w.prof != nullptr && w.prof->n < w.prof->cap;
-    if (prof) cudaEventRecord(w.prof->ev[2 * w.prof->n], w.stream);
+    const int cls = STAGE == ST_BICG_V ? KC_SPMV_V : (STAGE == ST_BICG_T ? KC_SPMV_T : (STAGE == ST_BICG_SETUP ? KC_SPMV_SETUP : KC_OTHER));
+    const bool prof = prof_begin(w.prof, w.stream, cls);
     if (op.kind == OP_SELL2)
         {
         static int wave = 0;
@@ -377,7 +356,7 @@ static int launch_spmv(const Operator &op, const KrylovWork &w, const SpmvArgs &
         if (grid > wave) grid = wave;
         k_spmv_csr<STAGE><<<grid, BLOCK, 0, w.stream>>>(op, a);
         }
-    if (prof) cudaEventRecord(w.prof->ev[2 * w.prof->n++ + 1], w.stream);
+    if (prof) prof_end(w.prof, w.stream);
     if (w.launches) ++*w.launches;
     FG_CUDA(cudaGetLastError());
     return FG_OK;
@@ -398,15 +377,39 @@ int spmv(const Operator &op, const KrylovWork &w, const double *x, double *y, bo
 // fused vector kernels of BiCGStab (reference src/algebra/bicg.h:185-232)
 // ------------------------------------------------------------------------------------------
 // p = r + beta (p - omega v) ; phat = D p                       (bicg.h:196-202)
+// Multi-GPU: beta is known when this kernel starts, so its first CTAs push D.p of the boundary rows
+// into the neighbours' ghost tails before doing their share of the update; the last of those CTAs
+// raises the halo flag the consuming SpMV waits on (fg_dist.cuh).  p is ping-ponged (read p, write
+// pn) so that the pushers can read the old direction of rows another CTA is updating.
 __global__ void __launch_bounds__(BLOCK)
-k_bicg_p(int n, const double *__restrict__ r, double *__restrict__ p, const double *__restrict__ v,
-         const double *__restrict__ D, double *__restrict__ phat, const KState *st)
+k_bicg_p(int n, const double *__restrict__ r, const double *__restrict__ p, double *__restrict__ pn,
+         const double *__restrict__ v, const double *__restrict__ D, double *__restrict__ phat,
+         const KState *st, DistDev *dist, unsigned int *ticket, int npush)
     {
     if (st->done) return;
     const bool first = st->nit == 0;
     const double omega = st->omega;
     const double beta = first ? 0.0 : bicg_beta(st);
     const int stride = gridDim.x * BLOCK;
+    if (dist != nullptr && (int)blockIdx.x < npush)
+        {
+        const double2 *p2 = reinterpret_cast<const double2 *>(p), *v2 = reinterpret_cast<const double2 *>(v),
+                      *r2 = reinterpret_cast<const double2 *>(r), *D2 = reinterpret_cast<const double2 *>(D);
+        dist_push(dist, 1, blockIdx.x * BLOCK + threadIdx.x, npush * BLOCK, [&](int row)
+            {
+            const double2 rr = r2[row], d = D2[row];
+            if (first) return make_double2(d.x * rr.x, d.y * rr.y);
+            const double2 pp = p2[row], vv = v2[row];
+            return make_double2(d.x * bicg_p_value(pp.x, vv.x, rr.x, omega, beta),
+                                d.y * bicg_p_value(pp.y, vv.y, rr.y, omega, beta));
+            });
+        __syncthreads();
+        if (threadIdx.x == 0)
+            {
+            const unsigned int t = atomicInc(ticket, (unsigned int)npush - 1);
+            if (t == (unsigned int)npush - 1) dist_raise(dist);
+            }
+        }
     for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += stride)
         {
         double pi;
@@ -414,7 +417,7 @@ k_bicg_p(int n, const double *__restrict__ r, double *__restrict__ p, const doub
             pi = r[i];  // p was set to r by the setup
         else
             pi = bicg_p_value(p[i], v[i], r[i], omega, beta);
-        p[i] = pi;
+        pn[i] = pi;
         phat[i] = D[i] * pi;
         }
     }
@@ -464,7 +467,6 @@ __global__ void __launch_bounds__(BLOCK)
 k_bicg_xr(int n, double *__restrict__ x, const double *__restrict__ phat,
           const double *__restrict__ shat, const double *__restrict__ s,
           const double *__restrict__ t, const double *__restrict__ rt, double *__restrict__ r,
-          const double *__restrict__ p, const double *__restrict__ v, const double *__restrict__ D,
           KState *st, const RedBuf red)
     {
     const int fh = st->final_half;
@@ -500,24 +502,6 @@ k_bicg_xr(int n, double *__restrict__ x, const double *__restrict__ phat,
             st->nit++;
             if (st->nit >= st->maxiter) st->status = FG_ITER_OVERFLOW;  // iter.h:119-124
             bicg_top_of_loop(st, tot[0], tot[1]);
-            }
-        }
-    if (red.dist != nullptr)
-        {  // multi-GPU: beta is known now — push D.p of the boundary rows for the next SpMV (last CTA)
-        __syncthreads();
-        if (!fh && !st->done)
-            {
-            const double omega = st->omega, beta = bicg_beta(st);
-            const double2 *p2 = reinterpret_cast<const double2 *>(p), *v2 = reinterpret_cast<const double2 *>(v),
-                          *r2 = reinterpret_cast<const double2 *>(r), *D2 = reinterpret_cast<const double2 *>(D);
-            dist_push(red.dist, 1, threadIdx.x, BLOCK, [&](int row)
-                {
-                const double2 pp = p2[row], vv = v2[row], rr = __ldcg(r2 + row), d = D2[row];
-                return make_double2(d.x * bicg_p_value(pp.x, vv.x, rr.x, omega, beta),
-                                    d.y * bicg_p_value(pp.y, vv.y, rr.y, omega, beta));
-                });
-            __syncthreads();
-            if (threadIdx.x == 0) dist_raise(red.dist);
             }
         }
     }
@@ -623,13 +607,16 @@ k_diag_precond(const Operator op, const unsigned char *__restrict__ mask, double
         }
     }
 
-#define FG_LAUNCH(w, kernel, grid, ...)                            \
+#define FG_LAUNCH_C(w, cls, kernel, grid, ...)                     \
     do                                                             \
         {                                                          \
+        const bool prof_ = prof_begin((w).prof, (w).stream, cls);  \
         kernel<<<(grid), BLOCK, 0, (w).stream>>>(__VA_ARGS__);     \
+        if (prof_) prof_end((w).prof, (w).stream);                 \
         if ((w).launches) ++*(w).launches;                         \
         FG_CUDA(cudaGetLastError());                               \
         } while (0)
+#define FG_LAUNCH(w, kernel, grid, ...) FG_LAUNCH_C(w, KC_OTHER, kernel, grid, __VA_ARGS__)
 
 int vec_mask(const KrylovWork &w, double *x)
     {
@@ -659,7 +646,7 @@ int krylov_alloc(KrylovWork &w, int n, int n_ghost, cudaStream_t stream, long lo
     w.stream = stream;
     w.launches = launch_counter;
     const size_t nb = sizeof(double) * (size_t)(w.nx > 0 ? w.nx : 1);
-    double **vecs[] = {&w.x, &w.b, &w.r, &w.rt, &w.p, &w.v, &w.s, &w.t, &w.phat, &w.shat, &w.D};
+    double **vecs[] = {&w.x, &w.b, &w.r, &w.rt, &w.p, &w.p2, &w.v, &w.s, &w.t, &w.phat, &w.shat, &w.D};
     if (ext)
         {
         w.x = ext[0];
@@ -688,7 +675,7 @@ int krylov_alloc(KrylovWork &w, int n, int n_ghost, cudaStream_t stream, long lo
 void krylov_free(KrylovWork &w)
     {
     if (w.arena) w.x = w.phat = w.shat = nullptr;  // owned by the exchange arena
-    double *vecs[] = {w.x, w.b, w.r, w.rt, w.p, w.v, w.s, w.t, w.phat, w.shat, w.D};
+    double *vecs[] = {w.x, w.b, w.r, w.rt, w.p, w.p2, w.v, w.s, w.t, w.phat, w.shat, w.D};
     for (double *v : vecs)
         if (v) cudaFree(v);
     if (w.st) cudaFree(w.st);
@@ -749,7 +736,9 @@ int halo_exchange(const KrylovWork &w, int which, int gate)
     {
     if (!w.dist) return FG_OK;
     const double *vec = which == 0 ? w.x : (which == 1 ? w.phat : w.shat);
+    const bool prof = prof_begin(w.prof, w.stream, KC_HALO);
     k_halo<<<w.halo_grid, BLOCK, 0, w.stream>>>(w.dist, vec, which, gate, w.st, w.red.ticket);
+    if (prof) prof_end(w.prof, w.stream);
     if (w.launches) ++*w.launches;
     FG_CUDA(cudaGetLastError());
     return FG_OK;
@@ -781,6 +770,11 @@ int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, pos
     const int gneed = grid_for(n, BLOCK * 2);
     const int gp = gneed < wave_p ? gneed : wave_p, gs = gneed < wave_s ? gneed : wave_s,
               gxr = gneed < wave_xr ? gneed : wave_xr;
+    // multi-GPU: the first npush CTAs of k_bicg_p push the boundary rows of D.p (>= 1 so that the
+    // halo epoch advances on every rank, even one without neighbours)
+    int npush = w.dist ? (w.nsend + BLOCK - 1) / BLOCK : 0;
+    if (w.dist && npush < 1) npush = 1;
+    if (npush > gp) npush = gp;
     FG_LAUNCH(w, k_init_state, 1, w.st, tol, maxiter);
     // r = b - A x0 (masked); rt = p = r; rhsn, first loop test
         {
@@ -789,12 +783,10 @@ int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, pos
         a.y = w.r;
         a.a0 = w.b;
         a.o0 = w.rt;
-        a.o1 = w.p;
         a.mask = w.mask;
         a.st = w.st;
         a.red = w.red;
         a.dist = w.dist;
-        a.D = w.D;
         FG_TRY(launch_spmv<ST_BICG_SETUP>(op, w, a));
         }
     int enq = 0;
@@ -806,7 +798,10 @@ int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, pos
         if (batch < 1) batch = 1;
         for (int k = 0; k < batch; k++)
             {
-            FG_LAUNCH(w, k_bicg_p, gp, n, w.r, w.p, w.v, w.D, w.phat, w.st);
+            // iteration `enq + k` of this solve reads p from one buffer and writes the other one
+            double *p_old = ((enq + k) & 1) ? w.p2 : w.p, *p_new = ((enq + k) & 1) ? w.p : w.p2;
+            FG_LAUNCH_C(w, KC_BICG_P, k_bicg_p, gp, n, w.r, p_old, p_new, w.v, w.D, w.phat, w.st, w.dist,
+                        w.red.ticket, npush);
             SpmvArgs a = {};
             a.dist = w.dist;
             a.x = w.phat;
@@ -816,12 +811,12 @@ int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, pos
             a.st = w.st;
             a.red = w.red;
             FG_TRY(launch_spmv<ST_BICG_V>(op, w, a));
-            FG_LAUNCH(w, k_bicg_s, gs, n, w.r, w.v, w.D, w.s, w.shat, w.st, w.red);
+            FG_LAUNCH_C(w, KC_BICG_S, k_bicg_s, gs, n, w.r, w.v, w.D, w.s, w.shat, w.st, w.red);
             a.x = w.shat;
             a.y = w.t;
             a.a0 = w.s;
             FG_TRY(launch_spmv<ST_BICG_T>(op, w, a));
-            FG_LAUNCH(w, k_bicg_xr, gxr, n, w.x, w.phat, w.shat, w.s, w.t, w.rt, w.r, w.p, w.v, w.D, w.st, w.red);
+            FG_LAUNCH_C(w, KC_BICG_XR, k_bicg_xr, gxr, n, w.x, w.phat, w.shat, w.s, w.t, w.rt, w.r, w.st, w.red);
             }
         enq += batch;
         if (post) FG_TRY(post(user));

@@ -75,6 +75,13 @@ struct fg_ctx
     double *sS = nullptr, *Aw = nullptr, *val = nullptr;
     KrylovWork kw;
     Operator op;
+    // energies / averages / max angle: tables built on first use
+    bool obs_ready = false;
+    int NFm = 0, n_extra = 0, nreg_tet = 0;
+    int *mtri_ind = nullptr, *mtri_reg = nullptr;
+    double *mtri_surf = nullptr, *mtri_nrm = nullptr, *mtri_dMs = nullptr;
+    int2 *extra_edges = nullptr;
+    double *d_scal = nullptr, *h_scal = nullptr;  // 8 doubles: reduction results (device / pinned)
     // step bookkeeping
     StepPrm sp = {};
     bool have_basis = false, prepared = false, space_field = false, assembled = false;
@@ -83,7 +90,7 @@ struct fg_ctx
     int profiling = 0;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    SpmvProf prof = {nullptr, 0, 0};
+    SpmvProf prof = {nullptr, 0, 0, nullptr, 2};
     };
 
 namespace
@@ -97,13 +104,16 @@ template <class T> int dev_upload(T **dst, const std::vector<T> &src, cudaStream
     return FG_OK;
     }
 
-#define CTX_LAUNCH(c, kernel, grid, ...)                           \
+#define CTX_LAUNCH_C(c, cls, kernel, grid, ...)                    \
     do                                                             \
         {                                                          \
+        const bool prof_ = prof_begin((c)->kw.prof, (c)->stream, cls); \
         kernel<<<(grid), BLOCK, 0, (c)->stream>>>(__VA_ARGS__);    \
+        if (prof_) prof_end((c)->kw.prof, (c)->stream);            \
         ++(c)->launches;                                           \
         FG_CUDA(cudaGetLastError());                               \
         } while (0)
+#define CTX_LAUNCH(c, kernel, grid, ...) CTX_LAUNCH_C(c, KC_OTHER, kernel, grid, __VA_ARGS__)
 
 int check_ctx(const fg_ctx *c)
     {
@@ -132,7 +142,7 @@ TetArrays tet_arrays(const fg_ctx *c)
 
 int launch_basis(fg_ctx *c, double angle)
     {
-    CTX_LAUNCH(c, k_basis, grid_for(c->NODt, BLOCK), c->NODt, c->cur, cos(angle), sin(angle), c->basis);
+    CTX_LAUNCH_C(c, KC_BASIS, k_basis, grid_for(c->NODt, BLOCK), c->NODt, c->cur, cos(angle), sin(angle), c->basis);
     c->have_basis = true;
     c->prepared = false;
     c->assembled = false;
@@ -153,16 +163,16 @@ int launch_elements(fg_ctx *c)
         if (c->h.npi_tet == 5)
             {
             if (c->space_field)
-                CTX_LAUNCH(c, (k_tet<5, true>), grid, A, c->cur, c->basis, c->sp, c->rec);
+                CTX_LAUNCH_C(c, KC_TET, (k_tet<5, true>), grid, A, c->cur, c->basis, c->sp, c->rec);
             else
-                CTX_LAUNCH(c, (k_tet<5, false>), grid, A, c->cur, c->basis, c->sp, c->rec);
+                CTX_LAUNCH_C(c, KC_TET, (k_tet<5, false>), grid, A, c->cur, c->basis, c->sp, c->rec);
             }
         else
             {
             if (c->space_field)
-                CTX_LAUNCH(c, (k_tet<1, true>), grid, A, c->cur, c->basis, c->sp, c->rec);
+                CTX_LAUNCH_C(c, KC_TET, (k_tet<1, true>), grid, A, c->cur, c->basis, c->sp, c->rec);
             else
-                CTX_LAUNCH(c, (k_tet<1, false>), grid, A, c->cur, c->basis, c->sp, c->rec);
+                CTX_LAUNCH_C(c, KC_TET, (k_tet<1, false>), grid, A, c->cur, c->basis, c->sp, c->rec);
             }
         }
     if (c->NFa > 0)
@@ -176,9 +186,9 @@ int launch_elements(fg_ctx *c)
         F.regions = c->reg_tri;
         const int grid = grid_for(c->NFa, BLOCK);
         if (c->h.npi_tri == 4)
-            CTX_LAUNCH(c, k_tri<4>, grid, F, c->cur, c->basis, c->trec);
+            CTX_LAUNCH_C(c, KC_TRI, k_tri<4>, grid, F, c->cur, c->basis, c->trec);
         else
-            CTX_LAUNCH(c, k_tri<1>, grid, F, c->cur, c->basis, c->trec);
+            CTX_LAUNCH_C(c, KC_TRI, k_tri<1>, grid, F, c->cur, c->basis, c->trec);
         }
     c->prepared = true;
     c->assembled = false;
@@ -221,7 +231,7 @@ int launch_assemble(fg_ctx *c, double dt)
     int grid = (c->h.nslice + BLOCK / 32 - 1) / (BLOCK / 32);
     if (grid > wave) grid = wave;
     if (grid < 1) grid = 1;
-    CTX_LAUNCH(c, k_assemble_sell, grid, R, c->cur, c->next, c->basis, c->rec, c->trec, cS, c->val,
+    CTX_LAUNCH_C(c, KC_ASSEMBLE, k_assemble_sell, grid, R, c->cur, c->next, c->basis, c->rec, c->trec, cS, c->val,
                c->kw.b, c->kw.x, c->kw.D);
     if (c->NODt > c->NODp)
         CTX_LAUNCH(c, k_ghost_guess, (c->NODt - c->NODp + BLOCK - 1) / BLOCK, c->NODp, c->NODt, c->nonmag,
@@ -234,7 +244,7 @@ int post_update(void *user)
     {
     fg_ctx *c = static_cast<fg_ctx *>(user);
     FG_TRY(halo_exchange(c->kw, 0, 2));  // multi-GPU: the solution of the ghost rows
-    CTX_LAUNCH(c, k_update, grid_for(c->NODt, BLOCK), c->NODt, c->NODp, c->nonmag, c->cur, c->next, c->basis,
+    CTX_LAUNCH_C(c, KC_UPDATE, k_update, grid_for(c->NODt, BLOCK), c->NODt, c->NODp, c->nonmag, c->cur, c->next, c->basis,
                c->kw.x, c->sp.dt, c->kw.st, c->kw.red);
     return FG_OK;
     }
@@ -394,6 +404,7 @@ static int create_ctx(const fg_mesh *mesh, const fg_params *prm, int device, con
     c->nblk = (long long)h.sptr[h.nslice] * SLICE;
     c->tol = prm->tol;
     c->maxiter = prm->maxiter;
+    c->nreg_tet = prm->nreg_tet;
 
 #define CK(x)                      \
     do                             \
@@ -493,6 +504,10 @@ static int create_ctx(const fg_mesh *mesh, const fg_params *prm, int device, con
             TetRegion &R = regs[r];
             memset(&R, 0, sizeof R);
             R.alpha = p.alpha_LLG;
+            R.A = p.A;
+            R.K = p.K;
+            R.K3 = p.K3;
+            R.Ms = p.Ms;
             if (p.Ms > 0)
                 {
                 R.Abis = 2.0 * p.A / (FG_MU0 * p.Ms);   // tetra.cpp:217
@@ -596,6 +611,7 @@ static int create_ctx(const fg_mesh *mesh, const fg_params *prm, int device, con
         CKCUDA(cudaMalloc(&c->d_dist, sizeof(DistDev)));
         int ng = ((int)rows.size() + BLOCK - 1) / BLOCK;
         c->kw.halo_grid = ng < 1 ? 1 : (ng > 64 ? 64 : ng);
+        c->kw.nsend = (int)rows.size();
         }
     else
         CK(krylov_alloc(c->kw, c->np, 0, s, &c->launches));
@@ -724,7 +740,9 @@ void fg_destroy(fg_ctx *c)
     void *ptrs[] = {c->cur, c->next, c->basis, c->nonmag, c->dofmask, c->stage, c->tet_ind, c->tet_da,
                     c->tet_detJ, c->ext_field, c->tet_reg, c->reg_tet, c->rec, c->tri_ind,
                     c->tri_reg, c->tri_surf, c->tri_dMs, c->reg_tri, c->trec, c->perm, c->sptr,
-                    c->scol, c->sdeg, c->iptr, c->tet_slot, c->itptr, c->sinct, c->sS, c->Aw, c->val};
+                    c->scol, c->sdeg, c->iptr, c->tet_slot, c->itptr, c->sinct, c->sS, c->Aw, c->val,
+                    c->mtri_ind, c->mtri_reg, c->mtri_surf, c->mtri_nrm, c->mtri_dMs, c->extra_edges,
+                    c->d_scal};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int q = 0; q < DIST_MAX_RANKS; q++)
@@ -732,10 +750,12 @@ void fg_destroy(fg_ctx *c)
     if (c->d_dist) cudaFree(c->d_dist);
     if (c->send_rows) cudaFree(c->send_rows);
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->h_scal) cudaFreeHost(c->h_scal);
     if (c->prof.ev)
         {
         for (int k = 0; k < 2 * c->prof.cap; k++) cudaEventDestroy(c->prof.ev[k]);
         delete[] c->prof.ev;
+        delete[] c->prof.cls;
         }
     krylov_free(c->kw);
     if (c->arena) cudaFree(c->arena);
@@ -930,6 +950,175 @@ int fg_step(fg_ctx *c, double angle, const double Hext[3], double dt, double pre
     if (c->profiling) FG_CUDA(cudaEventRecord(c->ev[1], c->stream));
     FG_TRY(launch_elements(c));
     return run_solve(c, dt, out);
+    }
+
+// ---- energies, averages, maximum angle ----
+namespace
+{
+// device tables of the magnetic surface triangles (msh.magTri) and of the mesh edges that have a
+// non-magnetic end, built the first time an observable is asked for
+int ensure_obs_tables(fg_ctx *c)
+    {
+    if (c->obs_ready) return FG_OK;
+    const HostSetup &h = c->h;
+    const size_t M = h.magTri.size();
+    std::vector<int> ind(3 * M), reg(M);
+    std::vector<double> surf(M), nrm(3 * M), dMs(M);
+    for (size_t k = 0; k < M; k++)
+        {
+        const size_t f = (size_t)h.magTri[k];
+        for (int i = 0; i < 3; i++)
+            {
+            ind[(size_t)i * M + k] = h.iperm[h.tri_ind[3 * f + i]];
+            nrm[(size_t)i * M + k] = h.tri_nrm[3 * f + i];
+            }
+        reg[k] = h.tri_reg[f];
+        surf[k] = h.tri_surf[f];
+        dMs[k] = h.tri_dMs[f];
+        }
+    FG_TRY(dev_upload(&c->mtri_ind, ind, c->stream));
+    FG_TRY(dev_upload(&c->mtri_reg, reg, c->stream));
+    FG_TRY(dev_upload(&c->mtri_surf, surf, c->stream));
+    FG_TRY(dev_upload(&c->mtri_nrm, nrm, c->stream));
+    FG_TRY(dev_upload(&c->mtri_dMs, dMs, c->stream));
+    c->NFm = (int)M;
+    std::vector<int2> ex(h.extra_edges.size() / 2);
+    for (size_t k = 0; k < ex.size(); k++)
+        ex[k] = make_int2(h.iperm[h.extra_edges[2 * k]], h.iperm[h.extra_edges[2 * k + 1]]);
+    FG_TRY(dev_upload(&c->extra_edges, ex, c->stream));
+    c->n_extra = (int)ex.size();
+    FG_CUDA(cudaMalloc(&c->d_scal, sizeof(double) * 8));
+    FG_CUDA(cudaMallocHost(&c->h_scal, sizeof(double) * 8));
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    c->obs_ready = true;
+    return FG_OK;
+    }
+
+int fetch_scalars(fg_ctx *c, int count)
+    {
+    FG_CUDA(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, c->stream));
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    return FG_OK;
+    }
+
+int obs_guard(fg_ctx *c, const char *who)
+    {
+    FG_TRY(check_ctx(c));
+    if (c->arena && !c->connected)
+        {
+        set_error("%s: distributed context not connected (fg_dist_connect)", who);
+        return FG_ERR_DIST;
+        }
+    return ensure_obs_tables(c);
+    }
+
+int run_energy(fg_ctx *c, const FieldPrm &f, bool space, double E[4])
+    {
+    if (!E)
+        {
+        set_error("fg_energy: null output");
+        return FG_ERR_INVALID;
+        }
+    if (space && !c->ext_field)
+        {
+        set_error("fg_energy_space: no space field set (fg_set_ext_space_field)");
+        return FG_ERR_STATE;
+        }
+    FG_CUDA(cudaMemsetAsync(c->d_scal, 0, sizeof(double) * 8, c->stream));
+    const TetArrays A = tet_arrays(c);
+    const int gt = grid_for(c->NTm, BLOCK);
+    // NEXT state, like Fem::energy (src/energy.cpp:26-27)
+    if (c->h.npi_tet == 5)
+        {
+        if (space) CTX_LAUNCH(c, (k_energy_tet<5, true>), gt, A, c->next, f, c->NODp, c->d_scal, c->kw.red);
+        else CTX_LAUNCH(c, (k_energy_tet<5, false>), gt, A, c->next, f, c->NODp, c->d_scal, c->kw.red);
+        }
+    else
+        {
+        if (space) CTX_LAUNCH(c, (k_energy_tet<1, true>), gt, A, c->next, f, c->NODp, c->d_scal, c->kw.red);
+        else CTX_LAUNCH(c, (k_energy_tet<1, false>), gt, A, c->next, f, c->NODp, c->d_scal, c->kw.red);
+        }
+    MagTriArrays F;
+    F.NFm = c->NFm;
+    F.ind = c->mtri_ind;
+    F.surf = c->mtri_surf;
+    F.nrm = c->mtri_nrm;
+    F.dMs = c->mtri_dMs;
+    F.reg = c->mtri_reg;
+    F.regions = c->reg_tri;
+    const int gf = grid_for(c->NFm, BLOCK);
+    if (c->h.npi_tri == 4) CTX_LAUNCH(c, k_energy_tri<4>, gf, F, c->next, c->NODp, c->d_scal + 4, c->kw.red);
+    else CTX_LAUNCH(c, k_energy_tri<1>, gf, F, c->next, c->NODp, c->d_scal + 4, c->kw.red);
+    FG_TRY(fetch_scalars(c, 6));
+    const double *r = c->h_scal;
+    E[0] = r[0];
+    E[1] = r[1] + r[4];  // volume + surface anisotropy
+    E[2] = r[2] + r[5];  // volume + surface charges
+    E[3] = r[3];
+    return FG_OK;
+    }
+}  // namespace
+
+int fg_energy(fg_ctx *c, const double Hext[3], double E[4])
+    {
+    FG_TRY(obs_guard(c, "fg_energy"));
+    if (!Hext)
+        {
+        set_error("fg_energy: null Hext");
+        return FG_ERR_INVALID;
+        }
+    FieldPrm f = {{Hext[0], Hext[1], Hext[2]}, 0.0};
+    return run_energy(c, f, false, E);
+    }
+
+int fg_energy_space(fg_ctx *c, double A_Hext, double E[4])
+    {
+    FG_TRY(obs_guard(c, "fg_energy_space"));
+    FieldPrm f = {{0.0, 0.0, 0.0}, A_Hext};
+    return run_energy(c, f, true, E);
+    }
+
+int fg_avg(fg_ctx *c, int what, int region, double out[3])
+    {
+    FG_TRY(obs_guard(c, "fg_avg"));
+    if (!out || (what != 0 && what != 1) || region < -1 || region >= c->nreg_tet)
+        {
+        set_error("fg_avg: bad argument (what=%d, region=%d of %d)", what, region, c->nreg_tet);
+        return FG_ERR_INVALID;
+        }
+    const TetArrays A = tet_arrays(c);
+    const int gt = grid_for(c->NTm, BLOCK);
+    FG_CUDA(cudaMemsetAsync(c->d_scal, 0, sizeof(double) * 4, c->stream));
+    if (c->h.npi_tet == 5) CTX_LAUNCH(c, k_avg<5>, gt, A, c->next, what, region, c->NODp, c->d_scal, c->kw.red);
+    else CTX_LAUNCH(c, k_avg<1>, gt, A, c->next, what, region, c->NODp, c->d_scal, c->kw.red);
+    FG_TRY(fetch_scalars(c, 4));
+    // sum / volume (src/mesh.cpp:104-105).  The sum runs over magTet, the volume is the region's
+    // (src/mesh.h:81-90): a non-magnetic region gives 0 / vol = 0, a region without any tet 0/0 = NaN.
+    double vol = c->h_scal[3];
+    if (vol == 0.0 && region >= 0)
+        for (size_t t = 0; t < c->h.tet_reg.size() && vol == 0.0; t++)
+            if (c->h.tet_reg[t] == region) vol = c->h.tet_detJ[t];  // any positive number: 0 / vol
+    for (int d = 0; d < 3; d++) out[d] = c->h_scal[d] / vol;
+    return FG_OK;
+    }
+
+int fg_max_angle(fg_ctx *c, double *angle)
+    {
+    FG_TRY(obs_guard(c, "fg_max_angle"));
+    if (!angle)
+        {
+        set_error("fg_max_angle: null output");
+        return FG_ERR_INVALID;
+        }
+    int grid = (c->h.nslice + BLOCK / 32 - 1) / (BLOCK / 32);
+    if (grid > MAX_GRID) grid = MAX_GRID;
+    if (grid < 1) grid = 1;
+    CTX_LAUNCH(c, k_max_angle, grid, c->h.nslice, c->sptr, c->scol, c->sdeg, c->next, c->n_extra,
+               c->extra_edges, c->d_scal, c->kw.red);
+    FG_TRY(fetch_scalars(c, 1));
+    const double min_dot = -c->h_scal[0];
+    *angle = acos(min_dot);  // src/mesh.h:305
+    return FG_OK;
     }
 
 // ---- taps ----
@@ -1323,15 +1512,17 @@ int fg_set_profiling(fg_ctx *c, int on)
     {
     FG_TRY(check_ctx(c));
     c->profiling = on == 1 ? 1 : 0;
-    if (on == 2)
+    if (on == 2 || on == 3)
         {
         if (!c->prof.ev)
             {
-            c->prof.cap = 4096;
+            c->prof.cap = 8192;
             c->prof.ev = new cudaEvent_t[2 * c->prof.cap];
+            c->prof.cls = new int[c->prof.cap];
             for (int k = 0; k < 2 * c->prof.cap; k++) FG_CUDA(cudaEventCreate(&c->prof.ev[k]));
             }
         c->prof.n = 0;
+        c->prof.mode = on;
         c->kw.prof = &c->prof;
         }
     else
@@ -1349,15 +1540,52 @@ int fg_get_spmv_times(fg_ctx *c, double *total_ms, int *launches)
         }
     FG_CUDA(cudaStreamSynchronize(c->stream));
     double sum = 0.0;
+    int cnt = 0;
+    for (int k = 0; k < c->prof.n; k++)
+        {
+        if (!prof_is_spmv(c->prof.cls[k])) continue;
+        float ms = 0.f;
+        FG_CUDA(cudaEventElapsedTime(&ms, c->prof.ev[2 * k], c->prof.ev[2 * k + 1]));
+        sum += ms;
+        cnt++;
+        }
+    *total_ms = sum;
+    *launches = cnt;
+    c->prof.n = 0;
+    return FG_OK;
+    }
+
+int fg_get_kernel_times(fg_ctx *c, double ms_out[FG_KERNEL_CLASSES], int launches_out[FG_KERNEL_CLASSES])
+    {
+    FG_TRY(check_ctx(c));
+    if (!ms_out || !launches_out)
+        {
+        set_error("fg_get_kernel_times: null argument");
+        return FG_ERR_INVALID;
+        }
+    static_assert(FG_KERNEL_CLASSES == KC_COUNT + 1, "kernel class table");
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < FG_KERNEL_CLASSES; k++)
+        {
+        ms_out[k] = 0.0;
+        launches_out[k] = 0;
+        }
     for (int k = 0; k < c->prof.n; k++)
         {
         float ms = 0.f;
         FG_CUDA(cudaEventElapsedTime(&ms, c->prof.ev[2 * k], c->prof.ev[2 * k + 1]));
-        sum += ms;
+        ms_out[c->prof.cls[k]] += ms;
+        launches_out[c->prof.cls[k]]++;
+        if (k + 1 < c->prof.n)
+            {  // time between the end of this kernel and the start of the next one in the record
+            FG_CUDA(cudaEventElapsedTime(&ms, c->prof.ev[2 * k + 1], c->prof.ev[2 * k + 2]));
+            if (ms < 1.0f)  // skip the host-side pauses between steps
+                {
+                ms_out[KC_COUNT] += ms;
+                launches_out[KC_COUNT]++;
+                }
+            }
         }
-    *total_ms = sum;
-    *launches = c->prof.n;
-    c->prof.n = 0;
     return FG_OK;
     }
 

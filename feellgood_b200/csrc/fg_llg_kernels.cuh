@@ -751,6 +751,254 @@ k_ghost_guess(int first, int last, const unsigned char *__restrict__ nonmag,
     }
 
 // ------------------------------------------------------------------------------------------
+// energies, averages, maximum angle — element-wise reductions over the state
+// that is already resident (the reference runs them serially on the host every accepted step).
+// ------------------------------------------------------------------------------------------
+struct FieldPrm
+    {
+    double Hext[3];   // uniform field (RtoR3)
+    double A_Hext;    // amplitude of the space field (R4toR3)
+    };
+
+// Fem::energy, src/energy.cpp:17-47: E[EXCHANGE, ANISOTROPY, DEMAG, ZEEMAN] of the magnetic tets on
+// the state `st` (the reference uses NEXT).  One thread per tet; Tet::exchangeEnergy /
+// uniaxialAnisotropyEnergy / cubicAnisotropyEnergy / demagEnergy / zeemanEnergy of
+// src/tetra.cpp:309-391, each a weight.dot(dens).  NOWN: device rows below it are owned; on a
+// slab-partitioned mesh a tet shared by several ranks is counted by each one for the fraction of
+// its nodes that rank owns (the fractions are exact binary numbers and sum to one).
+template <int NPI, bool SPACE>
+__global__ void __launch_bounds__(BLOCK)
+k_energy_tet(const TetArrays A, const NodeRec *__restrict__ st, const FieldPrm f, int NOWN,
+             double *__restrict__ out, const RedBuf red)
+    {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const int stride = gridDim.x * BLOCK;
+    for (int tm = blockIdx.x * BLOCK + threadIdx.x; tm < A.NTm; tm += stride)
+        {
+        TetIn T;
+        int4 ind;
+        tet_load<NPI>(A, tm, st, ind, T);
+        const TetRegion R = A.regions[__ldg(A.reg + tm)];
+        const double share = 0.25 * ((ind.x < NOWN) + (ind.y < NOWN) + (ind.z < NOWN) + (ind.w < NOWN));
+        double dU[3][3];  // dU[d][k] = d u_d / d x_k, src/tetra.h:183-201
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                {
+                double s = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) s += T.u[i][d] * T.da[i][k];
+                dU[d][k] = s;
+                }
+        double dens_ex = 0.0;  // |dudx|^2 + |dudy|^2 + |dudz|^2, tetra.cpp:314-316
+#pragma unroll
+        for (int k = 0; k < 3; k++) dens_ex += dU[0][k] * dU[0][k] + dU[1][k] * dU[1][k] + dU[2][k] * dU[2][k];
+        const double div = dU[0][0] + dU[1][1] + dU[2][2];
+        double e_ex = 0.0, e_an1 = 0.0, e_an3 = 0.0, e_dm = 0.0, e_ze = 0.0;
+#pragma unroll
+        for (int g = 0; g < NPI; g++)
+            {
+            const double w = T.detJ * tet_pds<NPI>(g);
+            double ug[3], phig = 0.0;
+#pragma unroll
+            for (int d = 0; d < 3; d++)
+                {
+                double su = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) su += T.u[i][d] * tet_a<NPI>(i, g);
+                ug[d] = su;
+                }
+#pragma unroll
+            for (int i = 0; i < 4; i++) phig += T.phi[i] * tet_a<NPI>(i, g);
+            e_ex += w * dens_ex;
+            e_dm += w * (div * phig);                                    // tetra.cpp:368-371
+            if (R.has_K)
+                {
+                const double q = dot3(R.uk, ug);
+                e_an1 += w * (q * q);                                    // tetra.cpp:325-327
+                }
+            if (R.has_K3)
+                {
+                const double al0 = dot3(ug, R.ex), al1 = dot3(ug, R.ey), al2 = dot3(ug, R.ez);
+                e_an3 += w * ((al0 * al1) * (al0 * al1) + (al1 * al2) * (al1 * al2) + (al2 * al0) * (al2 * al0));
+                }
+            double h[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++)
+                h[d] = SPACE ? __ldcs(A.ext_field + (size_t)(d * NPI + g) * A.NTm + tm) : f.Hext[d];
+            e_ze += w * dot3(ug, h);                                     // tetra.cpp:374-391
+            }
+        acc[0] += share * (R.A * e_ex);
+        double e_an = 0.0;
+        if (R.has_K) e_an += -R.K * e_an1;
+        if (R.has_K3) e_an += R.K3 * e_an3;
+        acc[1] += share * e_an;
+        acc[2] += share * (-0.5 * FG_MU0 * R.Ms * e_dm);
+        acc[3] += share * (SPACE ? -FG_MU0 * R.Ms * f.A_Hext * e_ze : -FG_MU0 * R.Ms * e_ze);
+        }
+    double tot[4];
+    if (grid_reduce<4>(acc, red, tot) != 1) return;
+#pragma unroll
+    for (int k = 0; k < 4; k++) out[k] = tot[k];
+    }
+
+// magnetic surface triangles of Fem::energy, src/energy.cpp:49-63 (msh.magTri)
+struct MagTriArrays
+    {
+    int NFm;
+    const int *ind;       // [3][NFm] device rows
+    const double *surf;   // NFm
+    const double *nrm;    // [3][NFm] unit normal (src/triangle.h:206-233)
+    const double *dMs;    // NFm
+    const int *reg;       // NFm
+    const TriRegion *regions;
+    };
+
+// Tri::anisotropyEnergy (src/triangle.cpp:38-43) -> out[0], Tri::demagEnergy (:80-85) -> out[1]
+template <int NPI>
+__global__ void __launch_bounds__(BLOCK)
+k_energy_tri(const MagTriArrays A, const NodeRec *__restrict__ st, int NOWN, double *__restrict__ out,
+             const RedBuf red)
+    {
+    double acc[2] = {0.0, 0.0};
+    const int stride = gridDim.x * BLOCK;
+    for (int fa = blockIdx.x * BLOCK + threadIdx.x; fa < A.NFm; fa += stride)
+        {
+        double u[3][3], ph[3], v[3], phiv;
+        int own = 0;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            {
+            const int nd = A.ind[(size_t)i * A.NFm + fa];
+            own += nd < NOWN;
+            load_rec(st + nd, u[i], v, ph[i], phiv);
+            }
+        const double share = own == 3 ? 1.0 : own / 3.0;
+        const TriRegion R = A.regions[A.reg[fa]];
+        const double surf = A.surf[fa];
+        const double n[3] = {A.nrm[fa], A.nrm[(size_t)A.NFm + fa], A.nrm[2 * (size_t)A.NFm + fa]};
+        double s_an = 0.0, s_dm = 0.0;
+#pragma unroll
+        for (int g = 0; g < NPI; g++)
+            {
+            double ug[3] = {0.0, 0.0, 0.0}, pg = 0.0;
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+                {
+#pragma unroll
+                for (int d = 0; d < 3; d++) ug[d] += u[i][d] * tri_a<NPI>(i, g);
+                pg += ph[i] * tri_a<NPI>(i, g);
+                }
+            const double wg = 2.0 * surf * tri_pds<NPI>(g);
+            const double q = dot3(ug, R.uk);
+            s_an += wg * (q * q);
+            s_dm += (dot3(ug, n) * pg) * wg;
+            }
+        if (R.Ks != 0.0) acc[0] += share * (-R.Ks * s_an);
+        acc[1] += share * (0.5 * FG_MU0 * A.dMs[fa] * s_dm);
+        }
+    double tot[2];
+    if (grid_reduce<2>(acc, red, tot) != 1) return;
+    out[0] = tot[0];
+    out[1] = tot[1];
+    }
+
+// mesh::avg, src/mesh.cpp:89-106: out[0..2] = sum_T weight . interp(component), out[3] = the volume
+// of the selected tets (region < 0: all magnetic regions).  what: 0 = u, 1 = v of `st`.
+template <int NPI>
+__global__ void __launch_bounds__(BLOCK)
+k_avg(const TetArrays A, const NodeRec *__restrict__ st, int what, int region, int NOWN,
+      double *__restrict__ out, const RedBuf red)
+    {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const int stride = gridDim.x * BLOCK;
+    for (int tm = blockIdx.x * BLOCK + threadIdx.x; tm < A.NTm; tm += stride)
+        {
+        if (region >= 0 && __ldg(A.reg + tm) != region) continue;
+        const int4 ind = __ldg(A.ind + tm);
+        const double detJ = __ldcs(A.detJ + tm);
+        const int nd[4] = {ind.x, ind.y, ind.z, ind.w};
+        double f[4][3];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            {
+            double u[3], v[3], phi, phiv;
+            load_rec(st + nd[i], u, v, phi, phiv);
+#pragma unroll
+            for (int d = 0; d < 3; d++) f[i][d] = what ? v[d] : u[d];
+            }
+        const double share = 0.25 * ((ind.x < NOWN) + (ind.y < NOWN) + (ind.z < NOWN) + (ind.w < NOWN));
+        double s[3] = {0.0, 0.0, 0.0}, vol = 0.0;
+#pragma unroll
+        for (int g = 0; g < NPI; g++)
+            {
+            const double w = detJ * tet_pds<NPI>(g);
+            vol += w;
+#pragma unroll
+            for (int d = 0; d < 3; d++)
+                {
+                double val = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) val += f[i][d] * tet_a<NPI>(i, g);
+                s[d] += w * val;
+                }
+            }
+#pragma unroll
+        for (int d = 0; d < 3; d++) acc[d] += share * s[d];
+        acc[3] += share * vol;
+        }
+    double tot[4];
+    if (grid_reduce<4>(acc, red, tot) != 1) return;
+#pragma unroll
+    for (int k = 0; k < 4; k++) out[k] = tot[k];
+    }
+
+// mesh::max_angle, src/mesh.h:295-306: min over the mesh edges of u_a . u_b.  The magnetic edges
+// are the off-diagonal blocks of the SELL pattern (one warp per slice, as in the SpMV); edges with
+// a non-magnetic end (never in the pattern) come as an explicit list.  The kernel reduces
+// max(-dot); the host returns acos(min(1, -that)).
+__global__ void __launch_bounds__(BLOCK)
+k_max_angle(int nslice, const int *__restrict__ sptr, const int *__restrict__ scol,
+            const int *__restrict__ sdeg, const NodeRec *__restrict__ st, int n_extra,
+            const int2 *__restrict__ extra, double *__restrict__ out, const RedBuf red)
+    {
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * (BLOCK / 32);
+    double mx = -1.0;  // = -(initial value 1.0 of the reference's transform_reduce)
+    for (int s = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); s < nslice; s += nwarps)
+        {
+        const int row = s * SLICE + lane;
+        const int p0 = __ldg(sptr + s), deg = sdeg[row];
+        if (deg <= 1) continue;
+        const double2 *q = reinterpret_cast<const double2 *>(st + row);
+        const double2 a = __ldg(q), b = __ldg(q + 1);
+        const int *cp = scol + (size_t)p0 * SLICE + lane;
+        for (int j = 0; j < deg; ++j, cp += SLICE)
+            {
+            const int c = __ldcs(cp);
+            if (c <= row) continue;  // each edge once (first < second); skips the diagonal block
+            const double2 *qc = reinterpret_cast<const double2 *>(st + c);
+            const double2 ca = __ldg(qc), cb = __ldg(qc + 1);
+            const double d = a.x * ca.x + a.y * ca.y + b.x * cb.x;
+            mx = fmax(mx, -d);
+            }
+        }
+    const int stride = gridDim.x * BLOCK;
+    for (int e = blockIdx.x * BLOCK + threadIdx.x; e < n_extra; e += stride)
+        {
+        const int2 ed = extra[e];
+        const double2 *qa = reinterpret_cast<const double2 *>(st + ed.x), *qb = reinterpret_cast<const double2 *>(st + ed.y);
+        const double2 a = __ldg(qa), b = __ldg(qa + 1), ca = __ldg(qb), cb = __ldg(qb + 1);
+        const double d = a.x * ca.x + a.y * ca.y + b.x * cb.x;
+        mx = fmax(mx, -d);
+        }
+    double tot;
+    if (!grid_reduce_max(mx, red, tot, -1.7976931348623157e308)) return;
+    out[0] = tot;
+    }
+
+// ------------------------------------------------------------------------------------------
 // state packing helpers (host <-> NodeRec)
 // ------------------------------------------------------------------------------------------
 // which: bit0 u, bit1 v, bit2 phi, bit3 phiv ; staging = [u(3N) | v(3N) | phi(N) | phiv(N)] in the

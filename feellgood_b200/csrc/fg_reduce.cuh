@@ -57,22 +57,30 @@ __device__ int grid_reduce(double (&v)[NV], const RedBuf red, double (&out)[NV])
         if (lane == 0) sm[k][wid] = s;
         }
     __syncthreads();
-    if (threadIdx.x != 0) return 2;
-#pragma unroll
-    for (int k = 0; k < NV; k++)
+    if (wid != 0) return 2;
+    __shared__ double tot[NV];
+    if (lane == 0)
         {
-        double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < BLOCK / 32; w++) s += sm[k][w];
-        out[k] = s;
+        for (int k = 0; k < NV; k++)
+            {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < BLOCK / 32; w++) s += sm[k][w];
+            tot[k] = s;
+            }
         }
-    if (red.dist != nullptr) dist_allreduce(red.dist, out, NV, false);
+    __syncwarp();
+    if (red.dist != nullptr) dist_allreduce_warp(red.dist, tot, NV, false);  // the whole warp takes part
+    if (lane != 0) return 2;
+#pragma unroll
+    for (int k = 0; k < NV; k++) out[k] = tot[k];
     return 1;
     }
 
 
-// Same protocol for a maximum (the v2max of src/solver.cpp:74-88).
-__device__ __forceinline__ bool grid_reduce_max(double v, const RedBuf red, double &out)
+// Same protocol for a maximum (the v2max of src/solver.cpp:74-88); `lowest` = identity element.
+__device__ __forceinline__ bool grid_reduce_max(double v, const RedBuf red, double &out, double lowest = 0.0)
     {
     __shared__ double smx[BLOCK / 32];
     __shared__ int is_last_mx;
@@ -94,19 +102,26 @@ __device__ __forceinline__ bool grid_reduce_max(double v, const RedBuf red, doub
     __syncthreads();
     if (!is_last_mx) return false;
     __threadfence();
-    double s = 0.0;
+    double s = lowest;
     for (int i = threadIdx.x; i < (int)gridDim.x; i += BLOCK) s = fmax(s, __ldcg(&red.partials[i]));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(0xffffffffu, s, o));
     __syncthreads();
     if (lane == 0) smx[wid] = s;
     __syncthreads();
-    if (threadIdx.x != 0) return false;
-    s = smx[0];
+    if (wid != 0) return false;
+    __shared__ double totmx[1];
+    if (lane == 0)
+        {
+        s = smx[0];
 #pragma unroll
-    for (int w = 1; w < BLOCK / 32; w++) s = fmax(s, smx[w]);
-    out = s;
-    if (red.dist != nullptr) dist_allreduce(red.dist, &out, 1, true);
+        for (int w = 1; w < BLOCK / 32; w++) s = fmax(s, smx[w]);
+        totmx[0] = s;
+        }
+    __syncwarp();
+    if (red.dist != nullptr) dist_allreduce_warp(red.dist, totmx, 1, true);
+    if (lane != 0) return false;
+    out = totmx[0];
     return true;
     }
 

@@ -181,6 +181,7 @@ int host_setup(const fg_mesh &m, const fg_params &prm, int n_owned, HostSetup &h
     h.tri_reg.assign(m.tri_reg, m.tri_reg + (size_t)NF);
     h.tri_dMs.assign(m.tri_dMs, m.tri_dMs + (size_t)NF);
     h.tri_surf.resize((size_t)NF);
+    h.tri_nrm.resize(3 * (size_t)NF);
     h.magTri.clear();
     h.actTri.clear();
     for (int f = 0; f < NF; f++)
@@ -198,6 +199,12 @@ int host_setup(const fg_mesh &m, const fg_params &prm, int n_owned, HostSetup &h
         const V3 nrm = cross(sub(m.node_p + 3 * (size_t)ind[1], p0),
                              sub(m.node_p + 3 * (size_t)ind[2], p0));
         h.tri_surf[f] = 0.5 * std::sqrt(dot(nrm, nrm));
+            {  // Tri::calc_norm, src/triangle.h:200-206 (Eigen normalize: untouched when the norm is 0)
+            const double z = dot(nrm, nrm), sq = z > 0 ? std::sqrt(z) : 1.0;
+            h.tri_nrm[3 * (size_t)f] = nrm.x / sq;
+            h.tri_nrm[3 * (size_t)f + 1] = nrm.y / sq;
+            h.tri_nrm[3 * (size_t)f + 2] = nrm.z / sq;
+            }
         const bool mag = h.magNode[ind[0]] && h.magNode[ind[1]] && h.magNode[ind[2]];
         const fg_tri_prm &tp = prm.prm_tri[h.tri_reg[f]];
         if (mag && !tp.suppress_charges)
@@ -226,18 +233,31 @@ int host_setup(const fg_mesh &m, const fg_params &prm, int n_owned, HostSetup &h
     // sort + unique each row; count edges; keep magnetic neighbours (+ self) for the pattern
     // (src/solver.h:75-104 with the filter of src/linear_algebra.h:43)
     std::vector<int> deg_all((size_t)NOD), deg_mag((size_t)NOD);
-#pragma omp parallel for schedule(dynamic, 1024)
-    for (int a = 0; a < NOD; a++)
+    h.extra_edges.clear();
+#pragma omp parallel
         {
-        int *b = adj.data() + aptr[a], *e = adj.data() + aptr[a + 1];
-        std::sort(b, e);
-        e = std::unique(b, e);
-        deg_all[a] = (int)(e - b);
-        int k = 0;
-        if (h.magNode[a])
+        std::vector<int> extra;  // edges with a non-magnetic end: in msh.edges, never in the pattern
+#pragma omp for schedule(dynamic, 1024) nowait
+        for (int a = 0; a < NOD; a++)
+            {
+            int *b = adj.data() + aptr[a], *e = adj.data() + aptr[a + 1];
+            std::sort(b, e);
+            e = std::unique(b, e);
+            deg_all[a] = (int)(e - b);
             for (int *q = b; q < e; ++q)
-                if (h.magNode[*q]) b[k++] = *q;
-        deg_mag[a] = k;
+                if (*q > a && !(h.magNode[a] && h.magNode[*q]))
+                    {
+                    extra.push_back(a);
+                    extra.push_back(*q);
+                    }
+            int k = 0;
+            if (h.magNode[a])
+                for (int *q = b; q < e; ++q)
+                    if (h.magNode[*q]) b[k++] = *q;
+            deg_mag[a] = k;
+            }
+#pragma omp critical
+        h.extra_edges.insert(h.extra_edges.end(), extra.begin(), extra.end());
         }
     h.n_edges = 0;
     h.n_edges_mag = 0;

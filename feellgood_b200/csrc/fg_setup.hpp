@@ -33,6 +33,7 @@ struct HostSetup
     std::vector<int> tri_ind;      // NF x 3
     std::vector<int> tri_reg;      // NF
     std::vector<double> tri_dMs, tri_surf;  // NF
+    std::vector<double> tri_nrm;   // NF x 3 unit normals (demag energy of the surface, src/triangle.cpp:80-85)
     std::vector<int> magTri;       // magnetic && !suppress_charges (rhs contributors)
     std::vector<int> actTri;       // magTri with Ks != 0 : the only ones whose Lp reaches the rhs
     // node-level pattern of K
@@ -40,6 +41,7 @@ struct HostSetup
     std::vector<double> S;         // nnzb
     std::vector<double> Aw;        // NOD
     long long n_edges = 0, n_edges_mag = 0;
+    std::vector<int> extra_edges;  // 2 x (n_edges - n_edges_mag): mesh edges with a non-magnetic end (max_angle)
     // incidences: entry = 4*tm + i (tm = compact magnetic tet index) / 3*fa + i
     std::vector<int> inc_ptr, inc;          // NOD+1, 4*n_magTet
     std::vector<int> inc_tri_ptr, inc_tri;  // NOD+1, 3*n_actTri

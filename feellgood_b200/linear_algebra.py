@@ -195,6 +195,31 @@ class LinAlgebra:
         assert field.shape == (self.NT, 3, self.npi)
         check(self._L.fg_set_ext_space_field(self._h, dp(field)))
 
+    # ---- observables of the resident NEXT state (Fem::energy, mesh::avg, mesh::max_angle) ----
+    def energy(self, Hext):
+        """Fem::energy (src/energy.cpp:5-68): E[exchange, anisotropy, demag, zeeman].  A 3-vector
+        is the uniform field (RtoR3), a scalar the amplitude of mesh.extSpaceField (R4toR3)."""
+        E = np.empty(4)
+        if np.ndim(Hext) == 0:
+            check(self._L.fg_energy_space(self._h, C.c_double(float(Hext)), dp(E)))
+        else:
+            H = f64(Hext)
+            assert H.shape == (3,)
+            check(self._L.fg_energy(self._h, dp(H), dp(E)))
+        return E
+
+    def avg(self, what="u", region=-1):
+        """mesh::avg (src/mesh.cpp:89-106) of all three components of u or v (NEXT)."""
+        out = np.empty(3)
+        check(self._L.fg_avg(self._h, C.c_int({"u": 0, "v": 1}[what]), C.c_int(region), dp(out)))
+        return out
+
+    def max_angle(self):
+        """mesh::max_angle (src/mesh.h:295-306), radians."""
+        a = C.c_double()
+        check(self._L.fg_max_angle(self._h, C.byref(a)))
+        return a.value
+
     # ---- the reference's LinAlgebra surface ----
     def base_projection(self, angle=None):
         """src/linear_algebra.cpp:3-11.  With angle=None the angle is drawn exactly like the
@@ -312,6 +337,16 @@ class LinAlgebra:
         ms, cnt = C.c_double(), C.c_int()
         check(self._L.fg_get_spmv_times(self._h, C.byref(ms), C.byref(cnt)))
         return ms.value, cnt.value
+
+    KERNEL_CLASSES = ("basis", "tet", "tri", "assemble", "spmv_setup", "bicg_p", "spmv_v", "bicg_s",
+                      "spmv_t", "bicg_xr", "halo", "update", "other", "gaps")
+
+    def kernel_times(self):
+        """{class: (device ms, launches)} since set_profiling(3); call before spmv_times()."""
+        ms = (C.c_double * 14)()
+        cnt = (C.c_int * 14)()
+        check(self._L.fg_get_kernel_times(self._h, ms, cnt))
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(self.KERNEL_CLASSES)}
 
     def phase_times(self):
         out = (C.c_double * 8)()

@@ -147,6 +147,21 @@ int fg_solve(fg_ctx *ctx, double dt, fg_step_result *out);
 int fg_step(fg_ctx *ctx, double angle, const double Hext[3], double dt, double prefactor,
             int idx_dir, double Vdrift, fg_step_result *out);
 
+/* ---- energies, averages, maximum angle: what Fem::compute_all / saver evaluate after every accepted
+ *      step.  Element-wise reductions over the resident NEXT state; on a
+ *      distributed context they are collective and return the global value on every rank. ---- */
+/* Fem::energy, src/energy.cpp:5-68 with a uniform applied field (RtoR3): E[0..3] = exchange,
+ * anisotropy (volume + surface), demag (volume + surface charges), zeeman — the ENERGY_TYPE order of
+ * src/fem.h:30-36.  Tet terms src/tetra.cpp:309-391, Tri terms src/triangle.cpp:38-43,80-85. */
+int fg_energy(fg_ctx *ctx, const double Hext[3], double E[4]);
+/* same with the space-dependent field times an amplitude (R4toR3, src/energy.cpp:41-43) */
+int fg_energy_space(fg_ctx *ctx, double A_Hext, double E[4]);
+/* mesh::avg, src/mesh.cpp:89-106: what = 0 Nodes::get_u_comp | 1 Nodes::get_v_comp (NEXT state), all
+ * three components at once; region = -1 for all magnetic regions, else a volume-region index. */
+int fg_avg(fg_ctx *ctx, int what, int region, double out[3]);
+/* mesh::max_angle, src/mesh.h:295-306 (radians; over ALL mesh edges, like the reference) */
+int fg_max_angle(fg_ctx *ctx, double *angle);
+
 /* ---- taps used by the parity tests ---- */
 int fg_get_basis(fg_ctx *ctx, double *ep, double *eq);              /* NOD x 3 each */
 /* element<N,NPI>::Kp / Lp (src/element.h:62,65) of tets [first, first+count): count x 64, x 8 */
@@ -242,6 +257,12 @@ int fg_get_phase_times(const fg_ctx *ctx, double out[8]);
  * with a CUDA-event pair on the context's stream (no host synchronisation is added; at most 4096
  * launches are kept).  fg_get_spmv_times returns their summed device time and count, and resets. */
 int fg_get_spmv_times(fg_ctx *ctx, double *total_ms, int *launches);
+/* fg_set_profiling(ctx, 3): the same bracketing around EVERY kernel of the step.  Returns the summed
+ * device milliseconds and launch counts per kernel class since the mode was set (and keeps them):
+ * 0 basis 1 tet 2 tri 3 assemble 4 spmv(setup) 5 bicg_p 6 spmv(v) 7 bicg_s 8 spmv(t) 9 bicg_xr
+ * 10 halo 11 update 12 other 13 gaps between consecutive kernels (idle stream time). */
+#define FG_KERNEL_CLASSES 14
+int fg_get_kernel_times(fg_ctx *ctx, double ms[FG_KERNEL_CLASSES], int launches[FG_KERNEL_CLASSES]);
 /* Microbenchmark of the solver's SpMV on the assembled K: runs `reps` launches back to back and
  * returns the mean milliseconds per launch (CUDA events on the context's stream). */
 int fg_bench_spmv(fg_ctx *ctx, int reps, double *ms_per_launch);

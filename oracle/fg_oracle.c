@@ -1417,7 +1417,7 @@ void fgo_get_edges(const fgo_ctx *c, int *edges)
 /* "next" rows: energies (src/energy.cpp:5-68, src/tetra.cpp:309-391, src/triangle.cpp:38-43,   */
 /* 80-85), averages (src/mesh.cpp:89-106), max_angle (src/mesh.h:295-306)                       */
 /* ------------------------------------------------------------------------------------------ */
-void fgo_energy(const fgo_ctx *c, const double Hext[3], double E[4])
+static void energy_core(const fgo_ctx *c, const double *Hext, int space, double fieldAmp, double E[4])
     {
     const int npi = c->npi;
     const double *a = fgo_tet_a(npi);
@@ -1486,14 +1486,23 @@ void fgo_energy(const fgo_ctx *c, const double Hext[3], double E[4])
                 }
             E[1] += prm->K3 * s;
             }
-        /* zeemanEnergy (uniform field) tetra.cpp:374-380 */
         s = 0;
-        for (int g = 0; g < npi; g++)
-            {
-            double ug[3] = {u[g], u[npi + g], u[2 * npi + g]};
-            s += w[g] * dot3(ug, Hext);
+        if (!space)
+            {   /* zeemanEnergy (uniform field) tetra.cpp:374-380 */
+            for (int g = 0; g < npi; g++)
+                {
+                double ug[3] = {u[g], u[npi + g], u[2 * npi + g]};
+                s += w[g] * dot3(ug, Hext);
+                }
+            E[3] += -FGO_MU0 * prm->Ms * s;
             }
-        E[3] += -FGO_MU0 * prm->Ms * s;
+        else
+            {   /* zeemanEnergy (space field x amplitude) tetra.cpp:382-391, energy.cpp:41-43 */
+            const double *sf = c->extSpaceField + (size_t)3 * npi * t; /* [d][g] */
+            for (int g = 0; g < npi; g++)
+                s += w[g] * (u[g] * sf[g] + u[npi + g] * sf[npi + g] + u[2 * npi + g] * sf[2 * npi + g]);
+            E[3] += -FGO_MU0 * prm->Ms * fieldAmp * s;
+            }
         }
     const int npt = c->npi_tri;
     const double *at = fgo_tri_a(npt);
@@ -1523,6 +1532,9 @@ void fgo_energy(const fgo_ctx *c, const double Hext[3], double E[4])
         }
     }
 
+void fgo_energy(const fgo_ctx *c, const double Hext[3], double E[4]) { energy_core(c, Hext, 0, 0.0, E); }
+void fgo_energy_space(const fgo_ctx *c, double fieldAmp, double E[4]) { energy_core(c, NULL, 1, fieldAmp, E); }
+
 double fgo_total_mag_vol(const fgo_ctx *c)
     {
     double vol = 0; /* mesh.h:81-90 */
@@ -1536,18 +1548,35 @@ double fgo_total_mag_vol(const fgo_ctx *c)
     return vol;
     }
 
-void fgo_avg(const fgo_ctx *c, int what, double out[3])
+/* settings.paramTetra[region].volume, src/mesh.h:81-90 (all tets of the region, magnetic or not) */
+double fgo_region_vol(const fgo_ctx *c, int region)
+    {
+    double vol = 0;
+    for (int t = 0; t < c->NT; t++)
+        if (c->tet_reg[t] == region)
+            {
+            double s = 0;
+            for (int g = 0; g < c->npi; g++) s += c->tet_w[(size_t)c->npi * t + g];
+            vol += s;
+            }
+    return vol;
+    }
+
+void fgo_avg(const fgo_ctx *c, int what, double out[3]) { fgo_avg_region(c, what, -1, out); }
+
+void fgo_avg_region(const fgo_ctx *c, int what, int region, double out[3])
     {
     const int npi = c->npi;
     const double *a = fgo_tet_a(npi);
     const double *field = what == 0 ? c->u[1] : c->v[1];
-    double vol = fgo_total_mag_vol(c);
+    double vol = region == -1 ? fgo_total_mag_vol(c) : fgo_region_vol(c, region);
     for (int d = 0; d < 3; d++)
         {
         double sum = 0;
         for (int m = 0; m < c->n_magTet; m++)
             {
             const int t = c->magTet[m];
+            if (c->tet_reg[t] != region && region != -1) continue;
             const int *ind = c->tet_ind + 4 * (size_t)t;
             const double *w = c->tet_w + (size_t)npi * t;
             double s = 0;

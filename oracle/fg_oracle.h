@@ -210,8 +210,13 @@ void fgo_get_edges(const fgo_ctx *c, int *edges /* E x 2 */);
 /* ---------------- "next" rows: energies and averages ------------------ */
 /* Fem::energy src/energy.cpp:5-68 on NEXT state; E[4] = exchange, anisotropy, demag, zeeman */
 void fgo_energy(const fgo_ctx *c, const double Hext[3], double E[4]);
+/* same with the space-dependent field x amplitude (R4toR3), src/energy.cpp:41-43, tetra.cpp:382-391 */
+void fgo_energy_space(const fgo_ctx *c, double fieldAmp, double E[4]);
 /* mesh::avg src/mesh.cpp:89-106 for u (what=0) or v (what=1) NEXT, all magnetic regions */
 void fgo_avg(const fgo_ctx *c, int what, double out[3]);
+/* same restricted to one volume region (region = -1: all magnetic regions) */
+void fgo_avg_region(const fgo_ctx *c, int what, int region, double out[3]);
+double fgo_region_vol(const fgo_ctx *c, int region);
 double fgo_total_mag_vol(const fgo_ctx *c);
 /* mesh::max_angle src/mesh.h:295-306 */
 double fgo_max_angle(const fgo_ctx *c);

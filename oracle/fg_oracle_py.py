@@ -365,9 +365,14 @@ class OracleCtx:
         self.L.fgo_energy(self.h, _dp(H), _dp(E))
         return E
 
-    def avg(self, what=0):
+    def energy_space(self, fieldAmp):
+        E = np.zeros(4)
+        self.L.fgo_energy_space(self.h, C.c_double(fieldAmp), _dp(E))
+        return E
+
+    def avg(self, what=0, region=-1):
         out = np.zeros(3)
-        self.L.fgo_avg(self.h, C.c_int(what), _dp(out))
+        self.L.fgo_avg_region(self.h, C.c_int(what), C.c_int(region), _dp(out))
         return out
 
     def total_mag_vol(self):

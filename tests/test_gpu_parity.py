@@ -222,6 +222,43 @@ def test_trajectory_averages(oracle, gpu_lib):
     oc.close()
 
 
+@pytest.mark.parametrize("name", ["small_cuboid", "small_cuboid_npi1", "ellipsoid"])
+def test_observables(oracle, gpu_lib, name):
+    """Fem::energy, mesh::avg (all regions and per region), mesh::max_angle on the resident state
+     against the oracle on the SAME state: sums of ~1e3 element terms in a
+    different order, so 1e-12 relative per energy term."""
+    case = {"small_cuboid": lambda: cases.small_cuboid(),
+            "small_cuboid_npi1": lambda: cases.small_cuboid(npi=1),
+            "ellipsoid": lambda: cases.ellipsoid()}[name]()
+    oc, la = _pair(case)
+    E_o, E_g = oc.energy(case.Hext), la.energy(case.Hext)
+    for k in range(4):
+        assert abs(E_g[k] - E_o[k]) <= 1e-12 * np.max(np.abs(E_o)), (k, E_g, E_o)
+    for what, w in (("u", 0), ("v", 1)):
+        assert rel_max(la.avg(what), oc.avg(w)) < 1e-12
+        for region in range(1, len(case.tet_regions)):
+            a_o, a_g = oc.avg(w, region), la.avg(what, region)
+            assert rel_max(a_g, a_o) < 1e-12, (what, region)   # non-magnetic region: 0 / vol = 0
+    assert np.all(np.isnan(la.avg("u", 0))) and np.all(np.isnan(oc.avg(0, 0)))  # no tet: 0 / 0
+    assert abs(la.max_angle() - oc.max_angle()) < 1e-14
+    la.close()
+    oc.close()
+
+
+def test_energy_space_field(oracle, gpu_lib):
+    """Zeeman energy with mesh.extSpaceField x amplitude (src/energy.cpp:41-43)."""
+    case = cases.small_cuboid()
+    oc, la = _pair(case)
+    rng = np.random.default_rng(11)
+    field = rng.standard_normal((case.mesh.NT, 3, case.npi)) * 1e4
+    oc.set_ext_space_field(field)
+    la.set_ext_space_field(field)
+    E_o, E_g = oc.energy_space(0.37), la.energy(0.37)
+    assert np.max(np.abs(E_g - E_o)) <= 1e-12 * np.max(np.abs(E_o))
+    la.close()
+    oc.close()
+
+
 def test_failure_semantics(oracle, gpu_lib):
     """solve() returns True (failure) on ITER_OVERFLOW and leaves NEXT and v_max untouched
     (src/solver.cpp:62-69)."""
