@@ -95,6 +95,15 @@ struct Settings
     bool recenter = false;
     int recentering_direction = FG_IDX_Z;
     int npi_tet = 5, npi_tri = 4;           // ONE_GAUSS_POINT -> 1, 1
+    // what Fem::time_integration / Fem::saver read (src/default-settings.yml:43,63-71,239)
+    double time_step = 5e-13;               // outputs.evol_time_step
+    double DUMAX = 0.02;                    // time_integration.max(du)
+    std::vector<std::string> evol_columns = {"t", "<Mx>", "<My>", "<Mz>", "E_ex", "E_demag", "E_zeeman", "E_tot"};
+    std::vector<std::string> region_names;  // volume region names, index = region (for "name:<Mx>")
+    // applied field: uniform (RtoR3, Settings::getField) or amplitude of mesh.extSpaceField (R4toR3,
+    // Settings::getFieldTime); set exactly one
+    std::function<Vec3(double)> field;
+    std::function<double(double)> field_time;
     };
 
 // What Mesh::mesh hands to the solver (src/mesh.h:38-135), as plain arrays
@@ -394,6 +403,33 @@ public:
     void evolution() { fgb200::check(fg_commit(ctx), "evolution"); }
     void set_ext_space_field(const double *field)
         { fgb200::check(fg_set_ext_space_field(ctx, field), "set_ext_space_field"); }
+    /** Fem::energy terms (src/energy.cpp:5-68) of the NEXT state: exchange, anisotropy, demag, zeeman */
+    template <class Vector3> std::array<double, 4> energy(const Vector3 &Hext) const
+        {
+        std::array<double, 4> E;
+        fgb200::check(fg_energy(ctx, Hext.data(), E.data()), "energy");
+        return E;
+        }
+    std::array<double, 4> energy(const double A_Hext) const
+        {
+        std::array<double, 4> E;
+        fgb200::check(fg_energy_space(ctx, A_Hext, E.data()), "energy");
+        return E;
+        }
+    /** mesh::avg (src/mesh.cpp:89-106): what = 0 u | 1 v, all three components */
+    std::array<double, 3> avg(int what, int region = -1) const
+        {
+        std::array<double, 3> a;
+        fgb200::check(fg_avg(ctx, what, region, a.data()), "avg");
+        return a;
+        }
+    /** mesh::max_angle (src/mesh.h:295-306) */
+    double max_angle() const
+        {
+        double a = 0.0;
+        fgb200::check(fg_max_angle(ctx, &a), "max_angle");
+        return a;
+        }
 
     algebra::iteration<double> iter;   // solver<DIM>::iter, src/solver.h:66
     fg_ctx *handle() const { return ctx; }
@@ -407,4 +443,259 @@ private:
     const int verbose;
     double DW_vz = 0.0;   // never initialised in the reference: 0 here
     double v_max = 0.0;
+    };
+
+// ---------------------------------------------------------------------------------------------
+// TimeStepper — reference src/time_integration.cpp:11-38
+// ---------------------------------------------------------------------------------------------
+class TimeStepper
+    {
+    const double hard_min;
+    const double hard_max;
+    double soft_max;
+
+public:
+    TimeStepper(const double initial, const double min, const double max)
+        : hard_min(min), hard_max(max * (1 + std::numeric_limits<float>::epsilon())), soft_max(initial)
+        {
+        }
+    void set_soft_limit(const double max) { soft_max = std::min(soft_max, max); }
+    double operator()(const double stride)
+        {
+        double step = std::min(stride, soft_max);
+        if (step > stride - 2 * hard_min && step < stride) step = stride - 2 * hard_min;
+        soft_max = std::max(soft_max, std::min(step * 1.1, hard_max));
+        return step;
+        }
+    };
+
+// LogStats — reference src/log-stats.h (Welford on the logarithms)
+class LogStats
+    {
+public:
+    void add(double x)
+        {
+        x = std::log(x);
+        n += 1;
+        double delta1 = x - m;
+        m += delta1 / n;
+        double delta2 = x - m;
+        s += delta1 * delta2;
+        }
+    long count() const { return n; }
+    double mean() const { return std::exp(m); }
+    double stddev() const { return std::sqrt(s / n); }
+
+private:
+    long n = 0;
+    double m = 0;
+    double s = 0;
+    };
+
+// Stats — reference src/time_integration.cpp:41-47
+struct Stats
+    {
+    LogStats good_dt, good_dumax, bad_dt;
+    double max_angle = 0.0;
+    };
+
+const int NB_ENERGY_TERMS = 4;
+enum ENERGY_TYPE { EXCHANGE = 0, ANISOTROPY = 1, DEMAG = 2, ZEEMAN = 3 };  // src/fem.h:27-36
+
+// ---------------------------------------------------------------------------------------------
+// Fem — the part of the reference's Fem that surrounds the hot path: vmax, E, Etot, Etot0, energy,
+// evolution, compute_all, saver (src/fem.h, src/energy.cpp, src/save.cpp:13-140) and
+// Fem::time_integration (src/time_integration.cpp:133-245).  The mesh state lives in the
+// LinAlgebra's device context; the demag solver (ScalFMM in the reference, outside the path) is the
+// callback run where compute_all calls myFMM.calc_demag: it reads the NEXT magnetisation
+// (LinAlgebra::get_state) and writes phi / phiv (LinAlgebra::set_potentials).
+// ---------------------------------------------------------------------------------------------
+class Fem
+    {
+public:
+    Fem(fgb200::Settings &s, LinAlgebra &la, std::function<void(LinAlgebra &)> demag_solver = nullptr)
+        : settings(s), linAlg(la), demag(std::move(demag_solver))
+        {
+        E.fill(0.0);
+        }
+
+    double vmax = 0.0;
+    std::array<double, NB_ENERGY_TERMS> E;
+    double Etot0 = INFINITY;  // avoid "WARNING: energy increased" on first time step
+    double Etot = 0.0;
+    Stats stats;
+    std::vector<std::vector<double>> evol;  // rows written by saver (also streamed to `out`)
+
+    /** src/energy.cpp:5-68 */
+    void energy(const double t)
+        {
+        if (settings.field_time)
+            E = linAlg.energy(settings.field_time(t));
+        else
+            E = linAlg.energy(settings.field ? settings.field(t) : fgb200::Vec3{{0.0, 0.0, 0.0}});
+        Etot = 0.0 + ((E[0] + E[1]) + (E[2] + E[3]));  // std::reduce on 4 doubles (libstdc++)
+        if (settings.verbose && (Etot > Etot0))
+            std::cout << "WARNING: energy increased from " << Etot0 << " to " << Etot << "\n";
+        }
+    /** src/fem.h:159-163 */
+    void evolution()
+        {
+        linAlg.evolution();
+        Etot0 = Etot;
+        }
+    /** src/fem.h:203-224 */
+    void compute_all(const double t)
+        {
+        if (demag) demag(linAlg);
+        energy(t);
+        evolution();
+        }
+    /** the .evol row of Fem::saver, src/save.cpp:13-140 */
+    void saver(const timing &t_prm, std::ostream *out, const int nt)
+        {
+        std::vector<double> row;
+        std::array<double, 3> au{}, av{}, H{};
+        int au_reg = -2, av_reg = -2;
+        bool have_H = false;
+        for (const std::string &col_name : settings.evol_columns)
+            {
+            int region = -1;
+            std::string keyVal = col_name;
+            const std::string::size_type colon_pos = col_name.rfind(':');
+            if (colon_pos != std::string::npos)
+                {
+                const std::string region_name = col_name.substr(0, colon_pos);
+                const auto it = std::find(settings.region_names.begin(), settings.region_names.end(), region_name);
+                if (it == settings.region_names.end())
+                    throw std::runtime_error("Error: no region named '" + region_name + "'");
+                region = (int)(it - settings.region_names.begin());
+                keyVal = col_name.substr(colon_pos + 1);
+                }
+            auto U = [&](int k) { if (au_reg != region) { au = linAlg.avg(0, region); au_reg = region; } return au[k]; };
+            auto V = [&](int k) { if (av_reg != region) { av = linAlg.avg(1, region); av_reg = region; } return av[k]; };
+            auto Hk = [&](int k)
+                {
+                if (!have_H)
+                    {
+                    const fgb200::Vec3 h = settings.field ? settings.field(t_prm.get_t()) : fgb200::Vec3{{NAN, NAN, NAN}};
+                    H = {h.v[0], h.v[1], h.v[2]};
+                    have_H = true;
+                    }
+                return H[k];
+                };
+            if (keyVal == "iter") row.push_back(nt);
+            else if (keyVal == "t") row.push_back(t_prm.get_t());
+            else if (keyVal == "dt") row.push_back(t_prm.get_dt());
+            else if (keyVal == "max_dm") row.push_back(vmax * t_prm.get_dt());
+            else if (keyVal == "max_angle") row.push_back(linAlg.max_angle());
+            else if (keyVal == "<Mx>") row.push_back(U(0));
+            else if (keyVal == "<My>") row.push_back(U(1));
+            else if (keyVal == "<Mz>") row.push_back(U(2));
+            else if (keyVal == "<dMx/dt>") row.push_back(V(0));
+            else if (keyVal == "<dMy/dt>") row.push_back(V(1));
+            else if (keyVal == "<dMz/dt>") row.push_back(V(2));
+            else if (keyVal == "E_ex") row.push_back(E[EXCHANGE]);
+            else if (keyVal == "E_aniso") row.push_back(E[ANISOTROPY]);
+            else if (keyVal == "E_demag") row.push_back(E[DEMAG]);
+            else if (keyVal == "E_zeeman") row.push_back(E[ZEEMAN]);
+            else if (keyVal == "E_tot") row.push_back(Etot);
+            else if (keyVal == "Hx") row.push_back(Hk(0));
+            else if (keyVal == "Hy") row.push_back(Hk(1));
+            else if (keyVal == "Hz") row.push_back(Hk(2));
+            else throw std::runtime_error("Error: invalid column name '" + keyVal + "'");
+            }
+        if (out)
+            {
+            for (size_t i = 0; i < row.size(); i++) *out << row[i] << (i + 1 == row.size() ? "\n" : "\t");
+            *out << std::flush;
+            }
+        evol.push_back(std::move(row));
+        }
+
+    /** src/time_integration.cpp:133-245; `out` receives the .evol rows (precision 16 like the
+     * reference), `stop` stands for exit_if_signal_received.  Returns the exit status. */
+    int time_integration(timing &t_prm, int &nt, std::ostream *out = nullptr,
+                         const std::function<bool()> &stop = nullptr)
+        {
+        compute_all(t_prm.get_t());
+        if (out)
+            {
+            *out << "## columns: ";
+            for (size_t i = 0; i + 1 < settings.evol_columns.size(); i++) *out << settings.evol_columns[i] << '\t';
+            *out << settings.evol_columns.back() << "\n";
+            out->precision(16);
+            }
+        int flag(0);
+        int nt_output(0);
+        int status(0);
+        double t_initial = t_prm.get_t();
+        double t_step = settings.time_step;
+        int step_count = (int)std::round((t_prm.tf - t_initial) / t_step);
+        TimeStepper stepper(t_prm.get_dt(), t_prm.DTMIN, t_prm.DTMAX);
+        stats = Stats();
+        stats.max_angle = linAlg.max_angle();
+        nt = 0;
+        for (int step_nb = 0; step_nb <= step_count; step_nb++)
+            {
+            double t_target = t_initial + step_nb * t_step;
+            while (t_prm.get_t() < t_target)
+                {
+                if (stop && stop()) return 1;
+                t_prm.set_dt(stepper(t_target - t_prm.get_t()));
+                bool last_step = (t_prm.get_dt() == t_target - t_prm.get_t());
+                if (settings.verbose)
+                    {
+                    std::cout << std::string(64, '-') << '\n';
+                    if (flag) std::cout << "  TRYING AGAIN with a smaller time step: retry " << flag << '\n';
+                    std::cout << "evol step = " << nt_output << ", step = " << nt << ", t = " << t_prm.get_t()
+                              << ", dt = " << t_prm.get_dt() << '\n';
+                    }
+                if (t_prm.is_dt_TooSmall())
+                    {
+                    std::cout << "\n**ABORTED**: dt < DTMIN\n";
+                    return 1;
+                    }
+                linAlg.base_projection();
+                if (settings.field_time)
+                    linAlg.prepareElements(settings.field_time(t_prm.get_t()), t_prm);
+                else
+                    linAlg.prepareElements(settings.field ? settings.field(t_prm.get_t()) : fgb200::Vec3{{0.0, 0.0, 0.0}}, t_prm);
+                bool err = linAlg.solve(t_prm);
+                vmax = linAlg.get_v_max();
+                if (err)
+                    {
+                    flag++;
+                    stepper.set_soft_limit(t_prm.get_dt() / 2);
+                    stats.bad_dt.add(t_prm.get_dt());
+                    continue;
+                    }
+                double dumax = t_prm.get_dt() * vmax;
+                stats.good_dt.add(t_prm.get_dt());
+                stats.good_dumax.add(dumax);
+                if (settings.verbose) std::cout << "  -> dumax = " << dumax << ",  vmax = " << vmax << std::endl;
+                stepper.set_soft_limit((settings.DUMAX / vmax) * 0.95);
+                if (dumax > settings.DUMAX)
+                    {
+                    flag++;
+                    continue;
+                    }
+                compute_all(t_prm.get_t());
+                nt++;
+                flag = 0;
+                // Prevent rounding errors from making us miss the target.
+                if (last_step)
+                    t_prm.set_t(t_target);
+                else
+                    t_prm.inc_t();
+                stats.max_angle = std::max(stats.max_angle, linAlg.max_angle());
+                }
+            saver(t_prm, out, nt_output++);
+            }
+        return status;
+        }
+
+private:
+    fgb200::Settings &settings;
+    LinAlgebra &linAlg;
+    std::function<void(LinAlgebra &)> demag;
     };

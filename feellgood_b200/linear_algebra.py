@@ -91,12 +91,18 @@ class Settings:
     TOL, MAXITER, verbose, recenter, recentering_direction, plus the NPI compile-time switch."""
 
     def __init__(self, paramTetra, paramTriangle=(), TOL=1e-6, MAXITER=700, verbose=False,
-                 recenter=False, recentering_direction=capi.FG_IDX_Z, npi_tet=5, npi_tri=4):
+                 recenter=False, recentering_direction=capi.FG_IDX_Z, npi_tet=5, npi_tri=4,
+                 time_step=1e-11, DUMAX=0.02, evol_columns=None, field=None, field_time=None):
         self.paramTetra = list(paramTetra)
         self.paramTriangle = list(paramTriangle)
         self.TOL, self.MAXITER, self.verbose = TOL, MAXITER, verbose
         self.recenter, self.recentering_direction = recenter, recentering_direction
         self.npi_tet, self.npi_tri = npi_tet, npi_tri
+        # what Fem::time_integration reads (feellgood_b200.fem): outputs.evol_time_step,
+        # time_integration.max(du) (default-settings.yml), outputs.evol_columns, and the applied
+        # field: `field` t -> 3-vector in A/m (RtoR3) or `field_time` t -> amplitude (R4toR3)
+        self.time_step, self.DUMAX, self.evol_columns = time_step, DUMAX, evol_columns
+        self.field, self.field_time = field, field_time
 
 
 class LinAlgebra:

@@ -401,8 +401,59 @@ def ref_lib():
         R.fgref_bicg_dir.restype = C.c_double
         R.fgref_dot.restype = C.c_double
         R.fgref_norm.restype = C.c_double
+        if hasattr(R, "fgref_ts_new"):
+            R.fgref_ts_new.restype = C.c_void_p
+            R.fgref_ts_new.argtypes = [C.c_double, C.c_double, C.c_double]
+            R.fgref_ts_free.argtypes = [C.c_void_p]
+            R.fgref_ts_set_soft_limit.argtypes = [C.c_void_p, C.c_double]
+            R.fgref_ts_step.restype = C.c_double
+            R.fgref_ts_step.argtypes = [C.c_void_p, C.c_double]
+            R.fgref_ls_new.restype = C.c_void_p
+            R.fgref_ls_free.argtypes = [C.c_void_p]
+            R.fgref_ls_add.argtypes = [C.c_void_p, C.c_double]
+            R.fgref_ls_get.argtypes = [C.c_void_p, c_double_p]
         _ref = R
     return _ref
+
+
+class RefTimeStepper:
+    """The reference's own TimeStepper (src/time_integration.cpp:11-38) from oracle/_ref."""
+
+    def __init__(self, initial, dtmin, dtmax):
+        self.R = ref_lib()
+        self.h = C.c_void_p(self.R.fgref_ts_new(initial, dtmin, dtmax))
+
+    def set_soft_limit(self, mx):
+        self.R.fgref_ts_set_soft_limit(self.h, mx)
+
+    def __call__(self, stride):
+        return self.R.fgref_ts_step(self.h, stride)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.R.fgref_ts_free(self.h)
+            self.h = None
+
+
+class RefLogStats:
+    """The reference's own LogStats (src/log-stats.h) from oracle/_ref."""
+
+    def __init__(self):
+        self.R = ref_lib()
+        self.h = C.c_void_p(self.R.fgref_ls_new())
+
+    def add(self, x):
+        self.R.fgref_ls_add(self.h, x)
+
+    def get(self):
+        out = np.zeros(3)
+        self.R.fgref_ls_get(self.h, _dp(out))
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.R.fgref_ls_free(self.h)
+            self.h = None
 
 
 class RefMatrix:

@@ -27,6 +27,12 @@
 #include "algebra/bicg.h"
 #include "algebra/cg.h"
 #include "time_integration.h"
+// the reference's own TimeStepper (cut out of src/time_integration.cpp:11-38 by oracle/Makefile at
+// build time, never stored in this repository) and LogStats (src/log-stats.h, STL-only)
+#include <cfloat>
+#include <algorithm>
+#include "timestepper_extract.h"
+#include "log-stats.h"
 
 namespace
     {
@@ -190,4 +196,19 @@ double fgref_norm(const double *x, int n)
     std::vector<double> X(x, x + n);
     return algebra::norm(X);
     }
+    /* ---- TimeStepper (src/time_integration.cpp:11-38) and LogStats (src/log-stats.h) ---- */
+void *fgref_ts_new(double initial, double dtmin, double dtmax) { return new TimeStepper(initial, dtmin, dtmax); }
+void fgref_ts_free(void *h) { delete (TimeStepper *)h; }
+void fgref_ts_set_soft_limit(void *h, double mx) { ((TimeStepper *)h)->set_soft_limit(mx); }
+double fgref_ts_step(void *h, double stride) { return (*(TimeStepper *)h)(stride); }
+void *fgref_ls_new(void) { return new LogStats; }
+void fgref_ls_free(void *h) { delete (LogStats *)h; }
+void fgref_ls_add(void *h, double x) { ((LogStats *)h)->add(x); }
+void fgref_ls_get(void *h, double out[3])
+    {
+    LogStats *l = (LogStats *)h;
+    out[0] = (double)l->count();
+    out[1] = l->mean();
+    out[2] = l->stddev();
     }
+}

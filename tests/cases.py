@@ -172,3 +172,66 @@ def rel_max(a, b):
     d = np.max(np.abs(a - b)) if a.size else 0.0
     s = np.max(np.abs(b)) if b.size else 0.0
     return 0.0 if d == 0.0 else d / s
+
+
+# ------------------------------------------------------------------------------------------
+class OracleLinAlgebra:
+    """The CPU oracle behind the LinAlgebra surface that feellgood_b200.fem.Fem drives, so that the
+    very same loop code can be run on the checker and on the GPU (test infrastructure)."""
+
+    def __init__(self, oc):
+        self.oc = oc
+        self.v_max = 0.0
+        self.iter = {}
+
+    def base_projection(self, angle=None):
+        from feellgood_b200.linear_algebra import M_2_PI, _c_rand, mt19937_uniform01
+        if angle is None:
+            angle = M_2_PI * mt19937_uniform01(_c_rand())
+        self.oc.base_projection(angle)
+
+    def prepareElements(self, Hext, t_prm):
+        if np.ndim(Hext) == 0:
+            self.oc.prepare_elements_space(float(Hext), t_prm.get_dt(), t_prm.prefactor)
+        else:
+            self.oc.prepare_elements(np.asarray(Hext, dtype=np.float64), t_prm.get_dt(), t_prm.prefactor)
+
+    def solve(self, t_prm):
+        failed = self.oc.solve(t_prm.get_dt())
+        self.iter = self.oc.iter_info()
+        self.v_max = self.oc.v_max()
+        return failed
+
+    def get_v_max(self):
+        return self.v_max
+
+    def evolution(self):
+        self.oc.evolution()
+
+    def energy(self, Hext):
+        return self.oc.energy_space(float(Hext)) if np.ndim(Hext) == 0 else self.oc.energy(Hext)
+
+    def avg(self, what="u", region=-1):
+        return self.oc.avg({"u": 0, "v": 1}[what], region)
+
+    def max_angle(self):
+        return self.oc.max_angle()
+
+    def get_state(self, step=1, what="uvpq"):
+        return self.oc.get_state(step)
+
+    def set_potentials(self, phi, phiv):
+        self.oc.set_potentials_next(phi, phiv)
+
+
+def local_demag_surrogate(mesh, Ms=795774.7):
+    """A cheap state-dependent stand-in for the demag solver (ScalFMM is outside the path): the
+    callback Fem.compute_all runs where the reference calls myFMM.calc_demag."""
+    p = mesh.node_p / np.max(np.abs(mesh.node_p))
+
+    def demag(la):
+        u, v = la.get_state(1, "uv")[:2]
+        phi = 2e-9 * Ms * np.sum(u * p, axis=1)
+        phiv = 2e-9 * Ms * np.sum(v * p, axis=1)
+        la.set_potentials(phi, phiv)
+    return demag

@@ -105,6 +105,99 @@ static void test_llg_loop()
     std::printf("llg loop: %s v_max=%.6g\n", linAlg.iter.infos().c_str(), linAlg.get_v_max());
     }
 
+// Fem::time_integration through the C++ drop-in: visible steps land on their targets, accepted steps
+// respect DUMAX, E_tot is the sum of its terms and decreases under damping in a fixed field.
+static void test_fem_time_integration()
+    {
+    fgb200::MeshView msh = cuboid(8, 4, 3, 2e-9);
+    fgb200::Settings s;
+    fg_tet_prm py{};
+    py.alpha_LLG = 0.5; py.A = 1.3e-11; py.Ms = 8e5; py.K = 1e4; py.K3 = 0;
+    py.uk[2] = 1; py.ex[0] = 1; py.ey[1] = 1; py.ez[2] = 1;
+    fg_tet_prm def = py;
+    s.paramTetra = {def, py};
+    s.paramTriangle = {fg_tri_prm{}};
+    s.time_step = 1e-12;
+    s.DUMAX = 0.05;
+    s.evol_columns = {"iter", "t", "dt", "max_dm", "max_angle", "<Mx>", "<My>", "<Mz>", "<dMz/dt>",
+                      "E_ex", "E_aniso", "E_demag", "E_zeeman", "E_tot", "Hy"};
+    s.field = [](double) { return fgb200::Vec3{{0.0, 8000.0, 0.0}}; };
+    srand(2);
+    LinAlgebra linAlg(s, msh);
+    const int NOD = msh.NOD();
+    std::vector<double> u(3 * (size_t)NOD);
+    for (int a = 0; a < NOD; a++)
+        {
+        const double x = msh.node_p[3 * a] * 1e8;
+        const double c[3] = {std::cos(x), 0.2, std::sin(x)};
+        const double nn = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+        for (int k = 0; k < 3; k++) u[3 * a + k] = c[k] / nn;
+        }
+    linAlg.set_state(u.data(), nullptr, nullptr, nullptr);
+    std::vector<double> un(3 * (size_t)NOD), phi(NOD), phiv(NOD, 0.0);
+    int demag_calls = 0;
+    Fem fem(s, linAlg, [&](LinAlgebra &la)
+        {  // stand-in for myFMM.calc_demag: a local function of the new magnetisation
+        la.get_state(1, un.data(), nullptr, nullptr, nullptr);
+        for (int a = 0; a < NOD; a++) phi[a] = 1e-3 * un[3 * a + 2];
+        la.set_potentials(phi.data(), phiv.data());
+        demag_calls++;
+        });
+    timing t_prm(3e-12, 1e-16, 5e-13);
+    int nt = -1;
+    std::ostringstream evol;
+    const int status = fem.time_integration(t_prm, nt, &evol);
+    CHECK(status == 0);
+    CHECK(nt >= 6);
+    CHECK(demag_calls == nt + 1);
+    CHECK(fem.evol.size() == 4);
+    for (size_t k = 0; k < fem.evol.size(); k++)
+        {
+        const std::vector<double> &r = fem.evol[k];
+        CHECK(r.size() == 15);
+        CHECK(r[0] == (double)k);
+        CHECK(r[1] == (double)k * 1e-12 || std::fabs(r[1] - k * 1e-12) < 1e-27);
+        CHECK(r[3] <= s.DUMAX);
+        CHECK(r[13] == 0.0 + ((r[9] + r[10]) + (r[11] + r[12])));
+        CHECK(r[14] == 8000.0);
+        if (k > 0) CHECK(r[13] < fem.evol[k - 1][13]);
+        }
+    CHECK(t_prm.get_t() == 3e-12);
+    CHECK(fem.stats.good_dt.count() >= nt);
+    CHECK(fem.stats.max_angle > 0.0 && fem.stats.max_angle < 3.2);
+    CHECK(evol.str().rfind("## columns: iter\tt\tdt", 0) == 0);
+    std::printf("fem loop: nt=%d good=%ld bad=%ld <dt>=%.3e Etot %.6e -> %.6e\n", nt, fem.stats.good_dt.count(),
+                fem.stats.bad_dt.count(), fem.stats.good_dt.mean(), fem.evol.front()[13], fem.evol.back()[13]);
+    }
+
+// TimeStepper / LogStats replay for the bit-exact comparison with the reference's own classes
+// (tests/test_host_shim.py feeds the call sequence of tests/golden/ref_timestepper.npz)
+static int replay_timestepper()
+    {
+    double init, mn, mx;
+    if (std::scanf("%lf %lf %lf", &init, &mn, &mx) != 3) return 2;
+    TimeStepper ts(init, mn, mx);
+    LogStats ls;
+    int op;
+    double val;
+    while (std::scanf("%d %lf", &op, &val) == 2)
+        {
+        if (op == 0)
+            std::printf("%.17g\n", ts(val));
+        else if (op == 1)
+            {
+            ts.set_soft_limit(val);
+            std::printf("nan\n");
+            }
+        else
+            {
+            ls.add(val);
+            std::printf("%ld %.17g %.17g\n", ls.count(), ls.mean(), ls.stddev());
+            }
+        }
+    return 0;
+    }
+
 // unit-tests/ut_algebra.cpp:160-190 (test_cg) and :245-275 (test_bicg): identity solves in 0 iterations
 static void test_identity_solves()
     {
@@ -167,6 +260,7 @@ static void test_laplacian_dirichlet()
 
 int main(int argc, char **argv)
     {
+    if (argc > 1 && !std::strcmp(argv[1], "--timestepper")) return replay_timestepper();
     if (argc > 1 && !std::strcmp(argv[1], "--link-check"))
         {
         std::printf("fg_version %d\n", fg_version());
@@ -177,6 +271,7 @@ int main(int argc, char **argv)
         test_identity_solves();
         test_laplacian_dirichlet();
         test_llg_loop();
+        test_fem_time_integration();
         }
     catch (const std::exception &e)
         {

@@ -8,6 +8,9 @@
                        oracle/_ref/libfgref_algebra.so) on seeded inputs: SparseMatrix::mult,
                        bicg, bicg_dir (both overloads), cg, cg_dir, timing.  These pin the oracle
                        (tests/test_oracle_vs_reference.py) and, through it, the CUDA path.
+  ref_timestepper.npz  outputs of the REFERENCE's own TimeStepper (cut out of
+                       src/time_integration.cpp at build time) and LogStats (src/log-stats.h) on
+                       seeded call sequences: pins feellgood_b200.fem and the C++ host mirror.
   llg_system.npz       the oracle's K, L_rhs, x0, solution and next state for one LLG step on a
                        small two-region cuboid with the reference's own SparseMatrix::add +
                        bicg_dir driving the solve (fgo_use_reference_algebra).
@@ -115,7 +118,59 @@ def llg_system():
     print("llg_system: failed", failed, info)
 
 
+def timestepper_script(seed=5489, n=400):
+    """Seeded call sequence for TimeStepper: (op, value) with op 0 = operator()(stride),
+    1 = set_soft_limit(value); mimics the accept / reject / dumax traffic of time_integration."""
+    rng = np.random.default_rng(seed)
+    ops = []
+    t, target = 0.0, 1e-12
+    for _ in range(n):
+        r = rng.random()
+        if r < 0.6:
+            stride = target - t
+            ops.append((0, stride))
+        elif r < 0.8:
+            ops.append((1, 10 ** rng.uniform(-15, -12)))
+        else:
+            target += 1e-12
+            ops.append((0, target - t))
+        t += 10 ** rng.uniform(-15, -13)
+        if t >= target:
+            target = t + 1e-12
+    return np.array(ops)
+
+
+def ref_timestepper():
+    """Outputs of the REFERENCE's own TimeStepper and LogStats (oracle/_ref) on seeded scripts."""
+    out = {}
+    for k, (init, mn, mx) in enumerate([(7.07e-15, 1e-16, 5e-13), (2.2e-13, 5e-14, 1e-12), (1e-13, 1e-15, 1e-13)]):
+        ops = timestepper_script(5489 + k)
+        ts = fo.RefTimeStepper(init, mn, mx)
+        res = []
+        for op, val in ops:
+            if op == 0:
+                res.append(ts(val))
+            else:
+                ts.set_soft_limit(val)
+                res.append(np.nan)
+        out["ts%d_prm" % k] = np.array([init, mn, mx])
+        out["ts%d_ops" % k] = ops
+        out["ts%d_out" % k] = np.array(res)
+    rng = np.random.default_rng(5489)
+    xs = 10 ** rng.uniform(-16, -12, size=257)
+    ls = fo.RefLogStats()
+    snap = []
+    for x in xs:
+        ls.add(x)
+        snap.append(ls.get())
+    out["ls_x"] = xs
+    out["ls_out"] = np.array(snap)
+    np.savez_compressed(os.path.join(HERE, "ref_timestepper.npz"), **out)
+    print("ref_timestepper: %d arrays" % len(out))
+
+
 if __name__ == "__main__":
-    ellipsoid()
-    ref_algebra()
-    llg_system()
+    which = sys.argv[1:] or ["ellipsoid", "ref_algebra", "llg_system", "ref_timestepper"]
+    for name in which:
+        {"ellipsoid": ellipsoid, "ref_algebra": ref_algebra, "llg_system": llg_system,
+         "ref_timestepper": ref_timestepper}[name]()
