@@ -82,6 +82,12 @@ struct fg_ctx
     double *mtri_surf = nullptr, *mtri_nrm = nullptr, *mtri_dMs = nullptr;
     int2 *extra_edges = nullptr;
     double *d_scal = nullptr, *h_scal = nullptr;  // 8 doubles: reduction results (device / pinned)
+    // charges + all-pairs demag: tables built on first use
+    bool demag_ready = false;
+    long long nsrc = 0;
+    double *node_pos = nullptr, *corr = nullptr, *tcorr = nullptr;
+    double4 *src = nullptr;
+    int *cptr = nullptr, *cidx = nullptr;
     // step bookkeeping
     StepPrm sp = {};
     bool have_basis = false, prepared = false, space_field = false, assembled = false;
@@ -742,7 +748,7 @@ void fg_destroy(fg_ctx *c)
                     c->tri_reg, c->tri_surf, c->tri_dMs, c->reg_tri, c->trec, c->perm, c->sptr,
                     c->scol, c->sdeg, c->iptr, c->tet_slot, c->itptr, c->sinct, c->sS, c->Aw, c->val,
                     c->mtri_ind, c->mtri_reg, c->mtri_surf, c->mtri_nrm, c->mtri_dMs, c->extra_edges,
-                    c->d_scal};
+                    c->d_scal, c->node_pos, c->corr, c->tcorr, c->src, c->cptr, c->cidx};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int q = 0; q < DIST_MAX_RANKS; q++)
@@ -1118,6 +1124,167 @@ int fg_max_angle(fg_ctx *c, double *angle)
     FG_TRY(fetch_scalars(c, 1));
     const double min_dot = -c->h_scal[0];
     *angle = acos(min_dot);  // src/mesh.h:305
+    return FG_OK;
+    }
+
+// ---- magnetic charges and the all-pairs demag potential ----
+namespace
+{
+int ensure_demag_tables(fg_ctx *c)
+    {
+    FG_TRY(ensure_obs_tables(c));
+    if (c->demag_ready) return FG_OK;
+    const HostSetup &h = c->h;
+    const size_t N = (size_t)c->NODt;
+    std::vector<double> pos(3 * N, 0.0);
+    for (size_t r = 0; r < N; r++)
+        {
+        const int a = h.perm[r];
+        if (a < 0) continue;
+        for (int d = 0; d < 3; d++) pos[3 * r + d] = h.node_p[3 * (size_t)a + d];
+        }
+    FG_TRY(dev_upload(&c->node_pos, pos, c->stream));
+    // source positions = Gauss points (getPtGauss): tets in device order, then msh.magTri
+    const int npi = h.npi_tet, npt = h.npi_tri;
+    double a[20], pds[5], at[12], pt[4];
+    tet_tables(npi, a, pds);
+    tri_tables(npt, at, pt);
+    const size_t M = (size_t)c->NTm, F = (size_t)c->NFm;
+    c->nsrc = (long long)(M * npi + F * npt);
+    std::vector<double4> src((size_t)c->nsrc);
+    for (size_t tm = 0; tm < M; tm++)
+        {
+        const int *ind = &h.tet_ind[4 * (size_t)h.magTet[tm]];
+        for (int g = 0; g < npi; g++)
+            {
+            double x[3] = {0, 0, 0};
+            for (int d = 0; d < 3; d++)
+                for (int i = 0; i < 4; i++) x[d] += h.node_p[3 * (size_t)ind[i] + d] * a[i * npi + g];
+            src[tm * npi + g] = make_double4(x[0], x[1], x[2], 0.0);
+            }
+        }
+    std::vector<int> cnt(N + 1, 0);
+    for (size_t k = 0; k < F; k++)
+        {
+        const int *ind = &h.tri_ind[3 * (size_t)h.magTri[k]];
+        for (int g = 0; g < npt; g++)
+            {
+            double x[3] = {0, 0, 0};
+            for (int d = 0; d < 3; d++)
+                for (int i = 0; i < 3; i++) x[d] += h.node_p[3 * (size_t)ind[i] + d] * at[i * npt + g];
+            src[M * npi + k * npt + g] = make_double4(x[0], x[1], x[2], 0.0);
+            }
+        for (int i = 0; i < 3; i++) cnt[(size_t)h.iperm[ind[i]] + 1]++;
+        }
+    FG_TRY(dev_upload(&c->src, src, c->stream));
+    // node -> (triangle, local node) incidences of msh.magTri, in triangle order
+    for (size_t r = 0; r < N; r++) cnt[r + 1] += cnt[r];
+    std::vector<int> cidx(3 * F), fill(cnt.begin(), cnt.end() - 1);
+    for (size_t k = 0; k < F; k++)
+        {
+        const int *ind = &h.tri_ind[3 * (size_t)h.magTri[k]];
+        for (int i = 0; i < 3; i++) cidx[(size_t)fill[h.iperm[ind[i]]]++] = (int)(3 * k + i);
+        }
+    FG_TRY(dev_upload(&c->cptr, cnt, c->stream));
+    FG_TRY(dev_upload(&c->cidx, cidx, c->stream));
+    FG_CUDA(cudaMalloc(&c->tcorr, sizeof(double) * (3 * F > 0 ? 3 * F : 1)));
+    FG_CUDA(cudaMalloc(&c->corr, sizeof(double) * N));
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    c->demag_ready = true;
+    return FG_OK;
+    }
+
+MagTriArrays mag_tri_arrays(const fg_ctx *c)
+    {
+    MagTriArrays F;
+    F.NFm = c->NFm;
+    F.ind = c->mtri_ind;
+    F.surf = c->mtri_surf;
+    F.nrm = c->mtri_nrm;
+    F.dMs = c->mtri_dMs;
+    F.reg = c->mtri_reg;
+    F.regions = c->reg_tri;
+    return F;
+    }
+
+// fmm::calc_charges (src/fmm_demag.h:155-185) on the NEXT state
+int launch_charges(fg_ctx *c, int which)
+    {
+    const TetArrays A = tet_arrays(c);
+    const int gt = grid_for(c->NTm, BLOCK);
+    if (c->NTm > 0)
+        {
+        if (c->h.npi_tet == 5) CTX_LAUNCH(c, k_charges_tet<5>, gt, A, c->next, which, c->src);
+        else CTX_LAUNCH(c, k_charges_tet<1>, gt, A, c->next, which, c->src);
+        }
+    double4 *src_tri = c->src + (size_t)c->NTm * c->h.npi_tet;
+    if (c->NFm > 0)
+        {
+        const MagTriArrays F = mag_tri_arrays(c);
+        const int gf = grid_for(c->NFm, BLOCK);
+        if (c->h.npi_tri == 4) CTX_LAUNCH(c, k_charges_tri<4>, gf, F, c->node_pos, c->next, which, src_tri, c->tcorr);
+        else CTX_LAUNCH(c, k_charges_tri<1>, gf, F, c->node_pos, c->next, which, src_tri, c->tcorr);
+        }
+    CTX_LAUNCH(c, k_corr_gather, (c->NODt + BLOCK - 1) / BLOCK, c->NODt, c->cptr, c->cidx, c->tcorr, c->corr);
+    return FG_OK;
+    }
+
+int demag_guard(fg_ctx *c, const char *who)
+    {
+    FG_TRY(check_ctx(c));
+    if (c->arena)
+        {
+        set_error("%s: not available on a distributed context (single-GPU stand-in for the FMM)", who);
+        return FG_ERR_STATE;
+        }
+    return ensure_demag_tables(c);
+    }
+}  // namespace
+
+int fg_calc_charges(fg_ctx *c, int which, double *srcDen, double *corr)
+    {
+    FG_TRY(demag_guard(c, "fg_calc_charges"));
+    if (which != 0 && which != 1)
+        {
+        set_error("fg_calc_charges: which must be 0 (u) or 1 (v)");
+        return FG_ERR_INVALID;
+        }
+    FG_TRY(launch_charges(c, which));
+    const HostSetup &h = c->h;
+    if (srcDen)
+        {
+        std::vector<double4> src((size_t)c->nsrc);
+        FG_CUDA(cudaMemcpyAsync(src.data(), c->src, sizeof(double4) * src.size(), cudaMemcpyDeviceToHost, c->stream));
+        FG_CUDA(cudaStreamSynchronize(c->stream));
+        // reference order (src/fmm_demag.h:160-170): magTet in ascending tet index, then magTri
+        const int npi = h.npi_tet;
+        std::vector<int> rank((size_t)h.NT, -1);
+        int r = 0;
+        for (int t = 0; t < h.NT; t++)
+            if (h.tet_to_mag[t] >= 0) rank[t] = r++;
+        for (size_t tm = 0; tm < (size_t)c->NTm; tm++)
+            for (int g = 0; g < npi; g++) srcDen[(size_t)rank[h.magTet[tm]] * npi + g] = src[tm * npi + g].w;
+        for (size_t k = (size_t)c->NTm * npi; k < src.size(); k++) srcDen[k] = src[k].w;
+        }
+    if (corr)
+        {
+        std::vector<double> tmp((size_t)c->NODt);
+        FG_CUDA(cudaMemcpyAsync(tmp.data(), c->corr, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, c->stream));
+        FG_CUDA(cudaStreamSynchronize(c->stream));
+        for (int a = 0; a < c->NOD; a++) corr[a] = tmp[(size_t)h.iperm[a]];
+        }
+    return FG_OK;
+    }
+
+int fg_demag_direct(fg_ctx *c, int second_order)
+    {
+    FG_TRY(demag_guard(c, "fg_demag_direct"));
+    for (int which = 0; which < (second_order ? 2 : 1); which++)
+        {
+        FG_TRY(launch_charges(c, which));
+        CTX_LAUNCH(c, k_demag_direct, (c->NODt + BLOCK - 1) / BLOCK, c->NODt, c->nonmag, c->node_pos, c->nsrc,
+                   c->src, c->corr, which, c->next);
+        }
     return FG_OK;
     }
 

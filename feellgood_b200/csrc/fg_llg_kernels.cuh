@@ -999,6 +999,183 @@ k_max_angle(int nslice, const int *__restrict__ sptr, const int *__restrict__ sc
     }
 
 // ------------------------------------------------------------------------------------------
+// magnetic charges (what the reference feeds ScalFMM, src/fmm_demag.h:155-185)
+// and an all-pairs evaluation of the potential they create (what the FMM approximates).
+// Sources are double4 {x, y, z, q}: the Gauss points are per-mesh constants, q is refreshed here.
+// ------------------------------------------------------------------------------------------
+// Tet::charges, src/tetra.cpp:347-359: q_g = -Ms w_g div(vec); which = 0: u, 1: v of `st`
+template <int NPI>
+__global__ void __launch_bounds__(BLOCK)
+k_charges_tet(const TetArrays A, const NodeRec *__restrict__ st, int which, double4 *__restrict__ src)
+    {
+    const int stride = gridDim.x * BLOCK;
+    for (int tm = blockIdx.x * BLOCK + threadIdx.x; tm < A.NTm; tm += stride)
+        {
+        TetIn T;
+        int4 ind;
+        tet_load<NPI>(A, tm, st, ind, T);
+        const double Ms = A.regions[__ldg(A.reg + tm)].Ms;
+        double sx = 0.0, sy = 0.0, sz = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            {
+            const double *f = which ? T.v[i] : T.u[i];
+            sx += f[0] * T.da[i][0];
+            sy += f[1] * T.da[i][1];
+            sz += f[2] * T.da[i][2];
+            }
+        const double dud_sum = sx + sy + sz;
+#pragma unroll
+        for (int g = 0; g < NPI; g++)
+            src[(size_t)tm * NPI + g].w = -Ms * (T.detJ * tet_pds<NPI>(g)) * dud_sum;
+        }
+    }
+
+// Tri::potential, src/triangle.cpp:87-125: potential at local node i of the linear charge s_k = vec_k . n
+__device__ __forceinline__ double tri_potential(const double p[3][3], const double sn[3], double surf,
+                                                double dMs, int i)
+    {
+    const int ii = (i + 1) % 3, iii = (i + 2) % 3;
+    double p1p2[3], p1p3[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        {
+        p1p2[k] = p[ii][k] - p[i][k];
+        p1p3[k] = p[iii][k] - p[i][k];
+        }
+    const double b = sqrt(dot3(p1p2, p1p2));
+    const double t = dot3(p1p2, p1p3) / b;
+    const double _2s = 2. * surf;
+    const double h = _2s / b;
+    const double c = (t - b) / h;
+    const double fc = sqrt(1.0 + c * c);
+    const double r = h * sqrt(1.0 + (t / h) * (t / h));
+    const double log_1 = log((c * t + h + fc * r) / (b * (c + fc)));
+    const double xi = b * log_1 / fc;
+    const double pot = xi * sn[i]
+                       + ((xi * (h + c * t) - b * (r - b)) * sn[ii] + b * (r - b - c * xi) * sn[iii]) * b
+                                 / (_2s * (1 + c * c));
+    return 0.5 * dMs * pot;
+    }
+
+// Tri::charges (src/triangle.cpp:45-59) into the source list and, per (triangle, local node), the
+// second-order correction of Tri::correctionCharges (src/triangle.cpp:61-78): minus the Gauss-point
+// terms of the triangle itself plus the analytic potential.  The node sums are a separate gather
+// (k_corr_gather) so that no atomics are needed and the result is reproducible.
+template <int NPI>
+__global__ void __launch_bounds__(BLOCK)
+k_charges_tri(const MagTriArrays A, const double *__restrict__ pos, const NodeRec *__restrict__ st,
+              int which, double4 *__restrict__ src, double *__restrict__ tcorr)
+    {
+    const int stride = gridDim.x * BLOCK;
+    for (int fa = blockIdx.x * BLOCK + threadIdx.x; fa < A.NFm; fa += stride)
+        {
+        double p[3][3], f[3][3], sn[3];
+        const double n[3] = {A.nrm[fa], A.nrm[(size_t)A.NFm + fa], A.nrm[2 * (size_t)A.NFm + fa]};
+        const double surf = A.surf[fa], dMs = A.dMs[fa];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            {
+            const int nd = A.ind[(size_t)i * A.NFm + fa];
+            double u[3], v[3], phi, phiv;
+            load_rec(st + nd, u, v, phi, phiv);
+#pragma unroll
+            for (int d = 0; d < 3; d++)
+                {
+                f[i][d] = which ? v[d] : u[d];
+                p[i][d] = pos[3 * (size_t)nd + d];
+                }
+            sn[i] = dot3(f[i], n);
+            }
+        double q[NPI], gp[NPI][3];
+#pragma unroll
+        for (int g = 0; g < NPI; g++)
+            {
+            double ug[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for (int d = 0; d < 3; d++)
+                {
+                double sp = 0.0;
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+                    {
+                    ug[d] += f[i][d] * tri_a<NPI>(i, g);
+                    sp += p[i][d] * tri_a<NPI>(i, g);
+                    }
+                gp[g][d] = sp;
+                }
+            q[g] = dMs != 0.0 ? dMs * ((2.0 * surf * tri_pds<NPI>(g)) * dot3(ug, n)) : 0.0;
+            src[(size_t)fa * NPI + g].w = q[g];
+            }
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            {
+            double cr = 0.0;
+#pragma unroll
+            for (int g = 0; g < NPI; g++)
+                {
+                const double dd[3] = {p[i][0] - gp[g][0], p[i][1] - gp[g][1], p[i][2] - gp[g][2]};
+                cr -= q[g] / sqrt(dot3(dd, dd));
+                }
+            cr += tri_potential(p, sn, surf, dMs, i);
+            tcorr[3 * (size_t)fa + i] = cr;
+            }
+        }
+    }
+
+// corr[row] = sum of the (triangle, node) corrections of the node, in triangle order
+__global__ void __launch_bounds__(BLOCK)
+k_corr_gather(int NODt, const int *__restrict__ cptr, const int *__restrict__ cidx,
+              const double *__restrict__ tcorr, double *__restrict__ corr)
+    {
+    const int row = blockIdx.x * BLOCK + threadIdx.x;
+    if (row >= NODt) return;
+    double s = 0.0;
+    for (int k = cptr[row]; k < cptr[row + 1]; k++) s += tcorr[cidx[k]];
+    corr[row] = s;
+    }
+
+// All-pairs potential, the sum scal_fmm::fmm::demag approximates (src/fmm_demag.h:187-223):
+// phi_i = (sum_j q_j / |p_i - x_j| + corr_i) / (4 pi) for the magnetic nodes; one thread per target,
+// the sources stream through shared memory in tiles of BLOCK.  which = 0: phi, 1: phiv of `next`.
+__global__ void __launch_bounds__(BLOCK)
+k_demag_direct(int NODt, const unsigned char *__restrict__ nonmag, const double *__restrict__ pos,
+               long long nsrc, const double4 *__restrict__ src, const double *__restrict__ corr,
+               int which, NodeRec *__restrict__ next)
+    {
+    __shared__ double4 tile[BLOCK];
+    const int row = blockIdx.x * BLOCK + threadIdx.x;
+    const bool active = row < NODt && !nonmag[row];
+    double px = 0.0, py = 0.0, pz = 0.0;
+    if (active)
+        {
+        px = pos[3 * (size_t)row];
+        py = pos[3 * (size_t)row + 1];
+        pz = pos[3 * (size_t)row + 2];
+        }
+    double s = 0.0;
+    for (long long j0 = 0; j0 < nsrc; j0 += BLOCK)
+        {
+        const long long j = j0 + threadIdx.x;
+        tile[threadIdx.x] = j < nsrc ? src[j] : make_double4(0.0, 0.0, 0.0, 0.0);
+        __syncthreads();
+        const int cnt = nsrc - j0 < BLOCK ? (int)(nsrc - j0) : BLOCK;
+        if (active)
+            for (int k = 0; k < cnt; k++)
+                {
+                const double4 q = tile[k];
+                const double dx = px - q.x, dy = py - q.y, dz = pz - q.z;
+                s += q.w / sqrt(dx * dx + dy * dy + dz * dz);
+                }
+        __syncthreads();
+        }
+    if (!active) return;
+    const double val = (s + corr[row]) / (4 * 3.14159265358979323846);
+    if (which) next[row].phiv = val;
+    else next[row].phi = val;
+    }
+
+// ------------------------------------------------------------------------------------------
 // state packing helpers (host <-> NodeRec)
 // ------------------------------------------------------------------------------------------
 // which: bit0 u, bit1 v, bit2 phi, bit3 phiv ; staging = [u(3N) | v(3N) | phi(N) | phiv(N)] in the

@@ -123,6 +123,7 @@ int host_setup(const fg_mesh &m, const fg_params &prm, int n_owned, HostSetup &h
         return FG_ERR_INVALID;
         }
     h.NOD = m.NOD;
+    h.node_p.assign(m.node_p, m.node_p + 3 * (size_t)m.NOD);
     if (n_owned < 0 || n_owned > m.NOD) n_owned = m.NOD;
     h.n_owned = n_owned;
     h.NT = m.NT;

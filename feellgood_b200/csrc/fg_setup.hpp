@@ -21,6 +21,7 @@ struct HostSetup
     {
     int NOD = 0, NT = 0, NF = 0;
     int npi_tet = 5, npi_tri = 4;
+    std::vector<double> node_p;    // NOD x 3 (Gauss points of the charges, Tri::potential)
     // all tets, in caller order (taps + energies)
     std::vector<int> tet_ind;      // NT x 4, oriented
     std::vector<double> tet_da;    // NT x 12

@@ -226,6 +226,18 @@ class LinAlgebra:
         check(self._L.fg_max_angle(self._h, C.byref(a)))
         return a.value
 
+    # ---- charges and the all-pairs demag stand-in (scal_fmm::fmm, src/fmm_demag.h) ----
+    def calc_charges(self, which=0):
+        """fmm::calc_charges (src/fmm_demag.h:155-185): (srcDen, corr) from u (0) or v (1), NEXT."""
+        nsrc = self.n_magTet * self.npi + self.n_magTri * self.settings.npi_tri
+        src, corr = np.empty(max(1, nsrc)), np.empty(self.NOD)
+        check(self._L.fg_calc_charges(self._h, C.c_int(which), dp(src), dp(corr)))
+        return src[:nsrc], corr
+
+    def demag_direct(self, second_order=True):
+        """All-pairs stand-in for myFMM.calc_demag: writes phi (and phiv) of NEXT on the device."""
+        check(self._L.fg_demag_direct(self._h, C.c_int(int(second_order))))
+
     # ---- the reference's LinAlgebra surface ----
     def base_projection(self, angle=None):
         """src/linear_algebra.cpp:3-11.  With angle=None the angle is drawn exactly like the

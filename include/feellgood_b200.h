@@ -162,6 +162,19 @@ int fg_avg(fg_ctx *ctx, int what, int region, double out[3]);
 /* mesh::max_angle, src/mesh.h:295-306 (radians; over ALL mesh edges, like the reference) */
 int fg_max_angle(fg_ctx *ctx, double *angle);
 
+/* ---- magnetic charges and an all-pairs demag potential (single GPU) ---- */
+/* fmm::calc_charges, src/fmm_demag.h:155-185, on the NEXT state: which = 0 u | 1 v.  srcDen holds
+ * n_magTet*npi_tet volume charges (Tet::charges, src/tetra.cpp:347-359) then n_magTri*npi_tri surface
+ * charges (Tri::charges, src/triangle.cpp:45-59) in the reference's order; corr (NOD) the second-order
+ * corrections of Tri::correctionCharges / Tri::potential (src/triangle.cpp:61-78,87-125).  Either
+ * output may be NULL. */
+int fg_calc_charges(fg_ctx *ctx, int which, double *srcDen, double *corr);
+/* Stand-in for scal_fmm::fmm::calc_demag (src/fmm_demag.h:98-103,187-223) on meshes small enough for
+ * an all-pairs sum: phi = (sum_j q_j / |p_i - x_j| + corr_i) / 4pi from u, and (second_order != 0, the
+ * reference's default FIRST_ORDER=OFF) phiv from v, written to the NEXT state of the magnetic nodes.
+ * ScalFMM itself stays outside the path (BASELINE north star); this is the sum it approximates. */
+int fg_demag_direct(fg_ctx *ctx, int second_order);
+
 /* ---- taps used by the parity tests ---- */
 int fg_get_basis(fg_ctx *ctx, double *ep, double *eq);              /* NOD x 3 each */
 /* element<N,NPI>::Kp / Lp (src/element.h:62,65) of tets [first, first+count): count x 64, x 8 */

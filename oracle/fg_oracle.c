@@ -1603,3 +1603,181 @@ double fgo_max_angle(const fgo_ctx *c)
         }
     return acos(min_dot);
     }
+
+/* ------------------------------------------------------------------------------------------ */
+/* "next" rows rank 2: magnetic charges feeding the demag solver (src/tetra.cpp:347-359,        */
+/* src/triangle.cpp:45-78,87-125, orchestration src/fmm_demag.h:155-223)                        */
+/* ------------------------------------------------------------------------------------------ */
+/* Tet::charges, src/tetra.cpp:347-359: -Ms * weight * div(vec) */
+void fgo_tet_charges(int npi, double Ms, const double da[12], const double *weight,
+                     const double *vec_nod /* [i*3+d] */, double *out)
+    {
+    double sx = 0, sy = 0, sz = 0;
+    for (int i = 0; i < 4; i++) sx += vec_nod[3 * i + 0] * da[3 * i + 0];
+    for (int i = 0; i < 4; i++) sy += vec_nod[3 * i + 1] * da[3 * i + 1];
+    for (int i = 0; i < 4; i++) sz += vec_nod[3 * i + 2] * da[3 * i + 2];
+    const double dud_sum = sx + sy + sz;
+    for (int g = 0; g < npi; g++) out[g] = -Ms * weight[g] * dud_sum;
+    }
+
+/* Tri::charges, src/triangle.cpp:45-59 */
+void fgo_tri_charges(int npi, double dMs, const double n[3], const double *weight,
+                     const double *vec_nod /* [i*3+d] */, double *out)
+    {
+    const double *a = fgo_tri_a(npi);
+    for (int g = 0; g < npi; g++) out[g] = 0.0;
+    if (dMs == 0.0) return;
+    for (int g = 0; g < npi; g++)
+        {
+        double ug[3] = {0, 0, 0};
+        for (int d = 0; d < 3; d++)
+            for (int i = 0; i < 3; i++) ug[d] += vec_nod[3 * i + d] * a[i * npi + g];
+        out[g] = dMs * (weight[g] * dot3(ug, n));
+        }
+    }
+
+/* Tri::potential, src/triangle.cpp:87-125: analytic potential at local node i of the linear
+ * surface charge of the triangle (p: 3 nodes x 3, vec_nod [i*3+d]) */
+double fgo_tri_potential(const double *p /* 9 */, const double *vec_nod /* 9 */, double surf,
+                         const double n[3], double dMs, int i)
+    {
+    const int ii = (i + 1) % 3, iii = (i + 2) % 3;
+    const double *p1 = p + 3 * i, *p2 = p + 3 * ii, *p3 = p + 3 * iii;
+    double p1p2[3], p1p3[3];
+    for (int k = 0; k < 3; k++) { p1p2[k] = p2[k] - p1[k]; p1p3[k] = p3[k] - p1[k]; }
+    const double b = sqrt(dot3(p1p2, p1p2));
+    const double t = dot3(p1p2, p1p3) / b;
+    const double _2s = 2. * surf;
+    const double h = _2s / b;
+    const double c = (t - b) / h;
+    const double fth = sqrt(1.0 + (t / h) * (t / h)), fc = sqrt(1.0 + c * c);
+    const double r = h * fth;
+    const double log_1 = log((c * t + h + fc * r) / (b * (c + fc)));
+    const double xi = b * log_1 / fc;
+    const double s1 = dot3(vec_nod + 3 * i, n), s2 = dot3(vec_nod + 3 * ii, n), s3 = dot3(vec_nod + 3 * iii, n);
+    const double pot = xi * s1
+                       + ((xi * (h + c * t) - b * (r - b)) * s2 + b * (r - b - c * xi) * s3) * b
+                                 / (_2s * (1 + c * c));
+    return 0.5 * dMs * pot;
+    }
+
+/* number of sources of fmm::calc_charges: magTet*NPI + magTri*NPI_tri (src/fmm_demag.h:88) */
+long long fgo_n_sources(const fgo_ctx *c)
+    { return (long long)c->n_magTet * c->npi + (long long)c->n_magTri * c->npi_tri; }
+
+/* source positions = Gauss points (getPtGauss, src/tetra.h:344-352, src/triangle.h:209-218) in the
+ * order of insertCharges (src/fmm_demag.h:82-83): tets of magTet, then triangles of magTri */
+void fgo_source_positions(const fgo_ctx *c, double *pos /* nsrc x 3 */)
+    {
+    const double *a = fgo_tet_a(c->npi), *at = fgo_tri_a(c->npi_tri);
+    size_t k = 0;
+    for (int m = 0; m < c->n_magTet; m++)
+        {
+        const int *ind = c->tet_ind + 4 * (size_t)c->magTet[m];
+        for (int g = 0; g < c->npi; g++, k++)
+            for (int d = 0; d < 3; d++)
+                {
+                double s = 0;
+                for (int i = 0; i < 4; i++) s += c->p[3 * (size_t)ind[i] + d] * a[i * c->npi + g];
+                pos[3 * k + d] = s;
+                }
+        }
+    for (int m = 0; m < c->n_magTri; m++)
+        {
+        const int *ind = c->tri_ind + 3 * (size_t)c->magTri[m];
+        for (int g = 0; g < c->npi_tri; g++, k++)
+            for (int d = 0; d < 3; d++)
+                {
+                double s = 0;
+                for (int i = 0; i < 3; i++) s += c->p[3 * (size_t)ind[i] + d] * at[i * c->npi_tri + g];
+                pos[3 * k + d] = s;
+                }
+        }
+    }
+
+/* fmm::calc_charges, src/fmm_demag.h:155-185, on the NEXT state: which = 0 u | 1 v */
+void fgo_calc_charges(const fgo_ctx *c, int which, double *srcDen, double *corr)
+    {
+    const double *field = which == 0 ? c->u[1] : c->v[1];
+    size_t nsrc = 0;
+    for (int m = 0; m < c->n_magTet; m++)
+        {
+        const int t = c->magTet[m];
+        const int *ind = c->tet_ind + 4 * (size_t)t;
+        double vn[12];
+        for (int i = 0; i < 4; i++)
+            for (int d = 0; d < 3; d++) vn[3 * i + d] = field[3 * (size_t)ind[i] + d];
+        fgo_tet_charges(c->npi, c->prm_tet[c->tet_reg[t]].Ms, c->tet_da + 12 * (size_t)t,
+                        c->tet_w + (size_t)c->npi * t, vn, srcDen + nsrc);
+        nsrc += c->npi;
+        }
+    for (int i = 0; i < c->NOD; i++) corr[i] = 0.0;
+    const double *at = fgo_tri_a(c->npi_tri);
+    for (int m = 0; m < c->n_magTri; m++)
+        {
+        const int f = c->magTri[m];
+        const int *ind = c->tri_ind + 3 * (size_t)f;
+        double surf, nrm[3], w[4], vn[9], pp[9], q[4];
+        fgo_tri_setup(c->p, ind, c->npi_tri, &surf, nrm, w);
+        for (int i = 0; i < 3; i++)
+            for (int d = 0; d < 3; d++)
+                {
+                vn[3 * i + d] = field[3 * (size_t)ind[i] + d];
+                pp[3 * i + d] = c->p[3 * (size_t)ind[i] + d];
+                }
+        fgo_tri_charges(c->npi_tri, c->tri_dMs[f], nrm, w, vn, q);
+        for (int g = 0; g < c->npi_tri; g++) srcDen[nsrc + g] = q[g];
+        nsrc += c->npi_tri;
+        /* Tri::correctionCharges, src/triangle.cpp:61-78 */
+        for (int i = 0; i < 3; i++)
+            {
+            for (int g = 0; g < c->npi_tri; g++)
+                {
+                double gp[3] = {0, 0, 0}, dd[3];
+                for (int d = 0; d < 3; d++)
+                    for (int k = 0; k < 3; k++) gp[d] += pp[3 * k + d] * at[k * c->npi_tri + g];
+                for (int d = 0; d < 3; d++) dd[d] = pp[3 * i + d] - gp[d];
+                corr[ind[i]] -= q[g] / sqrt(dot3(dd, dd));
+                }
+            corr[ind[i]] += fgo_tri_potential(pp, vn, surf, nrm, c->tri_dMs[f], i);
+            }
+        }
+    }
+
+/* All-pairs stand-in for scal_fmm::fmm::demag (src/fmm_demag.h:187-223): the potential the FMM
+ * approximates, phi_i = (sum_j q_j / |p_i - x_j| + corr_i) / (4 pi) on the magnetic nodes, written to
+ * NEXT phi (which = 0, from u) or phiv (which = 1, from v).  ScalFMM itself (third party, rev
+ * 22b9e4f6cf, P = 9) is absent here; this is what it converges to. */
+void fgo_demag_direct(fgo_ctx *c, int which)
+    {
+    const long long ns = fgo_n_sources(c);
+    double *src = (double *)malloc(sizeof(double) * (size_t)(ns > 0 ? ns : 1));
+    double *pos = (double *)malloc(sizeof(double) * 3 * (size_t)(ns > 0 ? ns : 1));
+    double *corr = (double *)malloc(sizeof(double) * (size_t)c->NOD);
+    fgo_calc_charges(c, which, src, corr);
+    fgo_source_positions(c, pos);
+    double *out = which == 0 ? c->phi[1] : c->phiv[1];
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < c->NOD; i++)
+        {
+        if (!c->magNode[i]) continue;
+        const double *pi = c->p + 3 * (size_t)i;
+        double s = 0.0;
+        for (long long j = 0; j < ns; j++)
+            {
+            const double dx = pi[0] - pos[3 * j], dy = pi[1] - pos[3 * j + 1], dz = pi[2] - pos[3 * j + 2];
+            s += src[j] / sqrt(dx * dx + dy * dy + dz * dz);
+            }
+        out[i] = (s + corr[i]) / (4 * 3.14159265358979323846);
+        }
+    free(src);
+    free(pos);
+    free(corr);
+    }
+
+/* scal_fmm::fmm::calc_demag, src/fmm_demag.h:98-103 (FIRST_ORDER off: second call for phiv) */
+void fgo_calc_demag_direct(fgo_ctx *c, int second_order)
+    {
+    fgo_demag_direct(c, 0);
+    if (second_order) fgo_demag_direct(c, 1);
+    }

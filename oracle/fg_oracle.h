@@ -221,6 +221,24 @@ double fgo_total_mag_vol(const fgo_ctx *c);
 /* mesh::max_angle src/mesh.h:295-306 */
 double fgo_max_angle(const fgo_ctx *c);
 
+/* ---------------- "next" rows rank 2: magnetic charges and the demag potential ------------- */
+/* Tet::charges src/tetra.cpp:347-359 ; Tri::charges src/triangle.cpp:45-59 ; Tri::potential
+ * src/triangle.cpp:87-125 (vec_nod is [i*3+d]) */
+void fgo_tet_charges(int npi, double Ms, const double da[12], const double *weight,
+                     const double *vec_nod, double *out);
+void fgo_tri_charges(int npi, double dMs, const double n[3], const double *weight,
+                     const double *vec_nod, double *out);
+double fgo_tri_potential(const double *p, const double *vec_nod, double surf, const double n[3],
+                         double dMs, int i);
+long long fgo_n_sources(const fgo_ctx *c);
+void fgo_source_positions(const fgo_ctx *c, double *pos);
+/* fmm::calc_charges src/fmm_demag.h:155-185 on NEXT: which = 0 u | 1 v ; corr has NOD entries */
+void fgo_calc_charges(const fgo_ctx *c, int which, double *srcDen, double *corr);
+/* all-pairs stand-in for fmm::demag src/fmm_demag.h:187-223 (ScalFMM is absent): writes NEXT phi
+ * (which = 0) or phiv (which = 1) of the magnetic nodes */
+void fgo_demag_direct(fgo_ctx *c, int which);
+void fgo_calc_demag_direct(fgo_ctx *c, int second_order);
+
 #ifdef __cplusplus
 }
 #endif

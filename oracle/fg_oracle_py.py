@@ -104,6 +104,9 @@ def lib():
         L.fgo_max_angle.restype = C.c_double
         L.fgo_max_angle.argtypes = [C.c_void_p]
         L.fgo_bicg_dir.restype = C.c_double
+        L.fgo_n_sources.restype = C.c_longlong
+        L.fgo_n_sources.argtypes = [C.c_void_p]
+        L.fgo_tri_potential.restype = C.c_double
         _lib = L
     return _lib
 
@@ -374,6 +377,22 @@ class OracleCtx:
         out = np.zeros(3)
         self.L.fgo_avg_region(self.h, C.c_int(what), C.c_int(region), _dp(out))
         return out
+
+    def n_sources(self):
+        return int(self.L.fgo_n_sources(self.h))
+
+    def source_positions(self):
+        pos = np.zeros((max(1, self.n_sources()), 3))
+        self.L.fgo_source_positions(self.h, _dp(pos))
+        return pos[:self.n_sources()]
+
+    def calc_charges(self, which=0):
+        src, corr = np.zeros(max(1, self.n_sources())), np.zeros(self.NOD)
+        self.L.fgo_calc_charges(self.h, C.c_int(which), _dp(src), _dp(corr))
+        return src[:self.n_sources()], corr
+
+    def demag_direct(self, second_order=True):
+        self.L.fgo_calc_demag_direct(self.h, C.c_int(int(second_order)))
 
     def total_mag_vol(self):
         return self.L.fgo_total_mag_vol(self.h)

@@ -259,6 +259,33 @@ def test_energy_space_field(oracle, gpu_lib):
     oc.close()
 
 
+@pytest.mark.parametrize("name", ["small_cuboid", "small_cuboid_npi1", "ellipsoid"])
+def test_charges_and_direct_demag(oracle, gpu_lib, name):
+    """fmm::calc_charges (Tet::charges, Tri::charges, Tri::correctionCharges / potential) and the
+    all-pairs potential that stands in for ScalFMM against the oracle."""
+    case = {"small_cuboid": lambda: cases.small_cuboid(),
+            "small_cuboid_npi1": lambda: cases.small_cuboid(npi=1),
+            "ellipsoid": lambda: cases.ellipsoid()}[name]()
+    oc, la = _pair(case)
+    for which in (0, 1):
+        src_o, corr_o = oc.calc_charges(which)
+        src_g, corr_g = la.calc_charges(which)
+        assert src_g.shape == src_o.shape
+        assert rel_max(src_g, src_o) < 1e-13
+        assert rel_max(corr_g, corr_o) < 1e-10      # cancellation between 1/r terms and the analytic potential
+    oc.demag_direct(True)
+    la.demag_direct(True)
+    _, _, phi_o, phiv_o = oc.get_state(1)
+    _, _, phi_g, phiv_g = la.get_state(1)
+    assert rel_max(phi_g, phi_o) < 1e-12 and rel_max(phiv_g, phiv_o) < 1e-12
+    mag = oc.masks()[0]
+    assert np.array_equal(phi_g[~mag], case.phi[~mag])                    # only magnetic nodes are targets
+    la.demag_direct(False)                                                 # FIRST_ORDER: phiv untouched
+    assert np.array_equal(la.get_state(1)[3], phiv_g)
+    la.close()
+    oc.close()
+
+
 def test_failure_semantics(oracle, gpu_lib):
     """solve() returns True (failure) on ITER_OVERFLOW and leaves NEXT and v_max untouched
     (src/solver.cpp:62-69)."""
