@@ -212,6 +212,91 @@ def compute_dMs(mesh, Ms_per_vol_region):
     return dMs
 
 
+def control_triangles(mesh, vol_names, surf_names, Ms_per_vol_region):
+    """mesh::controlTriangles (src/mesh.cpp:121-245) with diffTriHandler / assertNoErrInTriangle
+    (src/mesh.cpp:247-332): validates the surface elements against the faces of the tetrahedra,
+    creates the surface / interface triangles the mesh file does not list (new regions named
+    ``surface(vol)`` / ``interface(vol1, vol2)`` with the default surface parameters) and sets dMs.
+
+    vol_names / surf_names: region names, index 0 = "__default__" (Settings::paramTetra[0] /
+    paramTriangle[0]).  Must run BEFORE sort_nodes, like in the reference's mesh constructor.
+    Returns (ok, message, surf_names): on failure `message` is the reference's stderr text and the
+    mesh is untouched; on success surf_names includes the created regions, mesh.tri_ind / tri_reg are
+    extended and mesh.tri_dMs is set."""
+    if mesh.NT == 0:
+        return False, "Error: not a single tetrahedron is present in the mesh\n", list(surf_names)
+    nod = mesh.NOD
+    faces = _outward_faces(_oriented(mesh.node_p, mesh.tet_ind)).astype(np.int64)
+    f_reg = np.tile(mesh.tet_reg.astype(np.int64), 4)
+    tri = mesh.tri_ind.astype(np.int64).reshape(-1, 3)
+    allv = np.concatenate([faces, tri])
+    is_surf = np.concatenate([np.zeros(len(faces), bool), np.ones(len(tri), bool)])
+    reg = np.concatenate([f_reg, mesh.tri_reg.astype(np.int64)])
+    srt = np.sort(allv, axis=1)
+    flipped = _perm_parity(allv).astype(bool)
+    key = (srt[:, 0] * nod + srt[:, 1]) * nod + srt[:, 2]
+    order = np.argsort(key, kind="stable")
+    key, srt, is_surf, reg, flipped = key[order], srt[order], is_surf[order], reg[order], flipped[order]
+    start = np.flatnonzero(np.concatenate([[True], key[1:] != key[:-1]]))
+    gid = np.cumsum(np.concatenate([[True], key[1:] != key[:-1]])) - 1
+    ng = start.size
+    nb_surf = np.bincount(gid, weights=is_surf, minlength=ng).astype(np.int64)
+    nb_face = np.bincount(gid, weights=~is_surf, minlength=ng).astype(np.int64)
+    # sorted pair of the volume regions around the face: first >= second, -1 = none
+    big = np.full(ng, -1, dtype=np.int64)
+    np.maximum.at(big, gid[~is_surf], reg[~is_surf])
+    small_src = np.where(~is_surf, reg, np.iinfo(np.int64).max)
+    small = np.full(ng, np.iinfo(np.int64).max, dtype=np.int64)
+    np.minimum.at(small, gid, small_src)
+    second = np.where(nb_face >= 2, small, -1)
+    surf_reg = np.full(ng, -1, dtype=np.int64)
+    surf_reg[gid[is_surf]] = reg[is_surf]                 # the last one of the group, like the walk
+    # first group (in the sorted walk) that violates a rule decides the message
+    e1 = nb_surf > 1
+    e2 = ~e1 & (nb_face == 0)
+    e3 = ~e1 & ~e2 & (nb_face > 2)
+    e4 = ~e1 & ~e2 & ~e3 & (nb_face == 2) & (nb_surf == 1) & (big == second)
+    bad = np.flatnonzero(e1 | e2 | e3 | e4)
+    if bad.size:
+        g = bad[0]
+        if e1[g]:
+            msg = "Error: bad mesh. %d instances of the same surface triangle have been found\n" % nb_surf[g]
+        elif e2[g]:
+            msg = ("Error: bad mesh. A triangle which belongs to 1 surface region and no tetrahedron "
+                   "has been found\n")
+        elif e3[g]:
+            msg = "Error: bad mesh. A triangular face shared by %d tetrahedrons has been found" % nb_face[g]
+            msg += (" in the surface region %d\n" % surf_reg[g]) if nb_surf[g] == 1 else "\n"
+        else:
+            msg = "Error: bad mesh. An internal triangle has been found in the surface region %d\n" % surf_reg[g]
+        return False, msg, list(surf_names)
+    surf_names = list(surf_names)
+    if not surf_names or surf_names[0] != "__default__":
+        return False, "Internal Error: could not find default surface region.\n", surf_names
+    # missing surface / interface triangles, in walk order; node order = sorted indices
+    add = np.flatnonzero((nb_surf == 0) & ((nb_face == 1) | ((nb_face == 2) & (big != second))))
+    new_tri = srt[start[add]]
+    pairs = list(zip(big[add].tolist(), second[add].tolist()))
+    pair_to_region = {}
+    new_reg = np.zeros(len(pairs), dtype=np.int32)
+    for k, pr in enumerate(pairs):
+        if pr not in pair_to_region:
+            base = ("surface(%s)" % vol_names[pr[0]]) if pr[1] == -1 else \
+                   ("interface(%s, %s)" % (vol_names[pr[0]], vol_names[pr[1]]))
+            name, i = base, 0
+            while name in surf_names:
+                i += 1
+                name = "%s.%d" % (base, i)
+            surf_names.append(name)
+            pair_to_region[pr] = len(surf_names) - 1
+        new_reg[k] = pair_to_region[pr]
+    if len(add):
+        mesh.tri_ind = np.ascontiguousarray(np.concatenate([tri, new_tri]).astype(np.int32))
+        mesh.tri_reg = np.ascontiguousarray(np.concatenate([mesh.tri_reg.astype(np.int32), new_reg]))
+    mesh.tri_dMs = compute_dMs(mesh, Ms_per_vol_region)
+    return True, "", surf_names
+
+
 def sort_nodes(mesh):
     """mesh::sortNodes (src/mesh.cpp:334-367) along the longest axis chosen as in
     src/mesh.h:61-79.  A stable sort is used (std::sort leaves ties unspecified)."""

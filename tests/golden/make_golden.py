@@ -11,6 +11,7 @@
   ref_timestepper.npz  outputs of the REFERENCE's own TimeStepper (cut out of
                        src/time_integration.cpp at build time) and LogStats (src/log-stats.h) on
                        seeded call sequences: pins feellgood_b200.fem and the C++ host mirror.
+  bad_cuboids.npz      the four defective meshes of the reference's controlTriangles unit test.
   llg_system.npz       the oracle's K, L_rhs, x0, solution and next state for one LLG step on a
                        small two-region cuboid with the reference's own SparseMatrix::add +
                        bicg_dir driving the solve (fgo_use_reference_algebra).
@@ -169,8 +170,22 @@ def ref_timestepper():
     print("ref_timestepper: %d arrays" % len(out))
 
 
+def bad_cuboids():
+    """The reference's known-answer meshes for mesh::controlTriangles (unit-tests/meshes/
+    bad_cuboid_{1..4}.msh, used by ut_readMesh.cpp:78-133), parsed as they are (no node sort, no
+    dMs): 8 nodes and a dozen elements each."""
+    out = {}
+    for k in range(1, 5):
+        m = meshgen.read_msh("/root/reference/unit-tests/meshes/bad_cuboid_%d.msh" % k,
+                             ["whole_volume"], ["whole_surface"], scale=1.0)
+        for name in ("node_p", "tet_ind", "tet_reg", "tri_ind", "tri_reg"):
+            out["m%d_%s" % (k, name)] = getattr(m, name)
+    np.savez_compressed(os.path.join(HERE, "bad_cuboids.npz"), **out)
+    print("bad_cuboids: %d arrays" % len(out))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ellipsoid", "ref_algebra", "llg_system", "ref_timestepper"]
+    which = sys.argv[1:] or ["ellipsoid", "ref_algebra", "llg_system", "ref_timestepper", "bad_cuboids"]
     for name in which:
         {"ellipsoid": ellipsoid, "ref_algebra": ref_algebra, "llg_system": llg_system,
-         "ref_timestepper": ref_timestepper}[name]()
+         "ref_timestepper": ref_timestepper, "bad_cuboids": bad_cuboids}[name]()
