@@ -85,14 +85,20 @@ struct KState
     int final_half;  // converged on ||s||: x += alpha*phat still to apply (bicg.h:211-215)
     int updated;     // node update applied for this solve
     int failed;      // LinAlgebra::solve return value (src/solver.cpp:62-69)
-    int pad_;
+    int hist_cap;    // rows of hist (0 = off)
+    double *hist;    // optional per-iteration record [hist_cap][8]: rho_1, (v,rt), alpha, |s|^2, (t,s), (t,t),
+                     // omega, |r|^2 — diagnosis of breakdowns (fg_get_krylov_history)
     };
+__device__ __forceinline__ void khist(KState *st, int col, double v)
+    {
+    if (st->hist != nullptr && st->nit < st->hist_cap) st->hist[8 * (size_t)st->nit + col] = v;
+    }
 
 // buffers of the deterministic two-stage grid reduction
 struct DistDev;
 struct RedBuf
     {
-    double *partials;     // [RED_NV][MAX_GRID]
+    double *partials;     // [2 * RED_NV][MAX_GRID]: CTA partial sums and their compensations
     unsigned int *ticket; // one counter, self-resetting (atomicInc wrap)
     DistDev *dist;        // multi-GPU: the grid totals are all-reduced over the ranks (fg_dist.cuh)
     };
@@ -107,16 +113,27 @@ struct RedBuf
 //            so one warp streams a slice with fully coalesced 128 B / 512 B requests and every
 //            lane folds its own row left to right (no shuffles).  4 B of index per 32 B of values.
 //  OP_CSR:   any algebra::SparseMatrix (src/algebra/sparseMat.h), plain CSR.
-enum { OP_SELL2 = 0, OP_CSR = 1 };
+//  OP_NODE3: the same K, never materialised: K = cS P^T (S x I3) P + Dg, where S is
+//            the per-mesh scalar stiffness in the same SELL-32 layout (8 B value + 4 B index per
+//            node pair instead of 36 B per 2x2 block), P maps the 2 tangent-plane unknowns of a node
+//            to the 3-vector w = ep x0 + eq x1, and Dg is the state-dependent 2x2 node-diagonal part
+//            (alpha_eff mass + gyrotropic term).  The producer of an SpMV input writes w (double4
+//            per node: one aligned 32-byte sector per gather); the SpMV folds z_a = sum_b S_ab w_b and
+//            projects: y = cS (eq_a.z, ep_a.z) + Dg x_a.
+enum { OP_SELL2 = 0, OP_CSR = 1, OP_NODE3 = 2 };
 struct Operator
     {
     int kind;
-    int n;       // rows (OP_SELL2: 2 * padded node count)
+    int n;       // rows (OP_SELL2 / OP_NODE3: 2 * padded node count)
     int lanes;   // OP_CSR: lanes cooperating on one row: 2..32
-    const int *ptr;     // OP_CSR rowptr (n+1) | OP_SELL2 sptr (nslice+1)
-    const int *col;     // OP_CSR col | OP_SELL2 scol
-    const double *val;
-    int nslice;         // OP_SELL2
+    const int *ptr;     // OP_CSR rowptr (n+1) | OP_SELL2 / OP_NODE3 sptr (nslice+1)
+    const int *col;     // OP_CSR col | OP_SELL2 / OP_NODE3 scol
+    const double *val;  // OP_SELL2: 2x2 blocks | OP_NODE3: S (one double per stored node pair)
+    int nslice;         // OP_SELL2 / OP_NODE3
+    // OP_NODE3
+    const Basis *basis;
+    const double *Dg;   // 4 doubles per node row: (k00, k01), (k10, k11)
+    double cS;          // prefactor * s_dt (src/tetra.cpp:261)
     };
 
 // optional CUDA-event pairs around kernel launches: fg_set_profiling(ctx, 2) brackets every SpMV
@@ -153,6 +170,10 @@ struct KrylovWork
     int n;       // owned rows
     int nx;      // length of vectors that are SpMV inputs (n + ghost entries)
     double *x, *b, *r, *rt, *p, *p2, *v, *s, *t, *phat, *shat, *D;  // p2: ping-pong partner of p
+    // OP_NODE3: the 3-vector images (double4 per node, length nx/2) of the SpMV inputs x0 | phat
+    // (shared buffer) and shat, and the basis that maps between the two representations
+    double4 *w3p, *w3s;
+    const Basis *basis;
     const unsigned char *mask; // n : 1 = Dirichlet dof (lvd), may be NULL
     KState *st;                // device
     KState *h_st;              // pinned host mirror
@@ -171,13 +192,15 @@ struct KrylovWork
 
 
 // ---- fg_krylov.cu ----
-// ext (optional): externally owned storage for x, phat, shat (the multi-GPU exchange arena)
+// node3: also allocate the 3-vector images of the SpMV inputs (matrix-free LLG operator);
+// ext (optional): externally owned storage for x, w3p, w3s (the multi-GPU exchange arena)
 int krylov_alloc(KrylovWork &w, int n, int n_ghost, cudaStream_t stream, long long *launch_counter,
-                 double *const ext[3] = nullptr);
+                 bool node3 = false, double *const ext[3] = nullptr);
 void krylov_free(KrylovWork &w);
 int grid_for(long long work_items, int items_per_cta);
-// y = A x (optionally masked)
-int spmv(const Operator &op, const KrylovWork &w, const double *x, double *y, bool masked);
+// y = A x (optionally masked).  OP_NODE3: make_w builds the 3-vector image of x in w.w3s first;
+// pass false when w.w3s already holds it (repeated products with the same x)
+int spmv(const Operator &op, const KrylovWork &w, const double *x, double *y, bool masked, bool make_w = true);
 // BiCGStab with Jacobi preconditioner and Dirichlet mask, reference src/algebra/bicg.h:163-234.
 // w.x holds the initial guess, w.b the (already masked) rhs, w.D the (masked) inverse diagonal.
 // post_batch, if not NULL, is called after each enqueued batch of iterations (same stream) so the
@@ -191,8 +214,8 @@ int cg_run(const Operator &op, KrylovWork &w, double tol, int maxiter);
 int build_diag_precond_csr(const Operator &A, const KrylovWork &w);
 int vec_mask(const KrylovWork &w, double *x);                  // x[lvd] = 0
 int vec_axpy(const KrylovWork &w, double a, const double *x, double *y);  // y += a x
-// multi-GPU halo exchange of one of the arena vectors (fg_dist.cuh): which = 0 x | 1 phat | 2 shat;
+// multi-GPU halo exchange of the solution x (fg_dist.cuh);
 // gate = 1: skipped once the solve is done | 2: only when done and the node update is pending
-int halo_exchange(const KrylovWork &w, int which, int gate);
+int halo_exchange(const KrylovWork &w, int gate);
 
 }  // namespace fg

@@ -42,8 +42,9 @@ constexpr unsigned long long DIST_TIMEOUT_NS = 10000000000ull;  // 10 s before a
 // Control block at the start of every rank's exchange arena (one cudaMalloc, IPC-exported).
 struct DistCtrl
     {
-    // [epoch parity][source rank][32-bit half of value k]: low 32 bits data, high 32 bits epoch tag
-    unsigned long long ll[2][DIST_MAX_RANKS][2 * DIST_NV];
+    // [epoch parity][source rank][32-bit half of double k]: low 32 bits data, high 32 bits epoch tag;
+    // a sum carries 2 doubles per value (the value and its compensation, fg_reduce.cuh)
+    unsigned long long ll[2][DIST_MAX_RANKS][4 * DIST_NV];
     unsigned long long hflag[DIST_MAX_RANKS];            // halo epoch written by each source rank
     };
 
@@ -60,8 +61,10 @@ struct DistDev
     int send_ptr[DIST_MAX_RANKS + 1];      // my boundary rows grouped by destination
     const int *send_rows;                  // device rows (node index) to send
     long long send_dst[DIST_MAX_RANKS];    // node offset of my segment in the destination's ghost tail
-    // ghost tails of the three exchanged vectors on every rank (peer-mapped), as double2 per node
-    double2 *tail[3][DIST_MAX_RANKS];      // [0] x  [1] phat  [2] shat
+    // ghost tails of the exchanged vectors on every rank (peer-mapped): the solution x (double2 per
+    // node) and the 3-vector images of the two SpMV inputs (double4 per node, fg_common.cuh OP_NODE3)
+    double2 *tail[DIST_MAX_RANKS];         // x
+    double4 *wtail[2][DIST_MAX_RANKS];     // [0] w of D.p  [1] w of D.s
     };
 
 __device__ __forceinline__ void st_sys(unsigned long long *p, unsigned long long v)
@@ -97,24 +100,26 @@ __device__ __forceinline__ double ld_sys_f64(const double *p)
     return v;
     }
 
-// All-reduce of nv <= DIST_NV doubles over the ranks, executed by ONE FULL WARP per rank (warp 0 of
-// the last CTA of a reducing kernel).  v points to shared memory holding this rank's values on
-// entry and the rank-ordered result on exit.  op_max = false: sum in rank order; true: maximum.
+// All-reduce of nv <= DIST_NV values over the ranks, executed by ONE FULL WARP per rank (warp 0 of
+// the last CTA of a reducing kernel).  v points to shared memory.  op_max = false: v holds nv values
+// followed by their nv compensations (fg_reduce.cuh); the ranks' pairs are folded in rank order with
+// the same error-free addition, result in place.  op_max = true: v holds nv values, maximum in place.
 __device__ inline void dist_allreduce_warp(DistDev *d, double *v, int nv, bool op_max)
     {
-    __shared__ unsigned int rx[DIST_MAX_RANKS][2 * DIST_NV];
+    __shared__ unsigned int rx[DIST_MAX_RANKS][4 * DIST_NV];
     const int lane = threadIdx.x & 31;
+    const int nd = op_max ? nv : 2 * nv;  // doubles per rank
     unsigned long long e = 0;
     if (lane == 0) e = ++d->epoch;
     e = __shfl_sync(0xffffffffu, e, 0);
     if (d->error)
         {  // a previous spin timed out: do not wait again, poison the scalars
         if (lane == 0)
-            for (int k = 0; k < nv; k++) v[k] = nan("");
+            for (int k = 0; k < nd; k++) v[k] = nan("");
         __syncwarp();
         return;
         }
-    const int par = (int)(e & 1ull), nw = 2 * nv, world = d->world, rank = d->rank;
+    const int par = (int)(e & 1ull), nw = 2 * nd, world = d->world, rank = d->rank;
     const unsigned long long tag = (e & 0xffffffffull) << 32;
     const unsigned int *v32 = reinterpret_cast<const unsigned int *>(v);
     for (int idx = lane; idx < world * nw; idx += 32)
@@ -146,32 +151,44 @@ __device__ inline void dist_allreduce_warp(DistDev *d, double *v, int nv, bool o
     __syncwarp();
     if (lane == 0)
         {
+        auto get = [&](int src, int k) { return __hiloint2double((int)rx[src][2 * k + 1], (int)rx[src][2 * k]); };
         if (!ok)
             {
             d->error = 1;
-            for (int k = 0; k < nv; k++) v[k] = nan("");  // NaN residual => CANNOT_CONVERGE (iter.h:147)
+            for (int k = 0; k < nd; k++) v[k] = nan("");  // NaN residual => CANNOT_CONVERGE (iter.h:147)
             }
+        else if (op_max)
+            for (int k = 0; k < nv; k++)
+                {
+                double s = get(0, k);
+                for (int src = 1; src < world; src++) s = fmax(s, get(src, k));
+                v[k] = s;
+                }
         else
             for (int k = 0; k < nv; k++)
                 {
-                double s = __hiloint2double((int)rx[0][2 * k + 1], (int)rx[0][2 * k]);
+                double s = get(0, k), c = get(0, nv + k);
                 for (int src = 1; src < world; src++)
-                    {
-                    const double t = __hiloint2double((int)rx[src][2 * k + 1], (int)rx[src][2 * k]);
-                    s = op_max ? fmax(s, t) : s + t;
+                    {  // error-free fold in rank order: identical bits on every rank
+                    const double bs = get(src, k), be = get(src, nv + k);
+                    const double t = s + bs, bb = t - s;
+                    const double err = (s - (t - bb)) + (bs - bb);
+                    s = t;
+                    c += be + err;
                     }
                 v[k] = s;
+                v[nv + k] = c;
                 }
         }
     __syncwarp();
     }
 
-// Push f(row) for every boundary row of this rank into the neighbours' ghost tails of vector
-// `which`; executed by `nthreads` cooperating threads (thread index tid).  Each thread fences its
+// Push f(row) for every boundary row of this rank into the neighbours' ghost tails `tails` of one
+// exchanged vector; executed by `nthreads` cooperating threads (thread index tid).  Each thread fences its
 // own stores at system scope, so a later flag / all-reduce by any thread of the grid that is
 // ordered after them (block barrier + device-scope ticket) publishes them to the peers.
-template <class F>
-__device__ __forceinline__ void dist_push(const DistDev *d, int which, int tid, int nthreads, F f)
+template <class T, class F>
+__device__ __forceinline__ void dist_push(const DistDev *d, T *const *tails, int tid, int nthreads, F f)
     {
     const int nsend = d->send_ptr[d->world];
     bool any = false;
@@ -179,8 +196,8 @@ __device__ __forceinline__ void dist_push(const DistDev *d, int which, int tid, 
         {
         int q = 0;
         while (idx >= d->send_ptr[q + 1]) q++;
-        const double2 val = f(d->send_rows[idx]);
-        *(d->tail[which][q] + d->send_dst[q] + (idx - d->send_ptr[q])) = val;
+        const T val = f(d->send_rows[idx]);
+        *(tails[q] + d->send_dst[q] + (idx - d->send_ptr[q])) = val;
         any = true;
         }
     if (any) __threadfence_system();

@@ -52,6 +52,21 @@ __device__ __forceinline__ void bicg_top_of_loop(KState *st, double rr, double r
         }
     }
 
+__device__ __forceinline__ void load_basis_k(const Basis *p, double ep[3], double eq[3])
+    {
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    ep[0] = a.x; ep[1] = a.y; ep[2] = b.x;
+    eq[0] = b.y; eq[1] = c.x; eq[2] = c.y;
+    }
+// w = ep x0 + eq x1: the 3-vector image of the two tangent-plane unknowns of a node (element.h:81-96)
+__device__ __forceinline__ double4 node_w(const Basis *b, double x0, double x1)
+    {
+    double ep[3], eq[3];
+    load_basis_k(b, ep, eq);
+    return make_double4(ep[0] * x0 + eq[0] * x1, ep[1] * x0 + eq[1] * x1, ep[2] * x0 + eq[2] * x1, 0.0);
+    }
+
 // ------------------------------------------------------------------------------------------
 // SpMV with fused epilogues
 // ------------------------------------------------------------------------------------------
@@ -68,6 +83,7 @@ enum
 
 struct SpmvArgs
     {
+    const double4 *w;  // OP_NODE3: 3-vector image of x (gathered); x itself is read for the node-diagonal part
     const double *x;
     double *y;
     const double *a0;  // b | rt | s | p
@@ -98,9 +114,19 @@ template <int STAGE> __device__ __forceinline__ void spmv_finalize(KState *st, c
         bicg_top_of_loop(st, tot[1], tot[1]);  // rt == r: (rt, r) = ||r||^2
         }
     else if (STAGE == ST_BICG_V)
+        {
         st->alpha = st->rho1 / tot[0];
+        khist(st, 0, st->rho1);
+        khist(st, 1, tot[0]);
+        khist(st, 2, st->alpha);
+        }
     else if (STAGE == ST_BICG_T)
+        {
         st->omega = tot[0] / tot[1];
+        khist(st, 4, tot[0]);
+        khist(st, 5, tot[1]);
+        khist(st, 6, st->omega);
+        }
     else if (STAGE == ST_CG_SETUP)
         {
         st->rhsn = sqrt(fabs(tot[0]));
@@ -227,11 +253,6 @@ __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_sell(const Ope
     {
     if (stage_gated(STAGE))
         if (a.st->done) return;
-    if (STAGE == ST_BICG_V && a.dist != nullptr)
-        {  // the ghost entries of D.p were pushed by the neighbours' previous kernel: wait for them
-        if (threadIdx.x == 0) dist_wait(a.dist);
-        __syncthreads();
-        }
     const int lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * (BLOCK / 32);
     const double2 *x2 = reinterpret_cast<const double2 *>(a.x);
@@ -279,6 +300,73 @@ __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_sell(const Ope
     double tot[RED_NV];
     const int role = grid_reduce<RED_NV>(acc, a.red, tot);
     if (role == 0) return;
+    if (role == 1) spmv_finalize<STAGE>(a.st, tot);
+    }
+
+// ---- matrix-free LLG operator (OP_NODE3): K = cS P^T (S x I3) P + Dg, one warp per slice ---------
+// Streams 12 B per stored node pair (S, column) instead of 36 B per 2x2 block; the gather is one
+// aligned 32-byte sector (w_b as double4); the row epilogue projects z onto the node's (eq, ep) and
+// adds the 2x2 node-diagonal part.  Same SELL-32 traversal, same fused epilogues as k_spmv_sell.
+template <int STAGE>
+__global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_node3(const Operator op, const SpmvArgs a)
+    {
+    if (stage_gated(STAGE))
+        if (a.st->done) return;
+    if (STAGE == ST_BICG_V && a.dist != nullptr)
+        {  // the ghost entries of w(D.p) were pushed by the neighbours' k_bicg_p: wait for them
+        if (threadIdx.x == 0) dist_wait(a.dist);
+        __syncthreads();
+        }
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * (BLOCK / 32);
+    const double2 *x2 = reinterpret_cast<const double2 *>(a.x);
+    const double2 *Dg2 = reinterpret_cast<const double2 *>(op.Dg);
+    double acc[RED_NV] = {0.0, 0.0, 0.0, 0.0};
+    int s = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
+    int p0 = 0, p1 = 0;
+    if (s < op.nslice)
+        {
+        p0 = __ldg(op.ptr + s);
+        p1 = __ldg(op.ptr + s + 1);
+        }
+    while (s < op.nslice)
+        {
+        const int sn = s + nwarps;
+        int q0 = 0, q1 = 0;
+        if (sn < op.nslice)
+            {
+            q0 = __ldg(op.ptr + sn);
+            q1 = __ldg(op.ptr + sn + 1);
+            }
+        const int *cp = op.col + (size_t)p0 * SLICE + lane;
+        const double *sp = op.val + (size_t)p0 * SLICE + lane;
+        double z0 = 0.0, z1 = 0.0, z2 = 0.0;
+#pragma unroll 8
+        for (int j = p0; j < p1; ++j)
+            {
+            const int c = __ldcs(cp);
+            const double Sv = __ldcs(sp);
+            const double4 wv = a.w[c];
+            z0 += Sv * wv.x;
+            z1 += Sv * wv.y;
+            z2 += Sv * wv.z;
+            cp += SLICE;
+            sp += SLICE;
+            }
+        const int row = s * SLICE + lane;
+        double ep[3], eq[3];
+        load_basis_k(op.basis + row, ep, eq);
+        const double2 xa = x2[row], d0 = __ldcs(Dg2 + 2 * (size_t)row), d1 = __ldcs(Dg2 + 2 * (size_t)row + 1);
+        const double y0 = op.cS * (eq[0] * z0 + eq[1] * z1 + eq[2] * z2) + (d0.x * xa.x + d0.y * xa.y);
+        const double y1 = op.cS * (ep[0] * z0 + ep[1] * z1 + ep[2] * z2) + (d1.x * xa.x + d1.y * xa.y);
+        spmv_row2<STAGE>(a, row, y0, y1, acc);
+        s = sn;
+        p0 = q0;
+        p1 = q1;
+        }
+    if (!stage_reduces(STAGE)) return;
+    double tot[RED_NV];
+    const int role = grid_reduce<RED_NV>(acc, a.red, tot);
     if (role == 1) spmv_finalize<STAGE>(a.st, tot);
     }
 
@@ -340,7 +428,15 @@ static int launch_spmv(const Operator &op, const KrylovWork &w, const SpmvArgs &
     {
     const int cls = STAGE == ST_BICG_V ? KC_SPMV_V : (STAGE == ST_BICG_T ? KC_SPMV_T : (STAGE == ST_BICG_SETUP ? KC_SPMV_SETUP : KC_OTHER));
     const bool prof = prof_begin(w.prof, w.stream, cls);
-    if (op.kind == OP_SELL2)
+    if (op.kind == OP_NODE3)
+        {
+        static int wave = 0;
+        if (!wave) wave = resident_grid(k_spmv_node3<STAGE>);
+        const int need = (op.nslice + BLOCK / 32 - 1) / (BLOCK / 32);
+        const int grid = need < wave ? (need > 0 ? need : 1) : wave;
+        k_spmv_node3<STAGE><<<grid, BLOCK, 0, w.stream>>>(op, a);
+        }
+    else if (op.kind == OP_SELL2)
         {
         static int wave = 0;
         if (!wave) wave = resident_grid(k_spmv_sell<STAGE>);
@@ -362,9 +458,31 @@ static int launch_spmv(const Operator &op, const KrylovWork &w, const SpmvArgs &
     return FG_OK;
     }
 
-int spmv(const Operator &op, const KrylovWork &w, const double *x, double *y, bool masked)
+// plain y = A x; for OP_NODE3 the 3-vector image of x is built first (taps and microbenchmarks only:
+// the solver's own producers write it in the kernel that produces x)
+__global__ void __launch_bounds__(BLOCK)
+k_make_w(int nnode, const double *__restrict__ x, const Basis *__restrict__ basis, double4 *__restrict__ w3)
+    {
+    const int stride = gridDim.x * BLOCK;
+    for (int a = blockIdx.x * BLOCK + threadIdx.x; a < nnode; a += stride)
+        {
+        const double2 xv = reinterpret_cast<const double2 *>(x)[a];
+        w3[a] = node_w(basis + a, xv.x, xv.y);
+        }
+    }
+
+int spmv(const Operator &op, const KrylovWork &w, const double *x, double *y, bool masked, bool make_w)
     {
     SpmvArgs a = {};
+    if (op.kind == OP_NODE3 && !make_w)
+        a.w = w.w3s;
+    else if (op.kind == OP_NODE3)
+        {
+        k_make_w<<<grid_for(w.nx / 2, BLOCK), BLOCK, 0, w.stream>>>(w.nx / 2, x, op.basis, w.w3s);
+        if (w.launches) ++*w.launches;
+        FG_CUDA(cudaGetLastError());
+        a.w = w.w3s;
+        }
     a.x = x;
     a.y = y;
     a.mask = masked ? w.mask : nullptr;
@@ -377,31 +495,67 @@ int spmv(const Operator &op, const KrylovWork &w, const double *x, double *y, bo
 // fused vector kernels of BiCGStab (reference src/algebra/bicg.h:185-232)
 // ------------------------------------------------------------------------------------------
 // p = r + beta (p - omega v) ; phat = D p                       (bicg.h:196-202)
-// Multi-GPU: beta is known when this kernel starts, so its first CTAs push D.p of the boundary rows
-// into the neighbours' ghost tails before doing their share of the update; the last of those CTAs
-// raises the halo flag the consuming SpMV waits on (fg_dist.cuh).  p is ping-ponged (read p, write
-// pn) so that the pushers can read the old direction of rows another CTA is updating.
+// p is ping-ponged (read p, write pn): see the node-wise variant below.
 __global__ void __launch_bounds__(BLOCK)
 k_bicg_p(int n, const double *__restrict__ r, const double *__restrict__ p, double *__restrict__ pn,
          const double *__restrict__ v, const double *__restrict__ D, double *__restrict__ phat,
-         const KState *st, DistDev *dist, unsigned int *ticket, int npush)
+         const KState *st)
     {
     if (st->done) return;
     const bool first = st->nit == 0;
     const double omega = st->omega;
     const double beta = first ? 0.0 : bicg_beta(st);
     const int stride = gridDim.x * BLOCK;
+    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += stride)
+        {
+        double pi;
+        if (first)
+            pi = r[i];  // p = r (bicg.h:183)
+        else
+            pi = bicg_p_value(p[i], v[i], r[i], omega, beta);
+        pn[i] = pi;
+        phat[i] = D[i] * pi;
+        }
+    }
+
+// Node-wise variant for the matrix-free LLG operator: besides phat it writes w = P phat, the 3-vector
+// image the next SpMV gathers.  Multi-GPU: beta is known when this kernel starts, so its first
+// CTAs push w of the boundary rows into the neighbours' ghost tails before doing their share of the
+// update; the last of those CTAs raises the halo flag the consuming SpMV waits on (fg_dist.cuh).
+// p is ping-ponged (read p, write pn) so that the pushers can read the old direction of rows
+// another CTA is updating.
+__global__ void __launch_bounds__(BLOCK)
+k_bicg_p_node(int nnode, const double *__restrict__ r, const double *__restrict__ p, double *__restrict__ pn,
+              const double *__restrict__ v, const double *__restrict__ D, double *__restrict__ phat,
+              const Basis *__restrict__ basis, double4 *__restrict__ w3, const KState *st, DistDev *dist,
+              unsigned int *ticket, int npush)
+    {
+    if (st->done) return;
+    const bool first = st->nit == 0;
+    const double omega = st->omega;
+    const double beta = first ? 0.0 : bicg_beta(st);
+    const int stride = gridDim.x * BLOCK;
+    const double2 *p2 = reinterpret_cast<const double2 *>(p), *v2 = reinterpret_cast<const double2 *>(v),
+                  *r2 = reinterpret_cast<const double2 *>(r), *D2 = reinterpret_cast<const double2 *>(D);
+    auto value = [&](int row, double2 &pi)
+        {
+        const double2 rr = r2[row], d = D2[row];
+        if (first)
+            pi = rr;  // p = r (bicg.h:183)
+        else
+            {
+            const double2 pp = p2[row], vv = v2[row];
+            pi = make_double2(bicg_p_value(pp.x, vv.x, rr.x, omega, beta), bicg_p_value(pp.y, vv.y, rr.y, omega, beta));
+            }
+        return make_double2(d.x * pi.x, d.y * pi.y);
+        };
     if (dist != nullptr && (int)blockIdx.x < npush)
         {
-        const double2 *p2 = reinterpret_cast<const double2 *>(p), *v2 = reinterpret_cast<const double2 *>(v),
-                      *r2 = reinterpret_cast<const double2 *>(r), *D2 = reinterpret_cast<const double2 *>(D);
-        dist_push(dist, 1, blockIdx.x * BLOCK + threadIdx.x, npush * BLOCK, [&](int row)
+        dist_push(dist, dist->wtail[0], blockIdx.x * BLOCK + threadIdx.x, npush * BLOCK, [&](int row)
             {
-            const double2 rr = r2[row], d = D2[row];
-            if (first) return make_double2(d.x * rr.x, d.y * rr.y);
-            const double2 pp = p2[row], vv = v2[row];
-            return make_double2(d.x * bicg_p_value(pp.x, vv.x, rr.x, omega, beta),
-                                d.y * bicg_p_value(pp.y, vv.y, rr.y, omega, beta));
+            double2 pi;
+            const double2 ph = value(row, pi);
+            return node_w(basis + row, ph.x, ph.y);
             });
         __syncthreads();
         if (threadIdx.x == 0)
@@ -410,19 +564,29 @@ k_bicg_p(int n, const double *__restrict__ r, const double *__restrict__ p, doub
             if (t == (unsigned int)npush - 1) dist_raise(dist);
             }
         }
-    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += stride)
+    for (int a = blockIdx.x * BLOCK + threadIdx.x; a < nnode; a += stride)
         {
-        double pi;
-        if (first)
-            pi = r[i];  // p was set to r by the setup
-        else
-            pi = bicg_p_value(p[i], v[i], r[i], omega, beta);
-        pn[i] = pi;
-        phat[i] = D[i] * pi;
+        double2 pi;
+        const double2 ph = value(a, pi);
+        reinterpret_cast<double2 *>(pn)[a] = pi;
+        reinterpret_cast<double2 *>(phat)[a] = ph;
+        w3[a] = node_w(basis + a, ph.x, ph.y);
         }
     }
 
 // s = r - alpha v ; shat = D s ; ||s||^2 -> mid-iteration exit test    (bicg.h:207-218)
+__device__ __forceinline__ void bicg_s_finalize(KState *st, double ss)
+    {
+    khist(st, 3, ss);
+    if (it_finished(st, sqrt(fabs(ss))))
+        {
+        st->final_half = 1;  // x += alpha phat is applied by k_bicg_xr
+        st->done = 1;
+        }
+    else if (st->status == FG_ITER_OVERFLOW || st->status == FG_CANNOT_CONVERGE)
+        st->done = 1;
+    }
+
 __global__ void __launch_bounds__(BLOCK)
 k_bicg_s(int n, const double *__restrict__ r, const double *__restrict__ v,
          const double *__restrict__ D, double *__restrict__ s, double *__restrict__ shat, KState *st,
@@ -432,17 +596,6 @@ k_bicg_s(int n, const double *__restrict__ r, const double *__restrict__ v,
     const double alpha = st->alpha;
     double acc[1] = {0.0};
     const int stride = gridDim.x * BLOCK;
-    if (red.dist != nullptr)
-        {  // multi-GPU: D.s of the boundary rows goes to the neighbours first; the all-reduce of
-           // |s|^2 below is the barrier that publishes it (fg_dist.cuh)
-        const double2 *r2 = reinterpret_cast<const double2 *>(r), *v2 = reinterpret_cast<const double2 *>(v),
-                      *D2 = reinterpret_cast<const double2 *>(D);
-        dist_push(red.dist, 2, blockIdx.x * BLOCK + threadIdx.x, stride, [&](int row)
-            {
-            const double2 rr = r2[row], vv = v2[row], d = D2[row];
-            return make_double2(d.x * bicg_s_value(rr.x, vv.x, alpha), d.y * bicg_s_value(rr.y, vv.y, alpha));
-            });
-        }
     for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += stride)
         {
         const double si = bicg_s_value(r[i], v[i], alpha);
@@ -452,13 +605,48 @@ k_bicg_s(int n, const double *__restrict__ r, const double *__restrict__ v,
         }
     double tot[1];
     if (grid_reduce<1>(acc, red, tot) != 1) return;
-    if (it_finished(st, sqrt(fabs(tot[0]))))
+    bicg_s_finalize(st, tot[0]);
+    }
+
+// Node-wise variant (matrix-free LLG operator): also writes w = P shat.  Multi-GPU: w of the
+// boundary rows goes to the neighbours first; the all-reduce of |s|^2 below is the barrier that
+// publishes it (fg_dist.cuh).
+__global__ void __launch_bounds__(BLOCK)
+k_bicg_s_node(int nnode, const double *__restrict__ r, const double *__restrict__ v,
+              const double *__restrict__ D, double *__restrict__ s, double *__restrict__ shat,
+              const Basis *__restrict__ basis, double4 *__restrict__ w3, KState *st, const RedBuf red)
+    {
+    if (st->done) return;
+    const double alpha = st->alpha;
+    double acc[1] = {0.0};
+    const int stride = gridDim.x * BLOCK;
+    const double2 *r2 = reinterpret_cast<const double2 *>(r), *v2 = reinterpret_cast<const double2 *>(v),
+                  *D2 = reinterpret_cast<const double2 *>(D);
+    auto value = [&](int row, double2 &si)
         {
-        st->final_half = 1;  // x += alpha phat is applied by k_bicg_xr
-        st->done = 1;
+        const double2 rr = r2[row], vv = v2[row], d = D2[row];
+        si = make_double2(bicg_s_value(rr.x, vv.x, alpha), bicg_s_value(rr.y, vv.y, alpha));
+        return make_double2(d.x * si.x, d.y * si.y);
+        };
+    if (red.dist != nullptr)
+        dist_push(red.dist, red.dist->wtail[1], blockIdx.x * BLOCK + threadIdx.x, stride, [&](int row)
+            {
+            double2 si;
+            const double2 sh = value(row, si);
+            return node_w(basis + row, sh.x, sh.y);
+            });
+    for (int a = blockIdx.x * BLOCK + threadIdx.x; a < nnode; a += stride)
+        {
+        double2 si;
+        const double2 sh = value(a, si);
+        reinterpret_cast<double2 *>(s)[a] = si;
+        reinterpret_cast<double2 *>(shat)[a] = sh;
+        w3[a] = node_w(basis + a, sh.x, sh.y);
+        acc[0] += si.x * si.x + si.y * si.y;
         }
-    else if (st->status == FG_ITER_OVERFLOW || st->status == FG_CANNOT_CONVERGE)
-        st->done = 1;
+    double tot[1];
+    if (grid_reduce<1>(acc, red, tot) != 1) return;
+    bicg_s_finalize(st, tot[0]);
     }
 
 // x += alpha phat + omega shat ; r = s - omega t ; ||r||^2, (rt,r) -> next loop test
@@ -498,6 +686,7 @@ k_bicg_xr(int n, double *__restrict__ x, const double *__restrict__ phat,
             st->final_half = 0;
         else
             {
+            khist(st, 7, tot[0]);
             st->rho2 = st->rho1;
             st->nit++;
             if (st->nit >= st->maxiter) st->status = FG_ITER_OVERFLOW;  // iter.h:119-124
@@ -638,7 +827,7 @@ int build_diag_precond_csr(const Operator &A, const KrylovWork &w)
     }
 
 int krylov_alloc(KrylovWork &w, int n, int n_ghost, cudaStream_t stream, long long *launch_counter,
-                 double *const ext[3])
+                 bool node3, double *const ext[3])
     {
     w = KrylovWork();
     w.n = n;
@@ -648,11 +837,19 @@ int krylov_alloc(KrylovWork &w, int n, int n_ghost, cudaStream_t stream, long lo
     const size_t nb = sizeof(double) * (size_t)(w.nx > 0 ? w.nx : 1);
     double **vecs[] = {&w.x, &w.b, &w.r, &w.rt, &w.p, &w.p2, &w.v, &w.s, &w.t, &w.phat, &w.shat, &w.D};
     if (ext)
-        {
+        {  // multi-GPU: the exchanged vectors live in the IPC arena
         w.x = ext[0];
-        w.phat = ext[1];
-        w.shat = ext[2];
+        w.w3p = reinterpret_cast<double4 *>(ext[1]);
+        w.w3s = reinterpret_cast<double4 *>(ext[2]);
         w.arena = ext[0];
+        }
+    else if (node3)
+        {
+        const size_t wb = sizeof(double4) * (size_t)(w.nx / 2 > 0 ? w.nx / 2 : 1);
+        FG_CUDA(cudaMalloc(&w.w3p, wb));
+        FG_CUDA(cudaMalloc(&w.w3s, wb));
+        FG_CUDA(cudaMemsetAsync(w.w3p, 0, wb, stream));
+        FG_CUDA(cudaMemsetAsync(w.w3s, 0, wb, stream));
         }
     for (double **v : vecs)
         {
@@ -663,7 +860,7 @@ int krylov_alloc(KrylovWork &w, int n, int n_ghost, cudaStream_t stream, long lo
     FG_CUDA(cudaMemsetAsync(w.st, 0, sizeof(KState), stream));
     FG_CUDA(cudaMallocHost(&w.h_st, sizeof(KState)));
     memset(w.h_st, 0, sizeof(KState));
-    FG_CUDA(cudaMalloc(&w.red.partials, sizeof(double) * RED_NV * MAX_GRID));
+    FG_CUDA(cudaMalloc(&w.red.partials, sizeof(double) * 2 * RED_NV * MAX_GRID));  // values + compensations
     FG_CUDA(cudaMalloc(&w.red.ticket, sizeof(unsigned int)));
     FG_CUDA(cudaMemsetAsync(w.red.ticket, 0, sizeof(unsigned int), stream));
     w.red.dist = nullptr;
@@ -674,7 +871,13 @@ int krylov_alloc(KrylovWork &w, int n, int n_ghost, cudaStream_t stream, long lo
 
 void krylov_free(KrylovWork &w)
     {
-    if (w.arena) w.x = w.phat = w.shat = nullptr;  // owned by the exchange arena
+    if (w.arena)
+        {  // owned by the exchange arena
+        w.x = nullptr;
+        w.w3p = w.w3s = nullptr;
+        }
+    if (w.w3p) cudaFree(w.w3p);
+    if (w.w3s) cudaFree(w.w3s);
     double *vecs[] = {w.x, w.b, w.r, w.rt, w.p, w.p2, w.v, w.s, w.t, w.phat, w.shat, w.D};
     for (double *v : vecs)
         if (v) cudaFree(v);
@@ -691,8 +894,7 @@ void krylov_free(KrylovWork &w)
 // over NVLink peer memory, raise the halo epoch flag, wait for my own sources.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BLOCK)
-k_halo(DistDev *d, const double *__restrict__ vec, int which, int gate, const KState *st,
-       unsigned int *ticket)
+k_halo(DistDev *d, const double *__restrict__ vec, int gate, const KState *st, unsigned int *ticket)
     {
     if (gate == 1 && st->done) return;
     if (gate == 2 && (!st->done || st->updated)) return;
@@ -705,7 +907,7 @@ k_halo(DistDev *d, const double *__restrict__ vec, int which, int gate, const KS
         int q = 0;
         while (idx >= d->send_ptr[q + 1]) q++;
         const double2 val = v2[d->send_rows[idx]];
-        double2 *dst = d->tail[which][q] + d->send_dst[q] + (idx - d->send_ptr[q]);
+        double2 *dst = d->tail[q] + d->send_dst[q] + (idx - d->send_ptr[q]);
         *dst = val;
         }
     __threadfence_system();
@@ -732,12 +934,11 @@ k_halo(DistDev *d, const double *__restrict__ vec, int which, int gate, const KS
     __threadfence_system();
     }
 
-int halo_exchange(const KrylovWork &w, int which, int gate)
+int halo_exchange(const KrylovWork &w, int gate)
     {
     if (!w.dist) return FG_OK;
-    const double *vec = which == 0 ? w.x : (which == 1 ? w.phat : w.shat);
     const bool prof = prof_begin(w.prof, w.stream, KC_HALO);
-    k_halo<<<w.halo_grid, BLOCK, 0, w.stream>>>(w.dist, vec, which, gate, w.st, w.red.ticket);
+    k_halo<<<w.halo_grid, BLOCK, 0, w.stream>>>(w.dist, w.x, gate, w.st, w.red.ticket);
     if (prof) prof_end(w.prof, w.stream);
     if (w.launches) ++*w.launches;
     FG_CUDA(cudaGetLastError());
@@ -760,12 +961,21 @@ int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, pos
     {
     const int n = w.n;
     // one resident wave per vector kernel (their register counts differ)
-    static int wave_p = 0, wave_s = 0, wave_xr = 0;
-    if (!wave_p)
+    const bool node3 = op.kind == OP_NODE3;
+    static int wave_pn = 0, wave_sn = 0, wave_ps = 0, wave_ss = 0, wave_xr = 0;
+    if (!wave_xr)
         {
-        wave_p = resident_grid(k_bicg_p);
-        wave_s = resident_grid(k_bicg_s);
+        wave_pn = resident_grid(k_bicg_p_node);
+        wave_sn = resident_grid(k_bicg_s_node);
+        wave_ps = resident_grid(k_bicg_p);
+        wave_ss = resident_grid(k_bicg_s);
         wave_xr = resident_grid(k_bicg_xr);
+        }
+    const int wave_p = node3 ? wave_pn : wave_ps, wave_s = node3 ? wave_sn : wave_ss;
+    if (w.dist && !node3)
+        {
+        set_error("bicgstab_run: the multi-GPU path needs the matrix-free LLG operator");
+        return FG_ERR_STATE;
         }
     const int gneed = grid_for(n, BLOCK * 2);
     const int gp = gneed < wave_p ? gneed : wave_p, gs = gneed < wave_s ? gneed : wave_s,
@@ -782,6 +992,7 @@ int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, pos
         a.x = w.x;
         a.y = w.r;
         a.a0 = w.b;
+        a.w = w.w3p;  // image of the initial guess, written by the assembly
         a.o0 = w.rt;
         a.mask = w.mask;
         a.st = w.st;
@@ -800,10 +1011,14 @@ int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, pos
             {
             // iteration `enq + k` of this solve reads p from one buffer and writes the other one
             double *p_old = ((enq + k) & 1) ? w.p2 : w.p, *p_new = ((enq + k) & 1) ? w.p : w.p2;
-            FG_LAUNCH_C(w, KC_BICG_P, k_bicg_p, gp, n, w.r, p_old, p_new, w.v, w.D, w.phat, w.st, w.dist,
-                        w.red.ticket, npush);
+            if (node3)
+                FG_LAUNCH_C(w, KC_BICG_P, k_bicg_p_node, gp, n / 2, w.r, p_old, p_new, w.v, w.D, w.phat, w.basis,
+                            w.w3p, w.st, w.dist, w.red.ticket, npush);
+            else
+                FG_LAUNCH_C(w, KC_BICG_P, k_bicg_p, gp, n, w.r, p_old, p_new, w.v, w.D, w.phat, w.st);
             SpmvArgs a = {};
             a.dist = w.dist;
+            a.w = w.w3p;
             a.x = w.phat;
             a.y = w.v;
             a.a0 = w.rt;
@@ -811,7 +1026,12 @@ int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, pos
             a.st = w.st;
             a.red = w.red;
             FG_TRY(launch_spmv<ST_BICG_V>(op, w, a));
-            FG_LAUNCH_C(w, KC_BICG_S, k_bicg_s, gs, n, w.r, w.v, w.D, w.s, w.shat, w.st, w.red);
+            if (node3)
+                FG_LAUNCH_C(w, KC_BICG_S, k_bicg_s_node, gs, n / 2, w.r, w.v, w.D, w.s, w.shat, w.basis, w.w3s,
+                            w.st, w.red);
+            else
+                FG_LAUNCH_C(w, KC_BICG_S, k_bicg_s, gs, n, w.r, w.v, w.D, w.s, w.shat, w.st, w.red);
+            a.w = w.w3s;
             a.x = w.shat;
             a.y = w.t;
             a.a0 = w.s;

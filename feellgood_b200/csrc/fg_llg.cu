@@ -42,7 +42,7 @@ struct fg_ctx
     // multi-GPU (fg_dist_*): world == 1 on a single device
     int rank = 0, world = 1;
     void *arena = nullptr;
-    size_t arena_bytes = 0, tail_off[3] = {0, 0, 0};
+    size_t arena_bytes = 0, tail_off[3] = {0, 0, 0};  // ghost tails of x, w3p, w3s in the arena
     DistDev h_dist = {};
     DistDev *d_dist = nullptr;
     int *send_rows = nullptr;
@@ -72,7 +72,10 @@ struct fg_ctx
     // pattern and per-mesh constants
     int *perm = nullptr, *sptr = nullptr, *scol = nullptr, *sdeg = nullptr, *iptr = nullptr,
         *itptr = nullptr, *sinct = nullptr;
-    double *sS = nullptr, *Aw = nullptr, *val = nullptr;
+    double *sS = nullptr, *Aw = nullptr, *Sdiag = nullptr, *Dg = nullptr;
+    double *val = nullptr;       // assembled 2x2 blocks of K: only the parity tap materialises them
+    Operator op_K = {};          // the assembled-K operator of the tap (OP_SELL2)
+    bool use_blocks = false;     // fg_set_operator(ctx, 1): solve with the assembled 2x2 blocks (A/B checks)
     KrylovWork kw;
     Operator op;
     // energies / averages / max angle: tables built on first use
@@ -201,6 +204,8 @@ int launch_elements(fg_ctx *c)
     return FG_OK;
     }
 
+int launch_assemble_K(fg_ctx *c);
+
 int launch_assemble(fg_ctx *c, double dt)
     {
     if (!c->prepared)
@@ -213,12 +218,9 @@ int launch_assemble(fg_ctx *c, double dt)
         set_error("solve(dt=%g) does not match prepareElements(dt=%g)", dt, c->sp.dt);
         return FG_ERR_STATE;
         }
-    RowArrays R;
+    NodeAsmArrays R;
     R.nslice = c->h.nslice;
-    R.sptr = c->sptr;
-    R.scol = c->scol;
-    R.sdeg = c->sdeg;
-    R.sS = c->sS;
+    R.Sdiag = c->Sdiag;
     R.Aw = c->Aw;
     R.iptr = c->iptr;
     R.itptr = c->itptr;
@@ -230,26 +232,59 @@ int launch_assemble(fg_ctx *c, double dt)
     if (!wave)
         {
         int per_sm = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_sell, BLOCK, 0) != cudaSuccess || per_sm < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_node, BLOCK, 0) != cudaSuccess || per_sm < 1)
             per_sm = 1;
         wave = per_sm * NUM_SMS;
         }
     int grid = (c->h.nslice + BLOCK / 32 - 1) / (BLOCK / 32);
     if (grid > wave) grid = wave;
     if (grid < 1) grid = 1;
-    CTX_LAUNCH_C(c, KC_ASSEMBLE, k_assemble_sell, grid, R, c->cur, c->next, c->basis, c->rec, c->trec, cS, c->val,
-               c->kw.b, c->kw.x, c->kw.D);
+    c->op.cS = cS;
+    CTX_LAUNCH_C(c, KC_ASSEMBLE, k_assemble_node, grid, R, c->cur, c->next, c->basis, c->rec, c->trec, cS,
+                 c->Dg, c->kw.b, c->kw.x, c->kw.w3p, c->kw.D);
     if (c->NODt > c->NODp)
         CTX_LAUNCH(c, k_ghost_guess, (c->NODt - c->NODp + BLOCK - 1) / BLOCK, c->NODp, c->NODt, c->nonmag,
-                   c->next, c->basis, c->kw.x);
+                   c->next, c->basis, c->kw.x, c->kw.w3p);
+    if (c->use_blocks) FG_TRY(launch_assemble_K(c));
     c->assembled = true;
+    return FG_OK;
+    }
+
+// Parity tap only: materialise the 2x2 blocks of K (solver::buildMat, src/solver.h:110-129) in the
+// SELL layout with the row-assembly kernel; rhs / guess / diagonal go to Krylov scratch vectors.
+int launch_assemble_K(fg_ctx *c)
+    {
+    const size_t nval = 4 * (size_t)(c->nblk > 0 ? c->nblk : 1);
+    if (!c->val)
+        {
+        FG_CUDA(cudaMalloc(&c->val, sizeof(double) * nval));
+        c->op_K = c->op;
+        c->op_K.kind = OP_SELL2;
+        c->op_K.val = c->val;
+        }
+    RowArrays R;
+    R.nslice = c->h.nslice;
+    R.sptr = c->sptr;
+    R.scol = c->scol;
+    R.sdeg = c->sdeg;
+    R.sS = c->sS;
+    R.Aw = c->Aw;
+    R.iptr = c->iptr;
+    R.itptr = c->itptr;
+    R.sinct = c->sinct;
+    R.nonmag = c->nonmag;
+    int grid = (c->h.nslice + BLOCK / 32 - 1) / (BLOCK / 32);
+    if (grid > MAX_GRID) grid = MAX_GRID;
+    if (grid < 1) grid = 1;
+    CTX_LAUNCH(c, k_assemble_sell, grid, R, c->cur, c->next, c->basis, c->rec, c->trec, c->op.cS, c->val,
+               c->kw.t, c->kw.v, c->kw.s);
     return FG_OK;
     }
 
 int post_update(void *user)
     {
     fg_ctx *c = static_cast<fg_ctx *>(user);
-    FG_TRY(halo_exchange(c->kw, 0, 2));  // multi-GPU: the solution of the ghost rows
+    FG_TRY(halo_exchange(c->kw, 2));  // multi-GPU: the solution of the ghost rows
     CTX_LAUNCH_C(c, KC_UPDATE, k_update, grid_for(c->NODt, BLOCK), c->NODt, c->NODp, c->nonmag, c->cur, c->next, c->basis,
                c->kw.x, c->sp.dt, c->kw.st, c->kw.red);
     return FG_OK;
@@ -265,7 +300,7 @@ int run_solve(fg_ctx *c, double dt, fg_step_result *out)
     if (c->profiling) FG_CUDA(cudaEventRecord(c->ev[2], c->stream));
     FG_TRY(launch_assemble(c, dt));
     if (c->profiling) FG_CUDA(cudaEventRecord(c->ev[3], c->stream));
-    FG_TRY(bicgstab_run(c->op, c->kw, c->tol, c->maxiter, post_update, c));
+    FG_TRY(bicgstab_run(c->use_blocks ? c->op_K : c->op, c->kw, c->tol, c->maxiter, post_update, c));
     if (c->profiling)
         {
         FG_CUDA(cudaEventRecord(c->ev[4], c->stream));
@@ -571,24 +606,36 @@ static int create_ctx(const fg_mesh *mesh, const fg_params *prm, int device, con
     CK(dev_upload(&c->iptr, h.iptr, s));
     CK(dev_upload(&c->itptr, h.itptr, s));
     CK(dev_upload(&c->sinct, h.sinct, s));
-    const size_t nval = 4 * (size_t)(c->nblk > 0 ? c->nblk : 1);
-    CKCUDA(cudaMalloc(&c->val, sizeof(double) * nval));
-    CKCUDA(cudaMemsetAsync(c->val, 0, sizeof(double) * nval, s));
+        {  // S_aa in device row order (Jacobi diagonal of the never-assembled K)
+        std::vector<double> sd((size_t)c->NODp, 0.0);
+        for (int a = 0; a < h.NOD; a++)
+            {
+            if (h.iperm[a] >= c->NODp) continue;  // ghost node (multi-GPU): no row here
+            for (int j = h.nptr[a]; j < h.nptr[a + 1]; j++)
+                if (h.ncol[j] == a) sd[(size_t)h.iperm[a]] = h.S[j];
+            }
+        CK(dev_upload(&c->Sdiag, sd, s));
+        CKCUDA(cudaMalloc(&c->Dg, sizeof(double) * 4 * (size_t)c->NODp));
+        CKCUDA(cudaMemsetAsync(c->Dg, 0, sizeof(double) * 4 * (size_t)c->NODp, s));
+        CKCUDA(cudaStreamSynchronize(s));
+        }
     if (dd)
         {  // exchange arena: control block + the three halo-exchanged vectors, one IPC-exportable block
-        const size_t vb = ((sizeof(double) * 2 * (size_t)c->NODt + 255) / 256) * 256;
+        const size_t vb = ((sizeof(double) * 2 * (size_t)c->NODt + 255) / 256) * 256;   // x
+        const size_t wb = ((sizeof(double4) * (size_t)c->NODt + 255) / 256) * 256;      // w3p, w3s
         const size_t cb = ((sizeof(DistCtrl) + 255) / 256) * 256;
-        c->arena_bytes = cb + 3 * vb;
+        c->arena_bytes = cb + vb + 2 * wb;
         CKCUDA(cudaMalloc(&c->arena, c->arena_bytes));
         CKCUDA(cudaMemsetAsync(c->arena, 0, c->arena_bytes, s));
         char *base = static_cast<char *>(c->arena);
         double *ext[3];
-        for (int k = 0; k < 3; k++)
-            {
-            ext[k] = reinterpret_cast<double *>(base + cb + k * vb);
-            c->tail_off[k] = cb + k * vb + sizeof(double) * 2 * (size_t)c->NODp;
-            }
-        CK(krylov_alloc(c->kw, c->np, 2 * (c->NODt - c->NODp), s, &c->launches, ext));
+        ext[0] = reinterpret_cast<double *>(base + cb);
+        ext[1] = reinterpret_cast<double *>(base + cb + vb);
+        ext[2] = reinterpret_cast<double *>(base + cb + vb + wb);
+        c->tail_off[0] = cb + sizeof(double) * 2 * (size_t)c->NODp;
+        c->tail_off[1] = cb + vb + sizeof(double4) * (size_t)c->NODp;
+        c->tail_off[2] = cb + vb + wb + sizeof(double4) * (size_t)c->NODp;
+        CK(krylov_alloc(c->kw, c->np, 2 * (c->NODt - c->NODp), s, &c->launches, true, ext));
         c->kw.arena = c->arena;
         // halo plan: boundary rows in device order, grouped by destination rank
         DistDev &D = c->h_dist;
@@ -620,15 +667,19 @@ static int create_ctx(const fg_mesh *mesh, const fg_params *prm, int device, con
         c->kw.nsend = (int)rows.size();
         }
     else
-        CK(krylov_alloc(c->kw, c->np, 0, s, &c->launches));
+        CK(krylov_alloc(c->kw, c->np, 0, s, &c->launches, true));
     c->kw.mask = c->dofmask;
-    c->op.kind = OP_SELL2;
+    c->kw.basis = c->basis;
+    c->op.kind = OP_NODE3;   // K is never materialised on the step path
     c->op.n = c->np;
     c->op.lanes = 32;
     c->op.ptr = c->sptr;
     c->op.col = c->scol;
-    c->op.val = c->val;
+    c->op.val = c->sS;
     c->op.nslice = h.nslice;
+    c->op.basis = c->basis;
+    c->op.Dg = c->Dg;
+    c->op.cS = 0.0;
     for (int k = 0; k < 5; k++) CKCUDA(cudaEventCreate(&c->ev[k]));
     CKCUDA(cudaStreamSynchronize(s));
     // the per-mesh host tables no longer needed are released (their SELL images are on the device)
@@ -667,7 +718,7 @@ namespace
 struct DistBlob  // FG_DIST_BLOB_BYTES
     {
     cudaIpcMemHandle_t handle;       // 64 B
-    unsigned long long tail_off[3];  // byte offsets of the ghost tails of x, phat, shat in the arena
+    unsigned long long tail_off[3];  // byte offsets of the ghost tails of x, w3p, w3s in the arena
     int rank, n_ghost;
     char pad_[FG_DIST_BLOB_BYTES - 64 - 24 - 8];
     };
@@ -720,8 +771,9 @@ int fg_dist_connect(fg_ctx *c, const void *blobs)
         else
             c->peer_base[q] = c->arena;
         D.ctrl[q] = static_cast<DistCtrl *>(base);
-        for (int k = 0; k < 3; k++)
-            D.tail[k][q] = reinterpret_cast<double2 *>(static_cast<char *>(base) + B[q].tail_off[k]);
+        D.tail[q] = reinterpret_cast<double2 *>(static_cast<char *>(base) + B[q].tail_off[0]);
+        D.wtail[0][q] = reinterpret_cast<double4 *>(static_cast<char *>(base) + B[q].tail_off[1]);
+        D.wtail[1][q] = reinterpret_cast<double4 *>(static_cast<char *>(base) + B[q].tail_off[2]);
         if (D.send_ptr[q + 1] - D.send_ptr[q] + D.send_dst[q] > B[q].n_ghost)
             {
             set_error("fg_dist_connect: segment for rank %d exceeds its ghost range", q);
@@ -746,7 +798,7 @@ void fg_destroy(fg_ctx *c)
     void *ptrs[] = {c->cur, c->next, c->basis, c->nonmag, c->dofmask, c->stage, c->tet_ind, c->tet_da,
                     c->tet_detJ, c->ext_field, c->tet_reg, c->reg_tet, c->rec, c->tri_ind,
                     c->tri_reg, c->tri_surf, c->tri_dMs, c->reg_tri, c->trec, c->perm, c->sptr,
-                    c->scol, c->sdeg, c->iptr, c->tet_slot, c->itptr, c->sinct, c->sS, c->Aw, c->val,
+                    c->scol, c->sdeg, c->iptr, c->tet_slot, c->itptr, c->sinct, c->sS, c->Aw, c->val, c->Sdiag, c->Dg,
                     c->mtri_ind, c->mtri_reg, c->mtri_surf, c->mtri_nrm, c->mtri_dMs, c->extra_edges,
                     c->d_scal, c->node_pos, c->corr, c->tcorr, c->src, c->cptr, c->cidx};
     for (void *p : ptrs)
@@ -762,6 +814,11 @@ void fg_destroy(fg_ctx *c)
         for (int k = 0; k < 2 * c->prof.cap; k++) cudaEventDestroy(c->prof.ev[k]);
         delete[] c->prof.ev;
         delete[] c->prof.cls;
+        }
+    if (c->kw.st)
+        {
+        KState hs;
+        if (cudaMemcpy(&hs, c->kw.st, sizeof(KState), cudaMemcpyDeviceToHost) == cudaSuccess && hs.hist) cudaFree(hs.hist);
         }
     krylov_free(c->kw);
     if (c->arena) cudaFree(c->arena);
@@ -1493,6 +1550,7 @@ int fg_get_system(fg_ctx *c, double dt, double *val, double *rhs, double *x0)
     const HostSetup &h = c->h;
     if (val)
         {  // SELL-32 2x2 blocks -> the reference's CSR order (rows 2a, 2a+1 of node a, sorted columns)
+        if (!c->use_blocks) FG_TRY(launch_assemble_K(c));
         std::vector<double> sv(4 * (size_t)c->nblk);
         FG_CUDA(cudaMemcpyAsync(sv.data(), c->val, sizeof(double) * sv.size(), cudaMemcpyDeviceToHost, c->stream));
         FG_CUDA(cudaStreamSynchronize(c->stream));
@@ -1756,6 +1814,70 @@ int fg_get_kernel_times(fg_ctx *c, double ms_out[FG_KERNEL_CLASSES], int launche
     return FG_OK;
     }
 
+int fg_set_operator(fg_ctx *c, int kind)
+    {
+    FG_TRY(check_ctx(c));
+    if (kind != 0 && kind != 1)
+        {
+        set_error("fg_set_operator: kind must be 0 (matrix-free) or 1 (assembled 2x2 blocks)");
+        return FG_ERR_INVALID;
+        }
+    if (kind == 1 && c->arena)
+        {
+        set_error("fg_set_operator: the assembled-block operator is single-GPU only");
+        return FG_ERR_STATE;
+        }
+    c->use_blocks = kind == 1;
+    c->assembled = false;
+    return FG_OK;
+    }
+
+int fg_get_krylov_history(fg_ctx *c, int rows, double *out)
+    {
+    FG_TRY(check_ctx(c));
+    if (rows < 0 || (rows > 0 && !out))
+        {
+        set_error("fg_get_krylov_history: bad argument");
+        return FG_ERR_INVALID;
+        }
+    static const int CAP = 1024;
+    KState hs;
+    FG_CUDA(cudaMemcpy(&hs, c->kw.st, sizeof(KState), cudaMemcpyDeviceToHost));
+    if (!hs.hist)
+        {  // first call switches the recording on; the NEXT solves are recorded
+        double *buf = nullptr;
+        FG_CUDA(cudaMalloc(&buf, sizeof(double) * 8 * CAP));
+        FG_CUDA(cudaMemset(buf, 0, sizeof(double) * 8 * CAP));
+        hs.hist = buf;
+        hs.hist_cap = CAP;
+        FG_CUDA(cudaMemcpy(c->kw.st, &hs, sizeof(KState), cudaMemcpyHostToDevice));
+        if (rows > 0) memset(out, 0, sizeof(double) * 8 * (size_t)rows);
+        return FG_OK;
+        }
+    const int nr = rows < CAP ? rows : CAP;
+    if (nr > 0) FG_CUDA(cudaMemcpy(out, hs.hist, sizeof(double) * 8 * (size_t)nr, cudaMemcpyDeviceToHost));
+    return FG_OK;
+    }
+
+int fg_get_krylov_state(const fg_ctx *c, double out[8])
+    {
+    if (!c || !out)
+        {
+        set_error("fg_get_krylov_state: null argument");
+        return FG_ERR_INVALID;
+        }
+    const KState &st = *c->kw.h_st;
+    out[0] = st.rho1;
+    out[1] = st.rho2;
+    out[2] = st.alpha;
+    out[3] = st.omega;
+    out[4] = st.res;
+    out[5] = st.rhsn;
+    out[6] = st.nit;
+    out[7] = st.status;
+    return FG_OK;
+    }
+
 int fg_get_phase_times(const fg_ctx *c, double out[8])
     {
     if (!c || !out)
@@ -1780,9 +1902,9 @@ int fg_bench_spmv(fg_ctx *c, int reps, double *ms_per_launch)
         set_error("fg_bench_spmv: no assembled system");
         return FG_ERR_STATE;
         }
-    for (int k = 0; k < 3; k++) FG_TRY(spmv(c->op, c->kw, c->kw.x, c->kw.t, true));
+    for (int k = 0; k < 3; k++) FG_TRY(spmv(c->op, c->kw, c->kw.x, c->kw.t, true, k == 0));
     FG_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    for (int k = 0; k < reps; k++) FG_TRY(spmv(c->op, c->kw, c->kw.x, c->kw.t, true));
+    for (int k = 0; k < reps; k++) FG_TRY(spmv(c->op, c->kw, c->kw.x, c->kw.t, true, false));
     FG_CUDA(cudaEventRecord(c->ev[1], c->stream));
     FG_CUDA(cudaEventSynchronize(c->ev[1]));
     float ms = 0.f;

@@ -683,6 +683,93 @@ k_assemble_sell(const RowArrays A, const NodeRec *__restrict__ cur, const NodeRe
         }
     }
 
+// Production assembly for the matrix-free operator (OP_NODE3, fg_common.cuh): K itself is never
+// written.  Same record gather as above (one warp per slice, one lane per node row, fixed order, no
+// atomics); per node it emits the rhs (buildVect), the initial guess (buildInitGuess) with its
+// 3-vector image for the first SpMV, the state-dependent 2x2 node-diagonal part Dg of K
+// (alpha_eff mass + gyrotropic term, src/tetra.cpp:108-148) and the Jacobi diagonal 1/K(i,i)
+// (build_diag_precond), which also needs the constant diagonal entry S_aa.
+struct NodeAsmArrays
+    {
+    int nslice;
+    const double *Sdiag;               // NODp : S_aa
+    const double *Aw;                  // NODp lumped mass
+    const int *iptr;                   // SELL incidence lists: slice extents of the record stream
+    const int *itptr, *sinct;          // same for the active triangles
+    const unsigned char *nonmag;       // NODp : 1 = node outside the magnetic material (or pad row)
+    };
+
+__global__ void __launch_bounds__(BLOCK)
+k_assemble_node(const NodeAsmArrays A, const NodeRec *__restrict__ cur, const NodeRec *__restrict__ next,
+                const Basis *__restrict__ basis, const double4 *__restrict__ rec,
+                const double2 *__restrict__ trec, double cS, double *__restrict__ Dg,
+                double *__restrict__ rhs, double *__restrict__ x0, double4 *__restrict__ w0,
+                double *__restrict__ D)
+    {
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * (BLOCK / 32);
+    for (int s = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); s < A.nslice; s += nwarps)
+        {
+        const int row = s * SLICE + lane;
+        double Ma = 0.0, L0 = 0.0, L1 = 0.0;
+            {
+            const int i0 = __ldg(A.iptr + s), i1 = __ldg(A.iptr + s + 1);
+            const double2 *rp = reinterpret_cast<const double2 *>(rec + (size_t)i0 * SLICE + lane);
+#pragma unroll 4
+            for (int q = i0; q < i1; ++q, rp += 2 * SLICE)
+                {
+                const double2 r01 = __ldcs(rp), r23 = __ldcs(rp + 1);
+                Ma += r01.x;
+                L0 += r01.y;
+                L1 += r23.x;
+                }
+            const int t0 = __ldg(A.itptr + s), t1 = __ldg(A.itptr + s + 1);
+            const int *tp = A.sinct + (size_t)t0 * SLICE + lane;
+            for (int q = t0; q < t1; ++q, tp += SLICE)
+                {
+                const int idx = __ldcs(tp);
+                if (idx >= 0)
+                    {
+                    const double2 r = trec[idx];
+                    L0 += r.x;
+                    L1 += r.y;
+                    }
+                }
+            }
+        double2 *rhs2 = reinterpret_cast<double2 *>(rhs) + row, *x02 = reinterpret_cast<double2 *>(x0) + row,
+                *D2 = reinterpret_cast<double2 *>(D) + row, *G2 = reinterpret_cast<double2 *>(Dg) + 2 * (size_t)row;
+        if (A.nonmag[row] != 0)
+            {  // identity rows, zero rhs and guess (src/solver.cpp:46-48, linear_algebra.cpp:13-24)
+            *rhs2 = make_double2(0.0, 0.0);
+            *x02 = make_double2(0.0, 0.0);
+            *D2 = make_double2(0.0, 0.0);
+            G2[0] = make_double2(1.0, 0.0);
+            G2[1] = make_double2(0.0, 1.0);
+            w0[row] = make_double4(0.0, 0.0, 0.0, 0.0);
+            continue;
+            }
+        double m[3], vc[3], phi, phiv, ep[3], eq[3], un[3], vn[3];
+        load_rec(cur + row, m, vc, phi, phiv);
+        load_basis(basis + row, ep, eq);
+        load_rec(next + row, un, vn, phi, phiv);
+        const double g0 = dot3(vn, ep) / FG_GAMMA0, g1 = dot3(vn, eq) / FG_GAMMA0;
+        *rhs2 = make_double2(L0, L1);
+        *x02 = make_double2(g0, g1);
+        w0[row] = make_double4(ep[0] * g0 + eq[0] * g1, ep[1] * g0 + eq[1] * g1, ep[2] * g0 + eq[2] * g1, 0.0);
+        const double aw = A.Aw[row];
+        // node-diagonal part without S: Ma P_a^T P_a + a_w e_r . (m x e_c)
+        double k00, k01, k10, k11;
+        project_block(Ma, ep, eq, ep, eq, k00, k01, k10, k11);
+        gyro_block(aw, m, ep, eq, k00, k01, k10, k11);
+        G2[0] = make_double2(k00, k01);
+        G2[1] = make_double2(k10, k11);
+        // Jacobi: the full diagonal entries K(2a,2a), K(2a+1,2a+1) as the assembled matrix has them
+        project_block(cS * A.Sdiag[row] + Ma, ep, eq, ep, eq, k00, k01, k10, k11);
+        gyro_block(aw, m, ep, eq, k00, k01, k10, k11);
+        *D2 = make_double2(1.0 / k00, 1.0 / k11);
+        }
+    }
+
 // ------------------------------------------------------------------------------------------
 // Node update (src/solver.cpp:62-88): gated on the device-side outcome of the solve.
 // ------------------------------------------------------------------------------------------
@@ -735,19 +822,23 @@ k_update(int NOD, int NOWN, const unsigned char *__restrict__ nonmag, const Node
 // multi-GPU: initial guess of the ghost rows (their owner's assembly writes the same numbers there)
 __global__ void __launch_bounds__(BLOCK)
 k_ghost_guess(int first, int last, const unsigned char *__restrict__ nonmag,
-              const NodeRec *__restrict__ next, const Basis *__restrict__ basis, double *__restrict__ x0)
+              const NodeRec *__restrict__ next, const Basis *__restrict__ basis, double *__restrict__ x0,
+              double4 *__restrict__ w0)
     {
     const int row = first + blockIdx.x * BLOCK + threadIdx.x;
     if (row >= last) return;
     double2 g = make_double2(0.0, 0.0);
+    double4 w = make_double4(0.0, 0.0, 0.0, 0.0);
     if (!nonmag[row])
         {
         double un[3], vn[3], phi, phiv, ep[3], eq[3];
         load_rec(next + row, un, vn, phi, phiv);
         load_basis(basis + row, ep, eq);
         g = make_double2(dot3(vn, ep) / FG_GAMMA0, dot3(vn, eq) / FG_GAMMA0);
+        w = make_double4(ep[0] * g.x + eq[0] * g.y, ep[1] * g.x + eq[1] * g.y, ep[2] * g.x + eq[2] * g.y, 0.0);
         }
     reinterpret_cast<double2 *>(x0)[row] = g;
+    w0[row] = w;
     }
 
 // ------------------------------------------------------------------------------------------

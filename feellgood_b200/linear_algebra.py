@@ -371,6 +371,21 @@ class LinAlgebra:
         check(self._L.fg_get_phase_times(self._h, out))
         return dict(basis=out[0], elements=out[1], assemble=out[2], solve=out[3])
 
+    def set_operator(self, kind):
+        """"node3" (default): matrix-free K; "blocks": assembled 2x2 blocks (A/B checks)."""
+        check(self._L.fg_set_operator(self._h, C.c_int({"node3": 0, "blocks": 1}[kind])))
+
+    def krylov_history(self, rows=0):
+        """First call: start recording; later: (rows, 8) array rho_1,(v,rt),alpha,|s|^2,(t,s),(t,t),omega,|r|^2."""
+        out = np.zeros((max(rows, 1), 8))
+        check(self._L.fg_get_krylov_history(self._h, C.c_int(rows), dp(out)))
+        return out[:rows]
+
+    def krylov_state(self):
+        out = (C.c_double * 8)()
+        check(self._L.fg_get_krylov_state(self._h, out))
+        return dict(zip(("rho1", "rho2", "alpha", "omega", "res", "rhsn", "nit", "status"), out))
+
     def bench_spmv(self, reps=20):
         ms = C.c_double()
         check(self._L.fg_bench_spmv(self._h, C.c_int(reps), C.byref(ms)))

@@ -153,8 +153,15 @@ def build(name, scale=1.0):
 
 # ---- algorithmic bytes (the figures bench.py's roofline is computed from) --------
 def spmv_bytes(n, nnz):
-    """One SpMV launch in this library's layout: 8 B per value, one 4-byte node-column index per
-    2x2 block (= nnz/4 indices), node row pointer, x read once, y written once."""
+    """One launch of the matrix-free operator K = cS P^T (S x I3) P + Dg: per
+    stored node pair (= nnz/4) 8 B of S + 4 B of column index; per node (= n/2) the gathered
+    3-vector image of x (32 B, read once from HBM), its own basis (48 B), the 2x2 node-diagonal
+    block (32 B), x (16 B), the fused second operand (16 B), y written (16 B), slice pointer."""
+    return 12 * (nnz // 4) + (32 + 48 + 32 + 16 + 16 + 16) * (n // 2) + 4 * (n // 64)
+
+
+def spmv_bytes_blocks(n, nnz):
+    """The same product with the assembled 2x2 blocks (round-1 layout: 36 B per block)."""
     return 8 * nnz + nnz + 4 * (n // 2) + 8 * n + 8 * n
 
 
@@ -164,15 +171,29 @@ def spmv_bytes_csr(n, nnz):
 
 
 def iter_bytes(n, nnz):
-    """One BiCGStab iteration: 2 SpMV + 18 vector passes of 8n bytes (SURVEY.md §8d B_iter)."""
-    return 2 * spmv_bytes(n, nnz) + 18 * 8 * n
+    """One BiCGStab iteration: 2 SpMV + 18 vector passes of 8n bytes (SURVEY.md §8d B_iter) + the two
+    3-vector images the producers of the SpMV inputs write (32 B) from their basis (48 B)."""
+    return 2 * spmv_bytes(n, nnz) + 18 * 8 * n + 2 * (32 + 48) * (n // 2)
 
 
 def step_bytes(NOD, NT, n, nnz, iters):
     """B_step of SURVEY.md §8d with this library's matrix layout."""
     b_basis = 72 * NOD
-    b_asm = 124 * NT + 112 * NOD + 8 * nnz + 8 * n
+    # elements (124 B/tet tables, 112 B/node gathered) + records written and read back (2 x 128 B/tet)
+    # + per node rhs, guess and its image, Dg, D (K itself is never written)
+    b_asm = 124 * NT + 112 * NOD + 256 * NT + (16 + 16 + 32 + 32 + 16) * NOD
     b_guess = 88 * NOD
     b_setup = spmv_bytes(n, nnz) + 10 * 8 * n
     b_update = 136 * NOD
     return b_basis + b_asm + b_guess + b_setup + iters * iter_bytes(n, nnz) + b_update
+
+
+def step_bytes_survey(NOD, NT, n, nnz, iters):
+    """B_step exactly as SURVEY.md §8d defines it for the reference's data structures (CSR with 12 B
+    per nnz and 20 B per row, assembled K written once per step): the layout-independent yardstick.
+    This library moves fewer bytes than that (K is never materialised), so a rate computed from this
+    figure is an EQUIVALENT bandwidth and may exceed the HBM peak."""
+    b_spmv = spmv_bytes_csr(n, nnz)
+    b_iter = 2 * b_spmv + 18 * 8 * n
+    b_asm = 124 * NT + 112 * NOD + 8 * nnz + 8 * n
+    return 72 * NOD + b_asm + 88 * NOD + (b_spmv + 10 * 8 * n) + iters * b_iter + 136 * NOD

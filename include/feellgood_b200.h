@@ -266,6 +266,17 @@ void *fg_stream(const fg_ctx *ctx);
  * on = 0 off, 1 phase timers, 2 per-SpMV event pairs (see fg_get_spmv_times). */
 int fg_set_profiling(fg_ctx *ctx, int on);
 int fg_get_phase_times(const fg_ctx *ctx, double out[8]);
+/* Per-iteration record of the BiCGStab scalars (diagnosis): the first call switches the recording on
+ * (up to 1024 iterations per solve, overwritten by each solve); later calls copy the first `rows`
+ * rows of 8 doubles: rho_1, (v,rt), alpha, |s|^2, (t,s), (t,t), omega, |r|^2 (src/algebra/bicg.h:185-231). */
+int fg_get_krylov_history(fg_ctx *ctx, int rows, double *out);
+/* Which form of K the solver applies: 0 (default) the matrix-free operator K = cS P^T (S x I3) P + Dg,
+ * 1 the assembled 2x2 blocks (what solver::buildMat produces; single GPU) — same algorithm, kept for
+ * A/B checks of parity and bandwidth. */
+int fg_set_operator(fg_ctx *ctx, int kind);
+/* The Krylov scalars of the last solve as the device left them (diagnosis of breakdowns, src/algebra/
+ * bicg.h:189-194): out = rho_1, rho_2, alpha, omega, res, rhsnorm, iterations, status. */
+int fg_get_krylov_state(const fg_ctx *ctx, double out[8]);
 /* fg_set_profiling(ctx, 2): instead of the phase timers, bracket every SpMV launch of the solver
  * with a CUDA-event pair on the context's stream (no host synchronisation is added; at most 4096
  * launches are kept).  fg_get_spmv_times returns their summed device time and count, and resets. */
