@@ -128,6 +128,8 @@ struct Operator
     int lanes;   // OP_CSR: lanes cooperating on one row: 2..32
     const int *ptr;     // OP_CSR rowptr (n+1) | OP_SELL2 / OP_NODE3 sptr (nslice+1)
     const int *col;     // OP_CSR col | OP_SELL2 / OP_NODE3 scol
+    const short *col16; // OP_NODE3, optional: scol as 16-bit offsets from the lane's own row (2 B instead of
+                        // 4 B per stored pair); NULL when an offset of the mesh does not fit
     const double *val;  // OP_SELL2: 2x2 blocks | OP_NODE3: S (one double per stored node pair)
     int nslice;         // OP_SELL2 / OP_NODE3
     // OP_NODE3
@@ -135,6 +137,22 @@ struct Operator
     const double *Dg;   // 4 doubles per node row: (k00, k01), (k10, k11)
     double cS;          // prefactor * s_dt (src/tetra.cpp:261)
     };
+
+// 256-bit global accesses (sm_100: LDG.E.ENL2.256 / STG.E.ENL2.256): one request per 32-byte node image
+// instead of a 128-bit + 64-bit pair -- halves the L1 wavefronts of the SpMV gather.  p must be 32-byte
+// aligned (the images are double4 arrays in 256-byte-aligned allocations).
+#ifdef __CUDACC__
+__device__ __forceinline__ double4 ld256_nc(const double4 *p)
+    {
+    double4 r;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+    }
+__device__ __forceinline__ void st256(double4 *p, const double4 v)
+    {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+    }
+#endif
 
 // optional CUDA-event pairs around kernel launches: fg_set_profiling(ctx, 2) brackets every SpMV
 // launch, fg_set_profiling(ctx, 3) every kernel of the step (classes below)

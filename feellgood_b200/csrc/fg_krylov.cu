@@ -12,6 +12,8 @@
 #include <math.h>
 #include <stdio.h>
 
+#include <type_traits>
+
 #include "fg_common.cuh"
 #include "fg_reduce.cuh"
 
@@ -304,10 +306,14 @@ __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_sell(const Ope
     }
 
 // ---- matrix-free LLG operator (OP_NODE3): K = cS P^T (S x I3) P + Dg, one warp per slice ---------
-// Streams 12 B per stored node pair (S, column) instead of 36 B per 2x2 block; the gather is one
-// aligned 32-byte sector (w_b as double4); the row epilogue projects z onto the node's (eq, ep) and
-// adds the 2x2 node-diagonal part.  Same SELL-32 traversal, same fused epilogues as k_spmv_sell.
-template <int STAGE>
+// Streams 12 B per stored node pair (S, column) instead of 36 B per 2x2 block -- 10 B when the column
+// offsets of the mesh fit 16 bits (IDX16); the gather is ONE 256-bit request for the aligned 32-byte
+// image w_b (LDG.E.ENL2.256); the row epilogue projects z onto the node's (eq, ep) and adds the 2x2
+// node-diagonal part.  Inside the BiCGStab loop the preconditioned input vector itself is never
+// stored: the node's own unknowns are recovered from its image, x_a = (ep_a . w_a, eq_a . w_a)
+// (a.x == NULL); the taps and the setup stage pass x.  Same SELL-32 traversal, same fused epilogues
+// as k_spmv_sell.
+template <int STAGE, bool IDX16>
 __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_node3(const Operator op, const SpmvArgs a)
     {
     if (stage_gated(STAGE))
@@ -317,6 +323,8 @@ __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_node3(const Op
         if (threadIdx.x == 0) dist_wait(a.dist);
         __syncthreads();
         }
+    typedef typename std::conditional<IDX16, short, int>::type idx_t;
+    const idx_t *colbase = IDX16 ? reinterpret_cast<const idx_t *>(op.col16) : reinterpret_cast<const idx_t *>(op.col);
     const int lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * (BLOCK / 32);
     const double2 *x2 = reinterpret_cast<const double2 *>(a.x);
@@ -338,7 +346,9 @@ __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_node3(const Op
             q0 = __ldg(op.ptr + sn);
             q1 = __ldg(op.ptr + sn + 1);
             }
-        const int *cp = op.col + (size_t)p0 * SLICE + lane;
+        const int row = s * SLICE + lane;
+        const int cbase = IDX16 ? row : 0;  // 16-bit columns are offsets from the lane's own row
+        const idx_t *cp = colbase + (size_t)p0 * SLICE + lane;
         const double *sp = op.val + (size_t)p0 * SLICE + lane;
         double z0 = 0.0, z1 = 0.0, z2 = 0.0;
             {  // batches of U pairs; the column indices of the next batch are fetched while this batch
@@ -347,7 +357,7 @@ __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_node3(const Op
             constexpr int U = 8;
             int cn[U];
 #pragma unroll
-            for (int u = 0; u < U; u++) cn[u] = p0 + u < p1 ? __ldcs(cp + u * SLICE) : 0;
+            for (int u = 0; u < U; u++) cn[u] = p0 + u < p1 ? (int)__ldcs(cp + u * SLICE) : 0;
             for (int j = p0; j < p1; j += U)
                 {
                 int c[U];
@@ -355,28 +365,34 @@ __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_node3(const Op
 #pragma unroll
                 for (int u = 0; u < U; u++)
                     {
-                    c[u] = cn[u];
+                    c[u] = cbase + cn[u];
                     Sv[u] = j + u < p1 ? __ldcs(sp + u * SLICE) : 0.0;
                     }
                 cp += U * SLICE;
                 sp += U * SLICE;
 #pragma unroll
-                for (int u = 0; u < U; u++) cn[u] = j + U + u < p1 ? __ldcs(cp + u * SLICE) : 0;
+                for (int u = 0; u < U; u++) cn[u] = j + U + u < p1 ? (int)__ldcs(cp + u * SLICE) : 0;
 #pragma unroll
                 for (int u = 0; u < U; u++)
                     {
-                    const double2 wa = __ldg(reinterpret_cast<const double2 *>(a.w + c[u]));
-                    const double wz = __ldg(reinterpret_cast<const double *>(a.w + c[u]) + 2);
-                    z0 += Sv[u] * wa.x;
-                    z1 += Sv[u] * wa.y;
-                    z2 += Sv[u] * wz;
+                    const double4 wb = ld256_nc(a.w + c[u]);
+                    z0 += Sv[u] * wb.x;
+                    z1 += Sv[u] * wb.y;
+                    z2 += Sv[u] * wb.z;
                     }
                 }
             }
-        const int row = s * SLICE + lane;
         double ep[3], eq[3];
         load_basis_k(op.basis + row, ep, eq);
-        const double2 xa = x2[row], d0 = __ldcs(Dg2 + 2 * (size_t)row), d1 = __ldcs(Dg2 + 2 * (size_t)row + 1);
+        double2 xa;
+        if (a.x != nullptr)
+            xa = x2[row];
+        else
+            {  // x_a = P_a^T w_a (ep, eq orthonormal): the line is in L1/L2, the diagonal pair gathered it
+            const double4 wr = ld256_nc(a.w + row);
+            xa = make_double2(ep[0] * wr.x + ep[1] * wr.y + ep[2] * wr.z, eq[0] * wr.x + eq[1] * wr.y + eq[2] * wr.z);
+            }
+        const double2 d0 = __ldcs(Dg2 + 2 * (size_t)row), d1 = __ldcs(Dg2 + 2 * (size_t)row + 1);
         const double y0 = op.cS * (eq[0] * z0 + eq[1] * z1 + eq[2] * z2) + (d0.x * xa.x + d0.y * xa.y);
         const double y1 = op.cS * (ep[0] * z0 + ep[1] * z1 + ep[2] * z2) + (d1.x * xa.x + d1.y * xa.y);
         spmv_row2<STAGE>(a, row, y0, y1, acc);
@@ -450,11 +466,19 @@ static int launch_spmv(const Operator &op, const KrylovWork &w, const SpmvArgs &
     const bool prof = prof_begin(w.prof, w.stream, cls);
     if (op.kind == OP_NODE3)
         {
-        static int wave = 0;
-        if (!wave) wave = resident_grid(k_spmv_node3<STAGE>);
+        static int wave = 0, wave16 = 0;
+        if (!wave)
+            {
+            wave = resident_grid(k_spmv_node3<STAGE, false>);
+            wave16 = resident_grid(k_spmv_node3<STAGE, true>);
+            }
         const int need = (op.nslice + BLOCK / 32 - 1) / (BLOCK / 32);
-        const int grid = need < wave ? (need > 0 ? need : 1) : wave;
-        k_spmv_node3<STAGE><<<grid, BLOCK, 0, w.stream>>>(op, a);
+        const int wv = op.col16 ? wave16 : wave;
+        const int grid = need < wv ? (need > 0 ? need : 1) : wv;
+        if (op.col16)
+            k_spmv_node3<STAGE, true><<<grid, BLOCK, 0, w.stream>>>(op, a);
+        else
+            k_spmv_node3<STAGE, false><<<grid, BLOCK, 0, w.stream>>>(op, a);
         }
     else if (op.kind == OP_SELL2)
         {
@@ -538,8 +562,9 @@ k_bicg_p(int n, const double *__restrict__ r, const double *__restrict__ p, doub
         }
     }
 
-// Node-wise variant for the matrix-free LLG operator: besides phat it writes w = P phat, the 3-vector
-// image the next SpMV gathers.  Multi-GPU: beta is known when this kernel starts, so its first
+// Node-wise variant for the matrix-free LLG operator: it writes w = P phat, the 3-vector image the
+// next SpMV gathers; phat itself is stored only when asked for (phat != NULL): the solver recomputes
+// D p where it needs it (k_bicg_xr_node), which saves one vector write here and one read in the SpMV.  Multi-GPU: beta is known when this kernel starts, so its first
 // CTAs push w of the boundary rows into the neighbours' ghost tails before doing their share of the
 // update; the last of those CTAs raises the halo flag the consuming SpMV waits on (fg_dist.cuh).
 // p is ping-ponged (read p, write pn) so that the pushers can read the old direction of rows
@@ -589,8 +614,8 @@ k_bicg_p_node(int nnode, const double *__restrict__ r, const double *__restrict_
         double2 pi;
         const double2 ph = value(a, pi);
         reinterpret_cast<double2 *>(pn)[a] = pi;
-        reinterpret_cast<double2 *>(phat)[a] = ph;
-        w3[a] = node_w(basis + a, ph.x, ph.y);
+        if (phat != nullptr) reinterpret_cast<double2 *>(phat)[a] = ph;
+        st256(w3 + a, node_w(basis + a, ph.x, ph.y));
         }
     }
 
@@ -660,8 +685,8 @@ k_bicg_s_node(int nnode, const double *__restrict__ r, const double *__restrict_
         double2 si;
         const double2 sh = value(a, si);
         reinterpret_cast<double2 *>(s)[a] = si;
-        reinterpret_cast<double2 *>(shat)[a] = sh;
-        w3[a] = node_w(basis + a, sh.x, sh.y);
+        if (shat != nullptr) reinterpret_cast<double2 *>(shat)[a] = sh;
+        st256(w3 + a, node_w(basis + a, sh.x, sh.y));
         acc[0] += si.x * si.x + si.y * si.y;
         }
     double tot[1];
@@ -695,6 +720,67 @@ k_bicg_xr(int n, double *__restrict__ x, const double *__restrict__ phat,
             r[i] = ri;
             acc[0] += ri * ri;
             acc[1] += rt[i] * ri;
+            }
+        }
+    double tot[2];
+    const int role = grid_reduce<2>(acc, red, tot);
+    if (role == 0) return;
+    if (role == 1)
+        {
+        if (fh)
+            st->final_half = 0;
+        else
+            {
+            khist(st, 7, tot[0]);
+            st->rho2 = st->rho1;
+            st->nit++;
+            if (st->nit >= st->maxiter) st->status = FG_ITER_OVERFLOW;  // iter.h:119-124
+            bicg_top_of_loop(st, tot[0], tot[1]);
+            }
+        }
+    }
+
+// Node-wise variant for the matrix-free LLG operator: phat = D p and shat = D s are not stored by
+// their producers; they are recomputed here with the same single rounding (D p, then the same
+// update expression), so x is bit-identical to the stored-vector formulation.
+__global__ void __launch_bounds__(BLOCK)
+k_bicg_xr_node(int nnode, double *__restrict__ x, const double *__restrict__ p, const double *__restrict__ D,
+               const double *__restrict__ s, const double *__restrict__ t, const double *__restrict__ rt,
+               double *__restrict__ r, KState *st, const RedBuf red)
+    {
+    const int fh = st->final_half;
+    if (st->done && !fh) return;
+    const double alpha = st->alpha, omega = st->omega;
+    double acc[2] = {0.0, 0.0};
+    const int stride = gridDim.x * BLOCK;
+    double2 *x2 = reinterpret_cast<double2 *>(x), *r2 = reinterpret_cast<double2 *>(r);
+    const double2 *p2 = reinterpret_cast<const double2 *>(p), *D2 = reinterpret_cast<const double2 *>(D),
+                  *s2 = reinterpret_cast<const double2 *>(s), *t2 = reinterpret_cast<const double2 *>(t),
+                  *rt2 = reinterpret_cast<const double2 *>(rt);
+    if (fh)
+        {
+        for (int a = blockIdx.x * BLOCK + threadIdx.x; a < nnode; a += stride)
+            {
+            const double2 d = D2[a], pp = p2[a];
+            double2 xv = x2[a];
+            xv.x += alpha * __dmul_rn(d.x, pp.x);
+            xv.y += alpha * __dmul_rn(d.y, pp.y);
+            x2[a] = xv;
+            }
+        }
+    else
+        {
+        for (int a = blockIdx.x * BLOCK + threadIdx.x; a < nnode; a += stride)
+            {
+            const double2 d = D2[a], pp = p2[a], sv = s2[a], tv = t2[a], rtv = rt2[a];
+            double2 xv = x2[a];
+            xv.x = (xv.x + alpha * __dmul_rn(d.x, pp.x)) + omega * __dmul_rn(d.x, sv.x);
+            xv.y = (xv.y + alpha * __dmul_rn(d.y, pp.y)) + omega * __dmul_rn(d.y, sv.y);
+            x2[a] = xv;
+            const double2 ri = make_double2(sv.x - omega * tv.x, sv.y - omega * tv.y);
+            r2[a] = ri;
+            acc[0] += ri.x * ri.x + ri.y * ri.y;
+            acc[1] += rtv.x * ri.x + rtv.y * ri.y;
             }
         }
     double tot[2];
@@ -982,9 +1068,10 @@ int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, pos
     const int n = w.n;
     // one resident wave per vector kernel (their register counts differ)
     const bool node3 = op.kind == OP_NODE3;
-    static int wave_pn = 0, wave_sn = 0, wave_ps = 0, wave_ss = 0, wave_xr = 0;
+    static int wave_pn = 0, wave_sn = 0, wave_ps = 0, wave_ss = 0, wave_xr = 0, wave_xrn = 0;
     if (!wave_xr)
         {
+        wave_xrn = resident_grid(k_bicg_xr_node);
         wave_pn = resident_grid(k_bicg_p_node);
         wave_sn = resident_grid(k_bicg_s_node);
         wave_ps = resident_grid(k_bicg_p);
@@ -998,8 +1085,9 @@ int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, pos
         return FG_ERR_STATE;
         }
     const int gneed = grid_for(n, BLOCK * 2);
+    const int wave_x = node3 ? wave_xrn : wave_xr;
     const int gp = gneed < wave_p ? gneed : wave_p, gs = gneed < wave_s ? gneed : wave_s,
-              gxr = gneed < wave_xr ? gneed : wave_xr;
+              gxr = gneed < wave_x ? gneed : wave_x;
     // multi-GPU: the first npush CTAs of k_bicg_p push the boundary rows of D.p (>= 1 so that the
     // halo epoch advances on every rank, even one without neighbours)
     int npush = w.dist ? (w.nsend + BLOCK - 1) / BLOCK : 0;
@@ -1032,14 +1120,14 @@ int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, pos
             // iteration `enq + k` of this solve reads p from one buffer and writes the other one
             double *p_old = ((enq + k) & 1) ? w.p2 : w.p, *p_new = ((enq + k) & 1) ? w.p : w.p2;
             if (node3)
-                FG_LAUNCH_C(w, KC_BICG_P, k_bicg_p_node, gp, n / 2, w.r, p_old, p_new, w.v, w.D, w.phat, w.basis,
-                            w.w3p, w.st, w.dist, w.red.ticket, npush);
+                FG_LAUNCH_C(w, KC_BICG_P, k_bicg_p_node, gp, n / 2, w.r, p_old, p_new, w.v, w.D,
+                            static_cast<double *>(nullptr), w.basis, w.w3p, w.st, w.dist, w.red.ticket, npush);
             else
                 FG_LAUNCH_C(w, KC_BICG_P, k_bicg_p, gp, n, w.r, p_old, p_new, w.v, w.D, w.phat, w.st);
             SpmvArgs a = {};
             a.dist = w.dist;
             a.w = w.w3p;
-            a.x = w.phat;
+            a.x = node3 ? nullptr : w.phat;  // matrix-free: x_a is recovered from its image w_a
             a.y = w.v;
             a.a0 = w.rt;
             a.mask = w.mask;
@@ -1047,16 +1135,20 @@ int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, pos
             a.red = w.red;
             FG_TRY(launch_spmv<ST_BICG_V>(op, w, a));
             if (node3)
-                FG_LAUNCH_C(w, KC_BICG_S, k_bicg_s_node, gs, n / 2, w.r, w.v, w.D, w.s, w.shat, w.basis, w.w3s,
-                            w.st, w.red);
+                FG_LAUNCH_C(w, KC_BICG_S, k_bicg_s_node, gs, n / 2, w.r, w.v, w.D, w.s,
+                            static_cast<double *>(nullptr), w.basis, w.w3s, w.st, w.red);
             else
                 FG_LAUNCH_C(w, KC_BICG_S, k_bicg_s, gs, n, w.r, w.v, w.D, w.s, w.shat, w.st, w.red);
             a.w = w.w3s;
-            a.x = w.shat;
+            a.x = node3 ? nullptr : w.shat;
             a.y = w.t;
             a.a0 = w.s;
             FG_TRY(launch_spmv<ST_BICG_T>(op, w, a));
-            FG_LAUNCH_C(w, KC_BICG_XR, k_bicg_xr, gxr, n, w.x, w.phat, w.shat, w.s, w.t, w.rt, w.r, w.st, w.red);
+            if (node3)
+                FG_LAUNCH_C(w, KC_BICG_XR, k_bicg_xr_node, gxr, n / 2, w.x, p_new, w.D, w.s, w.t, w.rt, w.r, w.st,
+                            w.red);
+            else
+                FG_LAUNCH_C(w, KC_BICG_XR, k_bicg_xr, gxr, n, w.x, w.phat, w.shat, w.s, w.t, w.rt, w.r, w.st, w.red);
             }
         enq += batch;
         if (post) FG_TRY(post(user));

@@ -70,6 +70,7 @@ struct fg_ctx
     double2 *trec = nullptr;
     std::vector<TriRegion> h_reg_tri;
     // pattern and per-mesh constants
+    short *scol16 = nullptr;  // scol as 16-bit offsets from the row (NULL when one does not fit)
     int *perm = nullptr, *sptr = nullptr, *scol = nullptr, *sdeg = nullptr, *iptr = nullptr,
         *itptr = nullptr, *sinct = nullptr;
     double *sS = nullptr, *Aw = nullptr, *Sdiag = nullptr, *Dg = nullptr;
@@ -601,6 +602,32 @@ static int create_ctx(const fg_mesh *mesh, const fg_params *prm, int device, con
         }
     CK(dev_upload(&c->sptr, h.sptr, s));
     CK(dev_upload(&c->scol, h.scol, s));
+        {  // 16-bit column offsets for the matrix-free SpMV (2 B instead of 4 B per stored pair) when every
+           // neighbour of every row lies within +-32767 device rows (single-GPU meshes in the reference's
+           // sorted node order; ghost columns of a partitioned mesh usually do not)
+        const size_t ne = h.scol.size();
+        bool fits = getenv("FG_NO_COL16") == nullptr;
+        std::vector<short> c16;
+        if (fits) c16.resize(ne);
+        if (fits)
+            {
+            int bad = 0;
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+            for (int sl = 0; sl < h.nslice; sl++)
+                for (int j = h.sptr[sl]; j < h.sptr[sl + 1]; j++)
+                    for (int l = 0; l < SLICE; l++)
+                        {
+                        const size_t pos = (size_t)j * SLICE + l;
+                        const int d = h.scol[pos] - (sl * SLICE + l);
+                        if (d < -32767 || d > 32767)
+                            bad++;
+                        else
+                            c16[pos] = (short)d;
+                        }
+            fits = bad == 0;
+            }
+        if (fits && ne > 0) CK(dev_upload(&c->scol16, c16, s));
+        }
     CK(dev_upload(&c->sdeg, h.sdeg, s));
     CK(dev_upload(&c->sS, h.sS, s));
     CK(dev_upload(&c->iptr, h.iptr, s));
@@ -675,6 +702,7 @@ static int create_ctx(const fg_mesh *mesh, const fg_params *prm, int device, con
     c->op.lanes = 32;
     c->op.ptr = c->sptr;
     c->op.col = c->scol;
+    c->op.col16 = c->scol16;
     c->op.val = c->sS;
     c->op.nslice = h.nslice;
     c->op.basis = c->basis;
@@ -799,7 +827,7 @@ void fg_destroy(fg_ctx *c)
                     c->tet_detJ, c->ext_field, c->tet_reg, c->reg_tet, c->rec, c->tri_ind,
                     c->tri_reg, c->tri_surf, c->tri_dMs, c->reg_tri, c->trec, c->perm, c->sptr,
                     c->scol, c->sdeg, c->iptr, c->tet_slot, c->itptr, c->sinct, c->sS, c->Aw, c->val, c->Sdiag, c->Dg,
-                    c->mtri_ind, c->mtri_reg, c->mtri_surf, c->mtri_nrm, c->mtri_dMs, c->extra_edges,
+                    c->scol16, c->mtri_ind, c->mtri_reg, c->mtri_surf, c->mtri_nrm, c->mtri_dMs, c->extra_edges,
                     c->d_scal, c->node_pos, c->corr, c->tcorr, c->src, c->cptr, c->cidx};
     for (void *p : ptrs)
         if (p) cudaFree(p);
