@@ -328,11 +328,12 @@ def main():
     nnz_loc = la.nnz_local if hasattr(la, "nnz_local") else la.nnz
     roof = None
     if spmv_n > 0:
-        b_spmv = workloads.spmv_bytes(n_loc, nnz_loc)
+        col_bytes = getattr(la, "col_bytes", 4)
+        b_spmv = workloads.spmv_bytes(n_loc, nnz_loc, col_bytes)
         ach = b_spmv / (spmv_ms * 1e-3 / spmv_n) / 1e9
         roof = dict(bound="hbm", kernel="k_spmv_node3<STAGE>", achieved=ach, peak=peak, unit="GB/s",
                     frac=ach / peak, traffic=None, peak_source=peak_src,
-                    bytes_per_launch=b_spmv, launches=spmv_n, us_per_launch=1e3 * spmv_ms / spmv_n,
+                    bytes_per_launch=b_spmv, col_index_bytes=col_bytes, launches=spmv_n, us_per_launch=1e3 * spmv_ms / spmv_n,
                     share_of_step=spmv_ms / ms,
                     csr_equiv_gbs=workloads.spmv_bytes_csr(n_loc, nnz_loc)
                     / (spmv_ms * 1e-3 / spmv_n) / 1e9)
@@ -344,7 +345,7 @@ def main():
                     roof["traffic"] = tj.get("dram_bytes_per_launch")
             except Exception:
                 pass
-    b_step = workloads.step_bytes(w.mesh.NOD, w.mesh.NT, la.n, la.nnz, mean_it)
+    b_step = workloads.step_bytes(w.mesh.NOD, w.mesh.NT, la.n, la.nnz, mean_it, getattr(la, "col_bytes", 4))
     b_survey = workloads.step_bytes_survey(w.mesh.NOD, w.mesh.NT, la.n, la.nnz, mean_it)
     step_roof = dict(bytes_per_step=b_step, achieved=b_step / (ms * 1e-3 / args.steps) / 1e9 / world,
                      unit="GB/s per GPU", frac=b_step / (ms * 1e-3 / args.steps) / 1e9 / world / peak,

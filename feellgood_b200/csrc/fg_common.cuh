@@ -148,6 +148,13 @@ __device__ __forceinline__ double4 ld256_nc(const double4 *p)
     asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
     return r;
     }
+// streaming variant (evict-first): data read exactly once per step (the element records)
+__device__ __forceinline__ double4 ld256_cs(const double4 *p)
+    {
+    double4 r;
+    asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p) : "memory");
+    return r;
+    }
 __device__ __forceinline__ void st256(double4 *p, const double4 v)
     {
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");

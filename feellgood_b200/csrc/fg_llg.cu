@@ -95,6 +95,7 @@ struct fg_ctx
     // step bookkeeping
     StepPrm sp = {};
     bool have_basis = false, prepared = false, space_field = false, assembled = false;
+    bool iso_regions = true;   // no region has K or K3: the element fast path applies (k_tet_iso)
     double v_max = 0.0;
     // profiling
     int profiling = 0;
@@ -159,6 +160,13 @@ int launch_basis(fg_ctx *c, double angle)
     return FG_OK;
     }
 
+// the element fast path (k_tet_iso): no anisotropy anywhere, uniform field, no recentring drift
+static bool use_iso(const fg_ctx *c)
+    {
+    static const bool off = getenv("FG_NO_ISO") != nullptr;
+    return !off && c->iso_regions && !c->space_field && c->sp.idx_dir == FG_IDX_UNDEF;
+    }
+
 int launch_elements(fg_ctx *c)
     {
     if (!c->have_basis)
@@ -170,7 +178,14 @@ int launch_elements(fg_ctx *c)
         {
         const TetArrays A = tet_arrays(c);
         const int grid = grid_for(c->NTm, BLOCK);
-        if (c->h.npi_tet == 5)
+        if (use_iso(c))
+            {
+            if (c->h.npi_tet == 5)
+                CTX_LAUNCH_C(c, KC_TET, (k_tet_iso<5>), grid, A, c->cur, c->basis, c->sp, c->rec);
+            else
+                CTX_LAUNCH_C(c, KC_TET, (k_tet_iso<1>), grid, A, c->cur, c->basis, c->sp, c->rec);
+            }
+        else if (c->h.npi_tet == 5)
             {
             if (c->space_field)
                 CTX_LAUNCH_C(c, KC_TET, (k_tet<5, true>), grid, A, c->cur, c->basis, c->sp, c->rec);
@@ -558,6 +573,7 @@ static int create_ctx(const fg_mesh *mesh, const fg_params *prm, int device, con
                 }
             R.has_K = p.K != 0;
             R.has_K3 = p.K3 != 0;
+            if (p.Ms > 0 && (R.has_K || R.has_K3)) c->iso_regions = false;
             for (int k = 0; k < 3; k++)
                 {
                 R.uk[k] = p.uk[k];
@@ -873,6 +889,20 @@ int fg_get_sizes(const fg_ctx *c, long long out[10])
     out[7] = c->n;
     out[8] = 4LL * c->nnzb;
     out[9] = (long long)c->h.lvd.size();
+    return FG_OK;
+    }
+
+int fg_get_layout(const fg_ctx *c, long long out[4])
+    {
+    if (!c || !out)
+        {
+        set_error("fg_get_layout: null argument");
+        return FG_ERR_INVALID;
+        }
+    out[0] = c->scol16 ? 2 : 4;
+    out[1] = c->nblk;
+    out[2] = c->iso_regions ? 1 : 0;
+    out[3] = c->NODp;
     return FG_OK;
     }
 
@@ -1425,7 +1455,12 @@ int fg_get_elements(fg_ctx *c, int first, int count, double *Kp, double *Lp)
     FG_CUDA(cudaMemcpyAsync(dlist, list.data(), sizeof(int) * (size_t)cnt, cudaMemcpyHostToDevice, c->stream));
     const TetArrays A = tet_arrays(c);
     const int grid = (cnt + BLOCK - 1) / BLOCK;
-    if (c->h.npi_tet == 5)
+    if (use_iso(c))
+        {
+        if (c->h.npi_tet == 5) k_tet_tap<5, false, true><<<grid, BLOCK, 0, c->stream>>>(A, c->cur, c->basis, c->sp, dlist, cnt, dK, dL);
+        else k_tet_tap<1, false, true><<<grid, BLOCK, 0, c->stream>>>(A, c->cur, c->basis, c->sp, dlist, cnt, dK, dL);
+        }
+    else if (c->h.npi_tet == 5)
         {
         if (c->space_field) k_tet_tap<5, true><<<grid, BLOCK, 0, c->stream>>>(A, c->cur, c->basis, c->sp, dlist, cnt, dK, dL);
         else k_tet_tap<5, false><<<grid, BLOCK, 0, c->stream>>>(A, c->cur, c->basis, c->sp, dlist, cnt, dK, dL);

@@ -58,12 +58,12 @@ __device__ __forceinline__ void normalize3(double *a)
 
 __device__ __forceinline__ void load_rec(const NodeRec *p, double u[3], double v[3], double &phi,
                                          double &phiv)
-    {
-    const double2 *q = reinterpret_cast<const double2 *>(p);
-    const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
-    u[0] = a.x; u[1] = a.y; u[2] = b.x;
-    v[0] = b.y; v[1] = c.x; v[2] = c.y;
-    phi = d.x; phiv = d.y;
+    {  // 64-byte aligned record: two 256-bit requests (LDG.E.ENL2.256)
+    const double4 *q = reinterpret_cast<const double4 *>(p);
+    const double4 a = ld256_nc(q), b = ld256_nc(q + 1);
+    u[0] = a.x; u[1] = a.y; u[2] = a.z;
+    v[0] = a.w; v[1] = b.x; v[2] = b.y;
+    phi = b.z; phiv = b.w;
     }
 __device__ __forceinline__ void load_basis(const Basis *p, double ep[3], double eq[3])
     {
@@ -412,6 +412,150 @@ k_tet(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__restric
         }
     }
 
+// ---- fast path of Tet::integrales: no magnetocrystalline anisotropy in any region (K = K3 = 0),
+// uniform applied field, no recentring drift -- every permalloy-like material, all five BASELINE
+// configurations.  Same formulas and the same order of accumulation as tet_core (H_aniso = 0 is
+// dropped, not approximated), organised so that the Gauss loop keeps only u, contrib and the field
+// live: BE of a node is accumulated when its record is written (it needs only the node's own
+// gradient), the velocities are never loaded.  ~120 registers instead of 254: two to three times the
+// resident warps for the node gathers.
+struct TetIsoIn
+    {
+    double da[4][3];
+    double detJ;
+    double u[4][3], phi[4], phiv[4];
+    };
+struct TetIsoMid
+    {
+    double dU[3][3];  // grad U
+    double H[3];      // (Hd + Hext) + theta dt Hv : the field of tetra.cpp:292-303 with H_aniso = 0
+    };
+
+template <int NPI>
+__device__ __forceinline__ void tet_iso_front(const TetIsoIn &T, const TetRegion &R, const StepPrm &sp,
+                                              TetIsoMid &M, double contrib[4])
+    {
+    const double s_dt = FG_THETA * sp.dt * FG_GAMMA0;
+    const double th_dt = s_dt / FG_GAMMA0;
+    double Heff[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+        {
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            {
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) s += T.u[i][d] * T.da[i][k];
+            M.dU[d][k] = s;
+            }
+        double hd = 0.0, hv = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            {
+            hd -= T.phi[i] * T.da[i][d];
+            hv -= T.phiv[i] * T.da[i][d];
+            }
+        Heff[d] = hd + sp.Hext[d];                     // tetra.cpp:248-255, Hst = 0
+        M.H[d] = Heff[d] + __dmul_rn(th_dt, hv);       // :292 with H_aniso = 0 (two roundings, like tet_core)
+        }
+    double gsq = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        gsq += M.dU[0][k] * M.dU[0][k] + M.dU[1][k] * M.dU[1][k] + M.dU[2][k] * M.dU[2][k];
+#pragma unroll
+    for (int i = 0; i < 4; i++) contrib[i] = 0.0;
+#pragma unroll
+    for (int g = 0; g < NPI; g++)
+        {
+        const double w = T.detJ * tet_pds<NPI>(g);
+        double uH = -R.Abis * gsq;
+        double s = 0.0;
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+            {
+            double su = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) su += T.u[i][d] * tet_a<NPI>(i, g);
+            s += su * Heff[d];
+            }
+        uH += s;
+        const double wa = w * alpha_eff(sp.dt, R.alpha, uH);
+#pragma unroll
+        for (int i = 0; i < 4; i++) contrib[i] += tet_a<NPI>(i, g) * wa;
+        }
+    }
+
+// BE(:, i) of local node i (tetra.cpp:294-303), Gauss points in the reference's order
+template <int NPI>
+__device__ __forceinline__ void tet_iso_be(const double da_i[3], int i, double detJ, double Abis,
+                                           const TetIsoMid &M, double be[3])
+    {
+    double Ex[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+        {
+        Ex[d] = da_i[0] * M.dU[d][0] + da_i[1] * M.dU[d][1] + da_i[2] * M.dU[d][2];
+        be[d] = 0.0;
+        }
+#pragma unroll
+    for (int g = 0; g < NPI; g++)
+        {
+        const double w = detJ * tet_pds<NPI>(g);
+        const double ai_w = w * tet_a<NPI>(i, g);
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+            {
+            be[d] -= w * Abis * Ex[d];
+            be[d] += ai_w * M.H[d];
+            }
+        }
+    }
+
+constexpr int TET_ISO_CTAS_PER_SM = 2;
+template <int NPI>
+__global__ void __launch_bounds__(BLOCK, TET_ISO_CTAS_PER_SM)
+k_tet_iso(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__restrict__ basis,
+          const StepPrm sp, double4 *__restrict__ rec)
+    {
+    const int stride = gridDim.x * BLOCK;
+    for (int tm = blockIdx.x * BLOCK + threadIdx.x; tm < A.NTm; tm += stride)
+        {
+        TetIsoIn T;
+        const int4 ind = __ldg(A.ind + tm);
+        const int nd[4] = {ind.x, ind.y, ind.z, ind.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            {
+            const double4 *q = reinterpret_cast<const double4 *>(cur + nd[i]);
+            const double4 a = ld256_nc(q), b = ld256_nc(q + 1);
+            T.u[i][0] = a.x; T.u[i][1] = a.y; T.u[i][2] = a.z;
+            T.phi[i] = b.z; T.phiv[i] = b.w;
+            }
+#pragma unroll
+        for (int k = 0; k < 12; k++) T.da[k / 3][k % 3] = __ldcs(A.da + (size_t)k * A.NTm + tm);
+        T.detJ = __ldcs(A.detJ + tm);
+        const TetRegion &R = A.regions[__ldg(A.reg + tm)];
+        TetRegion Rl;
+        Rl.alpha = R.alpha;
+        Rl.Abis = R.Abis;
+        TetIsoMid M;
+        double contrib[4];
+        tet_iso_front<NPI>(T, Rl, sp, M, contrib);
+        const int4 s4 = __ldcs(A.slot + tm);
+        const int sl[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            {
+            if (sl[i] < 0) continue;
+            double ep[3], eq[3], be[3];
+            load_basis(basis + nd[i], ep, eq);
+            tet_iso_be<NPI>(T.da[i], i, T.detJ, Rl.Abis, M, be);
+            st256(rec + sl[i], make_double4(contrib[i], dot3(eq, be), dot3(ep, be), 0.0));
+            }
+        }
+    }
+
 // projection of one node pair: the 2x2 block of K / Kp (SURVEY.md §8a index facts)
 __device__ __forceinline__ void project_block(double E, const double ep_a[3], const double eq_a[3],
                                               const double ep_b[3], const double eq_b[3],
@@ -438,7 +582,7 @@ __device__ __forceinline__ void gyro_block(double aw, const double m[3], const d
 
 // Tap: full element Kp (8x8 row-major) and Lp (8) of the magnetic tets list[0..count), computed
 // with the same device functions as the production path (element.h:62,65 layout).
-template <int NPI, bool SPACE>
+template <int NPI, bool SPACE, bool ISO = false>
 __global__ void __launch_bounds__(BLOCK)
 k_tet_tap(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__restrict__ basis,
           const StepPrm sp, const int *__restrict__ list, int count, double *__restrict__ Kp,
@@ -454,7 +598,34 @@ k_tet_tap(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__res
     tet_field<NPI>(A, tm, sp, SPACE, Hext);
     const TetRegion R = A.regions[A.reg[tm]];
     double contrib[4], BE[3][4];
-    tet_core<NPI>(T, R, sp, Hext, contrib, BE);
+    if (ISO)
+        {  // the device functions of the production fast path (k_tet_iso)
+        TetIsoIn Ti;
+        for (int i = 0; i < 4; i++)
+            {
+            for (int k = 0; k < 3; k++)
+                {
+                Ti.da[i][k] = T.da[i][k];
+                Ti.u[i][k] = T.u[i][k];
+                }
+            Ti.phi[i] = T.phi[i];
+            Ti.phiv[i] = T.phiv[i];
+            }
+        Ti.detJ = T.detJ;
+        TetIsoMid M;
+        tet_iso_front<NPI>(Ti, R, sp, M, contrib);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            {
+            double be[3];
+            tet_iso_be<NPI>(Ti.da[i], i, Ti.detJ, R.Abis, M, be);
+            BE[0][i] = be[0];
+            BE[1][i] = be[1];
+            BE[2][i] = be[2];
+            }
+        }
+    else
+        tet_core<NPI>(T, R, sp, Hext, contrib, BE);
     const int nd[4] = {ind.x, ind.y, ind.z, ind.w};
     double ep[4][3], eq[4][3];
     for (int i = 0; i < 4; i++) load_basis(basis + nd[i], ep[i], eq[i]);
@@ -599,14 +770,14 @@ k_assemble_sell(const RowArrays A, const NodeRec *__restrict__ cur, const NodeRe
             // the records were written in incidence order: a pure coalesced stream (1 KB per warp
             // request), empty slots hold zeros
             const int i0 = __ldg(A.iptr + s), i1 = __ldg(A.iptr + s + 1);
-            const double2 *rp = reinterpret_cast<const double2 *>(rec + (size_t)i0 * SLICE + lane);
+            const double4 *rp = rec + (size_t)i0 * SLICE + lane;
 #pragma unroll 4
-            for (int q = i0; q < i1; ++q, rp += 2 * SLICE)
-                {
-                const double2 r01 = __ldcs(rp), r23 = __ldcs(rp + 1);
-                Ma += r01.x;
-                L0 += r01.y;
-                L1 += r23.x;
+            for (int q = i0; q < i1; ++q, rp += SLICE)
+                {  // one 256-bit request per record: a warp streams 1 KB contiguous
+                const double4 r = ld256_cs(rp);
+                Ma += r.x;
+                L0 += r.y;
+                L1 += r.z;
                 }
             const int t0 = __ldg(A.itptr + s), t1 = __ldg(A.itptr + s + 1);
             const int *tp = A.sinct + (size_t)t0 * SLICE + lane;
@@ -714,14 +885,14 @@ k_assemble_node(const NodeAsmArrays A, const NodeRec *__restrict__ cur, const No
         double Ma = 0.0, L0 = 0.0, L1 = 0.0;
             {
             const int i0 = __ldg(A.iptr + s), i1 = __ldg(A.iptr + s + 1);
-            const double2 *rp = reinterpret_cast<const double2 *>(rec + (size_t)i0 * SLICE + lane);
+            const double4 *rp = rec + (size_t)i0 * SLICE + lane;
 #pragma unroll 4
-            for (int q = i0; q < i1; ++q, rp += 2 * SLICE)
-                {
-                const double2 r01 = __ldcs(rp), r23 = __ldcs(rp + 1);
-                Ma += r01.x;
-                L0 += r01.y;
-                L1 += r23.x;
+            for (int q = i0; q < i1; ++q, rp += SLICE)
+                {  // one 256-bit request per record: a warp streams 1 KB contiguous
+                const double4 r = ld256_cs(rp);
+                Ma += r.x;
+                L0 += r.y;
+                L1 += r.z;
                 }
             const int t0 = __ldg(A.itptr + s), t1 = __ldg(A.itptr + s + 1);
             const int *tp = A.sinct + (size_t)t0 * SLICE + lane;

@@ -141,6 +141,10 @@ class LinAlgebra:
         (_, self.NT, self.NF, self.n_magTet, self.n_magTri, self.E, self.E_mag, self.n, self.nnz,
          self.nlvd) = list(out)
         self.npi = settings.npi_tet
+        lay = (C.c_longlong * 4)()
+        check(L.fg_get_layout(h, lay))
+        # device layout: index bytes per stored node pair, stored pairs (with padding), fast-path flag
+        self.col_bytes, self.stored_pairs, self.iso_fast_path = int(lay[0]), int(lay[1]), bool(lay[2])
         # linear_algebra.h:50-53
         self.idx_dir = settings.recentering_direction if settings.recenter else capi.FG_IDX_UNDEF
         self.DW_vz = 0.0   # never initialised in the reference: explicit here

@@ -113,6 +113,11 @@ int fg_create(const fg_mesh *mesh, const fg_params *prm, int device, fg_ctx **ou
 void fg_destroy(fg_ctx *ctx);
 /* out[0..9] = NOD, NT, NF, n_magTet, n_magTri, E, E_mag, n, nnz, nlvd */
 int fg_get_sizes(const fg_ctx *ctx, long long out[10]);
+/* device layout chosen for this mesh (no reference counterpart; bench.py's byte model reads it):
+ * out[0] = bytes of column index per stored node pair of the matrix-free operator (2 or 4),
+ * out[1] = stored node pairs including SELL padding, out[2] = 1 when the element fast path
+ * (no anisotropy in any region) is available, out[3] = padded node rows */
+int fg_get_layout(const fg_ctx *ctx, long long out[4]);
 
 /* ---- node state (Nodes::Node::d[CURRENT|NEXT], src/node.h:47-70) ---- */
 /* mesh::init_distrib + Fem ctor: set CURRENT u, v, phi, phiv and copy to NEXT; NULL = zeros */

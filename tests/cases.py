@@ -70,7 +70,7 @@ def smooth_state(p, rng, Ms=8e5, rough=0.15):
     return u, v, phi, phiv
 
 
-def small_cuboid(npi=5, seed=5489, nx=6, ny=5, nz=4, with_nonmag=True):
+def small_cuboid(npi=5, seed=5489, nx=6, ny=5, nz=4, with_nonmag=True, aniso=True):
     """Two magnetic regions (uniaxial / cubic anisotropy) + a non-magnetic one, surface triangles
     with Neel anisotropy on part of the boundary, one suppress_charges surface."""
     rng = np.random.default_rng(seed)
@@ -95,12 +95,16 @@ def small_cuboid(npi=5, seed=5489, nx=6, ny=5, nz=4, with_nonmag=True):
                    dict(Ms=0.0)]
     if not with_nonmag:
         tet_regions = tet_regions[:3]
+    if not aniso:   # K = K3 = 0 everywhere: the library's element fast path (k_tet_iso)
+        for r in tet_regions:
+            r.pop("K", None)
+            r.pop("K3", None)
     tri_regions = [dict(), dict(Ks=2.5e-4, uk=(0, 0, 1)), dict(Ks=1.0e-4, uk=(1, 0, 0), suppress_charges=True),
                    dict(Ks=0.0)]
     Ms = [r.get("Ms", 795774.7) for r in tet_regions]
     m.tri_dMs = meshgen.compute_dMs(m, Ms)
     u, v, phi, phiv = smooth_state(m.node_p, rng)
-    return Case("small_cuboid", m, tet_regions, tri_regions, u, v, phi, phiv,
+    return Case("small_cuboid" if aniso else "small_cuboid_iso", m, tet_regions, tri_regions, u, v, phi, phiv,
                 Hext=np.array([-24.6e-3, 4.3e-3, 1e-3]) / MU0, dt=2.0e-14, dtmax=5e-13,
                 angle=0.35580211334117789, npi=npi, npi_tri=4 if npi == 5 else 1)
 

@@ -31,10 +31,13 @@ def _prepare(case, oc, la):
     return t
 
 
-@pytest.fixture(scope="module", params=["small_cuboid", "small_cuboid_npi1", "ellipsoid"])
+@pytest.fixture(scope="module", params=["small_cuboid", "small_cuboid_npi1", "small_cuboid_iso",
+                                        "small_cuboid_iso_npi1", "ellipsoid"])
 def prepared(request, oracle, gpu_lib):
     case = {"small_cuboid": lambda: cases.small_cuboid(),
             "small_cuboid_npi1": lambda: cases.small_cuboid(npi=1),
+            "small_cuboid_iso": lambda: cases.small_cuboid(aniso=False),
+            "small_cuboid_iso_npi1": lambda: cases.small_cuboid(npi=1, aniso=False),
             "ellipsoid": lambda: cases.ellipsoid()}[request.param]()
     oc, la = _pair(case)
     t = _prepare(case, oc, la)
