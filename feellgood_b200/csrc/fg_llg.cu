@@ -180,10 +180,15 @@ int launch_elements(fg_ctx *c)
         const int grid = grid_for(c->NTm, BLOCK);
         if (use_iso(c))
             {
-            if (c->h.npi_tet == 5)
-                CTX_LAUNCH_C(c, KC_TET, (k_tet_iso<5>), grid, A, c->cur, c->basis, c->sp, c->rec);
+            static const bool pipe = getenv("FG_TET_NOPIPE") == nullptr;  // A/B switch of the prefetch pipeline
+            if (c->h.npi_tet == 5 && pipe)
+                CTX_LAUNCH_C(c, KC_TET, (k_tet_iso<5, true>), grid, A, c->cur, c->basis, c->sp, c->rec);
+            else if (c->h.npi_tet == 5)
+                CTX_LAUNCH_C(c, KC_TET, (k_tet_iso<5, false>), grid, A, c->cur, c->basis, c->sp, c->rec);
+            else if (pipe)
+                CTX_LAUNCH_C(c, KC_TET, (k_tet_iso<1, true>), grid, A, c->cur, c->basis, c->sp, c->rec);
             else
-                CTX_LAUNCH_C(c, KC_TET, (k_tet_iso<1>), grid, A, c->cur, c->basis, c->sp, c->rec);
+                CTX_LAUNCH_C(c, KC_TET, (k_tet_iso<1, false>), grid, A, c->cur, c->basis, c->sp, c->rec);
             }
         else if (c->h.npi_tet == 5)
             {

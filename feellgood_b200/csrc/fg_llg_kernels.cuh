@@ -513,16 +513,34 @@ __device__ __forceinline__ void tet_iso_be(const double da_i[3], int i, double d
     }
 
 constexpr int TET_ISO_CTAS_PER_SM = 2;
-template <int NPI>
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// The kernel is bound by the latency of its dependent gathers (ncu: long-scoreboard stalls, 16
+// resident warps per SM), so the chain connectivity -> node records -> ... -> node bases is shortened:
+// the connectivity and region of a thread's NEXT tetrahedron are fetched one iteration ahead, and the
+// bases of the current one are pulled into L2 as soon as the connectivity is known (no registers held),
+// so that the record epilogue finds them there.
+template <int NPI, bool PIPE>
 __global__ void __launch_bounds__(BLOCK, TET_ISO_CTAS_PER_SM)
 k_tet_iso(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__restrict__ basis,
           const StepPrm sp, double4 *__restrict__ rec)
     {
     const int stride = gridDim.x * BLOCK;
-    for (int tm = blockIdx.x * BLOCK + threadIdx.x; tm < A.NTm; tm += stride)
+    int tm = blockIdx.x * BLOCK + threadIdx.x;
+    if (tm >= A.NTm) return;
+    int4 ind = __ldg(A.ind + tm);
+    int reg = __ldg(A.reg + tm);
+    for (;;)
         {
+        const int tn = tm + stride;
+        const bool more = tn < A.NTm;
+        int4 ind_n = ind;
+        int reg_n = reg;
+        if (PIPE && more)
+            {
+            ind_n = __ldg(A.ind + tn);
+            reg_n = __ldg(A.reg + tn);
+            }
         TetIsoIn T;
-        const int4 ind = __ldg(A.ind + tm);
         const int nd[4] = {ind.x, ind.y, ind.z, ind.w};
 #pragma unroll
         for (int i = 0; i < 4; i++)
@@ -532,13 +550,22 @@ k_tet_iso(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__res
             T.u[i][0] = a.x; T.u[i][1] = a.y; T.u[i][2] = a.z;
             T.phi[i] = b.z; T.phiv[i] = b.w;
             }
+        if (PIPE)
+            {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                {  // a 48-byte basis may straddle two 128-byte lines
+                const char *bp = reinterpret_cast<const char *>(basis + nd[i]);
+                prefetch_l2(bp);
+                prefetch_l2(bp + 47);
+                }
+            }
 #pragma unroll
         for (int k = 0; k < 12; k++) T.da[k / 3][k % 3] = __ldcs(A.da + (size_t)k * A.NTm + tm);
         T.detJ = __ldcs(A.detJ + tm);
-        const TetRegion &R = A.regions[__ldg(A.reg + tm)];
         TetRegion Rl;
-        Rl.alpha = R.alpha;
-        Rl.Abis = R.Abis;
+        Rl.alpha = A.regions[reg].alpha;
+        Rl.Abis = A.regions[reg].Abis;
         TetIsoMid M;
         double contrib[4];
         tet_iso_front<NPI>(T, Rl, sp, M, contrib);
@@ -552,6 +579,18 @@ k_tet_iso(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__res
             load_basis(basis + nd[i], ep, eq);
             tet_iso_be<NPI>(T.da[i], i, T.detJ, Rl.Abis, M, be);
             st256(rec + sl[i], make_double4(contrib[i], dot3(eq, be), dot3(ep, be), 0.0));
+            }
+        if (!more) break;
+        tm = tn;
+        if (PIPE)
+            {
+            ind = ind_n;
+            reg = reg_n;
+            }
+        else
+            {
+            ind = __ldg(A.ind + tm);
+            reg = __ldg(A.reg + tm);
             }
         }
     }
