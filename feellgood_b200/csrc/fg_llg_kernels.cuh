@@ -515,10 +515,10 @@ __device__ __forceinline__ void tet_iso_be(const double da_i[3], int i, double d
 constexpr int TET_ISO_CTAS_PER_SM = 2;
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // The kernel is bound by the latency of its dependent gathers (ncu: long-scoreboard stalls, 16
-// resident warps per SM), so the chain connectivity -> node records -> ... -> node bases is shortened:
-// the connectivity and region of a thread's NEXT tetrahedron are fetched one iteration ahead, and the
-// bases of the current one are pulled into L2 as soon as the connectivity is known (no registers held),
-// so that the record epilogue finds them there.
+// resident warps per SM), so the chain connectivity -> node records / bases is taken off the critical
+// path (PIPE): the connectivity of a thread's tetrahedra is fetched TWO iterations ahead, and as soon
+// as iteration k starts the node records and bases of tetrahedron k+1 are pulled into L2
+// (prefetch.global.L2: no registers held), so the gathers of the next iteration are L2 hits.
 template <int NPI, bool PIPE>
 __global__ void __launch_bounds__(BLOCK, TET_ISO_CTAS_PER_SM)
 k_tet_iso(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__restrict__ basis,
@@ -528,18 +528,30 @@ k_tet_iso(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__res
     int tm = blockIdx.x * BLOCK + threadIdx.x;
     if (tm >= A.NTm) return;
     int4 ind = __ldg(A.ind + tm);
-    int reg = __ldg(A.reg + tm);
+    int4 ind1 = ind;  // connectivity of this thread's next tetrahedron
+    if (PIPE && tm + stride < A.NTm) ind1 = __ldg(A.ind + tm + stride);
     for (;;)
         {
         const int tn = tm + stride;
         const bool more = tn < A.NTm;
-        int4 ind_n = ind;
-        int reg_n = reg;
-        if (PIPE && more)
+        int4 ind2 = ind1;
+        if (PIPE)
             {
-            ind_n = __ldg(A.ind + tn);
-            reg_n = __ldg(A.reg + tn);
+            if (tn + stride < A.NTm) ind2 = __ldg(A.ind + tn + stride);
+            if (more)
+                {
+                const int nn[4] = {ind1.x, ind1.y, ind1.z, ind1.w};
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    {  // 64-byte record: one line; a 48-byte basis may straddle two 128-byte lines
+                    prefetch_l2(cur + nn[i]);
+                    const char *bp = reinterpret_cast<const char *>(basis + nn[i]);
+                    prefetch_l2(bp);
+                    prefetch_l2(bp + 47);
+                    }
+                }
             }
+        const int reg = __ldg(A.reg + tm);
         TetIsoIn T;
         const int nd[4] = {ind.x, ind.y, ind.z, ind.w};
 #pragma unroll
@@ -549,16 +561,6 @@ k_tet_iso(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__res
             const double4 a = ld256_nc(q), b = ld256_nc(q + 1);
             T.u[i][0] = a.x; T.u[i][1] = a.y; T.u[i][2] = a.z;
             T.phi[i] = b.z; T.phiv[i] = b.w;
-            }
-        if (PIPE)
-            {
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                {  // a 48-byte basis may straddle two 128-byte lines
-                const char *bp = reinterpret_cast<const char *>(basis + nd[i]);
-                prefetch_l2(bp);
-                prefetch_l2(bp + 47);
-                }
             }
 #pragma unroll
         for (int k = 0; k < 12; k++) T.da[k / 3][k % 3] = __ldcs(A.da + (size_t)k * A.NTm + tm);
@@ -584,14 +586,11 @@ k_tet_iso(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__res
         tm = tn;
         if (PIPE)
             {
-            ind = ind_n;
-            reg = reg_n;
+            ind = ind1;
+            ind1 = ind2;
             }
         else
-            {
             ind = __ldg(A.ind + tm);
-            reg = __ldg(A.reg + tm);
-            }
         }
     }
 

@@ -201,3 +201,43 @@ def test_solve_properties_and_reproducibility(full):
     assert la.solve(t) is False and la.iter["nit"] == nit
     u2, v2, _, _ = la.get_state(1)
     assert np.array_equal(u1, u2) and np.array_equal(v1, v2)
+
+
+@pytest.mark.parametrize("name,nsteps", [("sp4", 20), ("disk1m", 8)])
+def test_trajectory_vs_oracle_at_full_size(oracle, gpu_lib, name, nsteps):
+    """BASELINE configs 2 and 3 at their FULL size against the CPU oracle run whole (the north-star
+    criterion: average magnetisation and energies after a fixed number of steps within 1e-6
+    relative; per-step solutions within the solver tolerance)."""
+    import cases
+    from feellgood_b200 import workloads
+    from feellgood_b200.linear_algebra import M_2_PI, mt19937_uniform01
+    w = workloads.build(name)
+    z = np.zeros(w.mesh.NOD)
+    case = cases.Case(w.name, w.mesh, w.tet_regions, w.tri_regions, w.u, np.zeros_like(w.u), z, z, w.Hext,
+                      w.dt, w.dtmax, ANGLE, npi=w.npi, npi_tri=4 if w.npi == 5 else 1, tol=w.tol,
+                      maxiter=w.maxiter)
+    oc, la = cases.oracle_ctx(case), cases.gpu_linalg(case)
+    oc.set_state(case.u, case.v, case.phi, case.phiv)
+    la.set_state(case.u, case.v, case.phi, case.phiv)
+    t = cases.FixedTiming(case)
+    for step in range(nsteps):
+        ang = M_2_PI * mt19937_uniform01(2000 + step)
+        oc.base_projection(ang)
+        oc.prepare_elements(case.Hext, case.dt, case.prefactor)
+        failed_o = oc.solve(case.dt)
+        failed_g = la.step(case.Hext, t, angle=ang)
+        assert failed_g == failed_o is False, step
+        assert abs(la.iter["nit"] - oc.iter_info()["nit"]) <= 3, step
+        oc.evolution()
+        la.evolution()
+    u_o, u_g = oc.get_state(0)[0], la.get_state(0, "u")[0]
+    # 1e-6 relative to the unit magnetisation, component-wise (the vortex average is ~0 by symmetry,
+    # where a norm-wise relative bound is ill-posed: two converged solves differ by ~cond*TOL)
+    assert np.max(np.abs(u_g - u_o)) < 1e-6
+    assert np.max(np.abs(u_g.mean(axis=0) - u_o.mean(axis=0))) < 1e-6 * max(1e-2, np.max(np.abs(u_o.mean(axis=0))))
+    assert np.max(np.abs(la.avg("u") - oc.avg(0))) < 1e-6 * max(1e-2, np.max(np.abs(oc.avg(0))))
+    E_o, E_g = oc.energy(case.Hext), la.energy(case.Hext)
+    assert np.max(np.abs(E_g - E_o)) <= 1e-6 * np.max(np.abs(E_o)), (E_g, E_o)
+    assert abs(la.max_angle() - oc.max_angle()) < 1e-6
+    la.close()
+    oc.close()
