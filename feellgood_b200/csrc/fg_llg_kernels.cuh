@@ -14,8 +14,9 @@
 // so the global K is the projection of a NODxNOD scalar matrix whose off-diagonal part is constant
 // per mesh (S, built once) and whose diagonal gains one state-dependent number per node per step
 // (Malpha).  The per-step element kernel therefore emits, per (tet, local node), one 32-byte
-// record {sum_g a w alpha_eff, eq.BE, ep.BE}; k_assemble_sell gathers the records of a node through
-// its incidence list (no atomics, fixed order => deterministic) and writes the node's two matrix rows.
+// record {sum_g a w alpha_eff, BE(3)}; the assembly gathers the records of a node through its
+// incidence list (no atomics, fixed order => deterministic), projects the summed BE on the node's
+// basis once (L = (eq . BE, ep . BE)) and writes the node's part of the system.
 #pragma once
 #include "fg_common.cuh"
 #include "fg_reduce.cuh"
@@ -375,8 +376,9 @@ __device__ __forceinline__ void tet_field(const TetArrays &A, int tm, const Step
     }
 
 constexpr int TET_CTAS_PER_SM = 1;
-// one thread per magnetic tetrahedron; emits 4 records {contrib, eq.BE, ep.BE, 0}, each stored at
-// the slot of its node's incidence list so that the row assembly reads them as a stream
+// one thread per magnetic tetrahedron; emits 4 records {contrib, BE(3)} (32 B), each stored at the
+// slot of its node's incidence list so that the row assembly reads them as a stream.  The node bases
+// are not needed here: the assembly projects the summed BE of a node once.
 template <int NPI, bool SPACE>
 __global__ void __launch_bounds__(BLOCK, TET_CTAS_PER_SM)
 k_tet(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__restrict__ basis,
@@ -393,21 +395,16 @@ k_tet(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__restric
         const TetRegion R = A.regions[__ldg(A.reg + tm)];
         double contrib[4], BE[3][4];
         tet_core<NPI>(T, R, sp, Hext, contrib, BE);
-        const int nd[4] = {ind.x, ind.y, ind.z, ind.w};
         const int4 s4 = __ldcs(A.slot + tm);
         const int sl[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
         for (int i = 0; i < 4; i++)
             {
-            double ep[3], eq[3];
-            load_basis(basis + nd[i], ep, eq);
-            const double be[3] = {BE[0][i], BE[1][i], BE[2][i]};
-            // Lp = Perm P BE (tetra.cpp:306): rows 0..3 are the eq-projections, 4..7 the ep ones
-            // the record goes where the node's row will stream it from (its incidence slot)
+            // the record goes where the node's row will stream it from (its incidence slot); the
+            // projection Lp = Perm P BE (tetra.cpp:306) is applied once per NODE by the assembly,
+            // to the sum of the BE of its tetrahedra (P depends on the node only)
             if (sl[i] < 0) continue;
-            double2 *r2 = reinterpret_cast<double2 *>(rec + sl[i]);
-            r2[0] = make_double2(contrib[i], dot3(eq, be));
-            r2[1] = make_double2(dot3(ep, be), 0.0);
+            st256(rec + sl[i], make_double4(contrib[i], BE[0][i], BE[1][i], BE[2][i]));
             }
         }
     }
@@ -515,10 +512,12 @@ __device__ __forceinline__ void tet_iso_be(const double da_i[3], int i, double d
 constexpr int TET_ISO_CTAS_PER_SM = 2;
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // The kernel is bound by the latency of its dependent gathers (ncu: long-scoreboard stalls, 16
-// resident warps per SM), so the chain connectivity -> node records / bases is taken off the critical
-// path (PIPE): the connectivity of a thread's tetrahedra is fetched TWO iterations ahead, and as soon
-// as iteration k starts the node records and bases of tetrahedron k+1 are pulled into L2
-// (prefetch.global.L2: no registers held), so the gathers of the next iteration are L2 hits.
+// resident warps per SM) and by L1 throughput, so (i) the records carry BE itself and the node bases
+// are never gathered here (the assembly projects once per node: -192 B of gathers per tetrahedron
+// and one dependent stall less), (ii) PIPE: the connectivity and region of a thread's NEXT
+// tetrahedron are fetched one iteration ahead.  A deeper variant (connectivity two iterations ahead,
+// records of the next tetrahedron prefetched into L2) was slower: more LSU instructions and spills
+// (profiles/r01n_kernel_classes_n1_deep_prefetch.txt).
 template <int NPI, bool PIPE>
 __global__ void __launch_bounds__(BLOCK, TET_ISO_CTAS_PER_SM)
 k_tet_iso(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__restrict__ basis,
@@ -528,30 +527,18 @@ k_tet_iso(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__res
     int tm = blockIdx.x * BLOCK + threadIdx.x;
     if (tm >= A.NTm) return;
     int4 ind = __ldg(A.ind + tm);
-    int4 ind1 = ind;  // connectivity of this thread's next tetrahedron
-    if (PIPE && tm + stride < A.NTm) ind1 = __ldg(A.ind + tm + stride);
+    int reg = __ldg(A.reg + tm);
     for (;;)
         {
         const int tn = tm + stride;
         const bool more = tn < A.NTm;
-        int4 ind2 = ind1;
-        if (PIPE)
+        int4 ind_n = ind;
+        int reg_n = reg;
+        if (PIPE && more)
             {
-            if (tn + stride < A.NTm) ind2 = __ldg(A.ind + tn + stride);
-            if (more)
-                {
-                const int nn[4] = {ind1.x, ind1.y, ind1.z, ind1.w};
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-                    {  // 64-byte record: one line; a 48-byte basis may straddle two 128-byte lines
-                    prefetch_l2(cur + nn[i]);
-                    const char *bp = reinterpret_cast<const char *>(basis + nn[i]);
-                    prefetch_l2(bp);
-                    prefetch_l2(bp + 47);
-                    }
-                }
+            ind_n = __ldg(A.ind + tn);
+            reg_n = __ldg(A.reg + tn);
             }
-        const int reg = __ldg(A.reg + tm);
         TetIsoIn T;
         const int nd[4] = {ind.x, ind.y, ind.z, ind.w};
 #pragma unroll
@@ -577,20 +564,22 @@ k_tet_iso(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__res
         for (int i = 0; i < 4; i++)
             {
             if (sl[i] < 0) continue;
-            double ep[3], eq[3], be[3];
-            load_basis(basis + nd[i], ep, eq);
+            double be[3];
             tet_iso_be<NPI>(T.da[i], i, T.detJ, Rl.Abis, M, be);
-            st256(rec + sl[i], make_double4(contrib[i], dot3(eq, be), dot3(ep, be), 0.0));
+            st256(rec + sl[i], make_double4(contrib[i], be[0], be[1], be[2]));
             }
         if (!more) break;
         tm = tn;
         if (PIPE)
             {
-            ind = ind1;
-            ind1 = ind2;
+            ind = ind_n;
+            reg = reg_n;
             }
         else
+            {
             ind = __ldg(A.ind + tm);
+            reg = __ldg(A.reg + tm);
+            }
         }
     }
 
@@ -803,7 +792,8 @@ k_assemble_sell(const RowArrays A, const NodeRec *__restrict__ cur, const NodeRe
         {
         const int row = s * SLICE + lane;
         // ---- gather of the element records -------------------------------------------------
-        double Ma = 0.0, L0 = 0.0, L1 = 0.0;
+        double Ma = 0.0, L0 = 0.0, L1 = 0.0;  // L: the triangle part, already projected (k_tri)
+        double B0 = 0.0, B1 = 0.0, B2 = 0.0;  // sum of BE over the node's tetrahedra
             {
             // the records were written in incidence order: a pure coalesced stream (1 KB per warp
             // request), empty slots hold zeros
@@ -814,8 +804,9 @@ k_assemble_sell(const RowArrays A, const NodeRec *__restrict__ cur, const NodeRe
                 {  // one 256-bit request per record: a warp streams 1 KB contiguous
                 const double4 r = ld256_cs(rp);
                 Ma += r.x;
-                L0 += r.y;
-                L1 += r.z;
+                B0 += r.y;
+                B1 += r.z;
+                B2 += r.w;
                 }
             const int t0 = __ldg(A.itptr + s), t1 = __ldg(A.itptr + s + 1);
             const int *tp = A.sinct + (size_t)t0 * SLICE + lane;
@@ -851,7 +842,9 @@ k_assemble_sell(const RowArrays A, const NodeRec *__restrict__ cur, const NodeRe
             load_basis(basis + row, ep_a, eq_a);
             double un[3], vn[3];
             load_rec(next + row, un, vn, phi, phiv);
-            *rhs2 = make_double2(L0, L1);
+            // buildVect: L[2a] = eq . BE, L[2a+1] = ep . BE (Perm of tetra.cpp:306)
+            *rhs2 = make_double2(L0 + (eq_a[0] * B0 + eq_a[1] * B1 + eq_a[2] * B2),
+                                 L1 + (ep_a[0] * B0 + ep_a[1] * B1 + ep_a[2] * B2));
             *x02 = make_double2(dot3(vn, ep_a) / FG_GAMMA0, dot3(vn, eq_a) / FG_GAMMA0);
             }
         const double aw = nonmag ? 0.0 : A.Aw[row];
@@ -908,7 +901,7 @@ struct NodeAsmArrays
     const unsigned char *nonmag;       // NODp : 1 = node outside the magnetic material (or pad row)
     };
 
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, 4)
 k_assemble_node(const NodeAsmArrays A, const NodeRec *__restrict__ cur, const NodeRec *__restrict__ next,
                 const Basis *__restrict__ basis, const double4 *__restrict__ rec,
                 const double2 *__restrict__ trec, double cS, double *__restrict__ Dg,
@@ -920,7 +913,8 @@ k_assemble_node(const NodeAsmArrays A, const NodeRec *__restrict__ cur, const No
     for (int s = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); s < A.nslice; s += nwarps)
         {
         const int row = s * SLICE + lane;
-        double Ma = 0.0, L0 = 0.0, L1 = 0.0;
+        double Ma = 0.0, L0 = 0.0, L1 = 0.0;  // L: the triangle part, already projected (k_tri)
+        double B0 = 0.0, B1 = 0.0, B2 = 0.0;  // sum of BE over the node's tetrahedra
             {
             const int i0 = __ldg(A.iptr + s), i1 = __ldg(A.iptr + s + 1);
             const double4 *rp = rec + (size_t)i0 * SLICE + lane;
@@ -929,8 +923,9 @@ k_assemble_node(const NodeAsmArrays A, const NodeRec *__restrict__ cur, const No
                 {  // one 256-bit request per record: a warp streams 1 KB contiguous
                 const double4 r = ld256_cs(rp);
                 Ma += r.x;
-                L0 += r.y;
-                L1 += r.z;
+                B0 += r.y;
+                B1 += r.z;
+                B2 += r.w;
                 }
             const int t0 = __ldg(A.itptr + s), t1 = __ldg(A.itptr + s + 1);
             const int *tp = A.sinct + (size_t)t0 * SLICE + lane;
@@ -962,7 +957,8 @@ k_assemble_node(const NodeAsmArrays A, const NodeRec *__restrict__ cur, const No
         load_basis(basis + row, ep, eq);
         load_rec(next + row, un, vn, phi, phiv);
         const double g0 = dot3(vn, ep) / FG_GAMMA0, g1 = dot3(vn, eq) / FG_GAMMA0;
-        *rhs2 = make_double2(L0, L1);
+        // buildVect: L[2a] = eq . BE, L[2a+1] = ep . BE (Perm of tetra.cpp:306)
+        *rhs2 = make_double2(L0 + (eq[0] * B0 + eq[1] * B1 + eq[2] * B2), L1 + (ep[0] * B0 + ep[1] * B1 + ep[2] * B2));
         *x02 = make_double2(g0, g1);
         w0[row] = make_double4(ep[0] * g0 + eq[0] * g1, ep[1] * g0 + eq[1] * g1, ep[2] * g0 + eq[2] * g1, 0.0);
         const double aw = A.Aw[row];
