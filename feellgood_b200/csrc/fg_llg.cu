@@ -96,7 +96,6 @@ struct fg_ctx
     StepPrm sp = {};
     bool have_basis = false, prepared = false, space_field = false, assembled = false;
     bool iso_regions = true;   // no region has K or K3: the element fast path applies (k_tet_iso)
-    bool tet_async_attr = false;  // dynamic shared memory size of k_tet_iso_async raised on this device
     double v_max = 0.0;
     // profiling
     int profiling = 0;
@@ -179,25 +178,7 @@ int launch_elements(fg_ctx *c)
         {
         const TetArrays A = tet_arrays(c);
         const int grid = grid_for(c->NTm, BLOCK);
-        static const bool async_stage = getenv("FG_TET_NOASYNC") == nullptr;  // A/B switch of the cp.async staging
-        if (use_iso(c) && async_stage)
-            {
-            if (!c->tet_async_attr)
-                {  // once per context (= per device)
-                FG_CUDA(cudaFuncSetAttribute(k_tet_iso_async<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, TET_ASYNC_SMEM));
-                FG_CUDA(cudaFuncSetAttribute(k_tet_iso_async<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TET_ASYNC_SMEM));
-                c->tet_async_attr = true;
-                }
-            const bool prof_ = prof_begin(c->kw.prof, c->stream, KC_TET);
-            if (c->h.npi_tet == 5)
-                k_tet_iso_async<5><<<grid, BLOCK, TET_ASYNC_SMEM, c->stream>>>(A, c->cur, c->sp, c->rec);
-            else
-                k_tet_iso_async<1><<<grid, BLOCK, TET_ASYNC_SMEM, c->stream>>>(A, c->cur, c->sp, c->rec);
-            if (prof_) prof_end(c->kw.prof, c->stream);
-            ++c->launches;
-            FG_CUDA(cudaGetLastError());
-            }
-        else if (use_iso(c))
+        if (use_iso(c))
             {
             static const bool pipe = getenv("FG_TET_NOPIPE") == nullptr;  // A/B switch of the prefetch pipeline
             if (c->h.npi_tet == 5 && pipe)

@@ -517,7 +517,9 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 // and one dependent stall less), (ii) PIPE: the connectivity and region of a thread's NEXT
 // tetrahedron are fetched one iteration ahead.  A deeper variant (connectivity two iterations ahead,
 // records of the next tetrahedron prefetched into L2) was slower: more LSU instructions and spills
-// (profiles/r01n_kernel_classes_n1_deep_prefetch.txt).
+// (profiles/r01n_kernel_classes_n1_deep_prefetch.txt), and so was cp.async staging of the next
+// tetrahedron in shared memory (profiles/experiments/r01p_cp_async_element_staging.md): the kernel is
+// co-limited by the L1 tag stage (scattered 32-byte sectors) and DRAM, not by exposed latency alone.
 template <int NPI, bool PIPE>
 __global__ void __launch_bounds__(BLOCK, TET_ISO_CTAS_PER_SM)
 k_tet_iso(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__restrict__ basis,
@@ -580,121 +582,6 @@ k_tet_iso(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__res
             ind = __ldg(A.ind + tm);
             reg = __ldg(A.reg + tm);
             }
-        }
-    }
-
-// ---- k_tet_iso with asynchronous staging (cp.async / LDGSTS) -------------------------------------
-// Everything the NEXT tetrahedron of a thread needs from global memory -- the three useful 16-byte
-// chunks of each of its 4 node records (gathers) and its own da[12], detJ (streams) -- is copied
-// global -> shared by cp.async while the current tetrahedron is integrated: no registers are held by
-// loads in flight and the gather latency disappears from the dependent chain (the kernel was
-// long-scoreboard bound at 16 warps/SM).  A thread only ever touches its own column of the staging
-// arrays, so no barrier is needed: cp.async.wait_group orders a thread's own copies before its reads,
-// and the copies for tetrahedron k+1 are issued after the thread has moved tetrahedron k to registers.
-//   srec[12][BLOCK] double2 : chunks {u0,u1} {u2,v0} {phi,phiv} of nodes 0..3     48 KB
-//   sstr[13][BLOCK] double  : da[12], detJ                                         26 KB
-constexpr int TET_ASYNC_SMEM = 12 * BLOCK * 16 + 13 * BLOCK * 8;
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
-    {
-    const unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
-    }
-__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
-    {
-    const unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
-    }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-template <int NPI>
-__global__ void __launch_bounds__(BLOCK, TET_ISO_CTAS_PER_SM)
-k_tet_iso_async(const TetArrays A, const NodeRec *__restrict__ cur, const StepPrm sp, double4 *__restrict__ rec)
-    {
-    extern __shared__ __align__(16) unsigned char tet_smem[];
-    double2 *srec = reinterpret_cast<double2 *>(tet_smem);
-    double *sstr = reinterpret_cast<double *>(tet_smem + 12 * BLOCK * 16);
-    const int t = threadIdx.x;
-    const int stride = gridDim.x * BLOCK;
-    int tm = blockIdx.x * BLOCK + t;
-    if (tm >= A.NTm) return;  // no block-wide barrier below
-    auto issue = [&](int tmx, const int4 &indx)
-        {
-        const int nn[4] = {indx.x, indx.y, indx.z, indx.w};
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-            {
-            const char *g = reinterpret_cast<const char *>(cur + nn[i]);
-            cp_async16(srec + (3 * i + 0) * BLOCK + t, g);
-            cp_async16(srec + (3 * i + 1) * BLOCK + t, g + 16);
-            cp_async16(srec + (3 * i + 2) * BLOCK + t, g + 48);
-            }
-#pragma unroll
-        for (int k = 0; k < 12; k++) cp_async8(sstr + k * BLOCK + t, A.da + (size_t)k * A.NTm + tmx);
-        cp_async8(sstr + 12 * BLOCK + t, A.detJ + tmx);
-        cp_async_commit();
-        };
-    int4 ind = __ldg(A.ind + tm);
-    issue(tm, ind);
-    int reg = __ldg(A.reg + tm);
-    int4 ind1 = ind;
-    int reg1 = reg;
-    if (tm + stride < A.NTm)
-        {
-        ind1 = __ldg(A.ind + tm + stride);
-        reg1 = __ldg(A.reg + tm + stride);
-        }
-    for (;;)
-        {
-        const int tn = tm + stride;
-        const bool more = tn < A.NTm;
-        const int4 s4 = __ldcs(A.slot + tm);  // needed only by the epilogue: arrives under the arithmetic
-        TetIsoIn T;
-        cp_async_wait_all();
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-            {
-            const double2 c0 = srec[(3 * i + 0) * BLOCK + t], c1 = srec[(3 * i + 1) * BLOCK + t],
-                          c2 = srec[(3 * i + 2) * BLOCK + t];
-            T.u[i][0] = c0.x; T.u[i][1] = c0.y; T.u[i][2] = c1.x;
-            T.phi[i] = c2.x; T.phiv[i] = c2.y;
-            }
-#pragma unroll
-        for (int k = 0; k < 12; k++) T.da[k / 3][k % 3] = sstr[k * BLOCK + t];
-        T.detJ = sstr[12 * BLOCK + t];
-        // staging of the next tetrahedron: its copies land while this one is integrated
-        int4 ind2 = ind1;
-        int reg2 = reg1;
-        if (more)
-            {
-            issue(tn, ind1);
-            if (tn + stride < A.NTm)
-                {
-                ind2 = __ldg(A.ind + tn + stride);
-                reg2 = __ldg(A.reg + tn + stride);
-                }
-            }
-        TetRegion Rl;
-        Rl.alpha = A.regions[reg].alpha;
-        Rl.Abis = A.regions[reg].Abis;
-        TetIsoMid M;
-        double contrib[4];
-        tet_iso_front<NPI>(T, Rl, sp, M, contrib);
-        const int sl[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-            {
-            if (sl[i] < 0) continue;
-            double be[3];
-            tet_iso_be<NPI>(T.da[i], i, T.detJ, Rl.Abis, M, be);
-            st256(rec + sl[i], make_double4(contrib[i], be[0], be[1], be[2]));
-            }
-        if (!more) break;
-        tm = tn;
-        ind = ind1;
-        ind1 = ind2;
-        reg = reg1;
-        reg1 = reg2;
         }
     }
 
