@@ -120,6 +120,13 @@ struct RedBuf
 //            (alpha_eff mass + gyrotropic term).  The producer of an SpMV input writes w (double4
 //            per node: one aligned 32-byte sector per gather); the SpMV folds z_a = sum_b S_ab w_b and
 //            projects: y = cS (eq_a.z, ep_a.z) + Dg x_a.
+//            Inside the Krylov kernels (ep, eq) are decoded from a unit quaternion (32 B per node instead
+//            of 48) and Dg is applied in its closed form: with m x ep = eq, m x eq = -ep for the
+//            orthonormal right-handed triad (ep, eq, m) of Node::setBasis,
+//                Dg = [[a_w, Ma], [Ma, -a_w]]   (Ma = sum of the alpha_eff records, a_w = lumped mass),
+//            16 B per node instead of 32.  The explicit triple products of the reference
+//            (src/tetra.cpp:108-148) differ from this form by rounding only (~1e-16 relative, against a
+//            parity target of 1e-12); they are kept in the assembled-block operator and the taps.
 enum { OP_SELL2 = 0, OP_CSR = 1, OP_NODE3 = 2 };
 struct Operator
     {
@@ -133,9 +140,11 @@ struct Operator
     const double *val;  // OP_SELL2: 2x2 blocks | OP_NODE3: S (one double per stored node pair)
     int nslice;         // OP_SELL2 / OP_NODE3
     // OP_NODE3
-    const Basis *basis;
-    const double *Dg;   // 4 doubles per node row: (k00, k01), (k10, k11)
-    double cS;          // prefactor * s_dt (src/tetra.cpp:261)
+    const double4 *qbasis;       // tangent-plane basis of every node as a unit quaternion (32 B, one 256-bit
+                                 // request instead of 48 B): see basis_to_quat / quat_to_basis below
+    const double2 *Dm;           // state-dependent node-diagonal part: (Ma, a_w) per node row, see OP_NODE3 above
+    const unsigned char *nonmag; // 1 = identity row (node outside the magnetic material, pad row)
+    double cS;                   // prefactor * s_dt (src/tetra.cpp:261)
     };
 
 // 256-bit global accesses (sm_100: LDG.E.ENL2.256 / STG.E.ENL2.256): one request per 32-byte node image
@@ -148,6 +157,54 @@ __device__ __forceinline__ double4 ld256_nc(const double4 *p)
     asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
     return r;
     }
+// Tangent-plane basis <-> unit quaternion.  R = [ep | eq | ep x eq] is a rotation (Node::setBasis builds
+// an orthonormal right-handed triad), so 4 doubles carry it; the decoded (ep, eq) are orthonormal to
+// rounding and differ from the stored ones by a few 1e-16.  Every Krylov kernel decodes with this one
+// function, so the operator they apply is consistent.
+__device__ __forceinline__ double4 basis_to_quat(const double ep[3], const double eq[3])
+    {
+    const double n0 = ep[1] * eq[2] - ep[2] * eq[1], n1 = ep[2] * eq[0] - ep[0] * eq[2],
+                 n2 = ep[0] * eq[1] - ep[1] * eq[0];
+    const double r00 = ep[0], r10 = ep[1], r20 = ep[2], r01 = eq[0], r11 = eq[1], r21 = eq[2], r02 = n0,
+                 r12 = n1, r22 = n2;
+    const double tr = r00 + r11 + r22;
+    double w, x, y, z;
+    if (tr > 0.0)  // Shepperd's method: always divide by the largest component
+        {
+        const double s = 2.0 * sqrt(tr + 1.0);
+        w = 0.25 * s; x = (r21 - r12) / s; y = (r02 - r20) / s; z = (r10 - r01) / s;
+        }
+    else if (r00 > r11 && r00 > r22)
+        {
+        const double s = 2.0 * sqrt(fmax(1.0 + r00 - r11 - r22, 0.0));
+        w = (r21 - r12) / s; x = 0.25 * s; y = (r01 + r10) / s; z = (r02 + r20) / s;
+        }
+    else if (r11 > r22)
+        {
+        const double s = 2.0 * sqrt(fmax(1.0 + r11 - r00 - r22, 0.0));
+        w = (r02 - r20) / s; x = (r01 + r10) / s; y = 0.25 * s; z = (r12 + r21) / s;
+        }
+    else
+        {
+        const double s = 2.0 * sqrt(fmax(1.0 + r22 - r00 - r11, 0.0));
+        w = (r10 - r01) / s; x = (r02 + r20) / s; y = (r12 + r21) / s; z = 0.25 * s;
+        }
+    const double nn = w * w + x * x + y * y + z * z;
+    if (!(nn > 1e-300) || !(nn < 1e300)) return make_double4(0.0, 0.0, 0.0, 1.0);  // degenerate (u = 0): identity
+    const double inv = 1.0 / sqrt(nn);
+    return make_double4(x * inv, y * inv, z * inv, w * inv);
+    }
+__device__ __forceinline__ void quat_to_basis(const double4 q, double ep[3], double eq[3])
+    {
+    const double x = q.x, y = q.y, z = q.z, w = q.w;
+    ep[0] = 1.0 - 2.0 * (y * y + z * z);
+    ep[1] = 2.0 * (x * y + z * w);
+    ep[2] = 2.0 * (x * z - y * w);
+    eq[0] = 2.0 * (x * y - z * w);
+    eq[1] = 1.0 - 2.0 * (x * x + z * z);
+    eq[2] = 2.0 * (y * z + x * w);
+    }
+
 // streaming variant (evict-first): data read exactly once per step (the element records)
 __device__ __forceinline__ double4 ld256_cs(const double4 *p)
     {
@@ -198,7 +255,7 @@ struct KrylovWork
     // OP_NODE3: the 3-vector images (double4 per node, length nx/2) of the SpMV inputs x0 | phat
     // (shared buffer) and shat, and the basis that maps between the two representations
     double4 *w3p, *w3s;
-    const Basis *basis;
+    const double4 *qbasis;
     const unsigned char *mask; // n : 1 = Dirichlet dof (lvd), may be NULL
     KState *st;                // device
     KState *h_st;              // pinned host mirror

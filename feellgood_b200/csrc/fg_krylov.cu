@@ -54,15 +54,10 @@ __device__ __forceinline__ void bicg_top_of_loop(KState *st, double rr, double r
         }
     }
 
-__device__ __forceinline__ void load_basis_k(const Basis *p, double ep[3], double eq[3])
-    {
-    const double2 *q = reinterpret_cast<const double2 *>(p);
-    const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
-    ep[0] = a.x; ep[1] = a.y; ep[2] = b.x;
-    eq[0] = b.y; eq[1] = c.x; eq[2] = c.y;
-    }
+__device__ __forceinline__ void load_basis_k(const double4 *qb, double ep[3], double eq[3])
+    { quat_to_basis(ld256_nc(qb), ep, eq); }
 // w = ep x0 + eq x1: the 3-vector image of the two tangent-plane unknowns of a node (element.h:81-96)
-__device__ __forceinline__ double4 node_w(const Basis *b, double x0, double x1)
+__device__ __forceinline__ double4 node_w(const double4 *b, double x0, double x1)
     {
     double ep[3], eq[3];
     load_basis_k(b, ep, eq);
@@ -328,7 +323,6 @@ __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_node3(const Op
     const int lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * (BLOCK / 32);
     const double2 *x2 = reinterpret_cast<const double2 *>(a.x);
-    const double2 *Dg2 = reinterpret_cast<const double2 *>(op.Dg);
     double acc[RED_NV] = {0.0, 0.0, 0.0, 0.0};
     int s = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
     int p0 = 0, p1 = 0;
@@ -383,7 +377,7 @@ __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_node3(const Op
                 }
             }
         double ep[3], eq[3];
-        load_basis_k(op.basis + row, ep, eq);
+        load_basis_k(op.qbasis + row, ep, eq);
         double2 xa;
         if (a.x != nullptr)
             xa = x2[row];
@@ -392,9 +386,15 @@ __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_node3(const Op
             const double4 wr = ld256_nc(a.w + row);
             xa = make_double2(ep[0] * wr.x + ep[1] * wr.y + ep[2] * wr.z, eq[0] * wr.x + eq[1] * wr.y + eq[2] * wr.z);
             }
-        const double2 d0 = __ldcs(Dg2 + 2 * (size_t)row), d1 = __ldcs(Dg2 + 2 * (size_t)row + 1);
-        const double y0 = op.cS * (eq[0] * z0 + eq[1] * z1 + eq[2] * z2) + (d0.x * xa.x + d0.y * xa.y);
-        const double y1 = op.cS * (ep[0] * z0 + ep[1] * z1 + ep[2] * z2) + (d1.x * xa.x + d1.y * xa.y);
+        // node-diagonal part in closed form: Dg = [[a_w, Ma], [Ma, -a_w]] (fg_common.cuh, OP_NODE3)
+        const double2 dm = __ldcs(op.Dm + row);
+        double y0 = op.cS * (eq[0] * z0 + eq[1] * z1 + eq[2] * z2) + (dm.y * xa.x + dm.x * xa.y);
+        double y1 = op.cS * (ep[0] * z0 + ep[1] * z1 + ep[2] * z2) + (dm.x * xa.x - dm.y * xa.y);
+        if (op.nonmag[row] != 0)
+            {  // identity row (src/solver.cpp:46-48)
+            y0 = xa.x;
+            y1 = xa.y;
+            }
         spmv_row2<STAGE>(a, row, y0, y1, acc);
         s = sn;
         p0 = q0;
@@ -505,7 +505,7 @@ static int launch_spmv(const Operator &op, const KrylovWork &w, const SpmvArgs &
 // plain y = A x; for OP_NODE3 the 3-vector image of x is built first (taps and microbenchmarks only:
 // the solver's own producers write it in the kernel that produces x)
 __global__ void __launch_bounds__(BLOCK)
-k_make_w(int nnode, const double *__restrict__ x, const Basis *__restrict__ basis, double4 *__restrict__ w3)
+k_make_w(int nnode, const double *__restrict__ x, const double4 *__restrict__ basis, double4 *__restrict__ w3)
     {
     const int stride = gridDim.x * BLOCK;
     for (int a = blockIdx.x * BLOCK + threadIdx.x; a < nnode; a += stride)
@@ -522,7 +522,7 @@ int spmv(const Operator &op, const KrylovWork &w, const double *x, double *y, bo
         a.w = w.w3s;
     else if (op.kind == OP_NODE3)
         {
-        k_make_w<<<grid_for(w.nx / 2, BLOCK), BLOCK, 0, w.stream>>>(w.nx / 2, x, op.basis, w.w3s);
+        k_make_w<<<grid_for(w.nx / 2, BLOCK), BLOCK, 0, w.stream>>>(w.nx / 2, x, op.qbasis, w.w3s);
         if (w.launches) ++*w.launches;
         FG_CUDA(cudaGetLastError());
         a.w = w.w3s;
@@ -572,7 +572,7 @@ k_bicg_p(int n, const double *__restrict__ r, const double *__restrict__ p, doub
 __global__ void __launch_bounds__(BLOCK)
 k_bicg_p_node(int nnode, const double *__restrict__ r, const double *__restrict__ p, double *__restrict__ pn,
               const double *__restrict__ v, const double *__restrict__ D, double *__restrict__ phat,
-              const Basis *__restrict__ basis, double4 *__restrict__ w3, const KState *st, DistDev *dist,
+              const double4 *__restrict__ basis, double4 *__restrict__ w3, const KState *st, DistDev *dist,
               unsigned int *ticket, int npush)
     {
     if (st->done) return;
@@ -659,7 +659,7 @@ k_bicg_s(int n, const double *__restrict__ r, const double *__restrict__ v,
 __global__ void __launch_bounds__(BLOCK)
 k_bicg_s_node(int nnode, const double *__restrict__ r, const double *__restrict__ v,
               const double *__restrict__ D, double *__restrict__ s, double *__restrict__ shat,
-              const Basis *__restrict__ basis, double4 *__restrict__ w3, KState *st, const RedBuf red)
+              const double4 *__restrict__ basis, double4 *__restrict__ w3, KState *st, const RedBuf red)
     {
     if (st->done) return;
     const double alpha = st->alpha;
@@ -1121,7 +1121,7 @@ int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, pos
             double *p_old = ((enq + k) & 1) ? w.p2 : w.p, *p_new = ((enq + k) & 1) ? w.p : w.p2;
             if (node3)
                 FG_LAUNCH_C(w, KC_BICG_P, k_bicg_p_node, gp, n / 2, w.r, p_old, p_new, w.v, w.D,
-                            static_cast<double *>(nullptr), w.basis, w.w3p, w.st, w.dist, w.red.ticket, npush);
+                            static_cast<double *>(nullptr), w.qbasis, w.w3p, w.st, w.dist, w.red.ticket, npush);
             else
                 FG_LAUNCH_C(w, KC_BICG_P, k_bicg_p, gp, n, w.r, p_old, p_new, w.v, w.D, w.phat, w.st);
             SpmvArgs a = {};
@@ -1136,7 +1136,7 @@ int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, pos
             FG_TRY(launch_spmv<ST_BICG_V>(op, w, a));
             if (node3)
                 FG_LAUNCH_C(w, KC_BICG_S, k_bicg_s_node, gs, n / 2, w.r, w.v, w.D, w.s,
-                            static_cast<double *>(nullptr), w.basis, w.w3s, w.st, w.red);
+                            static_cast<double *>(nullptr), w.qbasis, w.w3s, w.st, w.red);
             else
                 FG_LAUNCH_C(w, KC_BICG_S, k_bicg_s, gs, n, w.r, w.v, w.D, w.s, w.shat, w.st, w.red);
             a.w = w.w3s;

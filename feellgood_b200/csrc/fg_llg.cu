@@ -73,7 +73,9 @@ struct fg_ctx
     short *scol16 = nullptr;  // scol as 16-bit offsets from the row (NULL when one does not fit)
     int *perm = nullptr, *sptr = nullptr, *scol = nullptr, *sdeg = nullptr, *iptr = nullptr,
         *itptr = nullptr, *sinct = nullptr;
-    double *sS = nullptr, *Aw = nullptr, *Sdiag = nullptr, *Dg = nullptr;
+    double *sS = nullptr, *Aw = nullptr, *Sdiag = nullptr;
+    double2 *Dm = nullptr;     // (Ma, a_w) per node row: the node-diagonal part of the matrix-free operator
+    double4 *qbasis = nullptr; // the basis of every node (owned + ghost) as a unit quaternion
     double *val = nullptr;       // assembled 2x2 blocks of K: only the parity tap materialises them
     Operator op_K = {};          // the assembled-K operator of the tap (OP_SELL2)
     bool use_blocks = false;     // fg_set_operator(ctx, 1): solve with the assembled 2x2 blocks (A/B checks)
@@ -153,7 +155,8 @@ TetArrays tet_arrays(const fg_ctx *c)
 
 int launch_basis(fg_ctx *c, double angle)
     {
-    CTX_LAUNCH_C(c, KC_BASIS, k_basis, grid_for(c->NODt, BLOCK), c->NODt, c->cur, cos(angle), sin(angle), c->basis);
+    CTX_LAUNCH_C(c, KC_BASIS, k_basis, grid_for(c->NODt, BLOCK), c->NODt, c->cur, cos(angle), sin(angle), c->basis,
+                 c->qbasis);
     c->have_basis = true;
     c->prepared = false;
     c->assembled = false;
@@ -262,7 +265,7 @@ int launch_assemble(fg_ctx *c, double dt)
     if (grid < 1) grid = 1;
     c->op.cS = cS;
     CTX_LAUNCH_C(c, KC_ASSEMBLE, k_assemble_node, grid, R, c->cur, c->next, c->basis, c->rec, c->trec, cS,
-                 c->Dg, c->kw.b, c->kw.x, c->kw.w3p, c->kw.D);
+                 c->Dm, c->kw.b, c->kw.x, c->kw.w3p, c->kw.D);
     if (c->NODt > c->NODp)
         CTX_LAUNCH(c, k_ghost_guess, (c->NODt - c->NODp + BLOCK - 1) / BLOCK, c->NODp, c->NODt, c->nonmag,
                    c->next, c->basis, c->kw.x, c->kw.w3p);
@@ -663,8 +666,10 @@ static int create_ctx(const fg_mesh *mesh, const fg_params *prm, int device, con
                 if (h.ncol[j] == a) sd[(size_t)h.iperm[a]] = h.S[j];
             }
         CK(dev_upload(&c->Sdiag, sd, s));
-        CKCUDA(cudaMalloc(&c->Dg, sizeof(double) * 4 * (size_t)c->NODp));
-        CKCUDA(cudaMemsetAsync(c->Dg, 0, sizeof(double) * 4 * (size_t)c->NODp, s));
+        CKCUDA(cudaMalloc(&c->Dm, sizeof(double2) * (size_t)c->NODp));
+        CKCUDA(cudaMemsetAsync(c->Dm, 0, sizeof(double2) * (size_t)c->NODp, s));
+        CKCUDA(cudaMalloc(&c->qbasis, sizeof(double4) * (size_t)c->NODt));
+        CKCUDA(cudaMemsetAsync(c->qbasis, 0, sizeof(double4) * (size_t)c->NODt, s));
         CKCUDA(cudaStreamSynchronize(s));
         }
     if (dd)
@@ -717,7 +722,7 @@ static int create_ctx(const fg_mesh *mesh, const fg_params *prm, int device, con
     else
         CK(krylov_alloc(c->kw, c->np, 0, s, &c->launches, true));
     c->kw.mask = c->dofmask;
-    c->kw.basis = c->basis;
+    c->kw.qbasis = c->qbasis;
     c->op.kind = OP_NODE3;   // K is never materialised on the step path
     c->op.n = c->np;
     c->op.lanes = 32;
@@ -726,8 +731,9 @@ static int create_ctx(const fg_mesh *mesh, const fg_params *prm, int device, con
     c->op.col16 = c->scol16;
     c->op.val = c->sS;
     c->op.nslice = h.nslice;
-    c->op.basis = c->basis;
-    c->op.Dg = c->Dg;
+    c->op.qbasis = c->qbasis;
+    c->op.Dm = c->Dm;
+    c->op.nonmag = c->nonmag;
     c->op.cS = 0.0;
     for (int k = 0; k < 5; k++) CKCUDA(cudaEventCreate(&c->ev[k]));
     CKCUDA(cudaStreamSynchronize(s));
@@ -847,7 +853,7 @@ void fg_destroy(fg_ctx *c)
     void *ptrs[] = {c->cur, c->next, c->basis, c->nonmag, c->dofmask, c->stage, c->tet_ind, c->tet_da,
                     c->tet_detJ, c->ext_field, c->tet_reg, c->reg_tet, c->rec, c->tri_ind,
                     c->tri_reg, c->tri_surf, c->tri_dMs, c->reg_tri, c->trec, c->perm, c->sptr,
-                    c->scol, c->sdeg, c->iptr, c->tet_slot, c->itptr, c->sinct, c->sS, c->Aw, c->val, c->Sdiag, c->Dg,
+                    c->scol, c->sdeg, c->iptr, c->tet_slot, c->itptr, c->sinct, c->sS, c->Aw, c->val, c->Sdiag, c->Dm, c->qbasis,
                     c->scol16, c->mtri_ind, c->mtri_reg, c->mtri_surf, c->mtri_nrm, c->mtri_dMs, c->extra_edges,
                     c->d_scal, c->node_pos, c->corr, c->tcorr, c->src, c->cptr, c->cidx};
     for (void *p : ptrs)

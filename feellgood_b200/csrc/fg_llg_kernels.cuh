@@ -102,8 +102,10 @@ __device__ __forceinline__ void node_set_basis(const double u[3], double cr, dou
         }
     }
 
+// Also writes the basis as a unit quaternion (32 B): what the Krylov kernels read (fg_common.cuh).
 __global__ void __launch_bounds__(BLOCK)
-k_basis(int NOD, const NodeRec *__restrict__ cur, double cr, double sr, Basis *__restrict__ basis)
+k_basis(int NOD, const NodeRec *__restrict__ cur, double cr, double sr, Basis *__restrict__ basis,
+        double4 *__restrict__ qbasis)
     {
     const int stride = gridDim.x * BLOCK;
     for (int a = blockIdx.x * BLOCK + threadIdx.x; a < NOD; a += stride)
@@ -115,6 +117,7 @@ k_basis(int NOD, const NodeRec *__restrict__ cur, double cr, double sr, Basis *_
         q[0] = make_double2(ep[0], ep[1]);
         q[1] = make_double2(ep[2], eq[0]);
         q[2] = make_double2(eq[1], eq[2]);
+        st256(qbasis + a, basis_to_quat(ep, eq));
         }
     }
 
@@ -906,7 +909,7 @@ struct NodeAsmArrays
 __global__ void __launch_bounds__(BLOCK, 4)
 k_assemble_node(const NodeAsmArrays A, const NodeRec *__restrict__ cur, const NodeRec *__restrict__ next,
                 const Basis *__restrict__ basis, const double4 *__restrict__ rec,
-                const double2 *__restrict__ trec, double cS, double *__restrict__ Dg,
+                const double2 *__restrict__ trec, double cS, double2 *__restrict__ Dm,
                 double *__restrict__ rhs, double *__restrict__ x0, double4 *__restrict__ w0,
                 double *__restrict__ D)
     {
@@ -943,14 +946,13 @@ k_assemble_node(const NodeAsmArrays A, const NodeRec *__restrict__ cur, const No
                 }
             }
         double2 *rhs2 = reinterpret_cast<double2 *>(rhs) + row, *x02 = reinterpret_cast<double2 *>(x0) + row,
-                *D2 = reinterpret_cast<double2 *>(D) + row, *G2 = reinterpret_cast<double2 *>(Dg) + 2 * (size_t)row;
+                *D2 = reinterpret_cast<double2 *>(D) + row;
         if (A.nonmag[row] != 0)
             {  // identity rows, zero rhs and guess (src/solver.cpp:46-48, linear_algebra.cpp:13-24)
             *rhs2 = make_double2(0.0, 0.0);
             *x02 = make_double2(0.0, 0.0);
             *D2 = make_double2(0.0, 0.0);
-            G2[0] = make_double2(1.0, 0.0);
-            G2[1] = make_double2(0.0, 1.0);
+            Dm[row] = make_double2(0.0, 0.0);  // identity row: the SpMV tests the nonmag flag
             w0[row] = make_double4(0.0, 0.0, 0.0, 0.0);
             continue;
             }
@@ -964,12 +966,10 @@ k_assemble_node(const NodeAsmArrays A, const NodeRec *__restrict__ cur, const No
         *x02 = make_double2(g0, g1);
         w0[row] = make_double4(ep[0] * g0 + eq[0] * g1, ep[1] * g0 + eq[1] * g1, ep[2] * g0 + eq[2] * g1, 0.0);
         const double aw = A.Aw[row];
-        // node-diagonal part without S: Ma P_a^T P_a + a_w e_r . (m x e_c)
+        // node-diagonal part without S, Ma P_a^T P_a + a_w e_r . (m x e_c), in its closed form
+        // [[a_w, Ma], [Ma, -a_w]] (fg_common.cuh OP_NODE3): the SpMV needs only the two numbers
+        Dm[row] = make_double2(Ma, aw);
         double k00, k01, k10, k11;
-        project_block(Ma, ep, eq, ep, eq, k00, k01, k10, k11);
-        gyro_block(aw, m, ep, eq, k00, k01, k10, k11);
-        G2[0] = make_double2(k00, k01);
-        G2[1] = make_double2(k10, k11);
         // Jacobi: the full diagonal entries K(2a,2a), K(2a+1,2a+1) as the assembled matrix has them
         project_block(cS * A.Sdiag[row] + Ma, ep, eq, ep, eq, k00, k01, k10, k11);
         gyro_block(aw, m, ep, eq, k00, k01, k10, k11);

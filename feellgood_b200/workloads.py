@@ -156,10 +156,11 @@ def spmv_bytes(n, nnz, col_bytes=4, reads_x=False):
     """One launch of the matrix-free operator K = cS P^T (S x I3) P + Dg: per
     stored node pair (= nnz/4) 8 B of S + `col_bytes` of column index (2 when the 16-bit row offsets
     fit the mesh, else 4); per node (= n/2) the gathered 3-vector image of x (32 B, read once from
-    HBM), its own basis (48 B), the 2x2 node-diagonal block (32 B), the fused second operand (16 B),
-    y written (16 B), one slice pointer per 32 nodes; x itself (16 B) only in the setup stage and the
-    taps -- inside the BiCGStab loop the node's unknowns are recovered from its image."""
-    return ((8 + col_bytes) * (nnz // 4) + (32 + 48 + 32 + 16 + 16 + (16 if reads_x else 0)) * (n // 2)
+    HBM), its basis as a unit quaternion (32 B), the node-diagonal pair (Ma, a_w) (16 B), the
+    identity-row flag (1 B), the fused second operand (16 B), y written (16 B), one slice pointer per
+    32 nodes; x itself (16 B) only in the setup stage and the taps -- inside the BiCGStab loop the
+    node's unknowns are recovered from its image."""
+    return ((8 + col_bytes) * (nnz // 4) + (32 + 32 + 16 + 1 + 16 + 16 + (16 if reads_x else 0)) * (n // 2)
             + 4 * (n // 64))
 
 
@@ -175,17 +176,17 @@ def spmv_bytes_csr(n, nnz):
 
 def iter_bytes(n, nnz, col_bytes=4):
     """One BiCGStab iteration as the library runs it (5 kernels): 2 SpMV + per node
-    p-update  R r,p,v,D (64) + basis (48), W p (16) + image of D p (32)            = 160 B
-    s-update  R r,v,D (48) + basis (48),   W s (16) + image of D s (32)            = 144 B
-    x/r       R x,p,D,s,t,rt (96),         W x,r (32)                              = 128 B
+    p-update  R r,p,v,D (64) + basis quaternion (32), W p (16) + image of D p (32)   = 144 B
+    s-update  R r,v,D (48) + basis quaternion (32),   W s (16) + image of D s (32)   = 128 B
+    x/r       R x,p,D,s,t,rt (96),                    W x,r (32)                     = 128 B
     (D p and D s are never stored: 13 vector reads + 5 writes + 2 images, against SURVEY.md §8d's
     minimal 18 passes for a formulation that stores them)."""
-    return 2 * spmv_bytes(n, nnz, col_bytes) + (160 + 144 + 128) * (n // 2)
+    return 2 * spmv_bytes(n, nnz, col_bytes) + (144 + 128 + 128) * (n // 2)
 
 
 def step_bytes(NOD, NT, n, nnz, iters, col_bytes=4):
     """B_step of SURVEY.md §8d with this library's matrix layout."""
-    b_basis = 72 * NOD
+    b_basis = (72 + 32) * NOD   # + the quaternion copy of the basis the Krylov kernels read
     # elements (124 B/tet tables, 112 B/node gathered) + records written and read back (2 x 128 B/tet)
     # + per node rhs, guess and its image, Dg, D (K itself is never written)
     b_asm = 124 * NT + 112 * NOD + 256 * NT + (16 + 16 + 32 + 32 + 16) * NOD

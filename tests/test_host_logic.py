@@ -120,13 +120,13 @@ def test_algorithmic_byte_model():
     n, nnz = 2000, 60000
     assert workloads.spmv_bytes_csr(n, nnz) == 12 * nnz + 20 * n
     assert workloads.spmv_bytes_blocks(n, nnz) == 9 * nnz + 4 * (n // 2) + 16 * n   # assembled 2x2 blocks
-    # matrix-free operator: 12 B (10 B with 16-bit column offsets) per node pair, 144 B per node
+    # matrix-free operator: 12 B (10 B with 16-bit column offsets) per node pair, 113 B per node
     # (+16 B when x itself is read: setup stage, taps), one slice pointer per 32 nodes
-    assert workloads.spmv_bytes(n, nnz) == 3 * nnz + 72 * n + 4 * (n // 64)
-    assert workloads.spmv_bytes(n, nnz, 2) == 10 * (nnz // 4) + 72 * n + 4 * (n // 64)
-    assert workloads.spmv_bytes(n, nnz, 4, True) == 3 * nnz + 80 * n + 4 * (n // 64)
+    assert workloads.spmv_bytes(n, nnz) == 3 * nnz + 113 * (n // 2) + 4 * (n // 64)
+    assert workloads.spmv_bytes(n, nnz, 2) == 10 * (nnz // 4) + 113 * (n // 2) + 4 * (n // 64)
+    assert workloads.spmv_bytes(n, nnz, 4, True) == 3 * nnz + 129 * (n // 2) + 4 * (n // 64)
     assert workloads.spmv_bytes(n, nnz) < workloads.spmv_bytes_blocks(n, nnz) < workloads.spmv_bytes_csr(n, nnz)
-    assert workloads.iter_bytes(n, nnz) == 2 * workloads.spmv_bytes(n, nnz) + 216 * n
+    assert workloads.iter_bytes(n, nnz) == 2 * workloads.spmv_bytes(n, nnz) + 200 * n
     # SURVEY.md §8d B_step, term by term
     assert workloads.step_bytes_survey(1000, 6000, n, nnz, 2) == (
         72 * 1000 + (124 * 6000 + 112 * 1000 + 8 * nnz + 8 * n) + 88 * 1000 + (12 * nnz + 20 * n + 80 * n)
