@@ -1,3 +1,4 @@
+#include <cstdlib>
 // fg_setup.cpp — once-per-mesh host preprocessing (see fg_setup.hpp).
 #include "fg_setup.hpp"
 
@@ -8,6 +9,18 @@
 
 namespace fg
 {
+int sell_window()
+    {
+    static const int w = []
+        {
+        const char *e = getenv("FG_SELL_WINDOW");
+        int v = e ? atoi(e) : SELL_WINDOW_DEFAULT;
+        if (v < SELL_C) v = SELL_C;
+        return (v / SELL_C) * SELL_C;
+        }();
+    return w;
+    }
+
 // Gauss tables, reference src/tetra.h:29-81.  The barycentric weights are evaluated with the same
 // expression as the reference (1 - u - v - w) so that they round identically.
 void tet_tables(int npi, double a[20], double pds[5])

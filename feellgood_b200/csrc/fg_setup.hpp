@@ -68,7 +68,10 @@ struct HostSetup
                                    // position in the node's SELL incidence list (-1: no row)
     };
 constexpr int SELL_C = 32;
-constexpr int SELL_WINDOW = 1024;
+constexpr int SELL_WINDOW_DEFAULT = 1024;
+// window of the row permutation (multiple of 32); FG_SELL_WINDOW overrides the default (experiments)
+int sell_window();
+#define SELL_WINDOW (fg::sell_window())
 
 // returns FG_OK or FG_ERR_*; message in err
 // n_owned < 0: all nodes are owned (single GPU)
