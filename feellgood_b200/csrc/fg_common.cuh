@@ -145,6 +145,7 @@ struct Operator
     const double2 *Dm;           // state-dependent node-diagonal part: (Ma, a_w) per node row, see OP_NODE3 above
     const unsigned char *nonmag; // 1 = identity row (node outside the magnetic material, pad row)
     double cS;                   // prefactor * s_dt (src/tetra.cpp:261)
+    int prefetch;                // 1: pull the row-epilogue operands and the next slice's indices into L2 early
     };
 
 // 256-bit global accesses (sm_100: LDG.E.ENL2.256 / STG.E.ENL2.256): one request per 32-byte node image
@@ -205,6 +206,7 @@ __device__ __forceinline__ void quat_to_basis(const double4 q, double ep[3], dou
     eq[2] = 2.0 * (y * z + x * w);
     }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // streaming variant (evict-first): data read exactly once per step (the element records)
 __device__ __forceinline__ double4 ld256_cs(const double4 *p)
     {

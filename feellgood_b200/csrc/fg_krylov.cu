@@ -341,6 +341,15 @@ __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_node3(const Op
             q1 = __ldg(op.ptr + sn + 1);
             }
         const int row = s * SLICE + lane;
+        if (op.prefetch)
+            {  // a slice is ~4 dependent memory phases (indices -> gathers, twice, -> row operands): pull
+               // the row-epilogue operands into L2 now, no registers held (measured 235/217 -> 231/212 us;
+               // also prefetching the first batch of the next slice was slower, 242/231 us:
+               // profiles/experiments/r01x_spmv_prefetch.md)
+            prefetch_l2(op.qbasis + row);
+            prefetch_l2(op.Dm + row);
+            if (a.a0 != nullptr) prefetch_l2(reinterpret_cast<const double2 *>(a.a0) + row);
+            }
         const int cbase = IDX16 ? row : 0;  // 16-bit columns are offsets from the lane's own row
         const idx_t *cp = colbase + (size_t)p0 * SLICE + lane;
         const double *sp = op.val + (size_t)p0 * SLICE + lane;

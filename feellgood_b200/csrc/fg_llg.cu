@@ -735,6 +735,8 @@ static int create_ctx(const fg_mesh *mesh, const fg_params *prm, int device, con
     c->op.Dm = c->Dm;
     c->op.nonmag = c->nonmag;
     c->op.cS = 0.0;
+    // early L2 prefetch of the SpMV row-epilogue operands; FG_SPMV_PF=0 switches it off (A/B)
+    c->op.prefetch = getenv("FG_SPMV_PF") ? atoi(getenv("FG_SPMV_PF")) : 1;
     for (int k = 0; k < 5; k++) CKCUDA(cudaEventCreate(&c->ev[k]));
     CKCUDA(cudaStreamSynchronize(s));
     // the per-mesh host tables no longer needed are released (their SELL images are on the device)

@@ -513,7 +513,6 @@ __device__ __forceinline__ void tet_iso_be(const double da_i[3], int i, double d
     }
 
 constexpr int TET_ISO_CTAS_PER_SM = 2;
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // The kernel is bound by the latency of its dependent gathers (ncu: long-scoreboard stalls, 16
 // resident warps per SM) and by L1 throughput, so (i) the records carry BE itself and the node bases
 // are never gathered here (the assembly projects once per node: -192 B of gathers per tetrahedron
