@@ -49,18 +49,55 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock, power and throttle reasons sampled DURING the timed region: NVML polled every 10 ms
+    from a thread (starts at once; the timed region of the default run is only ~0.2 s), nvidia-smi
+    `-lms` as a fallback, and a one-shot query right after the region if neither produced a sample."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    # nvmlClocksEventReason* bits
+    BITS = dict(hw_slowdown=0x8, hw_thermal_slowdown=0x40, sw_thermal_slowdown=0x20, sw_power_cap=0x4)
 
     def __init__(self, device):
         self.device = device
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.f = None
         self.p = None
+        self.th = None
+        self.stop_flag = False
+        self.samples = []      # (sm_mhz, max_mhz, power_w, reasons bitmask)
+        self.nvml = None
+
+    def _poll(self):
+        nv, h = self.nvml, self.h
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((float(sm), float(mx), float(pw), int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.h = nv.nvmlDeviceGetHandleByIndex(self.device)
+            self.nvml = nv
+            import threading
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
                  "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
@@ -68,21 +105,9 @@ class ClockSampler:
         except Exception:
             self.p = None
 
-    def stop(self):
-        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
-        if self.p is None:
-            return out
-        time.sleep(0.12)
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.f.read().splitlines():
+    def _parse_smi(self, text):
+        sm, mx, power, reasons = [], [], [], set()
+        for ln in text.splitlines():
             c = [x.strip() for x in ln.split(",")]
             if len(c) < 9:
                 continue
@@ -92,16 +117,53 @@ class ClockSampler:
                 power.append(float(c[3]))
             except ValueError:
                 continue
-            for k, nm in enumerate(names):
+            for k, nm in enumerate(self.NAMES):
                 if c[5 + k].lower().startswith("active"):
                     reasons.add(nm)
-        try:
-            os.unlink(self.f.name)
-        except OSError:
-            pass
+        return sm, mx, power, reasons
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        sm, mx, power, reasons, how = [], [], [], set(), None
+        if self.th is not None:
+            self.stop_flag = True
+            self.th.join(timeout=2)
+            for s_, m_, p_, r_ in self.samples:
+                sm.append(s_)
+                mx.append(m_)
+                power.append(p_)
+                for nm, bit in self.BITS.items():
+                    if r_ & bit:
+                        reasons.add(nm)
+            how = "nvml 10 ms poll"
+        elif self.p is not None:
+            time.sleep(0.12)
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except Exception:
+                self.p.kill()
+            self.f.flush()
+            self.f.seek(0)
+            sm, mx, power, reasons = self._parse_smi(self.f.read())
+            how = "nvidia-smi -lms 100"
+            try:
+                os.unlink(self.f.name)
+            except OSError:
+                pass
+        if not sm:
+            try:  # nothing caught inside the region: one query right after it (GPU still warm)
+                txt = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=20).stdout
+                sm, mx, power, reasons = self._parse_smi(txt)
+                how = "nvidia-smi once, right after the timed region"
+            except Exception:
+                pass
         if sm:
             out = dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)),
-                       reasons=sorted(reasons), power_w=float(np.median(power)), samples=len(sm))
+                       reasons=sorted(reasons), power_w=float(np.median(power)), samples=len(sm),
+                       how=how)
         return out
 
 
