@@ -162,7 +162,7 @@ __device__ __forceinline__ double4 ld256_nc(const double4 *p)
 // an orthonormal right-handed triad), so 4 doubles carry it; the decoded (ep, eq) are orthonormal to
 // rounding and differ from the stored ones by a few 1e-16.  Every Krylov kernel decodes with this one
 // function, so the operator they apply is consistent.
-__device__ __forceinline__ double4 basis_to_quat(const double ep[3], const double eq[3])
+__host__ __device__ __forceinline__ double4 basis_to_quat(const double ep[3], const double eq[3])
     {
     const double n0 = ep[1] * eq[2] - ep[2] * eq[1], n1 = ep[2] * eq[0] - ep[0] * eq[2],
                  n2 = ep[0] * eq[1] - ep[1] * eq[0];
@@ -195,7 +195,7 @@ __device__ __forceinline__ double4 basis_to_quat(const double ep[3], const doubl
     const double inv = 1.0 / sqrt(nn);
     return make_double4(x * inv, y * inv, z * inv, w * inv);
     }
-__device__ __forceinline__ void quat_to_basis(const double4 q, double ep[3], double eq[3])
+__host__ __device__ __forceinline__ void quat_to_basis(const double4 q, double ep[3], double eq[3])
     {
     const double x = q.x, y = q.y, z = q.z, w = q.w;
     ep[0] = 1.0 - 2.0 * (y * y + z * z);
