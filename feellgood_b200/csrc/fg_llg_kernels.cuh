@@ -27,18 +27,52 @@ namespace fg
 __constant__ double c_tet_a5[20], c_tet_pds5[5], c_tet_a1[4], c_tet_pds1[1];
 __constant__ double c_tri_a4[12], c_tri_pds4[4], c_tri_a1[3], c_tri_pds1[1];
 
-template <int NPI> __device__ __forceinline__ double tet_a(int i, int g)
-    { return NPI == 5 ? c_tet_a5[i * 5 + g] : c_tet_a1[i]; }
-template <int NPI> __device__ __forceinline__ double tet_pds(int g)
-    { return NPI == 5 ? c_tet_pds5[g] : c_tet_pds1[0]; }
+// The element math below (tet_core, tet_iso_front, tet_iso_be, alpha_eff) is __host__ __device__ so that
+// tests/cpp/device_math_test.cu can run it on the CPU; on the host the Gauss tables come from the same
+// tet_tables() that fills the __constant__ copies (fg_setup.cpp).  Device code is unchanged by this.
+void tet_tables(int npi, double a[20], double pds[5]);
+#ifndef __CUDA_ARCH__
+inline double host_tet_table(int npi, bool weights, int idx)
+    {
+    static double a5[20], p5[5], a1[4], p1[1];
+    static const bool init = (tet_tables(5, a5, p5), tet_tables(1, a1, p1), true);
+    (void)init;
+    return npi == 5 ? (weights ? p5[idx] : a5[idx]) : (weights ? p1[idx] : a1[idx]);
+    }
+#endif
+template <int NPI> __host__ __device__ __forceinline__ double tet_a(int i, int g)
+    {
+#ifdef __CUDA_ARCH__
+    return NPI == 5 ? c_tet_a5[i * 5 + g] : c_tet_a1[i];
+#else
+    return host_tet_table(NPI, false, NPI == 5 ? i * 5 + g : i);
+#endif
+    }
+template <int NPI> __host__ __device__ __forceinline__ double tet_pds(int g)
+    {
+#ifdef __CUDA_ARCH__
+    return NPI == 5 ? c_tet_pds5[g] : c_tet_pds1[0];
+#else
+    return host_tet_table(NPI, true, NPI == 5 ? g : 0);
+#endif
+    }
+// one rounding, whatever the compiler contracts around it
+__host__ __device__ __forceinline__ double mul_rn(double a, double b)
+    {
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+    }
 template <int NPI> __device__ __forceinline__ double tri_a(int i, int g)
     { return NPI == 4 ? c_tri_a4[i * 4 + g] : c_tri_a1[i]; }
 template <int NPI> __device__ __forceinline__ double tri_pds(int g)
     { return NPI == 4 ? c_tri_pds4[g] : c_tri_pds1[0]; }
 
-__device__ __forceinline__ double dot3(const double *a, const double *b)
+__host__ __device__ __forceinline__ double dot3(const double *a, const double *b)
     { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
-__device__ __forceinline__ void cross3(const double *a, const double *b, double *r)
+__host__ __device__ __forceinline__ void cross3(const double *a, const double *b, double *r)
     {
     r[0] = a[1] * b[2] - a[2] * b[1];
     r[1] = a[2] * b[0] - a[0] * b[2];
@@ -125,7 +159,7 @@ k_basis(int NOD, const NodeRec *__restrict__ cur, double cr, double sr, Basis *_
 // Tet::integrales, src/tetra.cpp:210-307
 // ------------------------------------------------------------------------------------------
 // src/tetra.cpp:47-75
-__device__ __forceinline__ double alpha_eff(double dt, double alpha, double h)
+__host__ __device__ __forceinline__ double alpha_eff(double dt, double alpha, double h)
     {
     const double reduced_dt = FG_GAMMA0 * dt;
     const double r = 0.1;
@@ -157,7 +191,7 @@ struct StepPrm
 // per-point tables U, V, H, H_aniso (4 x 3 x NPI doubles) never exist.  Every sum keeps the
 // reference's order of accumulation.
 template <int NPI>
-__device__ __forceinline__ void tet_core(const TetIn &T, const TetRegion &R, const StepPrm &sp,
+__host__ __device__ __forceinline__ void tet_core(const TetIn &T, const TetRegion &R, const StepPrm &sp,
                                          const double (&Hext)[3][NPI], double contrib[4],
                                          double BE[3][4])
     {
@@ -432,7 +466,7 @@ struct TetIsoMid
     };
 
 template <int NPI>
-__device__ __forceinline__ void tet_iso_front(const TetIsoIn &T, const TetRegion &R, const StepPrm &sp,
+__host__ __device__ __forceinline__ void tet_iso_front(const TetIsoIn &T, const TetRegion &R, const StepPrm &sp,
                                               TetIsoMid &M, double contrib[4])
     {
     const double s_dt = FG_THETA * sp.dt * FG_GAMMA0;
@@ -457,7 +491,7 @@ __device__ __forceinline__ void tet_iso_front(const TetIsoIn &T, const TetRegion
             hv -= T.phiv[i] * T.da[i][d];
             }
         Heff[d] = hd + sp.Hext[d];                     // tetra.cpp:248-255, Hst = 0
-        M.H[d] = Heff[d] + __dmul_rn(th_dt, hv);       // :292 with H_aniso = 0 (two roundings, like tet_core)
+        M.H[d] = Heff[d] + mul_rn(th_dt, hv);       // :292 with H_aniso = 0 (two roundings, like tet_core)
         }
     double gsq = 0.0;
 #pragma unroll
@@ -488,7 +522,7 @@ __device__ __forceinline__ void tet_iso_front(const TetIsoIn &T, const TetRegion
 
 // BE(:, i) of local node i (tetra.cpp:294-303), Gauss points in the reference's order
 template <int NPI>
-__device__ __forceinline__ void tet_iso_be(const double da_i[3], int i, double detJ, double Abis,
+__host__ __device__ __forceinline__ void tet_iso_be(const double da_i[3], int i, double detJ, double Abis,
                                            const TetIsoMid &M, double be[3])
     {
     double Ex[3];
