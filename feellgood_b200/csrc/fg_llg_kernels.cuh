@@ -65,10 +65,32 @@ __host__ __device__ __forceinline__ double mul_rn(double a, double b)
     return a * b;
 #endif
     }
-template <int NPI> __device__ __forceinline__ double tri_a(int i, int g)
-    { return NPI == 4 ? c_tri_a4[i * 4 + g] : c_tri_a1[i]; }
-template <int NPI> __device__ __forceinline__ double tri_pds(int g)
-    { return NPI == 4 ? c_tri_pds4[g] : c_tri_pds1[0]; }
+void tri_tables(int npi, double a[12], double pds[4]);
+#ifndef __CUDA_ARCH__
+inline double host_tri_table(int npi, bool weights, int idx)
+    {
+    static double a4[12], p4[4], a1[3], p1[1];
+    static const bool init = (tri_tables(4, a4, p4), tri_tables(1, a1, p1), true);
+    (void)init;
+    return npi == 4 ? (weights ? p4[idx] : a4[idx]) : (weights ? p1[idx] : a1[idx]);
+    }
+#endif
+template <int NPI> __host__ __device__ __forceinline__ double tri_a(int i, int g)
+    {
+#ifdef __CUDA_ARCH__
+    return NPI == 4 ? c_tri_a4[i * 4 + g] : c_tri_a1[i];
+#else
+    return host_tri_table(NPI, false, NPI == 4 ? i * 4 + g : i);
+#endif
+    }
+template <int NPI> __host__ __device__ __forceinline__ double tri_pds(int g)
+    {
+#ifdef __CUDA_ARCH__
+    return NPI == 4 ? c_tri_pds4[g] : c_tri_pds1[0];
+#else
+    return host_tri_table(NPI, true, NPI == 4 ? g : 0);
+#endif
+    }
 
 __host__ __device__ __forceinline__ double dot3(const double *a, const double *b)
     { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
@@ -79,7 +101,7 @@ __host__ __device__ __forceinline__ void cross3(const double *a, const double *b
     r[2] = a[0] * b[1] - a[1] * b[0];
     }
 // Eigen normalize(): z = squaredNorm(); if (z > 0) v /= sqrt(z)
-__device__ __forceinline__ void normalize3(double *a)
+__host__ __device__ __forceinline__ void normalize3(double *a)
     {
     const double z = dot3(a, a);
     if (z > 0.0)
@@ -112,7 +134,7 @@ __device__ __forceinline__ void load_basis(const Basis *p, double ep[3], double 
 // Node::setBasis, src/node.h:73-102.  cr = cos(r), sr = sin(r) are evaluated by the host libm so
 // that the rotation uses the very numbers the reference would.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void node_set_basis(const double u[3], double cr, double sr,
+__host__ __device__ __forceinline__ void node_set_basis(const double u[3], double cr, double sr,
                                                double ep[3], double eq[3])
     {
     int k = 0;
@@ -622,7 +644,7 @@ k_tet_iso(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__res
     }
 
 // projection of one node pair: the 2x2 block of K / Kp (SURVEY.md §8a index facts)
-__device__ __forceinline__ void project_block(double E, const double ep_a[3], const double eq_a[3],
+__host__ __device__ __forceinline__ void project_block(double E, const double ep_a[3], const double eq_a[3],
                                               const double ep_b[3], const double eq_b[3],
                                               double &k00, double &k01, double &k10, double &k11)
     {
@@ -632,7 +654,7 @@ __device__ __forceinline__ void project_block(double E, const double ep_a[3], co
     k11 = E * dot3(ep_a, eq_b);
     }
 // gyrotropic part of the diagonal block: a_w e_r . (m x e_c)
-__device__ __forceinline__ void gyro_block(double aw, const double m[3], const double ep[3],
+__host__ __device__ __forceinline__ void gyro_block(double aw, const double m[3], const double ep[3],
                                            const double eq[3], double &k00, double &k01,
                                            double &k10, double &k11)
     {
@@ -738,7 +760,7 @@ struct TriArrays
     };
 
 template <int NPI>
-__device__ __forceinline__ void tri_core(const TriRegion &R, double surf, double dMs,
+__host__ __device__ __forceinline__ void tri_core(const TriRegion &R, double surf, double dMs,
                                          const double u[3][3], double BE[3][3])
     {
     const double Kbis = 2.0 * R.Ks / dMs;

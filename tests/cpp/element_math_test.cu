@@ -5,7 +5,9 @@
 //   * tet_iso_front / tet_iso_be (fast path, K = K3 = 0) against tet_core on the same inputs: the
 //     two paths must agree bit for bit on the host (same formulas, same order of accumulation);
 //   * every case is printed as one JSON line {inputs, contrib[4], BE[12]} so that
-//     tests/test_device_math.py can check it against the independent dense numpy restatement.
+//     tests/test_device_math.py can check it against the independent dense numpy restatement;
+//   * node_set_basis orthonormality, the explicit node-diagonal block against its closed form, and
+//     tri_core (Tri::integrales, src/triangle.cpp:6-36), also printed for the numpy check.
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -120,10 +122,79 @@ template <int NPI> static int run(int ncase, std::mt19937 &gen)
     return fails;
     }
 
+// Node::setBasis (device version) and the node-diagonal block: the explicit triple products of
+// project_block + gyro_block (what the assembled-block operator and the Jacobi diagonal use) against
+// the closed form [[a_w, Ma], [Ma, -a_w]] the matrix-free SpMV applies (fg_common.cuh, OP_NODE3).
+static int check_basis_and_diagonal(std::mt19937 &gen)
+    {
+    std::normal_distribution<double> N(0.0, 1.0);
+    std::uniform_real_distribution<double> U(0.0, 1.0);
+    double worst_on = 0, worst_dg = 0;
+    for (int it = 0; it < 100000; it++)
+        {
+        double u[3] = {N(gen), N(gen), N(gen)};
+        if (it % 7 == 0) u[it % 3] = 0.0;
+        const double n = std::sqrt(dot3(u, u));
+        if (!(n > 0)) continue;
+        for (int d = 0; d < 3; d++) u[d] /= n;
+        const double r = 0.63661977236758134308 * U(gen);   // M_2_PI * U(0,1), linear_algebra.cpp:3-11
+        double ep[3], eq[3];
+        node_set_basis(u, std::cos(r), std::sin(r), ep, eq);
+        worst_on = std::fmax(worst_on, std::fmax(std::fabs(dot3(ep, u)), std::fabs(dot3(eq, u))));
+        worst_on = std::fmax(worst_on, std::fmax(std::fabs(dot3(ep, eq)), std::fabs(dot3(ep, ep) - 1)));
+        worst_on = std::fmax(worst_on, std::fabs(dot3(eq, eq) - 1));
+        const double Ma = 1e-27 * (0.1 + U(gen)), aw = 1e-27 * (0.1 + U(gen));   // ~ volume / 4 * alpha
+        double k00, k01, k10, k11;
+        project_block(Ma, ep, eq, ep, eq, k00, k01, k10, k11);
+        gyro_block(aw, u, ep, eq, k00, k01, k10, k11);
+        const double sc = std::fmax(Ma, aw);
+        worst_dg = std::fmax(worst_dg, std::fabs(k00 - aw) / sc);
+        worst_dg = std::fmax(worst_dg, std::fabs(k01 - Ma) / sc);
+        worst_dg = std::fmax(worst_dg, std::fabs(k10 - Ma) / sc);
+        worst_dg = std::fmax(worst_dg, std::fabs(k11 + aw) / sc);
+        }
+    std::fprintf(stderr, "basis orthonormality %.3e   explicit Dg - closed form %.3e (relative)\n", worst_on, worst_dg);
+    int fails = 0;
+    if (!(worst_on < 5e-15)) { std::fprintf(stderr, "FAIL basis\n"); fails++; }     // UT_TOL of ut_node.cpp
+    if (!(worst_dg < 1e-14)) { std::fprintf(stderr, "FAIL closed-form Dg\n"); fails++; }
+    return fails;
+    }
+
+// Tri::integrales (tri_core): one JSON line per case for the numpy check
+template <int NPI> static void run_tri(int ncase, std::mt19937 &gen)
+    {
+    std::normal_distribution<double> N(0.0, 1.0);
+    std::uniform_real_distribution<double> U(0.0, 1.0);
+    for (int it = 0; it < ncase; it++)
+        {
+        TriRegion R;
+        R.Ks = 2.5e-4 * (0.5 + U(gen));
+        double uk[3] = {N(gen), N(gen), N(gen)};
+        const double nk = std::sqrt(dot3(uk, uk));
+        for (int d = 0; d < 3; d++) R.uk[d] = uk[d] / nk;
+        double u[3][3];
+        for (int i = 0; i < 3; i++)
+            {
+            for (int d = 0; d < 3; d++) u[i][d] = N(gen);
+            const double n = std::sqrt(dot3(u[i], u[i]));
+            for (int d = 0; d < 3; d++) u[i][d] /= n;
+            }
+        const double surf = 2e-18 * (0.5 + U(gen)), dMs = 8e5;
+        double BE[3][3];
+        tri_core<NPI>(R, surf, dMs, u, BE);
+        std::printf("{\"tri\": 1, \"npi\": %d, \"Ks\": %.17g, \"surf\": %.17g, \"dMs\": %.17g, ", NPI, R.Ks, surf, dMs);
+        pr("uk", R.uk, 3); pr("u", &u[0][0], 9); pr("BE", &BE[0][0], 9, true);
+        std::printf("}\n");
+        }
+    }
+
 int main()
     {
     std::mt19937 gen(5489);
     int fails = run<5>(24, gen) + run<1>(12, gen);
+    fails += check_basis_and_diagonal(gen);
+    run_tri<4>(8, gen);
+    run_tri<1>(4, gen);
     std::fprintf(stderr, fails ? "ELEMENT_MATH_FAILED\n" : "ELEMENT_MATH_OK\n");
     return fails ? 1 : 0;
     }

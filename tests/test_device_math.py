@@ -36,8 +36,21 @@ def test_element_math_against_dense_restatement(tmp_path):
     exe = _nvcc(tmp_path, "element_math_test", os.path.join(CSRC, "fg_setup.cpp"))
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ELEMENT_MATH_OK" in r.stderr, r.stderr[-2000:]   # fast path == general core
-    rows = [json.loads(ln) for ln in r.stdout.splitlines() if ln.strip()]
+    allrows = [json.loads(ln) for ln in r.stdout.splitlines() if ln.strip()]
+    rows = [c for c in allrows if "tri" not in c]
+    tris = [c for c in allrows if "tri" in c]
     assert len(rows) == 36 and {c["npi"] for c in rows} == {1, 5}
+    assert len(tris) == 12 and {c["npi"] for c in tris} == {1, 4}
+    for c in tris:   # Tri::integrales: with ep = eq = axis d, Lp[i] = BE[d][i]
+        a, pds = npr.tri_tables(c["npi"])
+        weight = 2.0 * c["surf"] * pds          # triangle.h:121-122
+        u = np.array(c["u"]).reshape(3, 3)
+        BE_dev = np.array(c["BE"]).reshape(3, 3)
+        for d in range(3):
+            e = np.zeros((3, 3))
+            e[:, d] = 1.0
+            Lp = npr.tri_integrales(c["Ks"], c["uk"], c["dMs"], weight, u, e, e)
+            assert np.max(np.abs(Lp[:3] - BE_dev[d])) <= 1e-13 * np.max(np.abs(BE_dev))
     assert any(c["drift"] for c in rows) and any(c["K"] == 0 for c in rows) and any(c["K"] != 0 for c in rows)
     worst_be = worst_c = 0.0
     for c in rows:
