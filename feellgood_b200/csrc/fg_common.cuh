@@ -89,7 +89,7 @@ struct KState
     double *hist;    // optional per-iteration record [hist_cap][8]: rho_1, (v,rt), alpha, |s|^2, (t,s), (t,t),
                      // omega, |r|^2 — diagnosis of breakdowns (fg_get_krylov_history)
     };
-__device__ __forceinline__ void khist(KState *st, int col, double v)
+__host__ __device__ __forceinline__ void khist(KState *st, int col, double v)
     {
     if (st->hist != nullptr && st->nit < st->hist_cap) st->hist[8 * (size_t)st->nit + col] = v;
     }

@@ -16,44 +16,10 @@
 
 #include "fg_common.cuh"
 #include "fg_reduce.cuh"
+#include "fg_krylov_state.cuh"
 
 namespace fg
 {
-// ------------------------------------------------------------------------------------------
-// iteration monitor, reference src/algebra/iter.h:113-157
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool it_finished(KState *st, double nr)
-    {
-    st->res = fabs(nr);
-    if (isnan(st->res))
-        {
-        st->status = FG_CANNOT_CONVERGE;
-        return false;
-        }
-    if (st->res <= st->rhsn * st->resmax)
-        {
-        st->status = FG_CONVERGED;
-        return true;
-        }
-    return false;
-    }
-
-// `while (!iter.finished(norm(r)))`, then rho_1 and the breakdown test (bicg.h:185-195)
-__device__ __forceinline__ void bicg_top_of_loop(KState *st, double rr, double rho1_new)
-    {
-    if (it_finished(st, sqrt(fabs(rr))))
-        {
-        st->done = 1;
-        return;
-        }
-    st->rho1 = rho1_new;
-    if (st->nit > 0 && (st->rho2 == 0.0 || st->omega == 0.0))
-        {
-        st->status = FG_CANNOT_CONVERGE;
-        st->done = 1;
-        }
-    }
-
 __device__ __forceinline__ void load_basis_k(const double4 *qb, double ep[3], double eq[3])
     { quat_to_basis(ld256_nc(qb), ep, eq); }
 // w = ep x0 + eq x1: the 3-vector image of the two tangent-plane unknowns of a node (element.h:81-96)
@@ -67,17 +33,6 @@ __device__ __forceinline__ double4 node_w(const double4 *b, double x0, double x1
 // ------------------------------------------------------------------------------------------
 // SpMV with fused epilogues
 // ------------------------------------------------------------------------------------------
-enum
-    {
-    ST_PLAIN = 0,    // y = A x
-    ST_BICG_SETUP,   // r = b - A x (masked); rt = r (p = r implicit); ||b||^2, ||r||^2 (bicg.h:172-183)
-    ST_BICG_V,       // v = A phat (masked); (v, rt) -> alpha                    (bicg.h:203-206)
-    ST_BICG_T,       // t = A shat (masked); (t,s), (t,t) -> omega               (bicg.h:219-222)
-    ST_CG_SETUP,     // r = b - A x (masked); p = D r; ||b||^2, ||r||^2, (Dr,r)  (cg.h:24-34)
-    ST_CG_Q,         // q = A p (masked); (q,p) -> a                             (cg.h:45-52)
-    ST_RESID         // y = b - A x (masked)  [b -= A xd of the *_dir variants]
-    };
-
 struct SpmvArgs
     {
     const double4 *w;  // OP_NODE3: 3-vector image of x (gathered); x itself is read for the node-diagonal part
@@ -91,56 +46,6 @@ struct SpmvArgs
     RedBuf red;
     DistDev *dist;     // multi-GPU: halo protocol of the SpMV input (fg_dist.cuh)
     };
-
-// The two vector updates whose results cross GPUs are written with explicit roundings so that the
-// owner's value and the copy it pushes to a neighbour are bit-identical whatever the compiler
-// contracts elsewhere.   p = r + beta (p - omega v)  (bicg.h:196-201);   s = r - alpha v  (:207-208)
-__device__ __forceinline__ double bicg_p_value(double p, double v, double r, double omega, double beta)
-    { return __fma_rn(__fma_rn(-omega, v, p), beta, r); }
-__device__ __forceinline__ double bicg_s_value(double r, double v, double alpha)
-    { return __fma_rn(-alpha, v, r); }
-__device__ __forceinline__ double bicg_beta(const KState *st)
-    { return (st->rho1 / st->rho2) * (st->alpha / st->omega); }
-
-// finalisation of a reducing SpMV stage by the last CTA (the scalars of bicg.h / cg.h)
-template <int STAGE> __device__ __forceinline__ void spmv_finalize(KState *st, const double (&tot)[RED_NV])
-    {
-    if (STAGE == ST_BICG_SETUP)
-        {
-        st->rhsn = sqrt(fabs(tot[0]));
-        bicg_top_of_loop(st, tot[1], tot[1]);  // rt == r: (rt, r) = ||r||^2
-        }
-    else if (STAGE == ST_BICG_V)
-        {
-        st->alpha = st->rho1 / tot[0];
-        khist(st, 0, st->rho1);
-        khist(st, 1, tot[0]);
-        khist(st, 2, st->alpha);
-        }
-    else if (STAGE == ST_BICG_T)
-        {
-        st->omega = tot[0] / tot[1];
-        khist(st, 4, tot[0]);
-        khist(st, 5, tot[1]);
-        khist(st, 6, st->omega);
-        }
-    else if (STAGE == ST_CG_SETUP)
-        {
-        st->rhsn = sqrt(fabs(tot[0]));
-        st->rho1 = tot[2];  // rho
-        if (it_finished(st, sqrt(fabs(tot[1]))) || st->status == FG_CANNOT_CONVERGE) st->done = 1;
-        }
-    else if (STAGE == ST_CG_Q)
-        {
-        if (tot[0] == 0.0)
-            {
-            st->status = FG_CANNOT_CONVERGE;
-            st->done = 1;
-            }
-        else
-            st->alpha = st->rho1 / tot[0];
-        }
-    }
 
 // per-row epilogue shared by both layouts: applies the mask, writes y (and the fused outputs) and
 // accumulates the fused dot products.
@@ -629,18 +534,6 @@ k_bicg_p_node(int nnode, const double *__restrict__ r, const double *__restrict_
     }
 
 // s = r - alpha v ; shat = D s ; ||s||^2 -> mid-iteration exit test    (bicg.h:207-218)
-__device__ __forceinline__ void bicg_s_finalize(KState *st, double ss)
-    {
-    khist(st, 3, ss);
-    if (it_finished(st, sqrt(fabs(ss))))
-        {
-        st->final_half = 1;  // x += alpha phat is applied by k_bicg_xr
-        st->done = 1;
-        }
-    else if (st->status == FG_ITER_OVERFLOW || st->status == FG_CANNOT_CONVERGE)
-        st->done = 1;
-    }
-
 __global__ void __launch_bounds__(BLOCK)
 k_bicg_s(int n, const double *__restrict__ r, const double *__restrict__ v,
          const double *__restrict__ D, double *__restrict__ s, double *__restrict__ shat, KState *st,
@@ -734,19 +627,7 @@ k_bicg_xr(int n, double *__restrict__ x, const double *__restrict__ phat,
     double tot[2];
     const int role = grid_reduce<2>(acc, red, tot);
     if (role == 0) return;
-    if (role == 1)
-        {
-        if (fh)
-            st->final_half = 0;
-        else
-            {
-            khist(st, 7, tot[0]);
-            st->rho2 = st->rho1;
-            st->nit++;
-            if (st->nit >= st->maxiter) st->status = FG_ITER_OVERFLOW;  // iter.h:119-124
-            bicg_top_of_loop(st, tot[0], tot[1]);
-            }
-        }
+    if (role == 1) bicg_xr_finalize(st, tot[0], tot[1], fh);
     }
 
 // Node-wise variant for the matrix-free LLG operator: phat = D p and shat = D s are not stored by
@@ -795,19 +676,7 @@ k_bicg_xr_node(int nnode, double *__restrict__ x, const double *__restrict__ p, 
     double tot[2];
     const int role = grid_reduce<2>(acc, red, tot);
     if (role == 0) return;
-    if (role == 1)
-        {
-        if (fh)
-            st->final_half = 0;
-        else
-            {
-            khist(st, 7, tot[0]);
-            st->rho2 = st->rho1;
-            st->nit++;
-            if (st->nit >= st->maxiter) st->status = FG_ITER_OVERFLOW;  // iter.h:119-124
-            bicg_top_of_loop(st, tot[0], tot[1]);
-            }
-        }
+    if (role == 1) bicg_xr_finalize(st, tot[0], tot[1], fh);
     }
 
 // ------------------------------------------------------------------------------------------
@@ -844,13 +713,7 @@ k_cg_xr(int n, double *__restrict__ x, const double *__restrict__ p, const doubl
         }
     double tot[2];
     if (grid_reduce<2>(acc, red, tot) != 1) return;
-    st->rho2 = st->rho1;  // rho_1 = rho
-    st->rho1 = tot[1];
-    st->nit++;
-    if (st->nit >= st->maxiter) st->status = FG_ITER_OVERFLOW;
-    if (it_finished(st, sqrt(fabs(tot[0]))) || st->status == FG_ITER_OVERFLOW
-        || st->status == FG_CANNOT_CONVERGE)
-        st->done = 1;
+    cg_xr_finalize(st, tot[0], tot[1]);
     }
 
 // ------------------------------------------------------------------------------------------
@@ -860,17 +723,7 @@ __global__ void __launch_bounds__(BLOCK)
 k_init_state(KState *st, double tol, int maxiter)
     {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    st->rho1 = st->rho2 = st->alpha = st->beta = st->omega = 0.0;
-    st->res = 1.7976931348623157e308;  // iteration::reset, iter.h:92-98
-    st->rhsn = 1.0;
-    st->resmax = tol;
-    st->nit = 0;
-    st->maxiter = maxiter;
-    st->status = FG_UNDEFINED;
-    st->done = 0;
-    st->final_half = 0;
-    st->updated = 0;
-    st->failed = 0;
+    kstate_reset(st, tol, maxiter);
     }
 
 __global__ void __launch_bounds__(BLOCK)

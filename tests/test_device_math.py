@@ -83,3 +83,68 @@ def test_element_math_against_dense_restatement(tmp_path):
         worst_c = max(worst_c, np.max(np.abs(contrib_dev - contrib_np)) / np.max(np.abs(Kd)))
     assert worst_be < 1e-12, worst_be
     assert worst_c < 1e-12, worst_c
+
+
+def _emulate(exe, rowptr, col, val, rhs, x0, ld, tol, maxiter):
+    txt = ["%d %d %d %.17g %d" % (rhs.size, col.size, len(ld), tol, maxiter)]
+    for a, fmt in ((rowptr, "%d"), (col, "%d"), (val, "%.17g"), (rhs, "%.17g"), (x0, "%.17g"), (ld, "%d")):
+        txt.append(" ".join(fmt % v for v in a))
+    r = subprocess.run([exe], input="\n".join(txt) + "\n", capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.split("\n")
+    st, nit, res, rhsn = lines[0].split()
+    return np.array([float(v) for v in lines[1:1 + rhs.size]]), dict(status=int(st), nit=int(nit), res=float(res),
+                                                                     rhsn=float(rhsn))
+
+
+def test_device_bicgstab_state_machine_against_reference(oracle, tmp_path):
+    """The library's Krylov scalar code (iteration monitor, alpha/omega/rho, breakdown, overflow and
+    mid-iteration exit: fg_krylov_state.cuh) driven on the CPU in the kernels' order, against the
+    reference's own bicg_dir: the committed golden of the real reference and the oracle (which
+    reproduces the reference bit for bit, tests/test_oracle_vs_reference.py) on special cases."""
+    exe = _nvcc(tmp_path, "krylov_state_test")
+    gold = np.load(os.path.join(cases.GOLDEN, "ref_algebra.npz"))
+    rp, col, val, rhs, ld = (gold[k] for k in ("u_rowptr", "u_col", "u_val", "u_rhs", "u_ld"))
+    n = rhs.size
+    # (1) the reference's own run: same status, same iteration count, same solution to the tolerance
+    x, info = _emulate(exe, rp, col, val, rhs, np.zeros(n), ld, 1e-10, 200)
+    g_status, g_nit = int(gold["u_bicg_dir_info"][0]), int(gold["u_bicg_dir_info"][1])
+    assert info["status"] == g_status == 0 and abs(info["nit"] - g_nit) <= 1
+    assert np.linalg.norm(x - gold["u_bicg_dir_x"]) <= 1e-8 * np.linalg.norm(gold["u_bicg_dir_x"])
+    assert np.all(x[ld] == 0.0)                                   # masked dofs never move
+    rhs_m = rhs.copy()
+    rhs_m[ld] = 0.0
+    assert abs(info["rhsn"] - np.linalg.norm(rhs_m)) <= 1e-14 * info["rhsn"]
+    # (2) iteration overflow: maxiter full iterations + the half iteration up to the ||s|| test
+    for maxiter in (1, 3, 7):
+        x, info = _emulate(exe, rp, col, val, rhs, np.zeros(n), ld, 1e-10, maxiter)
+        xo, io = oracle.bicg_dir(rp, col, val, np.zeros(n), rhs, ld, tol=1e-10, maxiter=maxiter)
+        assert info["status"] == io["status"] == 1 and info["nit"] == io["nit"] == maxiter
+        assert np.linalg.norm(x - xo) <= 1e-9 * np.linalg.norm(xo)
+        assert abs(info["res"] - io["res"]) <= 1e-6 * io["res"]
+    # (3) loose tolerances: exits on ||s|| in the middle of an iteration (x += alpha phat only) or at the top
+    for tol in (1e-1, 1e-2, 1e-3, 1e-5):
+        x, info = _emulate(exe, rp, col, val, rhs, np.zeros(n), ld, tol, 200)
+        xo, io = oracle.bicg_dir(rp, col, val, np.zeros(n), rhs, ld, tol=tol, maxiter=200)
+        assert info["status"] == io["status"] == 0 and info["nit"] == io["nit"], (tol, info, io)
+        assert np.linalg.norm(x - xo) <= 1e-9 * np.linalg.norm(xo)
+        assert abs(info["res"] - io["res"]) <= 1e-6 * io["res"]
+    # (4) zero right-hand side and zero guess: converged before the first iteration, x untouched
+    x, info = _emulate(exe, rp, col, val, np.zeros(n), np.zeros(n), ld, 1e-10, 200)
+    xo, io = oracle.bicg_dir(rp, col, val, np.zeros(n), np.zeros(n), ld, tol=1e-10, maxiter=200)
+    assert info["status"] == io["status"] == 0 and info["nit"] == io["nit"] == 0 and np.all(x == 0.0)
+    # (5) a zero on the diagonal: 1/0 in the Jacobi preconditioner, NaN residual => CANNOT_CONVERGE
+    val_bad = val.copy()
+    i = int(np.setdiff1d(np.arange(n), ld)[5])
+    j = rp[i] + int(np.searchsorted(col[rp[i]:rp[i + 1]], i))
+    val_bad[j] = 0.0
+    x, info = _emulate(exe, rp, col, val_bad, rhs, np.zeros(n), ld, 1e-10, 200)
+    xo, io = oracle.bicg_dir(rp, col, val_bad, np.zeros(n), rhs, ld, tol=1e-10, maxiter=200)
+    assert info["status"] == io["status"] == 2, (info, io)
+    # (6) a non-zero initial guess
+    x0 = np.random.default_rng(3).standard_normal(n)
+    x0[ld] = 0.0
+    x, info = _emulate(exe, rp, col, val, rhs, x0, ld, 1e-10, 200)
+    xo, io = oracle.bicg_dir(rp, col, val, x0, rhs, ld, tol=1e-10, maxiter=200)
+    assert info["status"] == io["status"] == 0 and abs(info["nit"] - io["nit"]) <= 1
+    assert np.linalg.norm(x - xo) <= 1e-8 * np.linalg.norm(xo)
