@@ -6,10 +6,15 @@
 // TwoSum reduction trees).  tests/test_device_math.py compares status, iteration count and solution
 // with the reference's own bicg_dir (src/algebra/bicg.h:163-234, compiled unmodified in oracle/_ref).
 //
+// A second mode does the same for the Jacobi-preconditioned CG (src/algebra/cg.h:15-58; kernels k_cg_p,
+// k_spmv<ST_CG_SETUP|ST_CG_Q>, k_cg_xr).
+//
+// argv[1]: "bicg" (default) | "cg"
 // stdin:  n nnz nmask tol maxiter, then rowptr[n+1], col[nnz], val[nnz], rhs[n], x0[n], mask[nmask]
 // stdout: status nit res rhsn, then x[n]
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 #include <vector>
 
 #include "../../feellgood_b200/csrc/fg_krylov_state.cuh"
@@ -28,8 +33,9 @@ struct Sum   // error-free accumulation (the device's reduction trees are compen
     double get() const { return s + e; }
     };
 
-int main()
+int main(int argc, char **argv)
     {
+    const bool cg = argc > 1 && std::strcmp(argv[1], "cg") == 0;
     int n, nnz, nmask, maxiter;
     double tol;
     if (std::scanf("%d %d %d %lf %d", &n, &nnz, &nmask, &tol, &maxiter) != 5) return 2;
@@ -67,6 +73,65 @@ int main()
     st.hist = nullptr;
     st.hist_cap = 0;
     kstate_reset(&st, tol, maxiter);
+    if (cg)
+        {
+        std::vector<double> &q = t;
+            {  // ST_CG_SETUP: r = b - A x (masked); p = D r; ||b||^2, ||r||^2, (Dr, r)
+            spmv(x, v);
+            Sum bb, rr, zr;
+            for (int i = 0; i < n; i++)
+                {
+                const double ri = mask[i] ? 0.0 : b[i] - v[i];
+                const double z = D[i] * ri;
+                r[i] = ri;
+                p[i] = z;
+                bb.add(b[i] * b[i]);
+                rr.add(ri * ri);
+                zr.add(z * ri);
+                }
+            const double tot[RED_NV] = {bb.get(), rr.get(), zr.get(), 0.0};
+            spmv_finalize<ST_CG_SETUP>(&st, tot);
+            }
+        for (int guard = 0; guard < maxiter + 3 && !st.done; guard++)
+            {
+            // k_cg_p: p = (rho/rho_1) p + D r   (nit > 0)
+            if (!st.done && st.nit > 0)
+                {
+                const double f = st.rho1 / st.rho2;
+                for (int i = 0; i < n; i++) p[i] = std::fma(p[i], f, D[i] * r[i]);
+                }
+            // k_spmv<ST_CG_Q>
+            if (!st.done)
+                {
+                spmv(p, q);
+                Sum qp;
+                for (int i = 0; i < n; i++)
+                    {
+                    if (mask[i]) q[i] = 0.0;
+                    qp.add(q[i] * p[i]);
+                    }
+                const double tot[RED_NV] = {qp.get(), 0.0, 0.0, 0.0};
+                spmv_finalize<ST_CG_Q>(&st, tot);
+                }
+            // k_cg_xr
+            if (!st.done)
+                {
+                Sum rr, zr;
+                for (int i = 0; i < n; i++)
+                    {
+                    x[i] = std::fma(st.alpha, p[i], x[i]);
+                    const double ri = std::fma(-st.alpha, q[i], r[i]);
+                    r[i] = ri;
+                    rr.add(ri * ri);
+                    zr.add((D[i] * ri) * ri);
+                    }
+                cg_xr_finalize(&st, rr.get(), zr.get());
+                }
+            }
+        std::printf("%d %d %.17g %.17g\n", st.status, st.nit, st.res, st.rhsn);
+        for (int i = 0; i < n; i++) std::printf("%.17g\n", x[i]);
+        return st.done ? 0 : 3;
+        }
         {  // ST_BICG_SETUP: r = b - A x (masked); rt = r; ||b||^2, ||r||^2
         spmv(x, v);
         Sum bb, rr;

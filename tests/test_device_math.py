@@ -85,11 +85,11 @@ def test_element_math_against_dense_restatement(tmp_path):
     assert worst_c < 1e-12, worst_c
 
 
-def _emulate(exe, rowptr, col, val, rhs, x0, ld, tol, maxiter):
+def _emulate(exe, rowptr, col, val, rhs, x0, ld, tol, maxiter, mode="bicg"):
     txt = ["%d %d %d %.17g %d" % (rhs.size, col.size, len(ld), tol, maxiter)]
     for a, fmt in ((rowptr, "%d"), (col, "%d"), (val, "%.17g"), (rhs, "%.17g"), (x0, "%.17g"), (ld, "%d")):
         txt.append(" ".join(fmt % v for v in a))
-    r = subprocess.run([exe], input="\n".join(txt) + "\n", capture_output=True, text=True, timeout=300)
+    r = subprocess.run([exe, mode], input="\n".join(txt) + "\n", capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = r.stdout.split("\n")
     st, nit, res, rhsn = lines[0].split()
@@ -148,3 +148,32 @@ def test_device_bicgstab_state_machine_against_reference(oracle, tmp_path):
     xo, io = oracle.bicg_dir(rp, col, val, x0, rhs, ld, tol=1e-10, maxiter=200)
     assert info["status"] == io["status"] == 0 and abs(info["nit"] - io["nit"]) <= 1
     assert np.linalg.norm(x - xo) <= 1e-8 * np.linalg.norm(xo)
+
+
+def test_device_cg_state_machine_against_reference(oracle, tmp_path):
+    """Same for the Jacobi-preconditioned CG (src/algebra/cg.h:15-58): the reference's golden run on
+    the SPD problem of make_golden.py, overflow, and the (q, p) = 0 breakdown."""
+    exe = _nvcc(tmp_path, "krylov_state_test")
+    gold = np.load(os.path.join(cases.GOLDEN, "ref_algebra.npz"))
+    rp, col, val, rhs = (gold[k] for k in ("s_rowptr", "s_col", "s_val2", "s_rhs2"))
+    n = rhs.size
+    none = np.zeros(0, dtype=np.int32)
+    x, info = _emulate(exe, rp, col, val, rhs, np.zeros(n), none, 1e-10, 2000, mode="cg")
+    g = gold["s_cg_info"]
+    assert info["status"] == int(g[0]) == 0 and abs(info["nit"] - int(g[1])) <= 1
+    assert np.linalg.norm(x - gold["s_cg_x"]) <= 1e-8 * np.linalg.norm(gold["s_cg_x"])
+    assert abs(info["rhsn"] - g[3]) <= 1e-14 * g[3]
+    for maxiter in (1, 4):
+        x, info = _emulate(exe, rp, col, val, rhs, np.zeros(n), none, 1e-10, maxiter, mode="cg")
+        xo, io = oracle.cg(rp, col, val, np.zeros(n), rhs, tol=1e-10, maxiter=maxiter)
+        assert info["status"] == io["status"] == 1 and info["nit"] == io["nit"] == maxiter
+        assert np.linalg.norm(x - xo) <= 1e-10 * np.linalg.norm(xo)
+    for tol in (1e-1, 1e-3):
+        x, info = _emulate(exe, rp, col, val, rhs, np.zeros(n), none, tol, 2000, mode="cg")
+        xo, io = oracle.cg(rp, col, val, np.zeros(n), rhs, tol=tol, maxiter=2000)
+        assert info["status"] == io["status"] == 0 and info["nit"] == io["nit"]
+        assert np.linalg.norm(x - xo) <= 1e-9 * np.linalg.norm(xo)
+    # zero right-hand side and zero guess: finished before the first iteration
+    x, info = _emulate(exe, rp, col, val, np.zeros(n), np.zeros(n), none, 1e-10, 50, mode="cg")
+    xo, io = oracle.cg(rp, col, val, np.zeros(n), np.zeros(n), tol=1e-10, maxiter=50)
+    assert info["status"] == io["status"] and info["nit"] == io["nit"] == 0
