@@ -160,6 +160,12 @@ __host__ __device__ __forceinline__ void cg_xr_finalize(KState *st, double rr, d
         st->done = 1;
     }
 
+// LinAlgebra::solve's failure predicate (src/solver.cpp:62-69): ITER_OVERFLOW, CANNOT_CONVERGE, or an
+// ABSOLUTE residual above TOL -- a solve that converged relatively (res <= TOL |b|) is still declared
+// failed when |b| > 1 and res > TOL; the time-step controller then halves dt.
+__host__ __device__ __forceinline__ bool solve_failed(const KState *st)
+    { return st->status == FG_ITER_OVERFLOW || st->status == FG_CANNOT_CONVERGE || st->res > st->resmax; }
+
 // iteration::reset (iter.h:92-98) + the Krylov scalars
 __host__ __device__ __forceinline__ void kstate_reset(KState *st, double tol, int maxiter)
     {

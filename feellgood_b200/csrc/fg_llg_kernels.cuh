@@ -20,6 +20,7 @@
 #pragma once
 #include "fg_common.cuh"
 #include "fg_reduce.cuh"
+#include "fg_krylov_state.cuh"
 
 namespace fg
 {
@@ -1041,8 +1042,7 @@ k_update(int NOD, int NOWN, const unsigned char *__restrict__ nonmag, const Node
          double dt, KState *st, const RedBuf red)
     {
     if (!st->done || st->updated) return;
-    const bool failed = st->status == FG_ITER_OVERFLOW || st->status == FG_CANNOT_CONVERGE
-                        || st->res > st->resmax;
+    const bool failed = solve_failed(st);
     double v2max = 0.0;
     if (!failed)
         {

@@ -11,7 +11,7 @@
 //
 // argv[1]: "bicg" (default) | "cg"
 // stdin:  n nnz nmask tol maxiter, then rowptr[n+1], col[nnz], val[nnz], rhs[n], x0[n], mask[nmask]
-// stdout: status nit res rhsn, then x[n]
+// stdout: status nit res rhsn failed (LinAlgebra::solve's predicate, src/solver.cpp:62-69), then x[n]
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -128,7 +128,7 @@ int main(int argc, char **argv)
                 cg_xr_finalize(&st, rr.get(), zr.get());
                 }
             }
-        std::printf("%d %d %.17g %.17g\n", st.status, st.nit, st.res, st.rhsn);
+        std::printf("%d %d %.17g %.17g %d\n", st.status, st.nit, st.res, st.rhsn, (int)solve_failed(&st));
         for (int i = 0; i < n; i++) std::printf("%.17g\n", x[i]);
         return st.done ? 0 : 3;
         }
@@ -217,7 +217,7 @@ int main(int argc, char **argv)
             }
         if (st.done && !st.final_half) break;
         }
-    std::printf("%d %d %.17g %.17g\n", st.status, st.nit, st.res, st.rhsn);
+    std::printf("%d %d %.17g %.17g %d\n", st.status, st.nit, st.res, st.rhsn, (int)solve_failed(&st));
     for (int i = 0; i < n; i++) std::printf("%.17g\n", x[i]);
     return st.done ? 0 : 3;
     }

@@ -92,9 +92,9 @@ def _emulate(exe, rowptr, col, val, rhs, x0, ld, tol, maxiter, mode="bicg"):
     r = subprocess.run([exe, mode], input="\n".join(txt) + "\n", capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = r.stdout.split("\n")
-    st, nit, res, rhsn = lines[0].split()
+    st, nit, res, rhsn, failed = lines[0].split()
     return np.array([float(v) for v in lines[1:1 + rhs.size]]), dict(status=int(st), nit=int(nit), res=float(res),
-                                                                     rhsn=float(rhsn))
+                                                                     rhsn=float(rhsn), failed=bool(int(failed)))
 
 
 def test_device_bicgstab_state_machine_against_reference(oracle, tmp_path):
@@ -141,6 +141,16 @@ def test_device_bicgstab_state_machine_against_reference(oracle, tmp_path):
     x, info = _emulate(exe, rp, col, val_bad, rhs, np.zeros(n), ld, 1e-10, 200)
     xo, io = oracle.bicg_dir(rp, col, val_bad, np.zeros(n), rhs, ld, tol=1e-10, maxiter=200)
     assert info["status"] == io["status"] == 2, (info, io)
+    # (7) LinAlgebra::solve's failure predicate (src/solver.cpp:62-69): overflow and breakdown fail; a
+    #     relatively converged solve still FAILS when the absolute residual exceeds TOL (|b| > 1)
+    x, info = _emulate(exe, rp, col, val, rhs, np.zeros(n), ld, 1e-10, 3)
+    assert info["status"] == 1 and info["failed"]
+    big = 1e6 * rhs                                   # |b| ~ 1e7: res <= TOL |b| but res > TOL
+    x, info = _emulate(exe, rp, col, val, big, np.zeros(n), ld, 1e-6, 200)
+    assert info["status"] == 0 and info["res"] <= 1e-6 * info["rhsn"] and info["res"] > 1e-6 and info["failed"]
+    small = rhs / np.linalg.norm(rhs) * 0.5           # |b| < 1: relative convergence implies res <= TOL
+    x, info = _emulate(exe, rp, col, val, small, np.zeros(n), ld, 1e-6, 200)
+    assert info["status"] == 0 and info["res"] <= 1e-6 and not info["failed"]
     # (6) a non-zero initial guess
     x0 = np.random.default_rng(3).standard_normal(n)
     x0[ld] = 0.0
