@@ -53,6 +53,9 @@ def test_sizes_and_pattern(prepared):
     rp_o, col_o = oc.csr()
     rp_g, col_g = la.csr()
     assert np.array_equal(rp_o, rp_g) and np.array_equal(col_o, col_g)   # bit-exact index work
+    # the element fast path is offered exactly when no magnetic region has K or K3 (fg_get_layout)
+    assert la.iso_fast_path == case.name.startswith("small_cuboid_iso")
+    assert la.col_bytes in (2, 4) and la.stored_pairs * 4 >= la.nnz
 
 
 def test_tet_tables(prepared):
