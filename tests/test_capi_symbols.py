@@ -69,3 +69,10 @@ int main(void){printf("%zu %zu %zu %zu %zu %zu\n", sizeof(fg_tet_prm), sizeof(fg
         sizes = [int(x) for x in subprocess.check_output([exe], text=True).split()]
     assert sizes == [C.sizeof(capi.TetPrm), C.sizeof(capi.TriPrm), C.sizeof(capi.CMesh),
                      C.sizeof(capi.CParams), C.sizeof(capi.StepResult), C.sizeof(capi.IterResult)]
+
+
+def test_every_entry_point_is_documented():
+    """INTEGRATION.md maps every exported entry point to the reference call it replaces."""
+    doc = open(os.path.join(cases.ROOT, "INTEGRATION.md")).read()
+    missing = [s_ for s_ in _declared() if s_ not in doc]
+    assert not missing, missing
