@@ -262,7 +262,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        cb = cpu_leg(args.workload, max(2, min(args.steps, 12)), 1)
+        # K steps of the bounded sample (at most 60, and at most ~25 s of CPU work)
+        cb = cpu_leg(args.workload, max(2, min(args.steps, 60)), 1)
         line = dict(metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=args.gpus, steps=cb["steps"],
                     warmup=1, ms_per_step=1e3 / cb["value"], higher_is_better=True,
                     scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
@@ -418,7 +419,7 @@ def main():
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            cb = cpu_leg(args.workload, 6, 1, budget_s=15.0)
+            cb = cpu_leg(args.workload, 400, 1, budget_s=12.0)   # ~12 s of CPU work on the sample
         except Exception as e:  # the checker is optional for the measurement itself
             cb = dict(error=str(e))
 
