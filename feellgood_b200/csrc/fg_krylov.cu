@@ -11,7 +11,6 @@
 // All kernels are HBM-bandwidth bound: persistent grids of 148 SMs x 8 CTAs, coalesced streams.
 #include <math.h>
 #include <stdio.h>
-#include <stdlib.h>
 
 #include <type_traits>
 
@@ -214,7 +213,7 @@ __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_sell(const Ope
 // stored: the node's own unknowns are recovered from its image, x_a = (ep_a . w_a, eq_a . w_a)
 // (a.x == NULL); the taps and the setup stage pass x.  Same SELL-32 traversal, same fused epilogues
 // as k_spmv_sell.
-template <int STAGE, bool IDX16, bool SYNC>
+template <int STAGE, bool IDX16>
 __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_node3(const Operator op, const SpmvArgs a)
     {
     if (stage_gated(STAGE))
@@ -237,20 +236,8 @@ __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_node3(const Op
         p0 = __ldg(op.ptr + s);
         p1 = __ldg(op.ptr + s + 1);
         }
-    // SYNC (experiment, FG_SPMV_SYNC=1): the 8 warps of a CTA start every group of 8 consecutive slices
-    // together, so that the slices that share gathered columns are in L1 at the same time (an LRU model
-    // of the gather stream predicts 75 % instead of 48 % hits with window 256; the warps otherwise drift
-    // apart because slice widths differ).  The loop then runs on the CTA-uniform group base.
-    int gbase = blockIdx.x * (BLOCK / 32);
-    while (SYNC ? gbase < op.nslice : s < op.nslice)
+    while (s < op.nslice)
         {
-        if (SYNC && s >= op.nslice)
-            {  // a warp without a slice in the last group only keeps the barrier count
-            __syncthreads();
-            gbase += nwarps;
-            s += nwarps;
-            continue;
-            }
         const int sn = s + nwarps;
         int q0 = 0, q1 = 0;
         if (sn < op.nslice)
@@ -326,11 +313,6 @@ __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_node3(const Op
         s = sn;
         p0 = q0;
         p1 = q1;
-        if (SYNC)
-            {
-            __syncthreads();
-            gbase += nwarps;
-            }
         }
     if (!stage_reduces(STAGE)) return;
     double tot[RED_NV];
@@ -398,24 +380,19 @@ static int launch_spmv(const Operator &op, const KrylovWork &w, const SpmvArgs &
     const bool prof = prof_begin(w.prof, w.stream, cls);
     if (op.kind == OP_NODE3)
         {
-        static const bool sync = getenv("FG_SPMV_SYNC") != nullptr && atoi(getenv("FG_SPMV_SYNC")) != 0;
         static int wave = 0, wave16 = 0;
         if (!wave)
             {
-            wave = resident_grid(k_spmv_node3<STAGE, false, false>);
-            wave16 = resident_grid(k_spmv_node3<STAGE, true, false>);
+            wave = resident_grid(k_spmv_node3<STAGE, false>);
+            wave16 = resident_grid(k_spmv_node3<STAGE, true>);
             }
         const int need = (op.nslice + BLOCK / 32 - 1) / (BLOCK / 32);
         const int wv = op.col16 ? wave16 : wave;
         const int grid = need < wv ? (need > 0 ? need : 1) : wv;
-        if (sync && op.col16)
-            k_spmv_node3<STAGE, true, true><<<grid, BLOCK, 0, w.stream>>>(op, a);
-        else if (sync)
-            k_spmv_node3<STAGE, false, true><<<grid, BLOCK, 0, w.stream>>>(op, a);
-        else if (op.col16)
-            k_spmv_node3<STAGE, true, false><<<grid, BLOCK, 0, w.stream>>>(op, a);
+        if (op.col16)
+            k_spmv_node3<STAGE, true><<<grid, BLOCK, 0, w.stream>>>(op, a);
         else
-            k_spmv_node3<STAGE, false, false><<<grid, BLOCK, 0, w.stream>>>(op, a);
+            k_spmv_node3<STAGE, false><<<grid, BLOCK, 0, w.stream>>>(op, a);
         }
     else if (op.kind == OP_SELL2)
         {
