@@ -146,6 +146,8 @@ struct Operator
     const unsigned char *nonmag; // 1 = identity row (node outside the magnetic material, pad row)
     double cS;                   // prefactor * s_dt (src/tetra.cpp:261)
     int prefetch;                // 1: pull the row-epilogue operands and the next slice's indices into L2 early
+    const unsigned char *sghost; // partitioned operator (multi-GPU): 1 = the slice has a ghost column, i.e. it
+                                 // must wait for the halo of its SpMV input; NULL on one GPU
     };
 
 // 256-bit global accesses (sm_100: LDG.E.ENL2.256 / STG.E.ENL2.256): one request per 32-byte node image
@@ -225,7 +227,7 @@ __device__ __forceinline__ void st256(double4 *p, const double4 v)
 enum
     {
     KC_BASIS = 0, KC_TET, KC_TRI, KC_ASSEMBLE, KC_SPMV_SETUP, KC_BICG_P, KC_SPMV_V, KC_BICG_S,
-    KC_SPMV_T, KC_BICG_XR, KC_HALO, KC_UPDATE, KC_OTHER, KC_COUNT
+    KC_SPMV_T, KC_BICG_XR, KC_HALO, KC_UPDATE, KC_SOLVE, KC_OTHER, KC_COUNT
     };
 struct SpmvProf
     {
@@ -235,9 +237,10 @@ struct SpmvProf
     int mode;         // 2: SpMV launches only | 3: every kernel
     };
 inline bool prof_is_spmv(int cls) { return cls == KC_SPMV_SETUP || cls == KC_SPMV_V || cls == KC_SPMV_T; }
+inline bool prof_mode2(int cls) { return prof_is_spmv(cls) || cls == KC_SOLVE; }
 inline bool prof_begin(SpmvProf *p, cudaStream_t s, int cls)
     {
-    if (!p || p->n >= p->cap || (p->mode == 2 && !prof_is_spmv(cls))) return false;
+    if (!p || p->n >= p->cap || (p->mode == 2 && !prof_mode2(cls))) return false;
     p->cls[p->n] = cls;
     cudaEventRecord(p->ev[2 * p->n], s);
     return true;
@@ -272,6 +275,27 @@ struct KrylovWork
     void *arena;
     int halo_grid;
     int nsend;                 // boundary rows this rank pushes to its neighbours
+    // persistent solve kernel (fg_solve_pk.cuh)
+    struct PkSync *pk;         // barrier / reduction scratch (NULL: not allocated)
+    unsigned long long *pk_stamps, *h_pk_stamps;  // device / pinned host: in-kernel phase time stamps
+    int pk_stamp_cap;
+    int pk_stamps_on;
+    double pk_phase_us[16];    // summed in-kernel phase times since the stamps were switched on (PKP_* ids)
+    long long pk_phase_cnt[16];
+    };
+
+// phases of the persistent solve kernel (ids of its in-kernel time stamps)
+enum { PKP_START = 1, PKP_SETUP, PKP_A, PKP_B, PKP_C, PKP_D, PKP_E, PKP_HALO_X, PKP_UPDATE, PKP_END };
+
+// what the persistent solve kernel needs for the fused node update (src/solver.cpp:62-88)
+struct PkUpdate
+    {
+    const unsigned char *nonmag;
+    const NodeRec *cur;
+    NodeRec *next;
+    const Basis *basis;
+    double dt;
+    int NODp, NODt;
     };
 
 
@@ -292,6 +316,9 @@ int spmv(const Operator &op, const KrylovWork &w, const double *x, double *y, bo
 typedef int (*post_batch_fn)(void *user);
 int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, post_batch_fn post,
                  void *user);
+// The same solve (OP_NODE3 only) as ONE persistent cooperative kernel, fused with the node update when
+// upd != NULL (fg_solve_pk.cuh); one host synchronisation per solve.
+int bicgstab_run_pk(const Operator &op, KrylovWork &w, double tol, int maxiter, const PkUpdate *upd);
 // Jacobi-preconditioned CG, reference src/algebra/cg.h:15-58,68-121 (same conventions)
 int cg_run(const Operator &op, KrylovWork &w, double tol, int maxiter);
 // D = 1/diag(A) for a plain CSR operator (src/algebra/sparseMat.h:174-183), then masked

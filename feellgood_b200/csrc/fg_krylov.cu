@@ -213,23 +213,33 @@ __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_sell(const Ope
 // stored: the node's own unknowns are recovered from its image, x_a = (ep_a . w_a, eq_a . w_a)
 // (a.x == NULL); the taps and the setup stage pass x.  Same SELL-32 traversal, same fused epilogues
 // as k_spmv_sell.
-template <int STAGE, bool IDX16>
-__global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_node3(const Operator op, const SpmvArgs a)
+// The slice loop is a device function shared by the stand-alone kernel below and by the persistent solve
+// kernel (fg_solve_pk.cuh).  COH = false: the gathered images are read through the non-coherent path
+// (ld.global.nc: legal only when nothing writes them during the kernel, i.e. one GPU, one kernel per
+// phase); COH = true: plain coherent loads issued as volatile asm, for images that peers (multi-GPU ghost
+// tails) or other CTAs of the same persistent kernel write while it runs.  `pass` selects the slices of a
+// partitioned operator: 0 all, 1 only slices without ghost columns, 2 only slices with ghost columns
+// (op.sghost), so that the interior rows never wait for the halo.
+template <bool COH> __device__ __forceinline__ double4 ld_image(const double4 *p)
     {
-    if (stage_gated(STAGE))
-        if (a.st->done) return;
-    if (STAGE == ST_BICG_V && a.dist != nullptr)
-        {  // the ghost entries of w(D.p) were pushed by the neighbours' k_bicg_p: wait for them
-        if (threadIdx.x == 0) dist_wait(a.dist);
-        __syncthreads();
+    if (COH)
+        {
+        double4 r;
+        asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+        return r;
         }
+    return ld256_nc(p);
+    }
+
+template <int STAGE, bool IDX16, bool COH>
+__device__ __forceinline__ void spmv_node3_slices(const Operator &op, const SpmvArgs &a, int s, const int nwarps,
+                                                  const int lane, const int pass, double (&acc)[RED_NV])
+    {
     typedef typename std::conditional<IDX16, short, int>::type idx_t;
     const idx_t *colbase = IDX16 ? reinterpret_cast<const idx_t *>(op.col16) : reinterpret_cast<const idx_t *>(op.col);
-    const int lane = threadIdx.x & 31;
-    const int nwarps = gridDim.x * (BLOCK / 32);
     const double2 *x2 = reinterpret_cast<const double2 *>(a.x);
-    double acc[RED_NV] = {0.0, 0.0, 0.0, 0.0};
-    int s = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
+    if (pass != 0)  // first slice of this warp that belongs to the pass
+        while (s < op.nslice && (op.sghost[s] != 0) != (pass == 2)) s += nwarps;
     int p0 = 0, p1 = 0;
     if (s < op.nslice)
         {
@@ -238,7 +248,9 @@ __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_node3(const Op
         }
     while (s < op.nslice)
         {
-        const int sn = s + nwarps;
+        int sn = s + nwarps;
+        if (pass != 0)
+            while (sn < op.nslice && (op.sghost[sn] != 0) != (pass == 2)) sn += nwarps;
         int q0 = 0, q1 = 0;
         if (sn < op.nslice)
             {
@@ -283,7 +295,7 @@ __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_node3(const Op
 #pragma unroll
                 for (int u = 0; u < U; u++)
                     {
-                    const double4 wb = ld256_nc(a.w + c[u]);
+                    const double4 wb = ld_image<COH>(a.w + c[u]);
                     z0 += Sv[u] * wb.x;
                     z1 += Sv[u] * wb.y;
                     z2 += Sv[u] * wb.z;
@@ -297,7 +309,7 @@ __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_node3(const Op
             xa = x2[row];
         else
             {  // x_a = P_a^T w_a (ep, eq orthonormal): the line is in L1/L2, the diagonal pair gathered it
-            const double4 wr = ld256_nc(a.w + row);
+            const double4 wr = ld_image<COH>(a.w + row);
             xa = make_double2(ep[0] * wr.x + ep[1] * wr.y + ep[2] * wr.z, eq[0] * wr.x + eq[1] * wr.y + eq[2] * wr.z);
             }
         // node-diagonal part in closed form: Dg = [[a_w, Ma], [Ma, -a_w]] (fg_common.cuh, OP_NODE3)
@@ -314,12 +326,45 @@ __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_node3(const Op
         p0 = q0;
         p1 = q1;
         }
+    }
+
+template <int STAGE, bool IDX16, bool COH>
+__global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_node3(const Operator op, const SpmvArgs a)
+    {
+    if (stage_gated(STAGE))
+        if (a.st->done) return;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * (BLOCK / 32);
+    const int s0 = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
+    double acc[RED_NV] = {0.0, 0.0, 0.0, 0.0};
+    if (COH && STAGE == ST_BICG_V && a.dist != nullptr && op.sghost != nullptr)
+        {  // multi-GPU: the ghost entries of w(D.p) are pushed by the neighbours' k_bicg_p while this kernel
+           // runs.  Rows without ghost columns do not wait; the others are done after the halo flag of
+           // every source rank was seen, and they read the images with coherent loads (COH).
+        spmv_node3_slices<STAGE, IDX16, COH>(op, a, s0, nwarps, lane, 1, acc);
+        if (threadIdx.x == 0) dist_wait(a.dist);
+        __syncthreads();
+        spmv_node3_slices<STAGE, IDX16, COH>(op, a, s0, nwarps, lane, 2, acc);
+        }
+    else
+        {
+        if (STAGE == ST_BICG_V && a.dist != nullptr)
+            {
+            if (threadIdx.x == 0) dist_wait(a.dist);
+            __syncthreads();
+            }
+        spmv_node3_slices<STAGE, IDX16, COH>(op, a, s0, nwarps, lane, 0, acc);
+        }
     if (!stage_reduces(STAGE)) return;
     double tot[RED_NV];
     const int role = grid_reduce<RED_NV>(acc, a.red, tot);
     if (role == 1) spmv_finalize<STAGE>(a.st, tot);
     }
 
+}  // namespace fg
+#include "fg_solve_pk.cuh"
+namespace fg
+{
 // ---- plain CSR (algebra::SparseMatrix of the side solvers): G lanes per row ---------------------
 template <int STAGE>
 __global__ void __launch_bounds__(BLOCK) k_spmv_csr(const Operator op, const SpmvArgs a)
@@ -383,16 +428,25 @@ static int launch_spmv(const Operator &op, const KrylovWork &w, const SpmvArgs &
         static int wave = 0, wave16 = 0;
         if (!wave)
             {
-            wave = resident_grid(k_spmv_node3<STAGE, false>);
-            wave16 = resident_grid(k_spmv_node3<STAGE, true>);
+            wave = resident_grid(k_spmv_node3<STAGE, false, false>);
+            wave16 = resident_grid(k_spmv_node3<STAGE, true, false>);
             }
         const int need = (op.nslice + BLOCK / 32 - 1) / (BLOCK / 32);
         const int wv = op.col16 ? wave16 : wave;
         const int grid = need < wv ? (need > 0 ? need : 1) : wv;
-        if (op.col16)
-            k_spmv_node3<STAGE, true><<<grid, BLOCK, 0, w.stream>>>(op, a);
+        // a distributed context reads the images with coherent loads (peers write the ghost tails while
+        // the consuming kernel runs); one GPU keeps the non-coherent path
+        if (a.dist != nullptr)
+            {
+            if (op.col16)
+                k_spmv_node3<STAGE, true, true><<<grid, BLOCK, 0, w.stream>>>(op, a);
+            else
+                k_spmv_node3<STAGE, false, true><<<grid, BLOCK, 0, w.stream>>>(op, a);
+            }
+        else if (op.col16)
+            k_spmv_node3<STAGE, true, false><<<grid, BLOCK, 0, w.stream>>>(op, a);
         else
-            k_spmv_node3<STAGE, false><<<grid, BLOCK, 0, w.stream>>>(op, a);
+            k_spmv_node3<STAGE, false, false><<<grid, BLOCK, 0, w.stream>>>(op, a);
         }
     else if (op.kind == OP_SELL2)
         {
@@ -834,6 +888,15 @@ int krylov_alloc(KrylovWork &w, int n, int n_ghost, cudaStream_t stream, long lo
     w.red.dist = nullptr;
     FG_CUDA(cudaEventCreateWithFlags(&w.ev_poll, cudaEventDisableTiming));
     w.last_iters = 0;
+    if (node3)
+        {
+        FG_CUDA(cudaMalloc(&w.pk, sizeof(PkSync)));
+        FG_CUDA(cudaMemsetAsync(w.pk, 0, sizeof(PkSync), stream));
+        w.pk_stamp_cap = 8192;
+        FG_CUDA(cudaMalloc(&w.pk_stamps, sizeof(unsigned long long) * w.pk_stamp_cap));
+        FG_CUDA(cudaMemsetAsync(w.pk_stamps, 0, sizeof(unsigned long long) * w.pk_stamp_cap, stream));
+        FG_CUDA(cudaMallocHost(&w.h_pk_stamps, sizeof(unsigned long long) * w.pk_stamp_cap));
+        }
     return FG_OK;
     }
 
@@ -854,6 +917,9 @@ void krylov_free(KrylovWork &w)
     if (w.red.partials) cudaFree(w.red.partials);
     if (w.red.ticket) cudaFree(w.red.ticket);
     if (w.ev_poll) cudaEventDestroy(w.ev_poll);
+    if (w.pk) cudaFree(w.pk);
+    if (w.pk_stamps) cudaFree(w.pk_stamps);
+    if (w.h_pk_stamps) cudaFreeHost(w.h_pk_stamps);
     w = KrylovWork();
     }
 
@@ -1022,6 +1088,104 @@ int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, pos
             return FG_ERR_STATE;
             }
         batch = 4;
+        }
+    w.last_iters = w.h_st->nit;
+    return FG_OK;
+    }
+
+// ------------------------------------------------------------------------------------------
+// BiCGStab as one persistent cooperative kernel (fg_solve_pk.cuh)
+// ------------------------------------------------------------------------------------------
+template <int BS, bool IDX16> static int pk_wave(int sms)
+    {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_llg_solve<BS, IDX16>, BS, 0) != cudaSuccess || per_sm < 1)
+        return 0;
+    return per_sm * sms;
+    }
+
+int bicgstab_run_pk(const Operator &op, KrylovWork &w, double tol, int maxiter, const PkUpdate *upd)
+    {
+    if (op.kind != OP_NODE3 || !w.pk)
+        {
+        set_error("bicgstab_run_pk: needs the matrix-free LLG operator");
+        return FG_ERR_STATE;
+        }
+    int dev = 0, sms = NUM_SMS;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // CTA size: 1024 threads (one CTA per SM, 148 arrivals per barrier) once every warp of such a grid has a
+    // slice of its own; 256 threads below that, so that small meshes still spread over all SMs
+    static const int forced = getenv("FG_PK_BLOCK") ? atoi(getenv("FG_PK_BLOCK")) : 0;
+    int bs = op.nslice >= sms * 32 ? 1024 : 256;
+    if (forced == 256 || forced == 1024) bs = forced;
+    const bool i16 = op.col16 != nullptr;
+    int wave = bs == 1024 ? (i16 ? pk_wave<1024, true>(sms) : pk_wave<1024, false>(sms))
+                          : (i16 ? pk_wave<256, true>(sms) : pk_wave<256, false>(sms));
+    if (wave < 1)
+        {
+        set_error("bicgstab_run_pk: the solve kernel does not fit an SM");
+        return FG_ERR_CUDA;
+        }
+    if (wave > PK_MAX_GRID) wave = PK_MAX_GRID;
+    int grid = (op.nslice + bs / 32 - 1) / (bs / 32);
+    if (grid > wave) grid = wave;
+    if (grid < 1) grid = 1;
+    PkArgs a = {};
+    a.op = op;
+    a.NODp = w.n / 2;
+    a.NODt = w.nx / 2;
+    a.x = w.x; a.b = w.b; a.r = w.r; a.rt = w.rt; a.p = w.p; a.p2 = w.p2; a.v = w.v; a.s = w.s; a.t = w.t;
+    a.D = w.D;
+    a.w3p = w.w3p;
+    a.w3s = w.w3s;
+    a.mask = w.mask;
+    a.st = w.st;
+    a.sync = w.pk;
+    a.dist = w.dist;
+    a.tol = tol;
+    a.maxiter = maxiter;
+    if (upd)
+        {
+        a.nonmag = upd->nonmag;
+        a.cur = upd->cur;
+        a.next = upd->next;
+        a.basis = upd->basis;
+        a.dt = upd->dt;
+        a.NODp = upd->NODp;
+        a.NODt = upd->NODt;
+        }
+    a.stamps = w.pk_stamps_on ? w.pk_stamps : nullptr;
+    a.stamp_cap = w.pk_stamp_cap - 1;
+    void *args[] = {&a};
+    const void *fn = bs == 1024 ? (i16 ? (const void *)k_llg_solve<1024, true> : (const void *)k_llg_solve<1024, false>)
+                                : (i16 ? (const void *)k_llg_solve<256, true> : (const void *)k_llg_solve<256, false>);
+    const bool prof = prof_begin(w.prof, w.stream, KC_SOLVE);
+    FG_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(bs), args, 0, w.stream));
+    if (prof) prof_end(w.prof, w.stream);
+    if (w.launches) ++*w.launches;
+    if (w.pk_stamps_on)
+        FG_CUDA(cudaMemcpyAsync(w.h_pk_stamps, w.pk_stamps, sizeof(unsigned long long) * w.pk_stamp_cap,
+                                cudaMemcpyDeviceToHost, w.stream));
+    FG_TRY(poll_state(w));
+    if (w.pk_stamps_on)
+        {  // phase X = time between the stamp closing X and the previous stamp, as CTA 0 saw it
+        unsigned long long prev = 0;
+        for (int k = 0; k < w.pk_stamp_cap && w.h_pk_stamps[k] != 0ull; k++)
+            {
+            const int id = (int)(w.h_pk_stamps[k] >> 56);
+            const unsigned long long t = w.h_pk_stamps[k] & 0x00ffffffffffffffull;
+            if (k > 0 && id > 0 && id < 16)
+                {
+                w.pk_phase_us[id] += 1e-3 * (double)(t - prev);
+                w.pk_phase_cnt[id]++;
+                }
+            prev = t;
+            }
+        }
+    if (!w.h_st->done)
+        {
+        set_error("bicgstab_run_pk: the solve kernel returned without finishing");
+        return FG_ERR_STATE;
         }
     w.last_iters = w.h_st->nit;
     return FG_OK;

@@ -79,6 +79,8 @@ struct fg_ctx
     double *val = nullptr;       // assembled 2x2 blocks of K: only the parity tap materialises them
     Operator op_K = {};          // the assembled-K operator of the tap (OP_SELL2)
     bool use_blocks = false;     // fg_set_operator(ctx, 1): solve with the assembled 2x2 blocks (A/B checks)
+    int solver_kind = 0;         // fg_set_solver: 0 persistent kernel, 1 one kernel per phase
+    unsigned char *sghost = nullptr;  // multi-GPU: slices with a ghost column
     KrylovWork kw;
     Operator op;
     // energies / averages / max angle: tables built on first use
@@ -324,7 +326,20 @@ int run_solve(fg_ctx *c, double dt, fg_step_result *out)
     if (c->profiling) FG_CUDA(cudaEventRecord(c->ev[2], c->stream));
     FG_TRY(launch_assemble(c, dt));
     if (c->profiling) FG_CUDA(cudaEventRecord(c->ev[3], c->stream));
-    FG_TRY(bicgstab_run(c->use_blocks ? c->op_K : c->op, c->kw, c->tol, c->maxiter, post_update, c));
+    if (c->solver_kind == 0 && !c->use_blocks)
+        {
+        PkUpdate upd;
+        upd.nonmag = c->nonmag;
+        upd.cur = c->cur;
+        upd.next = c->next;
+        upd.basis = c->basis;
+        upd.dt = c->sp.dt;
+        upd.NODp = c->NODp;
+        upd.NODt = c->NODt;
+        FG_TRY(bicgstab_run_pk(c->op, c->kw, c->tol, c->maxiter, &upd));
+        }
+    else
+        FG_TRY(bicgstab_run(c->use_blocks ? c->op_K : c->op, c->kw, c->tol, c->maxiter, post_update, c));
     if (c->profiling)
         {
         FG_CUDA(cudaEventRecord(c->ev[4], c->stream));
@@ -652,6 +667,19 @@ static int create_ctx(const fg_mesh *mesh, const fg_params *prm, int device, con
             }
         if (fits && ne > 0) CK(dev_upload(&c->scol16, c16, s));
         }
+    if (dd)
+        {  // slices that gather a ghost entry: they wait for the halo, the others do not (fg_solve_pk.cuh)
+        std::vector<unsigned char> sg((size_t)h.nslice, 0);
+#pragma omp parallel for schedule(static)
+        for (int sl = 0; sl < h.nslice; sl++)
+            {
+            unsigned char g = 0;
+            for (size_t pos = (size_t)h.sptr[sl] * SLICE; pos < (size_t)h.sptr[sl + 1] * SLICE && !g; pos++)
+                if (h.scol[pos] >= h.NODp) g = 1;
+            sg[(size_t)sl] = g;
+            }
+        CK(dev_upload(&c->sghost, sg, s));
+        }
     CK(dev_upload(&c->sdeg, h.sdeg, s));
     CK(dev_upload(&c->sS, h.sS, s));
     CK(dev_upload(&c->iptr, h.iptr, s));
@@ -737,6 +765,11 @@ static int create_ctx(const fg_mesh *mesh, const fg_params *prm, int device, con
     c->op.cS = 0.0;
     // early L2 prefetch of the SpMV row-epilogue operands; FG_SPMV_PF=0 switches it off (A/B)
     c->op.prefetch = getenv("FG_SPMV_PF") ? atoi(getenv("FG_SPMV_PF")) : 1;
+    c->op.sghost = c->sghost;
+        {
+        const char *sv = getenv("FG_SOLVER");
+        c->solver_kind = (sv && (!strcmp(sv, "multi") || !strcmp(sv, "1"))) ? 1 : 0;
+        }
     for (int k = 0; k < 5; k++) CKCUDA(cudaEventCreate(&c->ev[k]));
     CKCUDA(cudaStreamSynchronize(s));
     // the per-mesh host tables no longer needed are released (their SELL images are on the device)
@@ -856,7 +889,7 @@ void fg_destroy(fg_ctx *c)
                     c->tet_detJ, c->ext_field, c->tet_reg, c->reg_tet, c->rec, c->tri_ind,
                     c->tri_reg, c->tri_surf, c->tri_dMs, c->reg_tri, c->trec, c->perm, c->sptr,
                     c->scol, c->sdeg, c->iptr, c->tet_slot, c->itptr, c->sinct, c->sS, c->Aw, c->val, c->Sdiag, c->Dm, c->qbasis,
-                    c->scol16, c->mtri_ind, c->mtri_reg, c->mtri_surf, c->mtri_nrm, c->mtri_dMs, c->extra_edges,
+                    c->scol16, c->sghost, c->mtri_ind, c->mtri_reg, c->mtri_surf, c->mtri_nrm, c->mtri_dMs, c->extra_edges,
                     c->d_scal, c->node_pos, c->corr, c->tcorr, c->src, c->cptr, c->cidx};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -1825,9 +1858,60 @@ int fg_set_profiling(fg_ctx *c, int on)
         c->prof.n = 0;
         c->prof.mode = on;
         c->kw.prof = &c->prof;
+        c->kw.pk_stamps_on = 1;
+        for (int k = 0; k < 16; k++)
+            {
+            c->kw.pk_phase_us[k] = 0.0;
+            c->kw.pk_phase_cnt[k] = 0;
+            }
         }
     else
+        {
         c->kw.prof = nullptr;
+        c->kw.pk_stamps_on = 0;
+        }
+    return FG_OK;
+    }
+
+int fg_set_solver(fg_ctx *c, int kind)
+    {
+    FG_TRY(check_ctx(c));
+    if (kind != 0 && kind != 1)
+        {
+        set_error("fg_set_solver: kind must be 0 (persistent kernel) or 1 (one kernel per phase)");
+        return FG_ERR_INVALID;
+        }
+    c->solver_kind = kind;
+    return FG_OK;
+    }
+
+int fg_get_solve_times(fg_ctx *c, double ms[9], long long count[9])
+    {
+    FG_TRY(check_ctx(c));
+    if (!ms || !count)
+        {
+        set_error("fg_get_solve_times: null argument");
+        return FG_ERR_INVALID;
+        }
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 9; k++)
+        {
+        ms[k] = 0.0;
+        count[k] = 0;
+        }
+    for (int k = 0; k < c->prof.n; k++)
+        {
+        if (c->prof.cls[k] != KC_SOLVE) continue;
+        float t = 0.f;
+        FG_CUDA(cudaEventElapsedTime(&t, c->prof.ev[2 * k], c->prof.ev[2 * k + 1]));
+        ms[0] += t;
+        count[0]++;
+        }
+    for (int id = PKP_SETUP; id <= PKP_UPDATE; id++)
+        {
+        ms[id - PKP_SETUP + 1] = 1e-3 * c->kw.pk_phase_us[id];
+        count[id - PKP_SETUP + 1] = c->kw.pk_phase_cnt[id];
+        }
     return FG_OK;
     }
 

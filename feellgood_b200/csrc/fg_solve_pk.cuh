@@ -1,0 +1,601 @@
+// fg_solve_pk.cuh — LinAlgebra::solve's Krylov part (src/solver.cpp:50-88: bicg_dir + node update) as ONE
+// persistent cooperative kernel.  Included by fg_krylov.cu after the SpMV slice loop.
+//
+// The multi-kernel driver (bicgstab_run) pays a launch ramp, a last-CTA reduction tail and a kernel drain
+// on each of its 5 kernels per iteration; at the per-rank size of an 8-GPU run (or on the reference's own
+// 10^4..10^6-tetrahedron meshes) those fixed costs are larger than the memory time of the kernels.  Here
+// the grid is resident for the whole solve:
+//   * static row ownership: warp g of the grid owns the SELL slices g, g + nwarps, ... in every phase, so
+//     every Krylov vector entry (r, p, v, s, t, x) is produced and consumed by the same thread; the only
+//     data that crosses threads are the 3-vector images w gathered by the SpMV and the scalars;
+//   * 5 grid-wide synchronisations per iteration (reference order src/algebra/bicg.h:185-232):
+//       A  p = r + beta (p - omega v), w_p = P D p            | barrier (+ halo flag)
+//       B  v = K D p, (v, rt)                                 | reduce  -> alpha
+//       C  s = r - alpha v, w_s = P D s, |s|^2                | one GPU: reduce -> exit test;
+//                                                             | multi-GPU: barrier only (+ halo flag), |s|^2
+//                                                             | travels with the next reduction and t is
+//                                                             | computed speculatively (discarded on exit)
+//       D  t = K D s, (t, s), (t, t)                          | reduce  -> omega
+//       E  x += alpha D p + omega D s, r = s - omega t        | reduce  -> rho, loop test
+//     i.e. 3 cross-GPU all-reduces per iteration instead of 4;
+//   * the barrier is a generation counter in global memory; the LAST arriving CTA sums the CTA partials
+//     in index order (error-free, fg_reduce.cuh), runs the cross-GPU all-reduce (fg_dist.cuh), raises the
+//     halo flags of the phase it closes and only then releases the generation, so every CTA of every rank
+//     reads bit-identical totals and runs the scalar state machine (fg_krylov_state.cuh) redundantly on a
+//     shared-memory copy of KState: no broadcast kernel, no host round trip until the solve is over;
+//   * multi-GPU: boundary images are pushed into the neighbours' ghost tails by the first CTAs at the
+//     start of phases A and C; slices with ghost columns are processed last in B and D, after the halo
+//     flag of every source was seen, so interior rows never wait for NVLink;
+//   * the node update of src/solver.cpp:62-88 (gated on the failure predicate) is the last phase.
+// Memory-model notes: a release/acquire pair at gpu scope (fence + atomic arrive / flag poll + fence by
+// thread 0, bar.sync around them) orders every CTA's writes before every other CTA's later reads; the
+// acquire fence also drops stale L1 lines.  Images are gathered with plain (coherent) loads issued as
+// volatile asm (ld_image<true>), never through ld.global.nc.
+#pragma once
+
+namespace fg
+{
+constexpr int PK_MAX_GRID = 1024;
+
+struct PkSync  // one per context, device memory, zeroed at creation
+    {
+    unsigned int count;  // arrivals at the open barrier
+    unsigned int pad0[31];
+    unsigned int gen;    // generation of the last released barrier
+    unsigned int pad1[31];
+    double tot[2][RED_NV];                    // totals of the last two reductions (slot = parity)
+    double part[2][2 * RED_NV][PK_MAX_GRID];  // CTA partials (values, then compensations)
+    };
+
+struct PkArgs
+    {
+    Operator op;
+    int NODp, NODt;
+    double *x, *b, *r, *rt, *p, *p2, *v, *s, *t;
+    const double *D;
+    double4 *w3p, *w3s;
+    const unsigned char *mask;
+    KState *st;
+    PkSync *sync;
+    DistDev *dist;
+    double tol;
+    int maxiter;
+    // fused node update (cur == NULL: none)
+    const unsigned char *nonmag;
+    const NodeRec *cur;
+    NodeRec *next;
+    const Basis *basis;
+    double dt;
+    unsigned long long *stamps;  // optional [cap] (phase id << 56 | globaltimer ns), written by CTA 0
+    int stamp_cap;
+    };
+
+
+template <int BS> struct PkShared
+    {
+    KState ks;
+    double red_s[RED_NV][BS / 32], red_e[RED_NV][BS / 32];
+    double tot[2 * RED_NV];
+    unsigned int gen;            // barrier generation this CTA waits for next (thread 0)
+    unsigned int nred;           // reductions so far (slot parity)
+    unsigned long long hepoch;   // halo epoch this CTA expects next
+    int nstamp;
+    };
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p)
+    {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+    }
+__device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v)
+    { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+template <int BS> __device__ __forceinline__ void pk_stamp(const PkArgs &a, PkShared<BS> &sh, int id)
+    {
+    if (a.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && sh.nstamp < a.stamp_cap)
+        a.stamps[sh.nstamp++] = ((unsigned long long)id << 56) | (now_ns() & 0x00ffffffffffffffull);
+    }
+
+// Grid barrier with an optional sum (NV > 0) or maximum (MAXOP) over the grid and the ranks.
+// halo: 0 none, 1 raise the halo flags on the neighbours when the barrier closes (every CTA's pushes of
+// this phase are then complete and fenced).  On return sh.tot[0..NV) holds the totals (all threads).
+template <int BS, int NV, bool MAXOP>
+__device__ void pk_sync(const PkArgs &a, PkShared<BS> &sh, const double (&acc)[RED_NV], const int halo)
+    {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int NW = BS / 32;
+    if (NV > 0)
+        {
+#pragma unroll
+        for (int k = 0; k < NV; k++)
+            {
+            double s = acc[k], e = 0.0;
+            if (MAXOP)
+                {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(0xffffffffu, s, o));
+                }
+            else
+                warp_sum_dd(s, e);
+            if (lane == 0)
+                {
+                sh.red_s[k][wid] = s;
+                sh.red_e[k][wid] = e;
+                }
+            }
+        }
+    __syncthreads();  // every thread's phase work (and its partial) is done
+    if (wid == 0)
+        {
+        const bool solo = gridDim.x == 1 && a.dist == nullptr;
+        const unsigned int slot = sh.nred & 1u;
+        // CTA partial, fixed tree
+        double ps[NV > 0 ? NV : 1], pe[NV > 0 ? NV : 1];
+        if (NV > 0)
+            {
+#pragma unroll
+            for (int k = 0; k < NV; k++)
+                {
+                double s = lane < NW ? sh.red_s[k][lane] : 0.0, e = lane < NW ? sh.red_e[k][lane] : 0.0;
+                if (MAXOP)
+                    {
+                    if (lane >= NW) s = -1.7976931348623157e308;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(0xffffffffu, s, o));
+                    }
+                else
+                    warp_sum_dd(s, e);
+                ps[k] = s;
+                pe[k] = e;
+                }
+            }
+        if (solo)
+            {
+            if (NV > 0 && lane == 0)
+                {
+#pragma unroll
+                for (int k = 0; k < NV; k++) sh.tot[k] = MAXOP ? ps[k] : ps[k] + pe[k];
+                }
+            }
+        else
+            {
+            if (NV > 0 && lane == 0)
+                {
+#pragma unroll
+                for (int k = 0; k < NV; k++)
+                    {
+                    a.sync->part[slot][k][blockIdx.x] = ps[k];
+                    if (!MAXOP) a.sync->part[slot][RED_NV + k][blockIdx.x] = pe[k];
+                    }
+                }
+            unsigned int last = 0;
+            unsigned int target = 0;
+            if (lane == 0)
+                {
+                target = ++sh.gen;
+                __threadfence();  // release (peer-memory pushes were fenced at system scope by their threads)
+                last = atomicAdd(&a.sync->count, 1u) == gridDim.x - 1 ? 1u : 0u;
+                }
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last)
+                {  // the whole warp: every CTA's partial is in
+                __threadfence();
+                if (NV > 0)
+                    {
+#pragma unroll
+                    for (int k = 0; k < NV; k++)
+                        {
+                        double s = MAXOP ? -1.7976931348623157e308 : 0.0, e = 0.0;
+                        for (int i = lane; i < (int)gridDim.x; i += 32)
+                            {
+                            if (MAXOP)
+                                s = fmax(s, __ldcg(&a.sync->part[slot][k][i]));
+                            else
+                                dd_add(s, e, __ldcg(&a.sync->part[slot][k][i]), __ldcg(&a.sync->part[slot][RED_NV + k][i]));
+                            }
+                        if (MAXOP)
+                            {
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(0xffffffffu, s, o));
+                            }
+                        else
+                            warp_sum_dd(s, e);
+                        if (lane == 0)
+                            {
+                            sh.tot[k] = s;
+                            sh.tot[NV + k] = e;
+                            }
+                        }
+                    __syncwarp();
+                    if (a.dist != nullptr) dist_allreduce_warp(a.dist, sh.tot, NV, MAXOP);
+                    }
+                if (lane == 0)
+                    {
+                    if (NV > 0)
+                        {
+#pragma unroll
+                        for (int k = 0; k < NV; k++) a.sync->tot[slot][k] = MAXOP ? sh.tot[k] : sh.tot[k] + sh.tot[NV + k];
+                        }
+                    a.sync->count = 0;
+                    if (halo && a.dist != nullptr) dist_raise(a.dist);  // fence.sys + flags on the neighbours
+                    __threadfence();
+                    st_release_u32(&a.sync->gen, target);
+                    }
+                }
+            else if (lane == 0)
+                {
+                while (ld_acquire_u32(&a.sync->gen) != target)
+                    ;
+                __threadfence();
+                }
+            __syncwarp();
+            if (NV > 0 && lane < NV) sh.tot[lane] = __ldcg(&a.sync->tot[slot][lane]);
+            }
+        if (lane == 0)
+            {
+            if (NV > 0) sh.nred++;
+            if (halo) sh.hepoch++;
+            }
+        }
+    __syncthreads();
+    }
+
+// multi-GPU consumer side: one lane waits until every source rank has raised halo epoch e
+__device__ inline void pk_halo_wait(DistDev *d, unsigned long long e)
+    {
+    if (d->error) return;
+    DistCtrl *me = d->ctrl[d->rank];
+    for (int src = 0; src < d->world; src++)
+        if (d->recv_from[src] && !wait_flag(&me->hflag[src], e))
+            {
+            d->error = 1;
+            return;
+            }
+    __threadfence_system();
+    }
+
+template <int STAGE, bool IDX16, int BS>
+__device__ __forceinline__ void pk_spmv(const PkArgs &a, PkShared<BS> &sh, const SpmvArgs &sa, const int g0,
+                                        const int nwarps, const int lane, const bool wait_halo, double (&acc)[RED_NV])
+    {
+    if (a.dist != nullptr && a.op.sghost != nullptr && wait_halo)
+        {
+        spmv_node3_slices<STAGE, IDX16, true>(a.op, sa, g0, nwarps, lane, 1, acc);
+        // the slices with ghost columns: wait for the neighbours' pushes of this phase (per warp: only
+        // warps that own such a slice wait)
+        int s = g0;
+        while (s < a.op.nslice && a.op.sghost[s] == 0) s += nwarps;
+        if (s < a.op.nslice)
+            {
+            if (lane == 0) pk_halo_wait(a.dist, sh.hepoch - 1);
+            __syncwarp();
+            spmv_node3_slices<STAGE, IDX16, true>(a.op, sa, g0, nwarps, lane, 2, acc);
+            }
+        }
+    else
+        spmv_node3_slices<STAGE, IDX16, true>(a.op, sa, g0, nwarps, lane, 0, acc);
+    }
+
+template <int BS, bool IDX16>
+__global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(const PkArgs a)
+    {
+    __shared__ PkShared<BS> sh;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * (BS / 32);
+    const int g0 = blockIdx.x * (BS / 32) + (threadIdx.x >> 5);  // first slice of this warp
+    const int gtid = blockIdx.x * BS + threadIdx.x, gthreads = gridDim.x * BS;
+    const int nslice = a.op.nslice;
+    const bool spec = a.dist != nullptr;  // speculative second SpMV: one all-reduce less per iteration
+    if (threadIdx.x == 0)
+        {
+        sh.ks = *a.st;
+        kstate_reset(&sh.ks, a.tol, a.maxiter);
+        if (blockIdx.x != 0) sh.ks.hist = nullptr;  // the history is recorded once
+        sh.gen = ld_acquire_u32(&a.sync->gen);
+        sh.nred = 0;
+        sh.hepoch = a.dist != nullptr ? a.dist->hepoch + 1 : 1;
+        sh.nstamp = 0;
+        }
+    __syncthreads();
+    pk_stamp(a, sh, PKP_START);
+    double acc[RED_NV];
+    const double2 *D2 = reinterpret_cast<const double2 *>(a.D);
+    SpmvArgs sa = {};
+    sa.mask = a.mask;
+
+    // ---- r = b - K x0 (masked); rt = r (p = r implicit); |b|^2, |r|^2           (bicg.h:172-183)
+#pragma unroll
+    for (int k = 0; k < RED_NV; k++) acc[k] = 0.0;
+    sa.w = a.w3p;  // image of the initial guess, written by the assembly (ghost rows: k_ghost_guess)
+    sa.x = a.x;
+    sa.y = a.r;
+    sa.a0 = a.b;
+    sa.o0 = a.rt;
+    spmv_node3_slices<ST_BICG_SETUP, IDX16, true>(a.op, sa, g0, nwarps, lane, 0, acc);
+    pk_sync<BS, 2, false>(a, sh, acc, 0);
+    if (threadIdx.x == 0)
+        {
+        const double tot[RED_NV] = {sh.tot[0], sh.tot[1], 0.0, 0.0};
+        spmv_finalize<ST_BICG_SETUP>(&sh.ks, tot);
+        }
+    __syncthreads();
+    pk_stamp(a, sh, PKP_SETUP);
+
+    int it = 0;
+    double *p_new = a.p;  // the direction of the last completed phase A
+    while (!sh.ks.done)
+        {
+        // ---- A: p = r + beta (p - omega v) ; w_p = P D p                        (bicg.h:196-202)
+        const double2 *p_old2 = reinterpret_cast<const double2 *>((it & 1) ? a.p2 : a.p);
+        p_new = (it & 1) ? a.p : a.p2;
+            {
+            const bool first = sh.ks.nit == 0;
+            const double omega = sh.ks.omega;
+            const double beta = first ? 0.0 : bicg_beta(&sh.ks);
+            const double2 *r2 = reinterpret_cast<const double2 *>(a.r), *v2 = reinterpret_cast<const double2 *>(a.v);
+            auto value = [&](int row, double2 &pi)
+                {
+                const double2 rr = r2[row], d = D2[row];
+                if (first)
+                    pi = rr;  // p = r (bicg.h:183)
+                else
+                    {
+                    const double2 pp = p_old2[row], vv = v2[row];
+                    pi = make_double2(bicg_p_value(pp.x, vv.x, rr.x, omega, beta), bicg_p_value(pp.y, vv.y, rr.y, omega, beta));
+                    }
+                return make_double2(d.x * pi.x, d.y * pi.y);
+                };
+            if (a.dist != nullptr)
+                dist_push(a.dist, a.dist->wtail[0], gtid, gthreads, [&](int row)
+                    {
+                    double2 pi;
+                    const double2 ph = value(row, pi);
+                    return node_w(a.op.qbasis + row, ph.x, ph.y);
+                    });
+            for (int s = g0; s < nslice; s += nwarps)
+                {
+                const int row = s * SLICE + lane;
+                double2 pi;
+                const double2 ph = value(row, pi);
+                reinterpret_cast<double2 *>(p_new)[row] = pi;
+                st256(a.w3p + row, node_w(a.op.qbasis + row, ph.x, ph.y));
+                }
+            }
+        pk_sync<BS, 0, false>(a, sh, acc, 1);
+        pk_stamp(a, sh, PKP_A);
+
+        // ---- B: v = K D p (masked) ; (v, rt) -> alpha                           (bicg.h:203-206)
+#pragma unroll
+        for (int k = 0; k < RED_NV; k++) acc[k] = 0.0;
+        sa.w = a.w3p;
+        sa.x = nullptr;
+        sa.y = a.v;
+        sa.a0 = a.rt;
+        sa.o0 = nullptr;
+        pk_spmv<ST_BICG_V, IDX16, BS>(a, sh, sa, g0, nwarps, lane, true, acc);
+        pk_sync<BS, 1, false>(a, sh, acc, 0);
+        if (threadIdx.x == 0)
+            {
+            const double tot[RED_NV] = {sh.tot[0], 0.0, 0.0, 0.0};
+            spmv_finalize<ST_BICG_V>(&sh.ks, tot);
+            }
+        __syncthreads();
+        pk_stamp(a, sh, PKP_B);
+
+        // ---- C: s = r - alpha v ; w_s = P D s ; |s|^2                           (bicg.h:207-218)
+        double ss_acc = 0.0;
+            {
+            const double alpha = sh.ks.alpha;
+            const double2 *r2 = reinterpret_cast<const double2 *>(a.r), *v2 = reinterpret_cast<const double2 *>(a.v);
+            auto value = [&](int row, double2 &si)
+                {
+                const double2 rr = r2[row], vv = v2[row], d = D2[row];
+                si = make_double2(bicg_s_value(rr.x, vv.x, alpha), bicg_s_value(rr.y, vv.y, alpha));
+                return make_double2(d.x * si.x, d.y * si.y);
+                };
+            if (a.dist != nullptr)
+                dist_push(a.dist, a.dist->wtail[1], gtid, gthreads, [&](int row)
+                    {
+                    double2 si;
+                    const double2 sh_ = value(row, si);
+                    return node_w(a.op.qbasis + row, sh_.x, sh_.y);
+                    });
+            for (int s = g0; s < nslice; s += nwarps)
+                {
+                const int row = s * SLICE + lane;
+                double2 si;
+                const double2 sh_ = value(row, si);
+                reinterpret_cast<double2 *>(a.s)[row] = si;
+                st256(a.w3s + row, node_w(a.op.qbasis + row, sh_.x, sh_.y));
+                ss_acc += si.x * si.x + si.y * si.y;
+                }
+            }
+        if (!spec)
+            {
+            acc[0] = ss_acc;
+            pk_sync<BS, 1, false>(a, sh, acc, 0);
+            if (threadIdx.x == 0) bicg_s_finalize(&sh.ks, sh.tot[0]);
+            __syncthreads();
+            }
+        else
+            pk_sync<BS, 0, false>(a, sh, acc, 1);
+        pk_stamp(a, sh, PKP_C);
+
+        // ---- D: t = K D s (masked) ; (t, s), (t, t) -> omega                    (bicg.h:219-222)
+        if (spec || !sh.ks.done)
+            {
+#pragma unroll
+            for (int k = 0; k < RED_NV; k++) acc[k] = 0.0;
+            sa.w = a.w3s;
+            sa.x = nullptr;
+            sa.y = a.t;
+            sa.a0 = a.s;
+            pk_spmv<ST_BICG_T, IDX16, BS>(a, sh, sa, g0, nwarps, lane, true, acc);
+            if (spec)
+                {
+                acc[2] = ss_acc;
+                pk_sync<BS, 3, false>(a, sh, acc, 0);
+                if (threadIdx.x == 0)
+                    {
+                    bicg_s_finalize(&sh.ks, sh.tot[2]);
+                    if (!sh.ks.done)
+                        {
+                        const double tot[RED_NV] = {sh.tot[0], sh.tot[1], 0.0, 0.0};
+                        spmv_finalize<ST_BICG_T>(&sh.ks, tot);
+                        }
+                    }
+                }
+            else
+                {
+                pk_sync<BS, 2, false>(a, sh, acc, 0);
+                if (threadIdx.x == 0)
+                    {
+                    const double tot[RED_NV] = {sh.tot[0], sh.tot[1], 0.0, 0.0};
+                    spmv_finalize<ST_BICG_T>(&sh.ks, tot);
+                    }
+                }
+            __syncthreads();
+            }
+        pk_stamp(a, sh, PKP_D);
+
+        // ---- E: x += alpha D p + omega D s ; r = s - omega t ; |r|^2, (rt, r)   (bicg.h:223-231, :185-195)
+        //      (loop ended on |s|: only x += alpha D p)
+            {
+            const int fh = sh.ks.final_half;
+            const bool skip = sh.ks.done && !fh;  // overflow / breakdown seen at the |s| test: x stays
+            const double alpha = sh.ks.alpha, omega = sh.ks.omega;
+            double2 *x2 = reinterpret_cast<double2 *>(a.x), *r2 = reinterpret_cast<double2 *>(a.r);
+            const double2 *p2 = reinterpret_cast<const double2 *>(p_new), *s2 = reinterpret_cast<const double2 *>(a.s),
+                          *t2 = reinterpret_cast<const double2 *>(a.t), *rt2 = reinterpret_cast<const double2 *>(a.rt);
+#pragma unroll
+            for (int k = 0; k < RED_NV; k++) acc[k] = 0.0;
+            if (skip)
+                ;
+            else if (fh)
+                {
+                for (int s = g0; s < nslice; s += nwarps)
+                    {
+                    const int row = s * SLICE + lane;
+                    const double2 d = D2[row], pp = p2[row];
+                    double2 xv = x2[row];
+                    xv.x += alpha * __dmul_rn(d.x, pp.x);
+                    xv.y += alpha * __dmul_rn(d.y, pp.y);
+                    x2[row] = xv;
+                    }
+                }
+            else
+                {
+                for (int s = g0; s < nslice; s += nwarps)
+                    {
+                    const int row = s * SLICE + lane;
+                    const double2 d = D2[row], pp = p2[row], sv = s2[row], tv = t2[row], rtv = rt2[row];
+                    double2 xv = x2[row];
+                    xv.x = (xv.x + alpha * __dmul_rn(d.x, pp.x)) + omega * __dmul_rn(d.x, sv.x);
+                    xv.y = (xv.y + alpha * __dmul_rn(d.y, pp.y)) + omega * __dmul_rn(d.y, sv.y);
+                    x2[row] = xv;
+                    const double2 ri = make_double2(sv.x - omega * tv.x, sv.y - omega * tv.y);
+                    r2[row] = ri;
+                    acc[0] += ri.x * ri.x + ri.y * ri.y;
+                    acc[1] += rtv.x * ri.x + rtv.y * ri.y;
+                    }
+                }
+            if (!sh.ks.done)
+                {
+                pk_sync<BS, 2, false>(a, sh, acc, 0);
+                if (threadIdx.x == 0) bicg_xr_finalize(&sh.ks, sh.tot[0], sh.tot[1], 0);
+                }
+            else
+                {  // the loop is over.  Multi-GPU: the x halo below reads rows of other CTAs
+                if (a.dist != nullptr)
+                    pk_sync<BS, 0, false>(a, sh, acc, 0);
+                else
+                    __syncthreads();  // every warp has read final_half
+                if (threadIdx.x == 0 && fh) bicg_xr_finalize(&sh.ks, 0.0, 0.0, 1);  // clears final_half
+                }
+            __syncthreads();
+            }
+        pk_stamp(a, sh, PKP_E);
+        it++;
+        }
+
+    // ---- node update (src/solver.cpp:62-88), gated on the failure predicate -----------------------
+    if (a.cur != nullptr)
+        {
+        const bool failed = solve_failed(&sh.ks);
+        const double2 *x2 = reinterpret_cast<const double2 *>(a.x);
+        if (a.dist != nullptr)
+            {  // the solution of my boundary rows goes into the neighbours' ghost tails of x
+            // x of rows owned by other CTAs was written before the last grid barrier of the loop
+            dist_push(a.dist, a.dist->tail, gtid, gthreads, [&](int row) { return x2[row]; });
+            pk_sync<BS, 0, false>(a, sh, acc, 1);
+            pk_stamp(a, sh, PKP_HALO_X);
+            }
+        double v2max = 0.0;
+        auto update_row = [&](int row, bool owned)
+            {
+            if (a.nonmag[row]) return;
+            const double2 xv = x2[row];
+            if (owned) v2max = fmax(v2max, xv.x * xv.x + xv.y * xv.y);
+            const double4 *q = reinterpret_cast<const double4 *>(a.cur + row);
+            const double4 ca = ld256_nc(q);
+            const double2 *bq = reinterpret_cast<const double2 *>(a.basis + row);
+            const double2 b0 = __ldg(bq), b1 = __ldg(bq + 1), b2 = __ldg(bq + 2);
+            const double ep[3] = {b0.x, b0.y, b1.x}, eq[3] = {b1.y, b2.x, b2.y};
+            const double u[3] = {ca.x, ca.y, ca.z};
+            const double vp = xv.x * FG_GAMMA0, vq = xv.y * FG_GAMMA0;  // mesh.h:185-186
+            double vn[3], un[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                {
+                vn[c] = vp * ep[c] + vq * eq[c];
+                un[c] = u[c] + a.dt * vn[c];
+                }
+            const double z = un[0] * un[0] + un[1] * un[1] + un[2] * un[2];  // Eigen normalize()
+            if (z > 0.0)
+                {
+                const double sq = sqrt(z);
+                un[0] /= sq;
+                un[1] /= sq;
+                un[2] /= sq;
+                }
+            double2 *o = reinterpret_cast<double2 *>(a.next + row);
+            o[0] = make_double2(un[0], un[1]);
+            o[1] = make_double2(un[2], vn[0]);
+            o[2] = make_double2(vn[1], vn[2]);
+            };
+        if (!failed)
+            {
+            for (int s = g0; s < nslice; s += nwarps) update_row(s * SLICE + lane, true);
+            if (a.NODt > a.NODp)
+                {  // ghost rows: their solution was pushed by the owners
+                if (gtid - lane < a.NODt - a.NODp)
+                    {  // warp-uniform: one lane waits for the owners' flags, then plain loads see the pushes
+                    if (lane == 0) pk_halo_wait(a.dist, sh.hepoch - 1);
+                    __syncwarp();
+                    for (int row = a.NODp + gtid; row < a.NODt; row += gthreads) update_row(row, false);
+                    }
+                }
+            }
+        acc[0] = v2max;
+        pk_sync<BS, 1, true>(a, sh, acc, 0);
+        if (threadIdx.x == 0)
+            {
+            sh.ks.failed = failed ? 1 : 0;
+            if (!failed)
+                {
+                sh.ks.v2max = sh.tot[0];
+                sh.ks.v_max = FG_GAMMA0 * sqrt(sh.tot[0]);
+                }
+            sh.ks.updated = 1;
+            }
+        pk_stamp(a, sh, PKP_UPDATE);
+        }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        {
+        *a.st = sh.ks;
+        if (a.stamps != nullptr && sh.nstamp < a.stamp_cap) a.stamps[sh.nstamp] = 0ull;  // terminator
+        }
+    }
+
+}  // namespace fg

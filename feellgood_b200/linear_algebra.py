@@ -361,14 +361,28 @@ class LinAlgebra:
         return ms.value, cnt.value
 
     KERNEL_CLASSES = ("basis", "tet", "tri", "assemble", "spmv_setup", "bicg_p", "spmv_v", "bicg_s",
-                      "spmv_t", "bicg_xr", "halo", "update", "other", "gaps")
+                      "spmv_t", "bicg_xr", "halo", "update", "solve", "other", "gaps")
 
     def kernel_times(self):
         """{class: (device ms, launches)} since set_profiling(3); call before spmv_times()."""
-        ms = (C.c_double * 14)()
-        cnt = (C.c_int * 14)()
+        ms = (C.c_double * 15)()
+        cnt = (C.c_int * 15)()
         check(self._L.fg_get_kernel_times(self._h, ms, cnt))
         return {k: (ms[i], cnt[i]) for i, k in enumerate(self.KERNEL_CLASSES)}
+
+    def set_solver(self, kind):
+        """"persistent" (default): one cooperative kernel per solve; "multi": one kernel per phase."""
+        check(self._L.fg_set_solver(self._h, C.c_int({"persistent": 0, "multi": 1}[kind])))
+
+    SOLVE_PHASES = ("kernel", "setup", "A_p", "B_spmv_v", "C_s", "D_spmv_t", "E_xr", "halo_x", "update")
+
+    def solve_times(self):
+        """{phase: (ms, count)} of the persistent solve kernel since set_profiling(2|3): "kernel" from
+        CUDA events around its launches, the phases from its in-kernel time stamps."""
+        ms = (C.c_double * 9)()
+        cnt = (C.c_longlong * 9)()
+        check(self._L.fg_get_solve_times(self._h, ms, cnt))
+        return {k: (ms[i], int(cnt[i])) for i, k in enumerate(self.SOLVE_PHASES)}
 
     def phase_times(self):
         out = (C.c_double * 8)()

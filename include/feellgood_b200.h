@@ -289,9 +289,22 @@ int fg_get_spmv_times(fg_ctx *ctx, double *total_ms, int *launches);
 /* fg_set_profiling(ctx, 3): the same bracketing around EVERY kernel of the step.  Returns the summed
  * device milliseconds and launch counts per kernel class since the mode was set (and keeps them):
  * 0 basis 1 tet 2 tri 3 assemble 4 spmv(setup) 5 bicg_p 6 spmv(v) 7 bicg_s 8 spmv(t) 9 bicg_xr
- * 10 halo 11 update 12 other 13 gaps between consecutive kernels (idle stream time). */
-#define FG_KERNEL_CLASSES 14
+ * 10 halo 11 update 12 solve (the persistent kernel: setup + all iterations + node update) 13 other
+ * 14 gaps between consecutive kernels (idle stream time). */
+#define FG_KERNEL_CLASSES 15
 int fg_get_kernel_times(fg_ctx *ctx, double ms[FG_KERNEL_CLASSES], int launches[FG_KERNEL_CLASSES]);
+/* How LinAlgebra::solve's Krylov part (src/solver.cpp:50-88) is executed: 0 (default) ONE persistent
+ * cooperative kernel per solve (grid barriers between the phases of src/algebra/bicg.h:185-232, node update
+ * fused), 1 one kernel per phase (5 per iteration) with the host polling the device-side iteration monitor.
+ * Same algorithm, same stopping rules; kept for A/B checks.  The environment variable FG_SOLVER=multi
+ * selects 1 for every context of the process. */
+int fg_set_solver(fg_ctx *ctx, int kind);
+/* fg_set_profiling(ctx, 2 or 3) with the persistent solve kernel: ms[0] / count[0] = summed device time
+ * (CUDA events) and number of solve-kernel launches since the mode was set; ms[1..8] / count[1..8] = time
+ * spent in the phases of the kernel, from %globaltimer stamps taken by its CTA 0 after the grid barrier
+ * that closes each phase: 1 setup (r = b - K x0), 2 A (p, image of D p), 3 B (v = K D p, alpha),
+ * 4 C (s, image of D s), 5 D (t = K D s, omega), 6 E (x, r, rho), 7 halo of x (multi-GPU), 8 node update. */
+int fg_get_solve_times(fg_ctx *ctx, double ms[9], long long count[9]);
 /* Microbenchmark of the solver's SpMV on the assembled K: runs `reps` launches back to back and
  * returns the mean milliseconds per launch (CUDA events on the context's stream). */
 int fg_bench_spmv(fg_ctx *ctx, int reps, double *ms_per_launch);
