@@ -261,6 +261,45 @@ def cpu_leg(workload_name, steps, warmup, budget_s=25.0, full=False):
                 serial=serial)
 
 
+def measure_traffic(args, kernel_regex, timeout_s=240):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from a fresh ncu
+    capture of this very command (2 steps after the warm-up) in a child process.  None when ncu is not
+    usable on this box or the capture does not finish in time."""
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None
+    out = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    out.close()
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none",
+           "-k", "regex:" + kernel_regex, "-s", "3", "-c", "1", "--csv", "--log-file", out.name,
+           sys.executable, os.path.abspath(__file__), "--workload", args.workload, "--scale", str(args.scale),
+           "--solver", args.solver, "--steps", "2", "--warmup", "3", "--no-e2e", "--no-cpu-baseline",
+           "--traffic", "off"]
+    try:
+        subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=timeout_s,
+                       env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0")))
+        tot, unit_mul = 0.0, dict(byte=1.0, Kbyte=1e3, Mbyte=1e6, Gbyte=1e9)
+        import csv
+        rows = [r for r in csv.reader(open(out.name)) if len(r) > 5]
+        hdr = next(r for r in rows if "Metric Name" in r)
+        iname, iunit, ival = hdr.index("Metric Name"), hdr.index("Metric Unit"), hdr.index("Metric Value")
+        n = 0
+        for r in rows:
+            if r is hdr or len(r) <= ival or not r[iname].startswith("dram__bytes_"):
+                continue
+            tot += float(r[ival].replace(",", "")) * unit_mul.get(r[iunit], 1.0)
+            n += 1
+        return (tot, "ncu, this run (1 launch after 3 of the same kernel)") if n == 2 and tot > 0 else None
+    except Exception:
+        return None
+    finally:
+        try:
+            os.unlink(out.name)
+        except OSError:
+            pass
+
+
 # ---------------------------------------------------------------------------------------------
 def main():
     # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner)
@@ -283,6 +322,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--solver", default="persistent", choices=["persistent", "multi"],
                     help="persistent: one cooperative kernel per solve (default); multi: one kernel per phase")
+    ap.add_argument("--traffic", default="ncu", choices=["ncu", "static", "off"],
+                    help="roofline.traffic: ncu = measure DRAM bytes of the dominant kernel with a fresh ncu "
+                         "capture in a child process (adds ~1 min); static = the committed capture in profiles/")
     ap.add_argument("--kernel-times", action="store_true",
                     help="bracket every kernel with CUDA events and print the per-class table (stderr)")
     args = ap.parse_args()
@@ -342,10 +384,12 @@ def main():
         torch.cuda.synchronize()
 
     iters = []
+    # the basis angle of step k (same stream on every rank), drawn before the timed loops: input data
+    n_ang = 2 * (args.warmup + args.steps) + 8
+    angles = [M_2_PI * mt19937_uniform01(1000 + k) for k in range(n_ang)]
 
     def one_step(k):
-        ang = M_2_PI * mt19937_uniform01(1000 + k)      # same angle stream on every rank
-        failed = la.step(w.Hext, tm, angle=ang)
+        failed = la.step(w.Hext, tm, angle=angles[k])
         la.evolution()
         iters.append(la.iter["nit"])
         return failed
@@ -397,6 +441,22 @@ def main():
     la.set_profiling(0)
     mean_it = float(np.mean(iters)) if iters else 0.0
     value = args.steps / (ms * 1e-3)
+    # ---- parity block: the state after warm-up + timed steps, comparable across N (same mesh, same angle
+    # stream, same dt): <m> over the magnetic volume (mesh::avg, collective on a partitioned mesh) and
+    # the summed BiCGStab iterations; when profiles/parity_ref.json holds the 1-GPU value for this
+    # workload and step count, the difference to it
+    avg_u = [float(x) for x in la.avg("u")]
+    parity = dict(after_steps=args.warmup + args.steps, avg_u=avg_u, sum_iters=int(np.sum(iters)),
+                  failed_steps=int(nfail), solver=args.solver)
+    try:
+        pr = json.load(open(os.path.join(ROOT, "profiles", "parity_ref.json")))
+        key = "%s:%d" % (w.name, args.warmup + args.steps)
+        if key in pr:
+            parity["ref_n1"] = pr[key]
+            parity["max_abs_diff_vs_n1"] = float(np.max(np.abs(np.array(avg_u) - np.array(pr[key]["avg_u"]))))
+            parity["sum_iters_diff_vs_n1"] = int(np.sum(iters)) - int(pr[key]["sum_iters"])
+    except Exception:
+        pass
 
     # ---- end-to-end leg: host buffers in and out every step -----------------------------------
     e2e = None
@@ -413,8 +473,7 @@ def main():
             # potentials in (Nodes::set_phi/set_phiv), the new u and v out (its next input)
             la.set_potentials(h_phi, h_phiv)
             la.evolution()
-            ang = M_2_PI * mt19937_uniform01(1000 + k)
-            failed = la.step(w.Hext, tm, angle=ang)
+            failed = la.step(w.Hext, tm, angle=angles[k])
             la.get_state_into(1, u=h_u, v=h_v)
             return failed
 
@@ -427,29 +486,55 @@ def main():
                    ms_per_step=ms_e / args.steps,
                    api="LinAlgebra.set_potentials + evolution + step + get_state (pinned host)")
 
-    # ---- roofline of the dominant kernel (SpMV) --------------------------------------------------
+    # ---- roofline of the dominant kernel ---------------------------------------------------------
+    # persistent solver: the solve kernel itself (setup product + all iterations + node update in one
+    # launch, CUDA events around it), with the time its CTA 0 spent in each phase from in-kernel
+    # %globaltimer stamps; multi-kernel solver: the SpMV launches
     peak, peak_src = measured_peak_gbs()
     n_loc = la.n_local if hasattr(la, "n_local") else la.n
     nnz_loc = la.nnz_local if hasattr(la, "nnz_local") else la.nnz
+    col_bytes = getattr(la, "col_bytes", 4)
+    b_spmv = workloads.spmv_bytes(n_loc, nnz_loc, col_bytes)
     roof = None
-    if spmv_n > 0:
-        col_bytes = getattr(la, "col_bytes", 4)
-        b_spmv = workloads.spmv_bytes(n_loc, nnz_loc, col_bytes)
+    if solve_t["kernel"][1] > 0:
+        kms, kn = solve_t["kernel"]
+        b_solve = workloads.solve_bytes(n_loc, nnz_loc, mean_it, col_bytes)
+        ach = b_solve / (kms * 1e-3 / kn) / 1e9
+        ph = {k: dict(us=1e3 * t / c, count=c) for k, (t, c) in solve_t.items() if c and k != "kernel"}
+        sp = [solve_t[k] for k in ("B_spmv_v", "D_spmv_t") if solve_t[k][1]]
+        sp_us = 1e3 * sum(t for t, _ in sp) / max(1, sum(c for _, c in sp))
+        roof = dict(bound="hbm", kernel="k_llg_solve<BS,IDX16> (persistent: r = b - K x0, %.2f BiCGStab "
+                    "iterations, node update)" % mean_it, achieved=ach, peak=peak, unit="GB/s",
+                    frac=ach / peak, traffic=None, traffic_source=None, peak_source=peak_src,
+                    bytes_per_launch=b_solve, col_index_bytes=col_bytes, launches=kn,
+                    us_per_launch=1e3 * kms / kn, share_of_step=kms / ms, phases=ph,
+                    spmv_phase=dict(us=sp_us, bytes=b_spmv, achieved=b_spmv / (sp_us * 1e-6) / 1e9 if sp_us else None,
+                                    frac=b_spmv / (sp_us * 1e-6) / 1e9 / peak if sp_us else None,
+                                    note="SpMV phase incl. its grid-wide reduction, timed inside the kernel",
+                                    csr_equiv_gbs=workloads.spmv_bytes_csr(n_loc, nnz_loc) / (sp_us * 1e-6) / 1e9
+                                    if sp_us else None))
+    elif spmv_n > 0:
         ach = b_spmv / (spmv_ms * 1e-3 / spmv_n) / 1e9
         roof = dict(bound="hbm", kernel="k_spmv_node3<STAGE>", achieved=ach, peak=peak, unit="GB/s",
-                    frac=ach / peak, traffic=None, peak_source=peak_src,
+                    frac=ach / peak, traffic=None, traffic_source=None, peak_source=peak_src,
                     bytes_per_launch=b_spmv, col_index_bytes=col_bytes, launches=spmv_n, us_per_launch=1e3 * spmv_ms / spmv_n,
                     share_of_step=spmv_ms / ms,
                     csr_equiv_gbs=workloads.spmv_bytes_csr(n_loc, nnz_loc)
                     / (spmv_ms * 1e-3 / spmv_n) / 1e9)
-        tfile = os.path.join(ROOT, "profiles", "spmv_traffic.json")
-        if os.path.exists(tfile):
-            try:
-                tj = json.load(open(tfile))
-                if tj.get("workload") == w.name and world == 1:
-                    roof["traffic"] = tj.get("dram_bytes_per_launch")
-            except Exception:
-                pass
+    if roof is not None and world == 1 and rank == 0:
+        tr = measure_traffic(args, roof["kernel"].split("<")[0]) if args.traffic == "ncu" else None
+        if tr is not None:
+            roof["traffic"], roof["traffic_source"] = tr
+        else:
+            tfile = os.path.join(ROOT, "profiles", "solve_traffic.json" if args.solver == "persistent" else "spmv_traffic.json")
+            if os.path.exists(tfile):
+                try:
+                    tj = json.load(open(tfile))
+                    if tj.get("workload") == w.name:
+                        roof["traffic"] = tj.get("dram_bytes_per_launch")
+                        roof["traffic_source"] = "static: %s (%s)" % (os.path.relpath(tfile, ROOT), tj.get("source", "ncu capture"))
+                except Exception:
+                    pass
     b_step = workloads.step_bytes(w.mesh.NOD, w.mesh.NT, la.n, la.nnz, mean_it, getattr(la, "col_bytes", 4))
     b_survey = workloads.step_bytes_survey(w.mesh.NOD, w.mesh.NT, la.n, la.nnz, mean_it)
     step_roof = dict(bytes_per_step=b_step, achieved=b_step / (ms * 1e-3 / args.steps) / 1e9 / world,
@@ -475,7 +560,7 @@ def main():
                                 l2="inputs exceed L2 (matrix %.0f MB >> 126 MB), no flush"
                                    % (8e-6 * la.nnz),
                                 parallelism="row-block slabs x%d" % world if world > 1 else "1 GPU"),
-                    roofline=roof, step_roofline=step_roof, cpu_baseline=cb, e2e=e2e,
+                    roofline=roof, step_roofline=step_roof, cpu_baseline=cb, e2e=e2e, parity=parity,
                     gpu_launches=int(launches), clocks=clk)
         emit(line)
     la.close()

@@ -148,6 +148,14 @@ struct Operator
     int prefetch;                // 1: pull the row-epilogue operands and the next slice's indices into L2 early
     const unsigned char *sghost; // partitioned operator (multi-GPU): 1 = the slice has a ghost column, i.e. it
                                  // must wait for the halo of its SpMV input; NULL on one GPU
+    // gather blocks (fg_setup.hpp): 256 rows = 8 slices whose gathered images (own rows + halo) are staged in
+    // shared memory by a thread group of the persistent kernel and addressed with 16-bit local indices
+    const unsigned short *lcol;  // local column index per stored pair, same layout as col / col16; NULL = none
+    const int *bptr;             // nblock + 1
+    const int *bhalo;            // device rows of the halo images
+    const unsigned char *bghost; // 1 = the halo of the block has a ghost row (multi-GPU), NULL on one GPU
+    int nblock;
+    int stage_cap;               // images a staging buffer must hold (256 + largest halo)
     };
 
 // 256-bit global accesses (sm_100: LDG.E.ENL2.256 / STG.E.ENL2.256): one request per 32-byte node image
@@ -277,11 +285,14 @@ struct KrylovWork
     int nsend;                 // boundary rows this rank pushes to its neighbours
     // persistent solve kernel (fg_solve_pk.cuh)
     struct PkSync *pk;         // barrier / reduction scratch (NULL: not allocated)
-    unsigned long long *pk_stamps, *h_pk_stamps;  // device / pinned host: in-kernel phase time stamps
-    int pk_stamp_cap;
+    unsigned long long *pk_phase_acc;  // device [32]: in-kernel phase times (ns) and counts, by PKP_* id
     int pk_stamps_on;
-    double pk_phase_us[16];    // summed in-kernel phase times since the stamps were switched on (PKP_* ids)
-    long long pk_phase_cnt[16];
+    // result mailbox of the persistent kernel: its last thread writes KState and a sequence number straight
+    // into mapped pinned host memory; the host spins on the number instead of waiting for a copy + event
+    unsigned long long *h_seq;     // pinned, mapped
+    unsigned long long seq;        // last sequence number handed to a kernel
+    KState *d_h_st;                // device views of h_st / h_seq
+    unsigned long long *d_h_seq;
     };
 
 // phases of the persistent solve kernel (ids of its in-kernel time stamps)

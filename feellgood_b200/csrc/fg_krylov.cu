@@ -9,6 +9,7 @@
 //     shuffles + a deterministic two-stage grid reduction (fixed grid => bitwise reproducible);
 //   * 5 kernels per BiCGStab iteration (reference: 2 parallel SpMV + 17 serial vector passes).
 // All kernels are HBM-bandwidth bound: persistent grids of 148 SMs x 8 CTAs, coalesced streams.
+#include <limits.h>
 #include <math.h>
 #include <stdio.h>
 
@@ -231,28 +232,75 @@ template <bool COH> __device__ __forceinline__ double4 ld_image(const double4 *p
     return ld256_nc(p);
     }
 
+// Which slices a warp owns.  Regular rounds: slice g + k W for k = 0 .. (W = warps of the grid, g = this
+// warp's index in the grid), so that at any moment the whole grid works on one contiguous front of W slices
+// (the gathered images of a front are shared through L2 and, inside a CTA, through L1).  The last,
+// incomplete round is dealt out per CTA instead (`tail`: at most one extra slice per warp), so that every SM
+// ends with the same number of slices to one, whatever the ratio of slices to warps (it is ~4 per warp on
+// the 8-GPU partition of the 20 M-tet mesh, where a round-robin tail left 17 SMs with 25 % more work).
+struct SliceIter
+    {
+    int first;     // g, or INT_MAX when the warp has no regular slice
+    int W;         // stride of the regular rounds
+    int main_end;  // regular slices are below this index
+    int tail;      // the warp's slice of the last round, or INT_MAX
+    __device__ __forceinline__ int begin() const { return first < main_end ? first : tail; }
+    __device__ __forceinline__ int next(int s) const
+        {
+        if (s >= main_end) return INT_MAX;  // s was the tail slice
+        const int n = s + W;
+        return n < main_end ? n : tail;
+        }
+    };
+// plain grid-stride ownership (stand-alone kernels)
+__device__ __forceinline__ SliceIter slices_strided(int g, int W, int nslice)
+    {
+    SliceIter it;
+    it.first = g;
+    it.W = W;
+    it.main_end = nslice;
+    it.tail = INT_MAX;
+    return it;
+    }
+// front + per-CTA tail (persistent kernel): nw warps per CTA
+__device__ __forceinline__ SliceIter slices_balanced(int nslice, int nw)
+    {
+    const int W = gridDim.x * nw, wid = threadIdx.x >> 5;
+    const int q = nslice / W, rem = nslice - q * W;
+    SliceIter it;
+    it.first = blockIdx.x * nw + wid;
+    it.W = W;
+    it.main_end = q * W;
+    const int t0 = it.main_end + (int)(((long long)rem * blockIdx.x) / gridDim.x);
+    const int t1 = it.main_end + (int)(((long long)rem * (blockIdx.x + 1)) / gridDim.x);
+    it.tail = t0 + wid < t1 ? t0 + wid : INT_MAX;
+    return it;
+    }
+
 template <int STAGE, bool IDX16, bool COH>
-__device__ __forceinline__ void spmv_node3_slices(const Operator &op, const SpmvArgs &a, int s, const int nwarps,
+__device__ __forceinline__ void spmv_node3_slices(const Operator &op, const SpmvArgs &a, const SliceIter it,
                                                   const int lane, const int pass, double (&acc)[RED_NV])
     {
+    const int s_end = op.nslice;
+    int s = it.begin();
     typedef typename std::conditional<IDX16, short, int>::type idx_t;
     const idx_t *colbase = IDX16 ? reinterpret_cast<const idx_t *>(op.col16) : reinterpret_cast<const idx_t *>(op.col);
     const double2 *x2 = reinterpret_cast<const double2 *>(a.x);
     if (pass != 0)  // first slice of this warp that belongs to the pass
-        while (s < op.nslice && (op.sghost[s] != 0) != (pass == 2)) s += nwarps;
+        while (s < s_end && (op.sghost[s] != 0) != (pass == 2)) s = it.next(s);
     int p0 = 0, p1 = 0;
-    if (s < op.nslice)
+    if (s < s_end)
         {
         p0 = __ldg(op.ptr + s);
         p1 = __ldg(op.ptr + s + 1);
         }
-    while (s < op.nslice)
+    while (s < s_end)
         {
-        int sn = s + nwarps;
+        int sn = it.next(s);
         if (pass != 0)
-            while (sn < op.nslice && (op.sghost[sn] != 0) != (pass == 2)) sn += nwarps;
+            while (sn < s_end && (op.sghost[sn] != 0) != (pass == 2)) sn = it.next(sn);
         int q0 = 0, q1 = 0;
-        if (sn < op.nslice)
+        if (sn < s_end)
             {
             q0 = __ldg(op.ptr + sn);
             q1 = __ldg(op.ptr + sn + 1);
@@ -341,10 +389,10 @@ __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_node3(const Op
         {  // multi-GPU: the ghost entries of w(D.p) are pushed by the neighbours' k_bicg_p while this kernel
            // runs.  Rows without ghost columns do not wait; the others are done after the halo flag of
            // every source rank was seen, and they read the images with coherent loads (COH).
-        spmv_node3_slices<STAGE, IDX16, COH>(op, a, s0, nwarps, lane, 1, acc);
+        spmv_node3_slices<STAGE, IDX16, COH>(op, a, slices_strided(s0, nwarps, op.nslice), lane, 1, acc);
         if (threadIdx.x == 0) dist_wait(a.dist);
         __syncthreads();
-        spmv_node3_slices<STAGE, IDX16, COH>(op, a, s0, nwarps, lane, 2, acc);
+        spmv_node3_slices<STAGE, IDX16, COH>(op, a, slices_strided(s0, nwarps, op.nslice), lane, 2, acc);
         }
     else
         {
@@ -353,7 +401,7 @@ __global__ void __launch_bounds__(BLOCK, SPMV_CTAS_PER_SM) k_spmv_node3(const Op
             if (threadIdx.x == 0) dist_wait(a.dist);
             __syncthreads();
             }
-        spmv_node3_slices<STAGE, IDX16, COH>(op, a, s0, nwarps, lane, 0, acc);
+        spmv_node3_slices<STAGE, IDX16, COH>(op, a, slices_strided(s0, nwarps, op.nslice), lane, 0, acc);
         }
     if (!stage_reduces(STAGE)) return;
     double tot[RED_NV];
@@ -880,8 +928,13 @@ int krylov_alloc(KrylovWork &w, int n, int n_ghost, cudaStream_t stream, long lo
         }
     FG_CUDA(cudaMalloc(&w.st, sizeof(KState)));
     FG_CUDA(cudaMemsetAsync(w.st, 0, sizeof(KState), stream));
-    FG_CUDA(cudaMallocHost(&w.h_st, sizeof(KState)));
+    FG_CUDA(cudaHostAlloc(&w.h_st, sizeof(KState), cudaHostAllocMapped));
     memset(w.h_st, 0, sizeof(KState));
+    FG_CUDA(cudaHostAlloc(&w.h_seq, sizeof(unsigned long long), cudaHostAllocMapped));
+    *w.h_seq = 0ull;
+    w.seq = 0ull;
+    FG_CUDA(cudaHostGetDevicePointer(&w.d_h_st, w.h_st, 0));
+    FG_CUDA(cudaHostGetDevicePointer(&w.d_h_seq, w.h_seq, 0));
     FG_CUDA(cudaMalloc(&w.red.partials, sizeof(double) * 2 * RED_NV * MAX_GRID));  // values + compensations
     FG_CUDA(cudaMalloc(&w.red.ticket, sizeof(unsigned int)));
     FG_CUDA(cudaMemsetAsync(w.red.ticket, 0, sizeof(unsigned int), stream));
@@ -892,10 +945,8 @@ int krylov_alloc(KrylovWork &w, int n, int n_ghost, cudaStream_t stream, long lo
         {
         FG_CUDA(cudaMalloc(&w.pk, sizeof(PkSync)));
         FG_CUDA(cudaMemsetAsync(w.pk, 0, sizeof(PkSync), stream));
-        w.pk_stamp_cap = 8192;
-        FG_CUDA(cudaMalloc(&w.pk_stamps, sizeof(unsigned long long) * w.pk_stamp_cap));
-        FG_CUDA(cudaMemsetAsync(w.pk_stamps, 0, sizeof(unsigned long long) * w.pk_stamp_cap, stream));
-        FG_CUDA(cudaMallocHost(&w.h_pk_stamps, sizeof(unsigned long long) * w.pk_stamp_cap));
+        FG_CUDA(cudaMalloc(&w.pk_phase_acc, sizeof(unsigned long long) * 32));
+        FG_CUDA(cudaMemsetAsync(w.pk_phase_acc, 0, sizeof(unsigned long long) * 32, stream));
         }
     return FG_OK;
     }
@@ -914,12 +965,12 @@ void krylov_free(KrylovWork &w)
         if (v) cudaFree(v);
     if (w.st) cudaFree(w.st);
     if (w.h_st) cudaFreeHost(w.h_st);
+    if (w.h_seq) cudaFreeHost(w.h_seq);
     if (w.red.partials) cudaFree(w.red.partials);
     if (w.red.ticket) cudaFree(w.red.ticket);
     if (w.ev_poll) cudaEventDestroy(w.ev_poll);
     if (w.pk) cudaFree(w.pk);
-    if (w.pk_stamps) cudaFree(w.pk_stamps);
-    if (w.h_pk_stamps) cudaFreeHost(w.h_pk_stamps);
+    if (w.pk_phase_acc) cudaFree(w.pk_phase_acc);
     w = KrylovWork();
     }
 
@@ -1154,8 +1205,14 @@ int bicgstab_run_pk(const Operator &op, KrylovWork &w, double tol, int maxiter, 
         a.NODp = upd->NODp;
         a.NODt = upd->NODt;
         }
-    a.stamps = w.pk_stamps_on ? w.pk_stamps : nullptr;
-    a.stamp_cap = w.pk_stamp_cap - 1;
+    a.phase_acc = w.pk_stamps_on ? w.pk_phase_acc : nullptr;
+    static const bool mailbox = getenv("FG_PK_MAILBOX") == nullptr || atoi(getenv("FG_PK_MAILBOX")) != 0;
+    if (mailbox)
+        {
+        a.h_st = w.d_h_st;
+        a.h_seq = w.d_h_seq;
+        a.seq = ++w.seq;
+        }
     void *args[] = {&a};
     const void *fn = bs == 1024 ? (i16 ? (const void *)k_llg_solve<1024, true> : (const void *)k_llg_solve<1024, false>)
                                 : (i16 ? (const void *)k_llg_solve<256, true> : (const void *)k_llg_solve<256, false>);
@@ -1163,25 +1220,35 @@ int bicgstab_run_pk(const Operator &op, KrylovWork &w, double tol, int maxiter, 
     FG_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(bs), args, 0, w.stream));
     if (prof) prof_end(w.prof, w.stream);
     if (w.launches) ++*w.launches;
-    if (w.pk_stamps_on)
-        FG_CUDA(cudaMemcpyAsync(w.h_pk_stamps, w.pk_stamps, sizeof(unsigned long long) * w.pk_stamp_cap,
-                                cudaMemcpyDeviceToHost, w.stream));
-    FG_TRY(poll_state(w));
-    if (w.pk_stamps_on)
-        {  // phase X = time between the stamp closing X and the previous stamp, as CTA 0 saw it
-        unsigned long long prev = 0;
-        for (int k = 0; k < w.pk_stamp_cap && w.h_pk_stamps[k] != 0ull; k++)
+    if (mailbox)
+        {  // spin on the sequence number the kernel's last thread writes (a few us after it, against ~20 us
+           // for copy + event); the stream is queried now and then so that a failed launch cannot hang us
+        volatile unsigned long long *seq = w.h_seq;
+        unsigned int spins = 0;
+        while (*seq != a.seq)
             {
-            const int id = (int)(w.h_pk_stamps[k] >> 56);
-            const unsigned long long t = w.h_pk_stamps[k] & 0x00ffffffffffffffull;
-            if (k > 0 && id > 0 && id < 16)
+            if ((++spins & 0xfffffu) == 0)
                 {
-                w.pk_phase_us[id] += 1e-3 * (double)(t - prev);
-                w.pk_phase_cnt[id]++;
+                const cudaError_t q = cudaStreamQuery(w.stream);
+                if (q != cudaErrorNotReady && *seq != a.seq)
+                    {
+                    if (q != cudaSuccess)
+                        {
+                        set_error("bicgstab_run_pk: %s", cudaGetErrorString(q));
+                        return FG_ERR_CUDA;
+                        }
+                    break;  // finished without writing the mailbox: fall back to the copy
+                    }
                 }
-            prev = t;
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
             }
+        if (*seq != a.seq) FG_TRY(poll_state(w));
+        __sync_synchronize();
         }
+    else
+        FG_TRY(poll_state(w));
     if (!w.h_st->done)
         {
         set_error("bicgstab_run_pk: the solve kernel returned without finishing");

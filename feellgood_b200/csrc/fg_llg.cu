@@ -81,6 +81,9 @@ struct fg_ctx
     bool use_blocks = false;     // fg_set_operator(ctx, 1): solve with the assembled 2x2 blocks (A/B checks)
     int solver_kind = 0;         // fg_set_solver: 0 persistent kernel, 1 one kernel per phase
     unsigned char *sghost = nullptr;  // multi-GPU: slices with a ghost column
+    unsigned short *lcol = nullptr;   // gather blocks of the persistent SpMV (fg_setup.hpp)
+    int *bptr = nullptr, *bhalo = nullptr;
+    unsigned char *bghost = nullptr;
     KrylovWork kw;
     Operator op;
     // energies / averages / max angle: tables built on first use
@@ -99,6 +102,7 @@ struct fg_ctx
     // step bookkeeping
     StepPrm sp = {};
     bool have_basis = false, prepared = false, space_field = false, assembled = false;
+    bool commit_pending = false;  // fg_commit is lazy: the next k_basis copies NEXT -> CURRENT on its way
     bool iso_regions = true;   // no region has K or K3: the element fast path applies (k_tet_iso)
     double v_max = 0.0;
     // profiling
@@ -141,6 +145,17 @@ int check_ctx(const fg_ctx *c)
     return FG_OK;
     }
 
+// mesh::evolution is executed lazily: fg_commit only marks it, the next base_projection copies NEXT ->
+// CURRENT inside k_basis (which reads every node record anyway); any other entry point that could see
+// CURRENT first performs the copy here.
+int flush_commit(fg_ctx *c)
+    {
+    if (!c->commit_pending) return FG_OK;
+    FG_CUDA(cudaMemcpyAsync(c->cur, c->next, sizeof(NodeRec) * (size_t)c->NODt, cudaMemcpyDeviceToDevice, c->stream));
+    c->commit_pending = false;
+    return FG_OK;
+    }
+
 TetArrays tet_arrays(const fg_ctx *c)
     {
     TetArrays A;
@@ -157,8 +172,15 @@ TetArrays tet_arrays(const fg_ctx *c)
 
 int launch_basis(fg_ctx *c, double angle)
     {
-    CTX_LAUNCH_C(c, KC_BASIS, k_basis, grid_for(c->NODt, BLOCK), c->NODt, c->cur, cos(angle), sin(angle), c->basis,
-                 c->qbasis);
+    if (c->commit_pending)
+        {  // evolution fused: read NEXT, write it to CURRENT, build the basis from it
+        CTX_LAUNCH_C(c, KC_BASIS, k_basis<true>, grid_for(c->NODt, BLOCK), c->NODt, c->next, c->cur, cos(angle), sin(angle),
+                     c->basis, c->qbasis);
+        c->commit_pending = false;
+        }
+    else
+        CTX_LAUNCH_C(c, KC_BASIS, k_basis<false>, grid_for(c->NODt, BLOCK), c->NODt, c->cur, c->cur, cos(angle), sin(angle),
+                     c->basis, c->qbasis);
     c->have_basis = true;
     c->prepared = false;
     c->assembled = false;
@@ -680,6 +702,13 @@ static int create_ctx(const fg_mesh *mesh, const fg_params *prm, int device, con
             }
         CK(dev_upload(&c->sghost, sg, s));
         }
+    if (h.stage_cap > 0)
+        {
+        CK(dev_upload(&c->lcol, h.lcol, s));
+        CK(dev_upload(&c->bptr, h.bptr, s));
+        CK(dev_upload(&c->bhalo, h.bhalo, s));
+        if (dd) CK(dev_upload(&c->bghost, h.bghost, s));
+        }
     CK(dev_upload(&c->sdeg, h.sdeg, s));
     CK(dev_upload(&c->sS, h.sS, s));
     CK(dev_upload(&c->iptr, h.iptr, s));
@@ -766,6 +795,12 @@ static int create_ctx(const fg_mesh *mesh, const fg_params *prm, int device, con
     // early L2 prefetch of the SpMV row-epilogue operands; FG_SPMV_PF=0 switches it off (A/B)
     c->op.prefetch = getenv("FG_SPMV_PF") ? atoi(getenv("FG_SPMV_PF")) : 1;
     c->op.sghost = c->sghost;
+    c->op.lcol = getenv("FG_NO_STAGE") ? nullptr : c->lcol;
+    c->op.bptr = c->bptr;
+    c->op.bhalo = c->bhalo;
+    c->op.bghost = c->bghost;
+    c->op.nblock = h.nblock;
+    c->op.stage_cap = h.stage_cap;
         {
         const char *sv = getenv("FG_SOLVER");
         c->solver_kind = (sv && (!strcmp(sv, "multi") || !strcmp(sv, "1"))) ? 1 : 0;
@@ -781,6 +816,8 @@ static int create_ctx(const fg_mesh *mesh, const fg_params *prm, int device, con
     std::vector<int>().swap(h.tet_slot);
     std::vector<int>().swap(h.sinct);
     std::vector<int>().swap(h.scol);
+    std::vector<unsigned short>().swap(h.lcol);
+    std::vector<int>().swap(h.bhalo);
     c->sp.idx_dir = FG_IDX_UNDEF;
     *out = c;
     return FG_OK;
@@ -889,7 +926,7 @@ void fg_destroy(fg_ctx *c)
                     c->tet_detJ, c->ext_field, c->tet_reg, c->reg_tet, c->rec, c->tri_ind,
                     c->tri_reg, c->tri_surf, c->tri_dMs, c->reg_tri, c->trec, c->perm, c->sptr,
                     c->scol, c->sdeg, c->iptr, c->tet_slot, c->itptr, c->sinct, c->sS, c->Aw, c->val, c->Sdiag, c->Dm, c->qbasis,
-                    c->scol16, c->sghost, c->mtri_ind, c->mtri_reg, c->mtri_surf, c->mtri_nrm, c->mtri_dMs, c->extra_edges,
+                    c->scol16, c->sghost, c->lcol, c->bptr, c->bhalo, c->bghost, c->mtri_ind, c->mtri_reg, c->mtri_surf, c->mtri_nrm, c->mtri_dMs, c->extra_edges,
                     c->d_scal, c->node_pos, c->corr, c->tcorr, c->src, c->cptr, c->cidx};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -955,6 +992,7 @@ int fg_get_layout(const fg_ctx *c, long long out[4])
 int fg_set_state(fg_ctx *c, const double *u, const double *v, const double *phi, const double *phiv)
     {
     FG_TRY(check_ctx(c));
+    FG_TRY(flush_commit(c));
     if (!u)
         {
         set_error("fg_set_state: u is required");
@@ -970,6 +1008,7 @@ int fg_set_state(fg_ctx *c, const double *u, const double *v, const double *phi,
 int fg_set_next_v(fg_ctx *c, const double *v)
     {
     FG_TRY(check_ctx(c));
+    FG_TRY(flush_commit(c));
     if (!v)
         {
         set_error("fg_set_next_v: null v");
@@ -981,6 +1020,7 @@ int fg_set_next_v(fg_ctx *c, const double *v)
 int fg_set_potentials(fg_ctx *c, const double *phi, const double *phiv)
     {
     FG_TRY(check_ctx(c));
+    FG_TRY(flush_commit(c));
     if (!phi || !phiv)
         {
         set_error("fg_set_potentials: null argument");
@@ -992,6 +1032,7 @@ int fg_set_potentials(fg_ctx *c, const double *phi, const double *phiv)
 int fg_get_state(fg_ctx *c, int step, double *u, double *v, double *phi, double *phiv)
     {
     FG_TRY(check_ctx(c));
+    FG_TRY(flush_commit(c));
     if (step != 0 && step != 1)
         {
         set_error("fg_get_state: step must be 0 (CURRENT) or 1 (NEXT)");
@@ -1014,7 +1055,9 @@ int fg_get_state(fg_ctx *c, int step, double *u, double *v, double *phi, double 
 int fg_commit(fg_ctx *c)
     {
     FG_TRY(check_ctx(c));
-    FG_CUDA(cudaMemcpyAsync(c->cur, c->next, sizeof(NodeRec) * (size_t)c->NODt, cudaMemcpyDeviceToDevice, c->stream));
+    static const bool eager = getenv("FG_EAGER_COMMIT") != nullptr;  // A/B: copy now instead of in k_basis
+    c->commit_pending = true;
+    if (eager) FG_TRY(flush_commit(c));
     c->have_basis = c->prepared = c->assembled = false;
     return FG_OK;
     }
@@ -1022,6 +1065,7 @@ int fg_commit(fg_ctx *c)
 int fg_set_ext_space_field(fg_ctx *c, const double *field)
     {
     FG_TRY(check_ctx(c));
+    FG_TRY(flush_commit(c));
     if (!field)
         {
         set_error("fg_set_ext_space_field: null field");
@@ -1077,6 +1121,7 @@ int fg_prepare_elements(fg_ctx *c, const double Hext[3], double dt, double prefa
                         double Vdrift)
     {
     FG_TRY(check_ctx(c));
+    FG_TRY(flush_commit(c));
     if (!Hext)
         {
         set_error("fg_prepare_elements: null Hext");
@@ -1091,6 +1136,7 @@ int fg_prepare_elements_space(fg_ctx *c, double A_Hext, double dt, double prefac
                               double Vdrift)
     {
     FG_TRY(check_ctx(c));
+    FG_TRY(flush_commit(c));
     FG_TRY(set_step_prm(c, nullptr, A_Hext, dt, prefactor, idx_dir, Vdrift, true));
     if (c->profiling) FG_CUDA(cudaEventRecord(c->ev[1], c->stream));
     return launch_elements(c);
@@ -1099,6 +1145,7 @@ int fg_prepare_elements_space(fg_ctx *c, double A_Hext, double dt, double prefac
 int fg_solve(fg_ctx *c, double dt, fg_step_result *out)
     {
     FG_TRY(check_ctx(c));
+    FG_TRY(flush_commit(c));
     return run_solve(c, dt, out);
     }
 
@@ -1393,6 +1440,7 @@ int launch_charges(fg_ctx *c, int which)
 int demag_guard(fg_ctx *c, const char *who)
     {
     FG_TRY(check_ctx(c));
+    FG_TRY(flush_commit(c));  // fg_demag_direct writes the potentials of NEXT
     if (c->arena)
         {
         set_error("%s: not available on a distributed context (single-GPU stand-in for the FMM)", who);
@@ -1453,6 +1501,7 @@ int fg_demag_direct(fg_ctx *c, int second_order)
 int fg_get_basis(fg_ctx *c, double *ep, double *eq)
     {
     FG_TRY(check_ctx(c));
+    FG_TRY(flush_commit(c));
     const size_t N = (size_t)c->NODp;
     std::vector<Basis> b(N);
     FG_CUDA(cudaMemcpyAsync(b.data(), c->basis, sizeof(Basis) * N, cudaMemcpyDeviceToHost, c->stream));
@@ -1472,6 +1521,7 @@ int fg_get_basis(fg_ctx *c, double *ep, double *eq)
 int fg_get_elements(fg_ctx *c, int first, int count, double *Kp, double *Lp)
     {
     FG_TRY(check_ctx(c));
+    FG_TRY(flush_commit(c));
     if (first < 0 || count < 0 || first + count > c->h.NT || !Kp || !Lp)
         {
         set_error("fg_get_elements: bad range [%d,%d) of %d", first, first + count, c->h.NT);
@@ -1541,6 +1591,7 @@ int fg_get_elements(fg_ctx *c, int first, int count, double *Kp, double *Lp)
 int fg_get_tri_elements(fg_ctx *c, int first, int count, double *Lp)
     {
     FG_TRY(check_ctx(c));
+    FG_TRY(flush_commit(c));
     if (first < 0 || count < 0 || first + count > c->h.NF || !Lp)
         {
         set_error("fg_get_tri_elements: bad range");
@@ -1649,6 +1700,7 @@ int fg_get_csr_pattern(const fg_ctx *c, int *rowptr, int *col)
 int fg_get_system(fg_ctx *c, double dt, double *val, double *rhs, double *x0)
     {
     FG_TRY(check_ctx(c));
+    FG_TRY(flush_commit(c));
     if (c->arena)
         {
         set_error("fg_get_system: not available on a distributed context");
@@ -1694,9 +1746,27 @@ int fg_get_system(fg_ctx *c, double dt, double *val, double *rhs, double *x0)
     return FG_OK;
     }
 
+int fg_get_precond(fg_ctx *c, double dt, double *D)
+    {
+    FG_TRY(check_ctx(c));
+    FG_TRY(flush_commit(c));
+    if (c->arena || !D)
+        {
+        set_error("fg_get_precond: null argument or distributed context");
+        return FG_ERR_STATE;
+        }
+    if (c->prepared || !c->assembled) FG_TRY(launch_assemble(c, dt));
+    std::vector<double> tmp(2 * (size_t)c->NODt);
+    FG_CUDA(cudaMemcpyAsync(tmp.data(), c->kw.D, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, c->stream));
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    dofs_to_caller(c, tmp, D);
+    return FG_OK;
+    }
+
 int fg_apply_operator(fg_ctx *c, const double *x, double *y)
     {
     FG_TRY(check_ctx(c));
+    FG_TRY(flush_commit(c));
     if (!x || !y)
         {
         set_error("fg_apply_operator: null argument");
@@ -1720,6 +1790,7 @@ int fg_apply_operator(fg_ctx *c, const double *x, double *y)
 int fg_get_solution(fg_ctx *c, double *Xw)
     {
     FG_TRY(check_ctx(c));
+    FG_TRY(flush_commit(c));
     if (!Xw)
         {
         set_error("fg_get_solution: null argument");
@@ -1859,11 +1930,8 @@ int fg_set_profiling(fg_ctx *c, int on)
         c->prof.mode = on;
         c->kw.prof = &c->prof;
         c->kw.pk_stamps_on = 1;
-        for (int k = 0; k < 16; k++)
-            {
-            c->kw.pk_phase_us[k] = 0.0;
-            c->kw.pk_phase_cnt[k] = 0;
-            }
+        if (c->kw.pk_phase_acc)
+            FG_CUDA(cudaMemsetAsync(c->kw.pk_phase_acc, 0, sizeof(unsigned long long) * 32, c->stream));
         }
     else
         {
@@ -1907,10 +1975,15 @@ int fg_get_solve_times(fg_ctx *c, double ms[9], long long count[9])
         ms[0] += t;
         count[0]++;
         }
-    for (int id = PKP_SETUP; id <= PKP_UPDATE; id++)
+    if (c->kw.pk_phase_acc)
         {
-        ms[id - PKP_SETUP + 1] = 1e-3 * c->kw.pk_phase_us[id];
-        count[id - PKP_SETUP + 1] = c->kw.pk_phase_cnt[id];
+        unsigned long long acc[32];
+        FG_CUDA(cudaMemcpy(acc, c->kw.pk_phase_acc, sizeof acc, cudaMemcpyDeviceToHost));
+        for (int id = PKP_SETUP; id <= PKP_UPDATE; id++)
+            {
+            ms[id - PKP_SETUP + 1] = 1e-6 * (double)acc[id];
+            count[id - PKP_SETUP + 1] = (long long)acc[16 + id];
+            }
         }
     return FG_OK;
     }
@@ -2052,6 +2125,7 @@ int fg_get_phase_times(const fg_ctx *c, double out[8])
 int fg_bench_spmv(fg_ctx *c, int reps, double *ms_per_launch)
     {
     FG_TRY(check_ctx(c));
+    FG_TRY(flush_commit(c));
     if (reps <= 0 || !ms_per_launch)
         {
         set_error("fg_bench_spmv: bad argument");

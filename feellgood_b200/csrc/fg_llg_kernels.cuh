@@ -160,15 +160,28 @@ __host__ __device__ __forceinline__ void node_set_basis(const double u[3], doubl
     }
 
 // Also writes the basis as a unit quaternion (32 B): what the Krylov kernels read (fg_common.cuh).
+// COMMIT: mesh::evolution (src/mesh.h:189-193) fused in: `src` is the NEXT record, copied to CURRENT (`dst`)
+// on the way (fg_commit is lazy), so the copy costs one 64-byte write per node instead of a pass of its own.
+template <bool COMMIT>
 __global__ void __launch_bounds__(BLOCK)
-k_basis(int NOD, const NodeRec *__restrict__ cur, double cr, double sr, Basis *__restrict__ basis,
+k_basis(int NOD, const NodeRec *__restrict__ src, NodeRec *dst, double cr, double sr, Basis *__restrict__ basis,
         double4 *__restrict__ qbasis)
     {
     const int stride = gridDim.x * BLOCK;
     for (int a = blockIdx.x * BLOCK + threadIdx.x; a < NOD; a += stride)
         {
         double u[3], v[3], phi, phiv, ep[3], eq[3];
-        load_rec(cur + a, u, v, phi, phiv);
+        if (COMMIT)
+            {
+            const double4 *q = reinterpret_cast<const double4 *>(src + a);
+            const double4 r0 = ld256_nc(q), r1 = ld256_nc(q + 1);
+            double4 *o = reinterpret_cast<double4 *>(dst + a);
+            st256(o, r0);
+            st256(o + 1, r1);
+            u[0] = r0.x; u[1] = r0.y; u[2] = r0.z;
+            }
+        else
+            load_rec(src + a, u, v, phi, phiv);
         node_set_basis(u, cr, sr, ep, eq);
         double2 *q = reinterpret_cast<double2 *>(basis + a);
         q[0] = make_double2(ep[0], ep[1]);

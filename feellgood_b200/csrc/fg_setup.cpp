@@ -3,6 +3,7 @@
 #include "fg_setup.hpp"
 
 #include <algorithm>
+#include <cstring>
 #include <cmath>
 #include <cstdio>
 #include <numeric>
@@ -319,19 +320,76 @@ int host_setup(const fg_mesh &m, const fg_params &prm, int n_owned, HostSetup &h
         h.perm[(size_t)NODp + (a - NOW)] = a;
         h.iperm[a] = NODp + (a - NOW);
         }
+    // FG_ORDER=window keeps the caller's (reference's) node order and only sorts inside windows; the default
+    // builds spatially compact blocks of GATHER_BLOCK rows first (recursive coordinate bisection of the owned
+    // nodes: the range is split at a multiple of the block size along the longest axis of its bounding
+    // box), then sorts inside each block by descending pair count.
         {
-        const int nwin = (NOW + SELL_WINDOW - 1) / SELL_WINDOW;
+        const char *eo = getenv("FG_ORDER");
+        h.order_kind = (eo && !strcmp(eo, "window")) ? 0 : 1;
+        }
+    std::vector<int> base((size_t)NOW);  // position p of the pre-order holds node base[p]
+    std::iota(base.begin(), base.end(), 0);
+    int win = SELL_WINDOW;
+    if (h.order_kind == 1)
+        {
+        win = GATHER_BLOCK;
+        struct Range { int lo, hi; };
+        std::vector<Range> todo;
+        todo.push_back({0, NOW});
+        const double *P = h.node_p.data();
+        // breadth-first: the ranges of one level are independent
+        while (!todo.empty())
+            {
+            std::vector<Range> next((size_t)2 * todo.size());
+            std::vector<char> used((size_t)2 * todo.size(), 0);
+#pragma omp parallel for schedule(dynamic, 1)
+            for (long long q = 0; q < (long long)todo.size(); q++)
+                {
+                const int lo = todo[(size_t)q].lo, hi = todo[(size_t)q].hi;
+                if (hi - lo <= GATHER_BLOCK) continue;
+                double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+                for (int p = lo; p < hi; p++)
+                    for (int c = 0; c < 3; c++)
+                        {
+                        const double v = P[3 * (size_t)base[(size_t)p] + c];
+                        mn[c] = std::min(mn[c], v);
+                        mx[c] = std::max(mx[c], v);
+                        }
+                int ax = 0;
+                if (mx[1] - mn[1] > mx[ax] - mn[ax]) ax = 1;
+                if (mx[2] - mn[2] > mx[ax] - mn[ax]) ax = 2;
+                const int nb = (hi - lo + GATHER_BLOCK - 1) / GATHER_BLOCK;
+                const int mid = lo + (nb / 2) * GATHER_BLOCK;  // left part: whole blocks
+                std::nth_element(base.begin() + lo, base.begin() + mid, base.begin() + hi, [&](int x, int y)
+                    {
+                    const double vx = P[3 * (size_t)x + ax], vy = P[3 * (size_t)y + ax];
+                    return vx < vy || (vx == vy && x < y);
+                    });
+                next[(size_t)2 * q] = {lo, mid};
+                next[(size_t)2 * q + 1] = {mid, hi};
+                used[(size_t)2 * q] = used[(size_t)2 * q + 1] = 1;
+                }
+            todo.clear();
+            for (size_t q = 0; q < next.size(); q++)
+                if (used[q]) todo.push_back(next[q]);
+            }
+        }
+        {
+        const int nwin = (NOW + win - 1) / win;
 #pragma omp parallel for schedule(static)
         for (int wdx = 0; wdx < nwin; wdx++)
             {
-            const int b = wdx * SELL_WINDOW, e = std::min(NOW, b + SELL_WINDOW);
+            const int b = wdx * win, e = std::min(NOW, b + win);
             int *q = &h.perm[(size_t)b];
-            std::iota(q, q + (e - b), b);
+            std::copy(base.begin() + b, base.begin() + e, q);
+            if (h.order_kind == 1) std::sort(q, q + (e - b));  // deterministic start: ascending node number
             std::stable_sort(q, q + (e - b), [&](int x, int y)
                 { return h.nptr[x + 1] - h.nptr[x] > h.nptr[y + 1] - h.nptr[y]; });
             for (int r = b; r < e; r++) h.iperm[(size_t)h.perm[(size_t)r]] = r;
             }
         }
+    std::vector<int>().swap(base);
     // magnetic tets follow the node order (sorted by their smallest device row) so that
     // neighbouring threads of the element kernel gather neighbouring node records
         {
@@ -483,6 +541,63 @@ int host_setup(const fg_mesh &m, const fg_params &prm, int n_owned, HostSetup &h
                 for (int q = h.inc_tri_ptr[a]; q < h.inc_tri_ptr[a + 1]; q++)
                     h.sinct[((size_t)h.itptr[s] + (q - h.inc_tri_ptr[a])) * SELL_C + l] = h.inc_tri[q];
                 }
+        }
+
+    // ---- gather blocks: halo lists and 16-bit local column indices (fg_setup.hpp) ---------------
+    h.nblock = 0;
+    h.stage_cap = 0;
+    if (h.order_kind == 1)
+        {
+        const int SPB = GATHER_BLOCK / SELL_C;  // slices per block
+        const int nb = (h.nslice + SPB - 1) / SPB;
+        h.nblock = nb;
+        h.bptr.assign((size_t)nb + 1, 0);
+        h.bghost.assign((size_t)nb, 0);
+        std::vector<std::vector<int>> halo((size_t)nb);
+#pragma omp parallel for schedule(dynamic, 64)
+        for (int b = 0; b < nb; b++)
+            {
+            const int r0 = b * GATHER_BLOCK, r1 = r0 + GATHER_BLOCK;
+            const int s0 = b * SPB, s1 = std::min(h.nslice, s0 + SPB);
+            std::vector<int> &hl = halo[(size_t)b];
+            for (size_t pos = (size_t)h.sptr[s0] * SELL_C; pos < (size_t)h.sptr[s1] * SELL_C; pos++)
+                {
+                const int c = h.scol[pos];
+                if (c < r0 || c >= r1) hl.push_back(c);
+                }
+            std::sort(hl.begin(), hl.end());
+            hl.erase(std::unique(hl.begin(), hl.end()), hl.end());
+            if (!hl.empty() && hl.back() >= NODp) h.bghost[(size_t)b] = 1;
+            }
+        int worst = 0;
+        for (int b = 0; b < nb; b++)
+            {
+            h.bptr[(size_t)b + 1] = h.bptr[(size_t)b] + (int)halo[(size_t)b].size();
+            worst = std::max(worst, (int)halo[(size_t)b].size());
+            }
+        if (GATHER_BLOCK + worst <= 65535)
+            {
+            h.stage_cap = GATHER_BLOCK + worst;
+            h.bhalo.resize((size_t)h.bptr[(size_t)nb]);
+            h.lcol.assign(h.scol.size(), 0);
+#pragma omp parallel for schedule(dynamic, 64)
+            for (int b = 0; b < nb; b++)
+                {
+                const std::vector<int> &hl = halo[(size_t)b];
+                std::copy(hl.begin(), hl.end(), h.bhalo.begin() + h.bptr[(size_t)b]);
+                const int r0 = b * GATHER_BLOCK, r1 = r0 + GATHER_BLOCK;
+                const int s0 = b * SPB, s1 = std::min(h.nslice, s0 + SPB);
+                for (size_t pos = (size_t)h.sptr[s0] * SELL_C; pos < (size_t)h.sptr[s1] * SELL_C; pos++)
+                    {
+                    const int c = h.scol[pos];
+                    if (c >= r0 && c < r1)
+                        h.lcol[pos] = (unsigned short)(c - r0);
+                    else
+                        h.lcol[pos] = (unsigned short)(GATHER_BLOCK
+                                                       + (int)(std::lower_bound(hl.begin(), hl.end(), c) - hl.begin()));
+                    }
+                }
+            }
         }
 
     // ---- masked dofs (src/linear_algebra.h:55-63) ---------------------------------------------

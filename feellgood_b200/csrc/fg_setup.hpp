@@ -66,7 +66,23 @@ struct HostSetup
     std::vector<int> tet_dev_ind;  // 4*n_magTet : device rows of the magnetic tets, device tet order
     std::vector<int> tet_slot;     // 4*n_magTet : where (tet, local node) writes its record = its
                                    // position in the node's SELL incidence list (-1: no row)
+    // ---- gather blocks of the matrix-free SpMV ----------------------------------
+    // With the compact ordering (order_kind == 1) the rows are cut into blocks of GATHER_BLOCK = 256
+    // consecutive device rows (8 slices) that are spatially compact (recursive coordinate bisection), so that
+    // the images a block gathers are its own 256 rows plus a small halo.  A thread group stages them once
+    // in shared memory and the stored pairs address them with 16-bit LOCAL indices, whatever the distance
+    // of the column in the global numbering (ghost columns of a partition included):
+    //   local index < 256            : row 256 b + index of the block itself
+    //   local index = 256 + k        : row bhalo[bptr[b] + k]
+    int order_kind = 0;            // 0 window-local sort of the caller's order | 1 compact blocks (RCB)
+    int nblock = 0;                // ceil(nslice / 8)
+    int stage_cap = 0;             // 256 + largest halo of a block (0: no block tables)
+    std::vector<int> bptr;         // nblock+1
+    std::vector<int> bhalo;        // bptr[nblock] device rows, ascending inside a block
+    std::vector<unsigned short> lcol;   // sptr[nslice]*32 : local index of the column node (pad: own row)
+    std::vector<unsigned char> bghost;  // nblock : 1 = the block's halo has a ghost row (>= NODp)
     };
+constexpr int GATHER_BLOCK = 256;
 constexpr int SELL_C = 32;
 constexpr int SELL_WINDOW_DEFAULT = 1024;
 // window of the row permutation (multiple of 32); FG_SELL_WINDOW overrides the default (experiments)

@@ -5,9 +5,11 @@
 // on each of its 5 kernels per iteration; at the per-rank size of an 8-GPU run (or on the reference's own
 // 10^4..10^6-tetrahedron meshes) those fixed costs are larger than the memory time of the kernels.  Here
 // the grid is resident for the whole solve:
-//   * static row ownership: warp g of the grid owns the SELL slices g, g + nwarps, ... in every phase, so
-//     every Krylov vector entry (r, p, v, s, t, x) is produced and consumed by the same thread; the only
-//     data that crosses threads are the 3-vector images w gathered by the SpMV and the scalars;
+//   * static row ownership (SliceIter): the grid sweeps the SELL slices as one front, a warp owns the same
+//     slices in every phase, the incomplete last round is dealt out per CTA so that all SMs carry the same
+//     load to one slice; every Krylov vector entry (r, p, v, s, t, x) is produced and consumed by the same
+//     thread; the only data that crosses threads are the 3-vector images w gathered by the SpMV and the
+//     scalars;
 //   * 5 grid-wide synchronisations per iteration (reference order src/algebra/bicg.h:185-232):
 //       A  p = r + beta (p - omega v), w_p = P D p            | barrier (+ halo flag)
 //       B  v = K D p, (v, rt)                                 | reduce  -> alpha
@@ -66,8 +68,11 @@ struct PkArgs
     NodeRec *next;
     const Basis *basis;
     double dt;
-    unsigned long long *stamps;  // optional [cap] (phase id << 56 | globaltimer ns), written by CTA 0
-    int stamp_cap;
+    unsigned long long *phase_acc;  // optional [32]: summed ns per phase id, then counts; CTA 0 adds to them
+    // result mailbox in mapped host memory (NULL: the host copies KState itself)
+    KState *h_st;
+    unsigned long long *h_seq;
+    unsigned long long seq;
     };
 
 
@@ -79,7 +84,7 @@ template <int BS> struct PkShared
     unsigned int gen;            // barrier generation this CTA waits for next (thread 0)
     unsigned int nred;           // reductions so far (slot parity)
     unsigned long long hepoch;   // halo epoch this CTA expects next
-    int nstamp;
+    unsigned long long t_prev;   // time stamp of the previous phase boundary (CTA 0, thread 0)
     };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p)
@@ -93,8 +98,16 @@ __device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v)
 
 template <int BS> __device__ __forceinline__ void pk_stamp(const PkArgs &a, PkShared<BS> &sh, int id)
     {
-    if (a.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && sh.nstamp < a.stamp_cap)
-        a.stamps[sh.nstamp++] = ((unsigned long long)id << 56) | (now_ns() & 0x00ffffffffffffffull);
+    if (a.phase_acc != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
+        {  // phase `id` = the time since the previous boundary, as CTA 0 saw it (barrier wait included)
+        const unsigned long long t = now_ns();
+        if (id != PKP_START)
+            {
+            a.phase_acc[id] += t - sh.t_prev;
+            a.phase_acc[16 + id] += 1ull;
+            }
+        sh.t_prev = t;
+        }
     }
 
 // Grid barrier with an optional sum (NV > 0) or maximum (MAXOP) over the grid and the ranks.
@@ -256,25 +269,25 @@ __device__ inline void pk_halo_wait(DistDev *d, unsigned long long e)
     }
 
 template <int STAGE, bool IDX16, int BS>
-__device__ __forceinline__ void pk_spmv(const PkArgs &a, PkShared<BS> &sh, const SpmvArgs &sa, const int g0,
-                                        const int nwarps, const int lane, const bool wait_halo, double (&acc)[RED_NV])
+__device__ __forceinline__ void pk_spmv(const PkArgs &a, PkShared<BS> &sh, const SpmvArgs &sa, const SliceIter it,
+                                        const int lane, const bool wait_halo, double (&acc)[RED_NV])
     {
     if (a.dist != nullptr && a.op.sghost != nullptr && wait_halo)
         {
-        spmv_node3_slices<STAGE, IDX16, true>(a.op, sa, g0, nwarps, lane, 1, acc);
+        spmv_node3_slices<STAGE, IDX16, true>(a.op, sa, it, lane, 1, acc);
         // the slices with ghost columns: wait for the neighbours' pushes of this phase (per warp: only
         // warps that own such a slice wait)
-        int s = g0;
-        while (s < a.op.nslice && a.op.sghost[s] == 0) s += nwarps;
+        int s = it.begin();
+        while (s < a.op.nslice && a.op.sghost[s] == 0) s = it.next(s);
         if (s < a.op.nslice)
             {
             if (lane == 0) pk_halo_wait(a.dist, sh.hepoch - 1);
             __syncwarp();
-            spmv_node3_slices<STAGE, IDX16, true>(a.op, sa, g0, nwarps, lane, 2, acc);
+            spmv_node3_slices<STAGE, IDX16, true>(a.op, sa, it, lane, 2, acc);
             }
         }
     else
-        spmv_node3_slices<STAGE, IDX16, true>(a.op, sa, g0, nwarps, lane, 0, acc);
+        spmv_node3_slices<STAGE, IDX16, true>(a.op, sa, it, lane, 0, acc);
     }
 
 template <int BS, bool IDX16>
@@ -282,10 +295,10 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
     {
     __shared__ PkShared<BS> sh;
     const int lane = threadIdx.x & 31;
-    const int nwarps = gridDim.x * (BS / 32);
-    const int g0 = blockIdx.x * (BS / 32) + (threadIdx.x >> 5);  // first slice of this warp
-    const int gtid = blockIdx.x * BS + threadIdx.x, gthreads = gridDim.x * BS;
+    // Row ownership (SliceIter, fg_krylov.cu): a front of W slices per round, the last round dealt out per CTA
+    const SliceIter own = slices_balanced(a.op.nslice, BS / 32);
     const int nslice = a.op.nslice;
+    const int gtid = blockIdx.x * BS + threadIdx.x, gthreads = gridDim.x * BS;
     const bool spec = a.dist != nullptr;  // speculative second SpMV: one all-reduce less per iteration
     if (threadIdx.x == 0)
         {
@@ -295,7 +308,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
         sh.gen = ld_acquire_u32(&a.sync->gen);
         sh.nred = 0;
         sh.hepoch = a.dist != nullptr ? a.dist->hepoch + 1 : 1;
-        sh.nstamp = 0;
+        sh.t_prev = 0ull;
         }
     __syncthreads();
     pk_stamp(a, sh, PKP_START);
@@ -312,7 +325,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
     sa.y = a.r;
     sa.a0 = a.b;
     sa.o0 = a.rt;
-    spmv_node3_slices<ST_BICG_SETUP, IDX16, true>(a.op, sa, g0, nwarps, lane, 0, acc);
+    spmv_node3_slices<ST_BICG_SETUP, IDX16, true>(a.op, sa, own, lane, 0, acc);
     pk_sync<BS, 2, false>(a, sh, acc, 0);
     if (threadIdx.x == 0)
         {
@@ -353,7 +366,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
                     const double2 ph = value(row, pi);
                     return node_w(a.op.qbasis + row, ph.x, ph.y);
                     });
-            for (int s = g0; s < nslice; s += nwarps)
+            for (int s = own.begin(); s < nslice; s = own.next(s))
                 {
                 const int row = s * SLICE + lane;
                 double2 pi;
@@ -373,7 +386,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
         sa.y = a.v;
         sa.a0 = a.rt;
         sa.o0 = nullptr;
-        pk_spmv<ST_BICG_V, IDX16, BS>(a, sh, sa, g0, nwarps, lane, true, acc);
+        pk_spmv<ST_BICG_V, IDX16, BS>(a, sh, sa, own, lane, true, acc);
         pk_sync<BS, 1, false>(a, sh, acc, 0);
         if (threadIdx.x == 0)
             {
@@ -401,7 +414,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
                     const double2 sh_ = value(row, si);
                     return node_w(a.op.qbasis + row, sh_.x, sh_.y);
                     });
-            for (int s = g0; s < nslice; s += nwarps)
+            for (int s = own.begin(); s < nslice; s = own.next(s))
                 {
                 const int row = s * SLICE + lane;
                 double2 si;
@@ -431,7 +444,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
             sa.x = nullptr;
             sa.y = a.t;
             sa.a0 = a.s;
-            pk_spmv<ST_BICG_T, IDX16, BS>(a, sh, sa, g0, nwarps, lane, true, acc);
+            pk_spmv<ST_BICG_T, IDX16, BS>(a, sh, sa, own, lane, true, acc);
             if (spec)
                 {
                 acc[2] = ss_acc;
@@ -474,7 +487,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
                 ;
             else if (fh)
                 {
-                for (int s = g0; s < nslice; s += nwarps)
+                for (int s = own.begin(); s < nslice; s = own.next(s))
                     {
                     const int row = s * SLICE + lane;
                     const double2 d = D2[row], pp = p2[row];
@@ -486,7 +499,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
                 }
             else
                 {
-                for (int s = g0; s < nslice; s += nwarps)
+                for (int s = own.begin(); s < nslice; s = own.next(s))
                     {
                     const int row = s * SLICE + lane;
                     const double2 d = D2[row], pp = p2[row], sv = s2[row], tv = t2[row], rtv = rt2[row];
@@ -566,7 +579,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
             };
         if (!failed)
             {
-            for (int s = g0; s < nslice; s += nwarps) update_row(s * SLICE + lane, true);
+            for (int s = own.begin(); s < nslice; s = own.next(s)) update_row(s * SLICE + lane, true);
             if (a.NODt > a.NODp)
                 {  // ghost rows: their solution was pushed by the owners
                 if (gtid - lane < a.NODt - a.NODp)
@@ -594,7 +607,12 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
     if (blockIdx.x == 0 && threadIdx.x == 0)
         {
         *a.st = sh.ks;
-        if (a.stamps != nullptr && sh.nstamp < a.stamp_cap) a.stamps[sh.nstamp] = 0ull;  // terminator
+        if (a.h_st != nullptr)
+            {  // the host is spinning on h_seq: outcome first, then the number (system-scope order)
+            *a.h_st = sh.ks;
+            __threadfence_system();
+            st_sys(a.h_seq, a.seq);
+            }
         }
     }
 

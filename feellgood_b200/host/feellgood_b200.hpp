@@ -11,6 +11,8 @@
 //   namespace algebra:                   src/algebra/{iter,sparseMat,bicg,cg}.h
 //       algoStatus, iteration<T>, MatrixShape, SparseMatrix{clear,set,add,operator(),mult,
 //       build_diag_precond}, bicg, bicg_dir (both overloads), cg, cg_dir
+//   template <int DIM> class solver      src/solver.h:20-143               (build_shape, buildMat<N>,
+//                                        buildVect<N>, K, L_rhs, iter: the base of the side solvers)
 //
 // Differences a maintainer has to know:
 //   * the node state (u, v, phi, phiv CURRENT/NEXT) that the reference keeps inside Mesh::mesh lives
@@ -116,6 +118,21 @@ struct MeshView
     int NOD() const { return (int)(node_p.size() / 3); }
     int NT() const { return (int)tet_reg.size(); }
     int NF() const { return (int)tri_reg.size(); }
+    int getNbNodes() const { return NOD(); }
+    // Mesh::mesh::edges (src/mesh.h:100-114): every tetrahedron edge once, as a sorted pair, sorted
+    using Edge = std::pair<int, int>;
+    std::vector<Edge> edges;
+    void build_edges()
+        {
+        edges.clear();
+        edges.reserve(tet_reg.size() * 6);
+        for (size_t t = 0; t < tet_reg.size(); t++)
+            for (int i = 0; i < 3; ++i)
+                for (int j = i + 1; j < 4; ++j) edges.push_back(std::minmax(tet_ind[4 * t + i], tet_ind[4 * t + j]));
+        std::sort(edges.begin(), edges.end());
+        edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+        edges.shrink_to_fit();
+        }
     };
 }  // namespace fgb200
 
@@ -314,6 +331,83 @@ void cg_dir(iteration<T> &iter, SparseMatrix &A, std::vector<T> &x, const std::v
     detail::store(iter, r);
     }
 }  // namespace algebra
+
+// ---------------------------------------------------------------------------------------------
+// solver<DIM_PROBLEM> — reference src/solver.h:20-143, the base of the side solvers (electrostatSolver:
+// DIM 1 with cg_dir, spinAcc: DIM 3 with bicg_dir).  Same protected surface: build_shape, buildMat<N>,
+// buildVect<N>, members msh, NOD, verbose, iter, K, L_rhs; K is an algebra::SparseMatrix whose mult and
+// Krylov solvers run on the GPU (fg_matrix_*).  The element matrix type only needs operator()(i, j)
+// (Eigen::Matrix qualifies; fgb200::Dense below is the Eigen-free stand-in).  The material parameter
+// vectors of the reference's constructor are not used by this base class and are left to the derived
+// solver.
+// ---------------------------------------------------------------------------------------------
+namespace fgb200
+{
+template <int R, int C = R> struct Dense
+    {
+    double a[R * C] = {};
+    double &operator()(int i, int j) { return a[i * C + j]; }
+    double operator()(int i, int j) const { return a[i * C + j]; }
+    };
+}  // namespace fgb200
+
+template <int DIM_PROBLEM> class solver
+    {
+public:
+    explicit solver(fgb200::MeshView &_msh, const std::string &name, const double _tol, const bool v,
+                    const int max_iter,
+                    const std::function<bool(fgb200::MeshView::Edge)> &edge_filter = [](fgb200::MeshView::Edge)
+                        { return true; })
+        : msh(&_msh), NOD(_msh.getNbNodes()), verbose(v), iter(name, _tol, v, max_iter),
+          K(build_shape(edge_filter)), L_rhs((size_t)DIM_PROBLEM * _msh.getNbNodes()) {}
+    virtual ~solver() = default;
+    /** check boundary conditions (src/solver.h:43) */
+    virtual void checkBoundaryConditions(void) const = 0;
+
+protected:
+    static const int DIM_PB = DIM_PROBLEM;
+    fgb200::MeshView *msh;
+    const int NOD;
+    const bool verbose;
+    algebra::iteration<double> iter;
+    algebra::SparseMatrix K;
+    std::vector<double> L_rhs;
+
+    /** src/solver.h:75-104: one DIM x DIM block per node and per relevant edge, both directions */
+    algebra::MatrixShape build_shape(const std::function<bool(fgb200::MeshView::Edge)> &edge_filter) const
+        {
+        if (msh->edges.empty() && msh->NT() > 0) msh->build_edges();
+        algebra::MatrixShape shape((size_t)DIM_PROBLEM * NOD);
+        auto add_block = [&shape](const int i, const int j)
+            {
+            for (int k = 0; k < DIM_PROBLEM; ++k)
+                for (int l = 0; l < DIM_PROBLEM; ++l) shape[(size_t)DIM_PROBLEM * i + k].insert(DIM_PROBLEM * j + l);
+            };
+        for (int i = 0; i < NOD; ++i) add_block(i, i);
+        for (auto edge : msh->edges)
+            if (edge_filter(edge))
+                {
+                add_block(edge.first, edge.second);
+                add_block(edge.second, edge.first);
+                }
+        return shape;
+        }
+    /** src/solver.h:110-129 */
+    template <int N, class Mat> void buildMat(std::array<int, N> &ind, Mat &Ke)
+        {
+        for (int ie = 0; ie < N; ie++)
+            for (int je = 0; je < N; je++)
+                for (int di = 0; di < DIM_PROBLEM; di++)
+                    for (int dj = 0; dj < DIM_PROBLEM; dj++)
+                        K.add(DIM_PROBLEM * ind[ie] + di, DIM_PROBLEM * ind[je] + dj, Ke(di * N + ie, dj * N + je));
+        }
+    /** src/solver.h:135-143 */
+    template <int N> void buildVect(std::array<int, N> &ind, std::vector<double> &Le)
+        {
+        for (int ie = 0; ie < N; ie++)
+            for (int di = 0; di < DIM_PROBLEM; di++) L_rhs[(size_t)DIM_PROBLEM * ind[ie] + di] += Le[(size_t)di * N + ie];
+        }
+    };
 
 // ---------------------------------------------------------------------------------------------
 // LinAlgebra — reference src/linear_algebra.h:33-121 + solver<2> (src/solver.h:26-143)

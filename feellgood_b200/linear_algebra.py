@@ -326,6 +326,12 @@ class LinAlgebra:
         check(self._L.fg_get_system(self._h, C.c_double(t_prm.get_dt()), dp(val), dp(rhs), dp(x0)))
         return val, rhs, x0
 
+    def jacobi_diagonal(self, t_prm):
+        """D = 1/diag(K), 0 on masked dofs (src/algebra/sparseMat.h:174-183), as the solver uses it."""
+        D = np.empty(self.n)
+        check(self._L.fg_get_precond(self._h, C.c_double(t_prm.get_dt()), dp(D)))
+        return D
+
     def apply_operator(self, x):
         x = f64(x)
         y = np.empty(self.n)

@@ -184,6 +184,14 @@ def iter_bytes(n, nnz, col_bytes=4):
     return 2 * spmv_bytes(n, nnz, col_bytes) + (144 + 128 + 128) * (n // 2)
 
 
+def solve_bytes(n, nnz, iters, col_bytes=4):
+    """One launch of the persistent solve kernel (k_llg_solve): the setup product r = b - K x0 (reads x0,
+    writes r and rt), `iters` BiCGStab iterations and the node update (reads x, u, the basis: 16 + 32 + 48 B;
+    writes u, v of NEXT: 48 B per node)."""
+    return (spmv_bytes(n, nnz, col_bytes, reads_x=True) + 16 * (n // 2) + iters * iter_bytes(n, nnz, col_bytes)
+            + (16 + 32 + 48 + 48) * (n // 2))
+
+
 def step_bytes(NOD, NT, n, nnz, iters, col_bytes=4):
     """B_step of SURVEY.md §8d with this library's matrix layout."""
     b_basis = (72 + 32) * NOD   # + the quaternion copy of the basis the Krylov kernels read

@@ -191,6 +191,9 @@ int fg_get_csr_pattern(const fg_ctx *ctx, int *rowptr, int *col);
  * (src/solver.cpp:9-59), for the system prepared by the last prepareElements.  Called after
  * fg_solve it returns the K and L_rhs that solve used, and x0 = the solution Xw. */
 int fg_get_system(fg_ctx *ctx, double dt, double *val, double *rhs, double *x0);
+/* SparseMatrix::build_diag_precond (src/algebra/sparseMat.h:174-183) as the solver uses it: D[i] = 1 / K(i,i),
+ * 0 on the masked dofs (n doubles), for the system prepared by the last prepareElements (or solved last). */
+int fg_get_precond(fg_ctx *ctx, double dt, double *D);
 /* y = K x with the device SpMV the solver itself uses, on the system assembled last (n each) */
 int fg_apply_operator(fg_ctx *ctx, const double *x, double *y);
 int fg_get_solution(fg_ctx *ctx, double *Xw); /* n */

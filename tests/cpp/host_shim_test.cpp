@@ -258,6 +258,85 @@ static void test_laplacian_dirichlet()
     CHECK(std::sqrt(r2) < 1e-8);
     }
 
+// A side solver written against the reference's solver<DIM> surface (src/solver.h:20-143), the way
+// electrostatSolver does (src/electrostatSolver.h:22-35, electrostatSolver.cpp): DIM 1, P1 Laplacian
+// assembled element by element with buildMat<4> / buildVect<4>, Dirichlet values through cg_dir.
+class laplaceSolver : public solver<1>
+    {
+public:
+    laplaceSolver(fgb200::MeshView &m, double tol, int max_iter) : solver<1>(m, "cg_dir", tol, false, max_iter) {}
+    void checkBoundaryConditions(void) const override {}
+    // grad-grad stiffness of every tetrahedron; x = 0 plane held at 0, x = xmax plane at 1
+    bool run(std::vector<double> &V, double xmax)
+        {
+        K.clear();
+        std::fill(L_rhs.begin(), L_rhs.end(), 0.0);
+        const auto &p = msh->node_p;
+        for (int t = 0; t < msh->NT(); t++)
+            {
+            std::array<int, 4> ind;
+            for (int i = 0; i < 4; i++) ind[i] = msh->tet_ind[4 * (size_t)t + i];
+            double J[3][3];
+            for (int c = 0; c < 3; c++)
+                for (int k = 0; k < 3; k++) J[c][k] = p[3 * (size_t)ind[k + 1] + c] - p[3 * (size_t)ind[0] + c];
+            const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0])
+                               + J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+            double inv[3][3];  // inverse of J
+            inv[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / det; inv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det;
+            inv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det; inv[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) / det;
+            inv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det; inv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
+            inv[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / det; inv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det;
+            inv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+            double g[4][3];  // gradients of the four hat functions
+            for (int c = 0; c < 3; c++)
+                {
+                g[0][c] = -(inv[0][c] + inv[1][c] + inv[2][c]);
+                for (int k = 0; k < 3; k++) g[k + 1][c] = inv[k][c];
+                }
+            fgb200::Dense<4> Ke;
+            for (int i = 0; i < 4; i++)
+                for (int j = 0; j < 4; j++)
+                    Ke(i, j) = std::fabs(det) / 6.0 * (g[i][0] * g[j][0] + g[i][1] * g[j][1] + g[i][2] * g[j][2]);
+            buildMat<4>(ind, Ke);
+            std::vector<double> Le(4, 0.0);
+            buildVect<4>(ind, Le);
+            }
+        std::vector<int> ld;
+        std::vector<double> Vd((size_t)NOD, 0.0);
+        for (int a = 0; a < NOD; a++)
+            {
+            const double x = p[3 * (size_t)a];
+            if (x < 1e-12 * xmax || x > xmax * (1 - 1e-12))
+                {
+                ld.push_back(a);
+                Vd[a] = x > 0.5 * xmax ? 1.0 : 0.0;
+                }
+            }
+        V.assign((size_t)NOD, 0.0);
+        iter.reset();
+        algebra::cg_dir(iter, K, V, L_rhs, Vd, ld);
+        return iter.status == algebra::CONVERGED;
+        }
+    int iterations() const { return iter.get_iteration(); }
+    int rows() const { return (int)K.size(); }
+    };
+
+static void test_solver_template()
+    {
+    const double h = 2e-9;
+    fgb200::MeshView msh = cuboid(10, 4, 3, h);
+    laplaceSolver ls(msh, 1e-10, 2000);
+    CHECK(ls.rows() == msh.NOD());
+    CHECK(!msh.edges.empty());
+    std::vector<double> V;
+    CHECK(ls.run(V, 10 * h));
+    CHECK(ls.iterations() > 0);
+    // the discrete harmonic function with these boundary values is exactly V = x / xmax (P1 elements)
+    double err = 0.0;
+    for (int a = 0; a < msh.NOD(); a++) err = std::max(err, std::fabs(V[a] - msh.node_p[3 * (size_t)a] / (10 * h)));
+    CHECK(err < 1e-8);
+    }
+
 int main(int argc, char **argv)
     {
     if (argc > 1 && !std::strcmp(argv[1], "--timestepper")) return replay_timestepper();
@@ -270,6 +349,7 @@ int main(int argc, char **argv)
         {
         test_identity_solves();
         test_laplacian_dirichlet();
+        test_solver_template();
         test_llg_loop();
         test_fem_time_integration();
         }
