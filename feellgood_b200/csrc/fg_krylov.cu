@@ -262,18 +262,19 @@ __device__ __forceinline__ SliceIter slices_strided(int g, int W, int nslice)
     it.tail = INT_MAX;
     return it;
     }
-// front + per-CTA tail (persistent kernel): nw warps per CTA
-__device__ __forceinline__ SliceIter slices_balanced(int nslice, int nw)
+// front + per-CTA tail (persistent kernel): n units (slices or gather blocks) dealt to `per_cta` owners per
+// CTA (warps or thread groups), this owner being number `id` of its CTA
+__device__ __forceinline__ SliceIter slices_balanced(int n, int per_cta, int id)
     {
-    const int W = gridDim.x * nw, wid = threadIdx.x >> 5;
-    const int q = nslice / W, rem = nslice - q * W;
+    const int W = gridDim.x * per_cta;
+    const int q = n / W, rem = n - q * W;
     SliceIter it;
-    it.first = blockIdx.x * nw + wid;
+    it.first = blockIdx.x * per_cta + id;
     it.W = W;
     it.main_end = q * W;
     const int t0 = it.main_end + (int)(((long long)rem * blockIdx.x) / gridDim.x);
     const int t1 = it.main_end + (int)(((long long)rem * (blockIdx.x + 1)) / gridDim.x);
-    it.tail = t0 + wid < t1 ? t0 + wid : INT_MAX;
+    it.tail = t0 + id < t1 ? t0 + id : INT_MAX;
     return it;
     }
 
@@ -1147,12 +1148,37 @@ int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, pos
 // ------------------------------------------------------------------------------------------
 // BiCGStab as one persistent cooperative kernel (fg_solve_pk.cuh)
 // ------------------------------------------------------------------------------------------
-template <int BS, bool IDX16> static int pk_wave(int sms)
+// the instantiation for a block size, column width and staging mode
+static const void *pk_kernel(int bs, bool i16, bool staged)
     {
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_llg_solve<BS, IDX16>, BS, 0) != cudaSuccess || per_sm < 1)
-        return 0;
-    return per_sm * sms;
+    if (staged)
+        return bs == 1024 ? (const void *)k_llg_solve<1024, true, true> : (const void *)k_llg_solve<256, true, true>;
+    if (bs == 1024) return i16 ? (const void *)k_llg_solve<1024, true, false> : (const void *)k_llg_solve<1024, false, false>;
+    return i16 ? (const void *)k_llg_solve<256, true, false> : (const void *)k_llg_solve<256, false, false>;
+    }
+
+// Launch shape of the persistent kernel for an operator: CTA size, and whether the gathered images are
+// staged in shared memory (returns true) with `smem` bytes of dynamic shared memory per CTA.
+bool pk_plan(const Operator &op, int *bs_out, size_t *smem_out)
+    {
+    int dev = 0, sms = NUM_SMS;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // CTA size: 1024 threads (one CTA per SM, 148 arrivals per barrier) once every warp of such a grid has a
+    // slice of its own; 256 threads below that, so that small meshes still spread over all SMs
+    static const int forced = getenv("FG_PK_BLOCK") ? atoi(getenv("FG_PK_BLOCK")) : 0;
+    int bs = op.nslice >= sms * 32 ? 1024 : 256;
+    if (forced == 256 || forced == 1024) bs = forced;
+    // gathered images staged in shared memory when the mesh has gather blocks, a buffer per thread group fits,
+    // and there are enough blocks to keep every group of a full grid busy (a group walks 8 slices per block:
+    // below that size one slice per warp through L1 has the shorter critical path)
+    static const int min_blocks = getenv("FG_STAGE_MIN_BLOCKS") ? atoi(getenv("FG_STAGE_MIN_BLOCKS")) : -1;
+    const int cap = (op.stage_cap + 3) & ~3;
+    size_t smem = (size_t)(bs / 128) * (size_t)cap * sizeof(double4);
+    const int need = min_blocks >= 0 ? min_blocks : sms * 8;
+    const bool staged = op.lcol != nullptr && op.stage_cap > 0 && smem <= (size_t)200 * 1024 && op.nblock >= need;
+    if (bs_out) *bs_out = bs;
+    if (smem_out) *smem_out = staged ? smem : 0;
+    return staged;
     }
 
 int bicgstab_run_pk(const Operator &op, KrylovWork &w, double tol, int maxiter, const PkUpdate *upd)
@@ -1162,23 +1188,26 @@ int bicgstab_run_pk(const Operator &op, KrylovWork &w, double tol, int maxiter, 
         set_error("bicgstab_run_pk: needs the matrix-free LLG operator");
         return FG_ERR_STATE;
         }
+    int bs = 0;
+    size_t smem = 0;
+    const bool staged = pk_plan(op, &bs, &smem);
+    const bool i16 = op.col16 != nullptr;
     int dev = 0, sms = NUM_SMS;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // CTA size: 1024 threads (one CTA per SM, 148 arrivals per barrier) once every warp of such a grid has a
-    // slice of its own; 256 threads below that, so that small meshes still spread over all SMs
-    static const int forced = getenv("FG_PK_BLOCK") ? atoi(getenv("FG_PK_BLOCK")) : 0;
-    int bs = op.nslice >= sms * 32 ? 1024 : 256;
-    if (forced == 256 || forced == 1024) bs = forced;
-    const bool i16 = op.col16 != nullptr;
-    int wave = bs == 1024 ? (i16 ? pk_wave<1024, true>(sms) : pk_wave<1024, false>(sms))
-                          : (i16 ? pk_wave<256, true>(sms) : pk_wave<256, false>(sms));
-    if (wave < 1)
+    const void *fn = pk_kernel(bs, i16, staged);
+    if (staged && smem > 48 * 1024)
+        FG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, bs, smem) != cudaSuccess || per_sm < 1)
         {
         set_error("bicgstab_run_pk: the solve kernel does not fit an SM");
         return FG_ERR_CUDA;
         }
+    int wave = per_sm * sms;
     if (wave > PK_MAX_GRID) wave = PK_MAX_GRID;
-    int grid = (op.nslice + bs / 32 - 1) / (bs / 32);
+    // units of ownership: gather blocks per thread group (staged) or slices per warp
+    const int units = staged ? op.nblock : op.nslice, per_cta = staged ? bs / 128 : bs / 32;
+    int grid = (units + per_cta - 1) / per_cta;
     if (grid > wave) grid = wave;
     if (grid < 1) grid = 1;
     PkArgs a = {};
@@ -1214,10 +1243,8 @@ int bicgstab_run_pk(const Operator &op, KrylovWork &w, double tol, int maxiter, 
         a.seq = ++w.seq;
         }
     void *args[] = {&a};
-    const void *fn = bs == 1024 ? (i16 ? (const void *)k_llg_solve<1024, true> : (const void *)k_llg_solve<1024, false>)
-                                : (i16 ? (const void *)k_llg_solve<256, true> : (const void *)k_llg_solve<256, false>);
     const bool prof = prof_begin(w.prof, w.stream, KC_SOLVE);
-    FG_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(bs), args, 0, w.stream));
+    FG_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(bs), args, smem, w.stream));
     if (prof) prof_end(w.prof, w.stream);
     if (w.launches) ++*w.launches;
     if (mailbox)

@@ -982,7 +982,8 @@ int fg_get_layout(const fg_ctx *c, long long out[4])
         set_error("fg_get_layout: null argument");
         return FG_ERR_INVALID;
         }
-    out[0] = c->scol16 ? 2 : 4;
+    // the persistent solver addresses staged images with 16-bit local indices whatever the global distance
+    out[0] = (c->solver_kind == 0 && pk_plan(c->op, nullptr, nullptr)) || c->scol16 ? 2 : 4;
     out[1] = c->nblk;
     out[2] = c->iso_regions ? 1 : 0;
     out[3] = c->NODp;

@@ -268,36 +268,198 @@ __device__ inline void pk_halo_wait(DistDev *d, unsigned long long e)
     __threadfence_system();
     }
 
-template <int STAGE, bool IDX16, int BS>
-__device__ __forceinline__ void pk_spmv(const PkArgs &a, PkShared<BS> &sh, const SpmvArgs &sa, const SliceIter it,
-                                        const int lane, const bool wait_halo, double (&acc)[RED_NV])
+// ---- gather blocks staged in shared memory (fg_setup.hpp, Operator::lcol) --------------------------------
+// A scattered 32-byte gather costs one L1 tag-stage wavefront per lane whether it hits or not: 62 M stored
+// pairs on the 20 M-tet mesh = 213 us of wavefronts per SM and product, which is what the SpMV measured
+// (217-227 us) before this path existed.  Here a group of 4 warps copies the images its block of 256 rows
+// needs (the block's own rows, contiguous, plus its halo list) into shared memory once with cp.async, and the
+// stored pairs read them with 16-bit local indices through the shared-memory pipe (8 cycles per warp and
+// pair instead of 32).  Each warp of the group owns slices w and 7 - w of the block: the slices of a block
+// are sorted by width, so every warp gets the same number of pairs.
+constexpr int PK_GROUP = 128;          // threads per group
+constexpr int PK_SPB = 8;              // slices per gather block
+__device__ __forceinline__ void pk_group_sync(int gid)
+    { asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "r"(PK_GROUP) : "memory"); }
+__device__ __forceinline__ void cp_async16(unsigned int dst_smem, const void *src)
+    { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int STAGE>
+__device__ __forceinline__ void pk_slice_staged(const Operator &op, const SpmvArgs &a, const int s, const int sl,
+                                                const int p0, const int p1, const double4 *stage, const int lane,
+                                                double (&acc)[RED_NV])
     {
+    const int row = s * SLICE + lane;
+    const unsigned short *cp = op.lcol + (size_t)p0 * SLICE + lane;
+    const double *sp = op.val + (size_t)p0 * SLICE + lane;
+    double z0 = 0.0, z1 = 0.0, z2 = 0.0;
+        {
+        constexpr int U = 8;
+        int cn[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) cn[u] = p0 + u < p1 ? (int)__ldcs(cp + u * SLICE) : 0;
+        for (int j = p0; j < p1; j += U)
+            {
+            int c[U];
+            double Sv[U];
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                {
+                c[u] = cn[u];
+                Sv[u] = j + u < p1 ? __ldcs(sp + u * SLICE) : 0.0;
+                }
+            cp += U * SLICE;
+            sp += U * SLICE;
+#pragma unroll
+            for (int u = 0; u < U; u++) cn[u] = j + U + u < p1 ? (int)__ldcs(cp + u * SLICE) : 0;
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                {
+                const double4 wb = stage[c[u]];
+                z0 += Sv[u] * wb.x;
+                z1 += Sv[u] * wb.y;
+                z2 += Sv[u] * wb.z;
+                }
+            }
+        }
+    double ep[3], eq[3];
+    load_basis_k(op.qbasis + row, ep, eq);
+    double2 xa;
+    if (a.x != nullptr)
+        xa = reinterpret_cast<const double2 *>(a.x)[row];
+    else
+        {  // x_a = P_a^T w_a: the node's own image is entry (slice in block, lane) of the staging buffer
+        const double4 wr = stage[sl * SLICE + lane];
+        xa = make_double2(ep[0] * wr.x + ep[1] * wr.y + ep[2] * wr.z, eq[0] * wr.x + eq[1] * wr.y + eq[2] * wr.z);
+        }
+    const double2 dm = __ldcs(op.Dm + row);
+    double y0 = op.cS * (eq[0] * z0 + eq[1] * z1 + eq[2] * z2) + (dm.y * xa.x + dm.x * xa.y);
+    double y1 = op.cS * (ep[0] * z0 + ep[1] * z1 + ep[2] * z2) + (dm.x * xa.x - dm.y * xa.y);
+    if (op.nonmag[row] != 0)
+        {  // identity row (src/solver.cpp:46-48)
+        y0 = xa.x;
+        y1 = xa.y;
+        }
+    spmv_row2<STAGE>(a, row, y0, y1, acc);
+    }
+
+// the blocks of this group (pass: 0 all | 1 blocks without ghost rows | 2 blocks with ghost rows)
+template <int STAGE>
+__device__ __forceinline__ void pk_blocks_staged(const PkArgs &a, const SpmvArgs &sa, const SliceIter &own,
+                                                 const int pass, double4 *stage, double (&acc)[RED_NV])
+    {
+    const Operator &op = a.op;
+    const int lane = threadIdx.x & 31, w4 = (threadIdx.x >> 5) & 3, tg = threadIdx.x & (PK_GROUP - 1),
+              gid = threadIdx.x / PK_GROUP;
+    const unsigned int sbase = (unsigned int)__cvta_generic_to_shared(stage);
+    const char *wbytes = reinterpret_cast<const char *>(sa.w);
+    for (int b = own.begin(); b < op.nblock; b = own.next(b))
+        {
+        if (pass != 0 && (op.bghost[b] != 0) != (pass == 2)) continue;
+        // slice extents of this warp's two slices, fetched under the shadow of the staging copies
+        const int sA = PK_SPB * b + w4, sB = PK_SPB * b + (PK_SPB - 1) - w4;
+        int pA0 = 0, pA1 = 0, pB0 = 0, pB1 = 0;
+        if (sA < op.nslice)
+            {
+            pA0 = __ldg(op.ptr + sA);
+            pA1 = __ldg(op.ptr + sA + 1);
+            }
+        if (sB < op.nslice)
+            {
+            pB0 = __ldg(op.ptr + sB);
+            pB1 = __ldg(op.ptr + sB + 1);
+            }
+        pk_group_sync(gid);  // the group is done with the images of its previous block
+        const int row0 = b * (PK_SPB * SLICE);
+        const int nown = min(PK_SPB * SLICE, a.NODp - row0);
+        const char *src = wbytes + (size_t)row0 * 32;
+        for (int i = tg; i < 2 * nown; i += PK_GROUP) cp_async16(sbase + 16 * i, src + 16 * i);
+        const int h0 = __ldg(op.bptr + b), nh = __ldg(op.bptr + b + 1) - h0;
+        for (int i = tg; i < 2 * nh; i += PK_GROUP)
+            {
+            const int g = __ldg(op.bhalo + h0 + (i >> 1));
+            cp_async16(sbase + PK_SPB * SLICE * 32 + 16 * i, wbytes + (size_t)g * 32 + 16 * (i & 1));
+            }
+        cp_async_wait_all();
+        pk_group_sync(gid);
+        if (sA < op.nslice) pk_slice_staged<STAGE>(op, sa, sA, w4, pA0, pA1, stage, lane, acc);
+        if (sB < op.nslice) pk_slice_staged<STAGE>(op, sa, sB, (PK_SPB - 1) - w4, pB0, pB1, stage, lane, acc);
+        }
+    }
+
+template <int STAGE, bool IDX16, bool STAGED, int BS>
+__device__ __forceinline__ void pk_spmv(const PkArgs &a, PkShared<BS> &sh, const SpmvArgs &sa, const SliceIter own,
+                                        const int lane, const bool wait_halo, double4 *stage, double (&acc)[RED_NV])
+    {
+    if (STAGED)
+        {
+        if (a.dist != nullptr && a.op.bghost != nullptr && wait_halo)
+            {
+            pk_blocks_staged<STAGE>(a, sa, own, 1, stage, acc);
+            // blocks whose halo has ghost rows: wait for the neighbours' pushes of this phase (per group:
+            // only groups that own such a block wait; the condition is uniform inside a group)
+            int b = own.begin();
+            while (b < a.op.nblock && a.op.bghost[b] == 0) b = own.next(b);
+            if (b < a.op.nblock)
+                {
+                if (lane == 0) pk_halo_wait(a.dist, sh.hepoch - 1);
+                __syncwarp();
+                pk_blocks_staged<STAGE>(a, sa, own, 2, stage, acc);
+                }
+            }
+        else
+            pk_blocks_staged<STAGE>(a, sa, own, 0, stage, acc);
+        return;
+        }
     if (a.dist != nullptr && a.op.sghost != nullptr && wait_halo)
         {
-        spmv_node3_slices<STAGE, IDX16, true>(a.op, sa, it, lane, 1, acc);
+        spmv_node3_slices<STAGE, IDX16, true>(a.op, sa, own, lane, 1, acc);
         // the slices with ghost columns: wait for the neighbours' pushes of this phase (per warp: only
         // warps that own such a slice wait)
-        int s = it.begin();
-        while (s < a.op.nslice && a.op.sghost[s] == 0) s = it.next(s);
+        int s = own.begin();
+        while (s < a.op.nslice && a.op.sghost[s] == 0) s = own.next(s);
         if (s < a.op.nslice)
             {
             if (lane == 0) pk_halo_wait(a.dist, sh.hepoch - 1);
             __syncwarp();
-            spmv_node3_slices<STAGE, IDX16, true>(a.op, sa, it, lane, 2, acc);
+            spmv_node3_slices<STAGE, IDX16, true>(a.op, sa, own, lane, 2, acc);
             }
         }
     else
-        spmv_node3_slices<STAGE, IDX16, true>(a.op, sa, it, lane, 0, acc);
+        spmv_node3_slices<STAGE, IDX16, true>(a.op, sa, own, lane, 0, acc);
     }
 
-template <int BS, bool IDX16>
+// every slice this warp owns: plain slices, or slices w and 7 - w of the group's gather blocks
+template <bool STAGED, class F>
+__device__ __forceinline__ void pk_for_slices(const SliceIter &own, const Operator &op, F f)
+    {
+    if (STAGED)
+        {
+        const int w4 = (threadIdx.x >> 5) & 3;
+        for (int b = own.begin(); b < op.nblock; b = own.next(b))
+            {
+            const int sA = PK_SPB * b + w4, sB = PK_SPB * b + (PK_SPB - 1) - w4;
+            if (sA < op.nslice) f(sA);
+            if (sB < op.nslice) f(sB);
+            }
+        }
+    else
+        for (int s = own.begin(); s < op.nslice; s = own.next(s)) f(s);
+    }
+
+extern __shared__ double4 pk_stage_smem[];  // STAGED: one staging buffer of stage_cap images per thread group
+
+template <int BS, bool IDX16, bool STAGED>
 __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(const PkArgs a)
     {
     __shared__ PkShared<BS> sh;
     const int lane = threadIdx.x & 31;
     // Row ownership (SliceIter, fg_krylov.cu): a front of W slices per round, the last round dealt out per CTA
-    const SliceIter own = slices_balanced(a.op.nslice, BS / 32);
-    const int nslice = a.op.nslice;
+    // STAGED: the units are gather blocks of 8 slices, owned by thread groups of 4 warps
+    const SliceIter own = STAGED ? slices_balanced(a.op.nblock, BS / PK_GROUP, threadIdx.x / PK_GROUP)
+                                 : slices_balanced(a.op.nslice, BS / 32, threadIdx.x >> 5);
+    double4 *const stage = STAGED ? pk_stage_smem + (size_t)(threadIdx.x / PK_GROUP) * (size_t)((a.op.stage_cap + 3) & ~3)
+                                  : nullptr;
     const int gtid = blockIdx.x * BS + threadIdx.x, gthreads = gridDim.x * BS;
     const bool spec = a.dist != nullptr;  // speculative second SpMV: one all-reduce less per iteration
     if (threadIdx.x == 0)
@@ -325,7 +487,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
     sa.y = a.r;
     sa.a0 = a.b;
     sa.o0 = a.rt;
-    spmv_node3_slices<ST_BICG_SETUP, IDX16, true>(a.op, sa, own, lane, 0, acc);
+    pk_spmv<ST_BICG_SETUP, IDX16, STAGED, BS>(a, sh, sa, own, lane, false, stage, acc);
     pk_sync<BS, 2, false>(a, sh, acc, 0);
     if (threadIdx.x == 0)
         {
@@ -366,14 +528,14 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
                     const double2 ph = value(row, pi);
                     return node_w(a.op.qbasis + row, ph.x, ph.y);
                     });
-            for (int s = own.begin(); s < nslice; s = own.next(s))
+            pk_for_slices<STAGED>(own, a.op, [&](const int s)
                 {
                 const int row = s * SLICE + lane;
                 double2 pi;
                 const double2 ph = value(row, pi);
                 reinterpret_cast<double2 *>(p_new)[row] = pi;
                 st256(a.w3p + row, node_w(a.op.qbasis + row, ph.x, ph.y));
-                }
+                });
             }
         pk_sync<BS, 0, false>(a, sh, acc, 1);
         pk_stamp(a, sh, PKP_A);
@@ -386,7 +548,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
         sa.y = a.v;
         sa.a0 = a.rt;
         sa.o0 = nullptr;
-        pk_spmv<ST_BICG_V, IDX16, BS>(a, sh, sa, own, lane, true, acc);
+        pk_spmv<ST_BICG_V, IDX16, STAGED, BS>(a, sh, sa, own, lane, true, stage, acc);
         pk_sync<BS, 1, false>(a, sh, acc, 0);
         if (threadIdx.x == 0)
             {
@@ -414,7 +576,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
                     const double2 sh_ = value(row, si);
                     return node_w(a.op.qbasis + row, sh_.x, sh_.y);
                     });
-            for (int s = own.begin(); s < nslice; s = own.next(s))
+            pk_for_slices<STAGED>(own, a.op, [&](const int s)
                 {
                 const int row = s * SLICE + lane;
                 double2 si;
@@ -422,7 +584,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
                 reinterpret_cast<double2 *>(a.s)[row] = si;
                 st256(a.w3s + row, node_w(a.op.qbasis + row, sh_.x, sh_.y));
                 ss_acc += si.x * si.x + si.y * si.y;
-                }
+                });
             }
         if (!spec)
             {
@@ -444,7 +606,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
             sa.x = nullptr;
             sa.y = a.t;
             sa.a0 = a.s;
-            pk_spmv<ST_BICG_T, IDX16, BS>(a, sh, sa, own, lane, true, acc);
+            pk_spmv<ST_BICG_T, IDX16, STAGED, BS>(a, sh, sa, own, lane, true, stage, acc);
             if (spec)
                 {
                 acc[2] = ss_acc;
@@ -487,7 +649,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
                 ;
             else if (fh)
                 {
-                for (int s = own.begin(); s < nslice; s = own.next(s))
+                pk_for_slices<STAGED>(own, a.op, [&](const int s)
                     {
                     const int row = s * SLICE + lane;
                     const double2 d = D2[row], pp = p2[row];
@@ -495,11 +657,11 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
                     xv.x += alpha * __dmul_rn(d.x, pp.x);
                     xv.y += alpha * __dmul_rn(d.y, pp.y);
                     x2[row] = xv;
-                    }
+                    });
                 }
             else
                 {
-                for (int s = own.begin(); s < nslice; s = own.next(s))
+                pk_for_slices<STAGED>(own, a.op, [&](const int s)
                     {
                     const int row = s * SLICE + lane;
                     const double2 d = D2[row], pp = p2[row], sv = s2[row], tv = t2[row], rtv = rt2[row];
@@ -511,7 +673,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
                     r2[row] = ri;
                     acc[0] += ri.x * ri.x + ri.y * ri.y;
                     acc[1] += rtv.x * ri.x + rtv.y * ri.y;
-                    }
+                    });
                 }
             if (!sh.ks.done)
                 {
@@ -579,7 +741,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
             };
         if (!failed)
             {
-            for (int s = own.begin(); s < nslice; s = own.next(s)) update_row(s * SLICE + lane, true);
+            pk_for_slices<STAGED>(own, a.op, [&](const int s) { update_row(s * SLICE + lane, true); });
             if (a.NODt > a.NODp)
                 {  // ghost rows: their solution was pushed by the owners
                 if (gtid - lane < a.NODt - a.NODp)

@@ -379,6 +379,9 @@ class LinAlgebra:
     def set_solver(self, kind):
         """"persistent" (default): one cooperative kernel per solve; "multi": one kernel per phase."""
         check(self._L.fg_set_solver(self._h, C.c_int({"persistent": 0, "multi": 1}[kind])))
+        lay = (C.c_longlong * 4)()
+        check(self._L.fg_get_layout(self._h, lay))
+        self.col_bytes = int(lay[0])   # the persistent kernel may address staged images with 2-byte indices
 
     SOLVE_PHASES = ("kernel", "setup", "A_p", "B_spmv_v", "C_s", "D_spmv_t", "E_xr", "halo_x", "update")
 
