@@ -170,8 +170,9 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU legs: the oracle port (reference algorithm, plain C + OpenMP) on the host cores
 # ---------------------------------------------------------------------------------------------
-FULL_NT = dict(ellipsoid=499, sp4=186000, disk1m=942000, tube5m=8 * 152 * 690 * 6, film20m=19969200)
-SAMPLE_SCALE = dict(ellipsoid=1.0, sp4=1.0, disk1m=0.45, tube5m=0.2, film20m=0.25)
+FULL_NT = dict(ellipsoid=499, sp4=186000, disk1m=942000, tube5m=8 * 152 * 690 * 6, film20m=19969200,
+               film20m_k=19969200)
+SAMPLE_SCALE = dict(ellipsoid=1.0, sp4=1.0, disk1m=0.45, tube5m=0.2, film20m=0.25, film20m_k=0.25)
 
 
 def _cpu_run(w, steps, warmup, threads, budget_s, min_steps=2):
@@ -435,8 +436,11 @@ def main():
     if args.kernel_times and solve_t["kernel"][1]:
         for k, (t, cnt) in solve_t.items():
             if cnt:
-                log("  rank %d solve.%-10s %5d x  %8.3f ms/step  %8.1f us each"
-                    % (rank, k, cnt, t / args.steps, 1e3 * t / cnt))
+                bd = la.solve_breakdown.get(k)
+                log("  rank %d solve.%-10s %5d x  %8.3f ms/step  %8.1f us each%s"
+                    % (rank, k, cnt, t / args.steps, 1e3 * t / cnt,
+                       "   (work %.1f us, cross-GPU %.1f us)" % (1e3 * bd["work_ms"] / cnt, 1e3 * bd["cross_gpu_ms"] / cnt)
+                       if bd else ""))
     spmv_ms, spmv_n = la.spmv_times()
     la.set_profiling(0)
     mean_it = float(np.mean(iters)) if iters else 0.0

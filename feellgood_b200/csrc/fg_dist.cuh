@@ -187,7 +187,10 @@ __device__ inline void dist_allreduce_warp(DistDev *d, double *v, int nv, bool o
 // exchanged vector; executed by `nthreads` cooperating threads (thread index tid).  Each thread fences its
 // own stores at system scope, so a later flag / all-reduce by any thread of the grid that is
 // ordered after them (block barrier + device-scope ticket) publishes them to the peers.
-template <class T, class F>
+// FENCE = false: the caller orders the stores itself (the persistent kernel: block barrier, then one
+// system-scope fence per CTA before it arrives at the grid barrier that raises the halo flag -- the pushes
+// then overlap the CTA's own rows instead of stalling their threads for an NVLink round trip).
+template <bool FENCE = true, class T, class F>
 __device__ __forceinline__ void dist_push(const DistDev *d, T *const *tails, int tid, int nthreads, F f)
     {
     const int nsend = d->send_ptr[d->world];
@@ -200,7 +203,7 @@ __device__ __forceinline__ void dist_push(const DistDev *d, T *const *tails, int
         *(tails[q] + d->send_dst[q] + (idx - d->send_ptr[q])) = val;
         any = true;
         }
-    if (any) __threadfence_system();
+    if (FENCE && any) __threadfence_system();
     }
 
 // After a dist_push by a whole CTA: one thread raises the halo epoch flag on every destination.

@@ -946,8 +946,8 @@ int krylov_alloc(KrylovWork &w, int n, int n_ghost, cudaStream_t stream, long lo
         {
         FG_CUDA(cudaMalloc(&w.pk, sizeof(PkSync)));
         FG_CUDA(cudaMemsetAsync(w.pk, 0, sizeof(PkSync), stream));
-        FG_CUDA(cudaMalloc(&w.pk_phase_acc, sizeof(unsigned long long) * 32));
-        FG_CUDA(cudaMemsetAsync(w.pk_phase_acc, 0, sizeof(unsigned long long) * 32, stream));
+        FG_CUDA(cudaMalloc(&w.pk_phase_acc, sizeof(unsigned long long) * 64));
+        FG_CUDA(cudaMemsetAsync(w.pk_phase_acc, 0, sizeof(unsigned long long) * 64, stream));
         }
     return FG_OK;
     }

@@ -9,6 +9,7 @@
 #include <stddef.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -59,6 +60,10 @@ struct fg_ctx
     double *h_stage = nullptr;   // 8*NOD doubles, pinned host
     // tets
     int4 *tet_ind = nullptr, *tet_slot = nullptr;
+    // chunks of 256 tetrahedra and their distinct nodes (k_tet_iso_st)
+    int *tch_ptr = nullptr, *tch_nodes = nullptr;
+    ushort4 *tet_loc = nullptr;
+    int tch_n = 0, tch_cap = 0;
     double *tet_da = nullptr, *tet_detJ = nullptr, *ext_field = nullptr;
     int *tet_reg = nullptr;
     TetRegion *reg_tet = nullptr;
@@ -205,7 +210,50 @@ int launch_elements(fg_ctx *c)
         {
         const TetArrays A = tet_arrays(c);
         const int grid = grid_for(c->NTm, BLOCK);
-        if (use_iso(c))
+        // A/B (FG_TET_STAGE=1): node records of a chunk of tetrahedra staged in shared memory (k_tet_st).  Measured
+        // slower than the free-running gather kernels on the 20 M-tet film (r02g: 1.51 against 1.35 ms isotropic,
+        // 2.92 against 2.10 ms with anisotropy): the element kernel is co-limited by DRAM (0.87 ms), FP64
+        // (~0.8 ms) and L1 (0.88 ms), and the barriers of a staged chunk loop overlap the three worse than 16
+        // independent warps do.  Off by default.
+        static const bool tet_stage = getenv("FG_TET_STAGE") != nullptr && atoi(getenv("FG_TET_STAGE")) != 0;
+        const bool iso = use_iso(c);
+        const size_t st_smem = 2 * (size_t)c->tch_cap * tet_stage_doubles(iso) * sizeof(double);
+        if (tet_stage && c->tch_n > 0 && st_smem <= 160 * 1024)
+            {  // the chunk's distinct node records staged in shared memory (k_tet_st)
+            TetChunks C;
+            C.nchunk = c->tch_n;
+            C.cap = c->tch_cap;
+            C.ptr = c->tch_ptr;
+            C.nodes = c->tch_nodes;
+            C.loc = c->tet_loc;
+            typedef void (*kfn)(const TetArrays, const TetChunks, const NodeRec *, const StepPrm, double4 *);
+            const int five = c->h.npi_tet == 5 ? 1 : 0, space = c->space_field ? 1 : 0;
+            static const kfn table[2][3] = {{k_tet_st<1, true, false>, k_tet_st<1, false, false>, k_tet_st<1, false, true>},
+                                            {k_tet_st<5, true, false>, k_tet_st<5, false, false>, k_tet_st<5, false, true>}};
+            const int variant = iso ? 0 : 1 + space;
+            const kfn fn = table[five][variant];
+            static int waves[2][3] = {{0, 0, 0}, {0, 0, 0}};
+            static size_t wave_smem[2][3] = {{0, 0, 0}, {0, 0, 0}};
+            int &wave = waves[five][variant];
+            if (!wave || wave_smem[five][variant] != st_smem)
+                {
+                if (st_smem > 48 * 1024)
+                    FG_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem));
+                int per_sm = 1, sms = NUM_SMS;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, BLOCK, st_smem) != cudaSuccess || per_sm < 1)
+                    per_sm = 1;
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+                wave = per_sm * sms;
+                wave_smem[five][variant] = st_smem;
+                }
+            const int g = c->tch_n < wave ? c->tch_n : wave;
+            const bool prof_ = prof_begin(c->kw.prof, c->stream, KC_TET);
+            fn<<<g, BLOCK, st_smem, c->stream>>>(A, C, c->cur, c->sp, c->rec);
+            if (prof_) prof_end(c->kw.prof, c->stream);
+            ++c->launches;
+            FG_CUDA(cudaGetLastError());
+            }
+        else if (use_iso(c))
             {
             static const bool pipe = getenv("FG_TET_NOPIPE") == nullptr;  // A/B switch of the prefetch pipeline
             if (c->h.npi_tet == 5 && pipe)
@@ -589,6 +637,44 @@ static int create_ctx(const fg_mesh *mesh, const fg_params *prm, int device, con
             reg[tm] = h.tet_reg[t];
             }
         CK(dev_upload(&c->tet_ind, ind, s));
+            {  // chunks of TET_CHUNK consecutive tetrahedra (they are sorted by their smallest device row):
+               // the distinct nodes of a chunk and the 16-bit local indices of every tetrahedron in that list
+            const int nch = (int)((M + TET_CHUNK - 1) / TET_CHUNK);
+            std::vector<int> cptr((size_t)nch + 1, 0);
+            std::vector<std::vector<int>> lists((size_t)nch);
+            std::vector<ushort4> loc(M);
+#pragma omp parallel for schedule(dynamic, 64)
+            for (int ch = 0; ch < nch; ch++)
+                {
+                const size_t t0 = (size_t)ch * TET_CHUNK, t1 = std::min(M, t0 + TET_CHUNK);
+                std::vector<int> &L = lists[(size_t)ch];
+                L.assign(h.tet_dev_ind.begin() + 4 * t0, h.tet_dev_ind.begin() + 4 * t1);
+                std::sort(L.begin(), L.end());
+                L.erase(std::unique(L.begin(), L.end()), L.end());
+                for (size_t tm = t0; tm < t1; tm++)
+                    {
+                    unsigned short q[4];
+                    for (int i = 0; i < 4; i++)
+                        q[i] = (unsigned short)(std::lower_bound(L.begin(), L.end(), h.tet_dev_ind[4 * tm + i]) - L.begin());
+                    loc[tm] = make_ushort4(q[0], q[1], q[2], q[3]);
+                    }
+                }
+            int cap = 1;
+            for (int ch = 0; ch < nch; ch++)
+                {
+                cptr[(size_t)ch + 1] = cptr[(size_t)ch] + (int)lists[(size_t)ch].size();
+                cap = std::max(cap, (int)lists[(size_t)ch].size());
+                }
+            std::vector<int> nodes((size_t)cptr[(size_t)nch]);
+            for (int ch = 0; ch < nch; ch++)
+                std::copy(lists[(size_t)ch].begin(), lists[(size_t)ch].end(), nodes.begin() + cptr[(size_t)ch]);
+            c->tch_n = nch;
+            c->tch_cap = cap;
+            CK(dev_upload(&c->tch_ptr, cptr, s));
+            CK(dev_upload(&c->tch_nodes, nodes, s));
+            CK(dev_upload(&c->tet_loc, loc, s));
+            CKCUDA(cudaStreamSynchronize(s));
+            }
             {
             std::vector<int4> slot(M);
             for (size_t tm = 0; tm < M; tm++)
@@ -925,7 +1011,7 @@ void fg_destroy(fg_ctx *c)
     void *ptrs[] = {c->cur, c->next, c->basis, c->nonmag, c->dofmask, c->stage, c->tet_ind, c->tet_da,
                     c->tet_detJ, c->ext_field, c->tet_reg, c->reg_tet, c->rec, c->tri_ind,
                     c->tri_reg, c->tri_surf, c->tri_dMs, c->reg_tri, c->trec, c->perm, c->sptr,
-                    c->scol, c->sdeg, c->iptr, c->tet_slot, c->itptr, c->sinct, c->sS, c->Aw, c->val, c->Sdiag, c->Dm, c->qbasis,
+                    c->scol, c->sdeg, c->iptr, c->tch_ptr, c->tch_nodes, c->tet_loc, c->tet_slot, c->itptr, c->sinct, c->sS, c->Aw, c->val, c->Sdiag, c->Dm, c->qbasis,
                     c->scol16, c->sghost, c->lcol, c->bptr, c->bhalo, c->bghost, c->mtri_ind, c->mtri_reg, c->mtri_surf, c->mtri_nrm, c->mtri_dMs, c->extra_edges,
                     c->d_scal, c->node_pos, c->corr, c->tcorr, c->src, c->cptr, c->cidx};
     for (void *p : ptrs)
@@ -1932,7 +2018,7 @@ int fg_set_profiling(fg_ctx *c, int on)
         c->kw.prof = &c->prof;
         c->kw.pk_stamps_on = 1;
         if (c->kw.pk_phase_acc)
-            FG_CUDA(cudaMemsetAsync(c->kw.pk_phase_acc, 0, sizeof(unsigned long long) * 32, c->stream));
+            FG_CUDA(cudaMemsetAsync(c->kw.pk_phase_acc, 0, sizeof(unsigned long long) * 64, c->stream));
         }
     else
         {
@@ -1954,7 +2040,7 @@ int fg_set_solver(fg_ctx *c, int kind)
     return FG_OK;
     }
 
-int fg_get_solve_times(fg_ctx *c, double ms[9], long long count[9])
+int fg_get_solve_times(fg_ctx *c, double ms[27], long long count[9])
     {
     FG_TRY(check_ctx(c));
     if (!ms || !count)
@@ -1963,11 +2049,8 @@ int fg_get_solve_times(fg_ctx *c, double ms[9], long long count[9])
         return FG_ERR_INVALID;
         }
     FG_CUDA(cudaStreamSynchronize(c->stream));
-    for (int k = 0; k < 9; k++)
-        {
-        ms[k] = 0.0;
-        count[k] = 0;
-        }
+    for (int k = 0; k < 27; k++) ms[k] = 0.0;
+    for (int k = 0; k < 9; k++) count[k] = 0;
     for (int k = 0; k < c->prof.n; k++)
         {
         if (c->prof.cls[k] != KC_SOLVE) continue;
@@ -1978,12 +2061,14 @@ int fg_get_solve_times(fg_ctx *c, double ms[9], long long count[9])
         }
     if (c->kw.pk_phase_acc)
         {
-        unsigned long long acc[32];
+        unsigned long long acc[64];
         FG_CUDA(cudaMemcpy(acc, c->kw.pk_phase_acc, sizeof acc, cudaMemcpyDeviceToHost));
         for (int id = PKP_SETUP; id <= PKP_UPDATE; id++)
             {
             ms[id - PKP_SETUP + 1] = 1e-6 * (double)acc[id];
             count[id - PKP_SETUP + 1] = (long long)acc[16 + id];
+            ms[9 + id - PKP_SETUP + 1] = 1e-6 * (double)acc[32 + id];   // until the last CTA arrived
+            ms[18 + id - PKP_SETUP + 1] = 1e-6 * (double)acc[48 + id];  // cross-GPU part of the barrier
             }
         }
     return FG_OK;

@@ -657,6 +657,146 @@ k_tet_iso(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__res
         }
     }
 
+// ---- k_tet_iso with the node records of a chunk of tetrahedra staged in shared memory ------------------
+// The tetrahedra are sorted by their smallest device row, so the 256 tetrahedra of a chunk touch only ~100
+// distinct nodes, each of them ~10 times.  Gathering them from global memory costs one L1 tag-stage wavefront
+// per lane and 32-byte sector (8 x 32 per warp and tetrahedron: more than half of the kernel's L1 time, ncu
+// r01v); here a CTA copies the chunk's distinct node records once into shared memory with cp.async (48 of
+// the 64 bytes: u, phi, phiv), double-buffered across chunks, and the tetrahedra read them with 16-bit
+// local indices.  Same arithmetic as k_tet_iso (same device functions), so the records are bit-identical.
+struct TetChunks
+    {
+    int nchunk;                // ceil(NTm / 256)
+    int cap;                   // largest number of distinct nodes of a chunk
+    const int *ptr;            // nchunk + 1
+    const int *nodes;          // device rows of the distinct nodes, ascending inside a chunk
+    const ushort4 *loc;        // NTm : local indices of the 4 nodes of a tetrahedron inside its chunk's list
+    };
+constexpr int TET_CHUNK = 256;
+// staged record: ISO u0 u1 | u2 v0 | phi phiv (48 B; v0 rides along: 16-byte copies) ; general: the whole NodeRec
+__host__ __device__ constexpr int tet_stage_doubles(bool iso) { return iso ? 6 : 8; }
+
+__device__ __forceinline__ void tet_cp_async16(unsigned int dst_smem, const void *src)
+    { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory"); }
+
+// ISO: the fast path (tet_iso_front / tet_iso_be, no anisotropy, uniform field, no drift); otherwise the
+// general element (tet_core: anisotropies, space-dependent field, recentring drift), whose 254 registers allow
+// only 8 resident warps per SM: with the records staged and double-buffered it no longer depends on
+// occupancy to hide the gather latency.
+template <int NPI, bool ISO, bool SPACE>
+__global__ void __launch_bounds__(BLOCK, ISO ? TET_ISO_CTAS_PER_SM : 1)
+k_tet_st(const TetArrays A, const TetChunks C, const NodeRec *__restrict__ cur, const StepPrm sp,
+         double4 *__restrict__ rec)
+    {
+    extern __shared__ double tet_stage[];  // 2 buffers of cap staged records
+    constexpr int SD = tet_stage_doubles(ISO), NQ = ISO ? 3 : 4;  // doubles and 16-byte pieces per record
+    const int tid = threadIdx.x;
+    const unsigned int sb0 = (unsigned int)__cvta_generic_to_shared(tet_stage);
+    const unsigned int bufbytes = (unsigned int)C.cap * SD * 8u;
+    auto issue = [&](int c, int k)
+        {
+        if (c < C.nchunk)
+            {
+            const int n0 = __ldg(C.ptr + c), nn = __ldg(C.ptr + c + 1) - n0;
+            const unsigned int sb = sb0 + (unsigned int)k * bufbytes;
+            for (int i = tid; i < NQ * nn; i += BLOCK)
+                {
+                const int e = i / NQ, q = i - NQ * e;
+                const int node = __ldg(C.nodes + n0 + e);
+                const int off = ISO ? (q == 2 ? 48 : 16 * q) : 16 * q;
+                tet_cp_async16(sb + (unsigned int)(SD * 8 * e + 16 * q), reinterpret_cast<const char *>(cur + node) + off);
+                }
+            }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+    int c = blockIdx.x, k = 0;
+    issue(c, 0);
+    for (; c < C.nchunk; c += gridDim.x, k ^= 1)
+        {
+        issue(c + gridDim.x, k ^ 1);  // next chunk of this CTA into the other buffer
+        const int tm = c * TET_CHUNK + tid;
+        const bool act = tm < A.NTm;
+        ushort4 lc = make_ushort4(0, 0, 0, 0);
+        int reg = 0;
+        int4 s4 = make_int4(-1, -1, -1, -1);
+        double da[4][3], detJ = 0.0;
+        if (act)
+            {  // the coalesced streams of this tetrahedron travel while the node records land
+            lc = __ldcs(C.loc + tm);
+            reg = __ldg(A.reg + tm);
+#pragma unroll
+            for (int q = 0; q < 12; q++) da[q / 3][q % 3] = __ldcs(A.da + (size_t)q * A.NTm + tm);
+            detJ = __ldcs(A.detJ + tm);
+            s4 = __ldcs(A.slot + tm);
+            }
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        if (act)
+            {
+            const double *buf = tet_stage + (size_t)k * C.cap * SD;
+            const int nd[4] = {lc.x, lc.y, lc.z, lc.w};
+            const int sl[4] = {s4.x, s4.y, s4.z, s4.w};
+            if (ISO)
+                {
+                TetIsoIn T;
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    {
+#pragma unroll
+                    for (int d = 0; d < 3; d++) T.da[i][d] = da[i][d];
+                    const double *r = buf + (size_t)nd[i] * SD;
+                    const double2 a = *reinterpret_cast<const double2 *>(r), b = *reinterpret_cast<const double2 *>(r + 4);
+                    T.u[i][0] = a.x; T.u[i][1] = a.y; T.u[i][2] = r[2];
+                    T.phi[i] = b.x; T.phiv[i] = b.y;
+                    }
+                T.detJ = detJ;
+                TetRegion Rl;
+                Rl.alpha = A.regions[reg].alpha;
+                Rl.Abis = A.regions[reg].Abis;
+                TetIsoMid M;
+                double contrib[4];
+                tet_iso_front<NPI>(T, Rl, sp, M, contrib);
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    {
+                    if (sl[i] < 0) continue;
+                    double be[3];
+                    tet_iso_be<NPI>(T.da[i], i, T.detJ, Rl.Abis, M, be);
+                    st256(rec + sl[i], make_double4(contrib[i], be[0], be[1], be[2]));
+                    }
+                }
+            else
+                {
+                TetIn T;
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    {
+#pragma unroll
+                    for (int d = 0; d < 3; d++) T.da[i][d] = da[i][d];
+                    const double2 *r = reinterpret_cast<const double2 *>(buf + (size_t)nd[i] * SD);
+                    const double2 a = r[0], b = r[1], cc = r[2], e = r[3];
+                    T.u[i][0] = a.x; T.u[i][1] = a.y; T.u[i][2] = b.x;
+                    T.v[i][0] = b.y; T.v[i][1] = cc.x; T.v[i][2] = cc.y;
+                    T.phi[i] = e.x; T.phiv[i] = e.y;
+                    }
+                T.detJ = detJ;
+                double Hext[3][NPI];
+                tet_field<NPI>(A, tm, sp, SPACE, Hext);
+                const TetRegion R = A.regions[reg];
+                double contrib[4], BE[3][4];
+                tet_core<NPI>(T, R, sp, Hext, contrib, BE);
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    {
+                    if (sl[i] < 0) continue;
+                    st256(rec + sl[i], make_double4(contrib[i], BE[0][i], BE[1][i], BE[2][i]));
+                    }
+                }
+            }
+        __syncthreads();  // this buffer is the target of the prefetch issued at the top of the next turn
+        }
+    }
+
 // projection of one node pair: the 2x2 block of K / Kp (SURVEY.md §8a index facts)
 __host__ __device__ __forceinline__ void project_block(double E, const double ep_a[3], const double eq_a[3],
                                               const double ep_b[3], const double eq_b[3],

@@ -108,7 +108,14 @@ __device__ int grid_reduce(double (&v)[NV], const RedBuf red, double (&out)[NV])
             }
         }
     __syncwarp();
-    if (red.dist != nullptr) dist_allreduce_warp(red.dist, tot, NV, false);  // the whole warp takes part
+    if (red.dist != nullptr)
+        {  // the whole warp takes part.  The all-reduce also publishes halo pushes of this kernel's other CTAs
+           // to the peers (k_bicg_s_node), hence system-scope fences around it: release before the mailbox
+           // stores, acquire after the spin
+        __threadfence_system();
+        dist_allreduce_warp(red.dist, tot, NV, false);
+        __threadfence_system();
+        }
     if (lane != 0) return 2;
 #pragma unroll
     for (int k = 0; k < NV; k++) out[k] = tot[k] + tot[NV + k];
@@ -156,7 +163,12 @@ __device__ __forceinline__ bool grid_reduce_max(double v, const RedBuf red, doub
         totmx[0] = s;
         }
     __syncwarp();
-    if (red.dist != nullptr) dist_allreduce_warp(red.dist, totmx, 1, true);  // max: no compensation
+    if (red.dist != nullptr)
+        {
+        __threadfence_system();
+        dist_allreduce_warp(red.dist, totmx, 1, true);  // max: no compensation
+        __threadfence_system();
+        }
     if (lane != 0) return false;
     out = totmx[0];
     return true;

@@ -45,6 +45,7 @@ struct PkSync  // one per context, device memory, zeroed at creation
     unsigned int pad0[31];
     unsigned int gen;    // generation of the last released barrier
     unsigned int pad1[31];
+    unsigned long long t_last, t_ar;          // profiling: when the last CTA arrived / the cross-GPU part ended
     double tot[2][RED_NV];                    // totals of the last two reductions (slot = parity)
     double part[2][2 * RED_NV][PK_MAX_GRID];  // CTA partials (values, then compensations)
     };
@@ -68,7 +69,9 @@ struct PkArgs
     NodeRec *next;
     const Basis *basis;
     double dt;
-    unsigned long long *phase_acc;  // optional [32]: summed ns per phase id, then counts; CTA 0 adds to them
+    unsigned long long *phase_acc;  // optional [64]: per phase id summed ns [0,16), counts [16,32), ns until the
+                                    // last CTA of this GPU arrived at the closing barrier [32,48), ns of the
+                                    // cross-GPU part of that barrier (all-reduce over the ranks) [48,64)
     // result mailbox in mapped host memory (NULL: the host copies KState itself)
     KState *h_st;
     unsigned long long *h_seq;
@@ -105,6 +108,15 @@ template <int BS> __device__ __forceinline__ void pk_stamp(const PkArgs &a, PkSh
             {
             a.phase_acc[id] += t - sh.t_prev;
             a.phase_acc[16 + id] += 1ull;
+            if (gridDim.x > 1 || a.dist != nullptr)
+                {
+                const unsigned long long tl = __ldcg(&a.sync->t_last), ta = __ldcg(&a.sync->t_ar);
+                if (tl >= sh.t_prev && ta >= tl && t >= ta)
+                    {
+                    a.phase_acc[32 + id] += tl - sh.t_prev;
+                    a.phase_acc[48 + id] += ta - tl;
+                    }
+                }
             }
         sh.t_prev = t;
         }
@@ -187,13 +199,20 @@ __device__ void pk_sync(const PkArgs &a, PkShared<BS> &sh, const double (&acc)[R
             if (lane == 0)
                 {
                 target = ++sh.gen;
-                __threadfence();  // release (peer-memory pushes were fenced at system scope by their threads)
+                // release.  A barrier that raises the halo flags publishes this CTA's pushes into peer memory
+                // (plain stores by any of its threads, ordered before this point by the bar.sync above): one
+                // system-scope fence per CTA, issued when the stores have long been on their way
+                if (halo && a.dist != nullptr)
+                    __threadfence_system();
+                else
+                    __threadfence();
                 last = atomicAdd(&a.sync->count, 1u) == gridDim.x - 1 ? 1u : 0u;
                 }
             last = __shfl_sync(0xffffffffu, last, 0);
             if (last)
                 {  // the whole warp: every CTA's partial is in
                 __threadfence();
+                if (a.phase_acc != nullptr && lane == 0) a.sync->t_last = now_ns();
                 if (NV > 0)
                     {
 #pragma unroll
@@ -231,6 +250,7 @@ __device__ void pk_sync(const PkArgs &a, PkShared<BS> &sh, const double (&acc)[R
                         for (int k = 0; k < NV; k++) a.sync->tot[slot][k] = MAXOP ? sh.tot[k] : sh.tot[k] + sh.tot[NV + k];
                         }
                     a.sync->count = 0;
+                    if (a.phase_acc != nullptr) a.sync->t_ar = now_ns();
                     if (halo && a.dist != nullptr) dist_raise(a.dist);  // fence.sys + flags on the neighbours
                     __threadfence();
                     st_release_u32(&a.sync->gen, target);
@@ -522,7 +542,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
                 return make_double2(d.x * pi.x, d.y * pi.y);
                 };
             if (a.dist != nullptr)
-                dist_push(a.dist, a.dist->wtail[0], gtid, gthreads, [&](int row)
+                dist_push<false>(a.dist, a.dist->wtail[0], gtid, gthreads, [&](int row)
                     {
                     double2 pi;
                     const double2 ph = value(row, pi);
@@ -570,7 +590,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
                 return make_double2(d.x * si.x, d.y * si.y);
                 };
             if (a.dist != nullptr)
-                dist_push(a.dist, a.dist->wtail[1], gtid, gthreads, [&](int row)
+                dist_push<false>(a.dist, a.dist->wtail[1], gtid, gthreads, [&](int row)
                     {
                     double2 si;
                     const double2 sh_ = value(row, si);
@@ -702,7 +722,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
         if (a.dist != nullptr)
             {  // the solution of my boundary rows goes into the neighbours' ghost tails of x
             // x of rows owned by other CTAs was written before the last grid barrier of the loop
-            dist_push(a.dist, a.dist->tail, gtid, gthreads, [&](int row) { return x2[row]; });
+            dist_push<false>(a.dist, a.dist->tail, gtid, gthreads, [&](int row) { return x2[row]; });
             pk_sync<BS, 0, false>(a, sh, acc, 1);
             pk_stamp(a, sh, PKP_HALO_X);
             }

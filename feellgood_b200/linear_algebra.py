@@ -388,9 +388,11 @@ class LinAlgebra:
     def solve_times(self):
         """{phase: (ms, count)} of the persistent solve kernel since set_profiling(2|3): "kernel" from
         CUDA events around its launches, the phases from its in-kernel time stamps."""
-        ms = (C.c_double * 9)()
+        ms = (C.c_double * 27)()
         cnt = (C.c_longlong * 9)()
         check(self._L.fg_get_solve_times(self._h, ms, cnt))
+        self.solve_breakdown = {k: dict(work_ms=ms[9 + i], cross_gpu_ms=ms[18 + i], count=int(cnt[i]))
+                                for i, k in enumerate(self.SOLVE_PHASES) if i > 0}
         return {k: (ms[i], int(cnt[i])) for i, k in enumerate(self.SOLVE_PHASES)}
 
     def phase_times(self):

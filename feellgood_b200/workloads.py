@@ -97,6 +97,17 @@ def film20m(scale=1.0):
                 config="configs[4] synthetic 20M-tet extended film 1290x1290x2 cells (2 nm)")
 
 
+def film20m_k(scale=1.0):
+    """Config 5's mesh with a uniaxial anisotropy (K = 3e5 J/m^3 along y, the material of the reference's
+    ci-tests/full_test.py:33-36): exercises the GENERAL element kernel (k_tet) instead of the isotropic
+    fast path, so that its throughput is measured by the same bench."""
+    w = film20m(scale)
+    w.name = "film20m_k" if scale == 1.0 else "film20m_k_x%.3g" % scale
+    w.config = "configs[4] mesh with uniaxial anisotropy K = 3e5 J/m^3 along y (general element kernel)"
+    w.tet_regions = [dict(), dict(alpha=0.02, A=1.3e-11, Ms=8e5, K=3e5, uk=(0, 1, 0))]
+    return w
+
+
 def sp4(scale=1.0):
     """Config 2: muMAG standard problem 4, 500 x 125 x 3 nm permalloy, 250 x 62 x 2 cells
     (186k tets), s-state, reversal field 1 = (-24.6, 4.3, 0) mT."""
@@ -142,7 +153,7 @@ def tube5m(scale=1.0):
 
 
 BUILDERS = dict(ellipsoid=lambda scale=1.0: ellipsoid(), sp4=sp4, disk1m=disk1m, tube5m=tube5m,
-                film20m=film20m)
+                film20m=film20m, film20m_k=film20m_k)
 
 
 def build(name, scale=1.0):

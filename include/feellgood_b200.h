@@ -306,8 +306,11 @@ int fg_set_solver(fg_ctx *ctx, int kind);
  * (CUDA events) and number of solve-kernel launches since the mode was set; ms[1..8] / count[1..8] = time
  * spent in the phases of the kernel, from %globaltimer stamps taken by its CTA 0 after the grid barrier
  * that closes each phase: 1 setup (r = b - K x0), 2 A (p, image of D p), 3 B (v = K D p, alpha),
- * 4 C (s, image of D s), 5 D (t = K D s, omega), 6 E (x, r, rho), 7 halo of x (multi-GPU), 8 node update. */
-int fg_get_solve_times(fg_ctx *ctx, double ms[9], long long count[9]);
+ * 4 C (s, image of D s), 5 D (t = K D s, omega), 6 E (x, r, rho), 7 halo of x (multi-GPU), 8 node update.
+ * ms[9 + k] = of phase k, the time until the LAST CTA of this GPU arrived at the closing barrier (its work);
+ * ms[18 + k] = the cross-GPU part of that barrier (all-reduce over the ranks: latency + waiting for the
+ * slowest rank); the remainder of ms[k] is the release of the barrier. */
+int fg_get_solve_times(fg_ctx *ctx, double ms[27], long long count[9]);
 /* Microbenchmark of the solver's SpMV on the assembled K: runs `reps` launches back to back and
  * returns the mean milliseconds per launch (CUDA events on the context's stream). */
 int fg_bench_spmv(fg_ctx *ctx, int reps, double *ms_per_launch);

@@ -203,11 +203,12 @@ def test_solve_properties_and_reproducibility(full):
     assert np.array_equal(u1, u2) and np.array_equal(v1, v2)
 
 
-@pytest.mark.parametrize("name,nsteps", [("sp4", 20), ("disk1m", 8)])
+@pytest.mark.parametrize("name,nsteps", [("sp4", 20), ("disk1m", 8), ("tube5m", 5), ("film20m", 3)])
 def test_trajectory_vs_oracle_at_full_size(oracle, gpu_lib, name, nsteps):
-    """BASELINE configs 2 and 3 at their FULL size against the CPU oracle run whole (the north-star
-    criterion: average magnetisation and energies after a fixed number of steps within 1e-6
-    relative; per-step solutions within the solver tolerance)."""
+    """BASELINE configs 2 to 5 at their FULL size against the CPU oracle run whole, all host threads (the
+    north-star criterion: average magnetisation and energies after a fixed number of steps within 1e-6
+    relative; per-step solutions within the solver tolerance).  The 5 M- and 20 M-tet meshes take the
+    oracle ~1 and ~4 s per step on 16 threads."""
     import cases
     from feellgood_b200 import workloads
     from feellgood_b200.linear_algebra import M_2_PI, mt19937_uniform01
@@ -217,6 +218,8 @@ def test_trajectory_vs_oracle_at_full_size(oracle, gpu_lib, name, nsteps):
                       w.dt, w.dtmax, ANGLE, npi=w.npi, npi_tri=4 if w.npi == 5 else 1, tol=w.tol,
                       maxiter=w.maxiter)
     oc, la = cases.oracle_ctx(case), cases.gpu_linalg(case)
+    import os
+    oc.set_num_threads(os.cpu_count() or 1)
     oc.set_state(case.u, case.v, case.phi, case.phiv)
     la.set_state(case.u, case.v, case.phi, case.phiv)
     t = cases.FixedTiming(case)
