@@ -340,7 +340,7 @@ def main():
             return 0
         # the WHOLE workload the product arm runs, W warm-up + K timed steps, cut only if the run would
         # exceed ~4 minutes (the counts really done are what the line reports)
-        cb = cpu_leg(args.workload, args.steps, args.warmup, budget_s=float(os.environ.get("FG_REF_BUDGET_S", "150")),
+        cb = cpu_leg(args.workload, args.steps, args.warmup, budget_s=float(os.environ.get("FG_REF_BUDGET_S", "120")),
                      full=True)
         line = dict(metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=args.gpus, steps=cb["steps"],
                     warmup=cb["warmup"], ms_per_step=1e3 / cb["value"], higher_is_better=True,
@@ -357,6 +357,13 @@ def main():
         raise SystemExit("bench.py: no CUDA device (this framework has no CPU fallback; "
                          "use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)
+    try:  # run (and first-touch the pinned buffers) on the cores next to this rank's GPU: the end-to-end leg
+        # moves 64 B per node and step over PCIe, and a buffer on the other socket halves that rate
+        import pynvml as _nv
+        _nv.nvmlInit()
+        _nv.nvmlDeviceSetCpuAffinity(_nv.nvmlDeviceGetHandleByIndex(local_rank))
+    except Exception:
+        pass
     dist = None
     if world > 1:
         import torch.distributed as dist

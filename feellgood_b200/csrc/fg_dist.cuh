@@ -104,15 +104,23 @@ __device__ __forceinline__ double ld_sys_f64(const double *p)
 // the last CTA of a reducing kernel).  v points to shared memory.  op_max = false: v holds nv values
 // followed by their nv compensations (fg_reduce.cuh); the ranks' pairs are folded in rank order with
 // the same error-free addition, result in place.  op_max = true: v holds nv values, maximum in place.
+// `e` = the epoch of this all-reduce (the same number on every rank); `err` = where a timeout is recorded.
+__device__ inline void dist_allreduce_warp_e(const DistDev *d, int *err, unsigned long long e, double *v, int nv,
+                                             bool op_max);
 __device__ inline void dist_allreduce_warp(DistDev *d, double *v, int nv, bool op_max)
+    {
+    unsigned long long e = 0;
+    if ((threadIdx.x & 31) == 0) e = ++d->epoch;
+    e = __shfl_sync(0xffffffffu, e, 0);
+    dist_allreduce_warp_e(d, &d->error, e, v, nv, op_max);
+    }
+__device__ inline void dist_allreduce_warp_e(const DistDev *d, int *err, unsigned long long e, double *v, int nv,
+                                             bool op_max)
     {
     __shared__ unsigned int rx[DIST_MAX_RANKS][4 * DIST_NV];
     const int lane = threadIdx.x & 31;
     const int nd = op_max ? nv : 2 * nv;  // doubles per rank
-    unsigned long long e = 0;
-    if (lane == 0) e = ++d->epoch;
-    e = __shfl_sync(0xffffffffu, e, 0);
-    if (d->error)
+    if (*err)
         {  // a previous spin timed out: do not wait again, poison the scalars
         if (lane == 0)
             for (int k = 0; k < nd; k++) v[k] = nan("");
@@ -129,56 +137,79 @@ __device__ inline void dist_allreduce_warp(DistDev *d, double *v, int nv, bool o
         }
     DistCtrl *me = d->ctrl[rank];
     bool ok = true;
-    for (int idx = lane; idx < world * nw; idx += 32)
-        {
-        const int src = idx / nw, w = idx - src * nw;
-        const unsigned long long *p = &me->ll[par][src][w];
-        unsigned long long x = ld_sys(p);
-        if ((x & 0xffffffff00000000ull) != tag)
+        {  // every lane polls its (up to 4) mailbox words together: independent loads per round, not one
+           // L2 round trip per word (96 words on 8 ranks and 3 values)
+        constexpr int MAXS = (DIST_MAX_RANKS * 4 * DIST_NV + 31) / 32;
+        const int total = world * nw;
+        unsigned int need = 0;  // bit q: word lane + 32 q has not arrived yet
+#pragma unroll
+        for (int q = 0; q < MAXS; q++)
+            if (lane + 32 * q < total) need |= 1u << q;
+        unsigned long long t0 = 0;
+        unsigned int k = 0;
+        while (need)
             {
-            const unsigned long long t0 = now_ns();
-            unsigned int k = 0;
-            while (((x = ld_sys(p)) & 0xffffffff00000000ull) != tag)
-                if ((++k & 1023u) == 0 && now_ns() - t0 > DIST_TIMEOUT_NS)
+            unsigned long long x[MAXS];
+#pragma unroll
+            for (int q = 0; q < MAXS; q++)
+                {
+                const int idx = lane + 32 * q, src = idx / nw;
+                x[q] = (need >> q) & 1u ? ld_sys(&me->ll[par][src][idx - src * nw]) : 0ull;
+                }
+#pragma unroll
+            for (int q = 0; q < MAXS; q++)
+                if (((need >> q) & 1u) && (x[q] & 0xffffffff00000000ull) == tag)
+                    {
+                    const int idx = lane + 32 * q, src = idx / nw;
+                    rx[src][idx - src * nw] = (unsigned int)x[q];
+                    need &= ~(1u << q);
+                    }
+            if (need && (++k & 1023u) == 0)
+                {
+                if (t0 == 0)
+                    t0 = now_ns();
+                else if (now_ns() - t0 > DIST_TIMEOUT_NS)
                     {
                     ok = false;
                     break;
                     }
+                }
             }
-        rx[src][w] = (unsigned int)x;
         }
     ok = __all_sync(0xffffffffu, ok);
     __syncwarp();
-    if (lane == 0)
+    auto get = [&](int src, int k) { return __hiloint2double((int)rx[src][2 * k + 1], (int)rx[src][2 * k]); };
+    if (!ok)
         {
-        auto get = [&](int src, int k) { return __hiloint2double((int)rx[src][2 * k + 1], (int)rx[src][2 * k]); };
-        if (!ok)
+        if (lane == 0)
             {
-            d->error = 1;
+            *err = 1;
             for (int k = 0; k < nd; k++) v[k] = nan("");  // NaN residual => CANNOT_CONVERGE (iter.h:147)
             }
-        else if (op_max)
-            for (int k = 0; k < nv; k++)
-                {
-                double s = get(0, k);
-                for (int src = 1; src < world; src++) s = fmax(s, get(src, k));
-                v[k] = s;
-                }
+        }
+    else if (lane < nv)
+        {  // lane k folds value k over the ranks, in rank order: identical bits on every rank
+        const int k = lane;
+        if (op_max)
+            {
+            double s = get(0, k);
+            for (int src = 1; src < world; src++) s = fmax(s, get(src, k));
+            v[k] = s;
+            }
         else
-            for (int k = 0; k < nv; k++)
-                {
-                double s = get(0, k), c = get(0, nv + k);
-                for (int src = 1; src < world; src++)
-                    {  // error-free fold in rank order: identical bits on every rank
-                    const double bs = get(src, k), be = get(src, nv + k);
-                    const double t = s + bs, bb = t - s;
-                    const double err = (s - (t - bb)) + (bs - bb);
-                    s = t;
-                    c += be + err;
-                    }
-                v[k] = s;
-                v[nv + k] = c;
+            {
+            double s = get(0, k), c = get(0, nv + k);
+            for (int src = 1; src < world; src++)
+                {  // error-free fold
+                const double bs = get(src, k), be = get(src, nv + k);
+                const double t = s + bs, bb = t - s;
+                const double er = (s - (t - bb)) + (bs - bb);
+                s = t;
+                c += be + er;
                 }
+            v[k] = s;
+            v[nv + k] = c;
+            }
         }
     __syncwarp();
     }
@@ -206,14 +237,54 @@ __device__ __forceinline__ void dist_push(const DistDev *d, T *const *tails, int
     if (FENCE && any) __threadfence_system();
     }
 
+// The same push dealt out in chunks of 32 consecutive send-list entries (one coalesced warp store into the
+// peer's tail): chunk j goes to CTA j mod G, to its warp nw-1, nw-2, ... -- the warps of a CTA that are the
+// last to receive a slice of an incomplete round (SliceIter), so the push rides in otherwise idle issue slots.
+// No fence here (see dist_push<false>); returns true when this thread stored something.
+template <class T, class F>
+__device__ __forceinline__ bool dist_push_warps(const DistDev *d, T *const *tails, int nw, F f)
+    {
+    const int nsend = d->send_ptr[d->world];
+    const int nchunk = (nsend + 31) >> 5, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    bool any = false;
+    for (int j = blockIdx.x + gridDim.x * (nw - 1 - wid); j < nchunk; j += gridDim.x * nw)
+        {
+        const int idx = 32 * j + lane;
+        if (idx >= nsend) continue;
+        int q = 0;
+        while (idx >= d->send_ptr[q + 1]) q++;
+        const T val = f(d->send_rows[idx]);
+        *(tails[q] + d->send_dst[q] + (idx - d->send_ptr[q])) = val;
+        any = true;
+        }
+    return any;
+    }
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+    {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+    }
+// spin with acquire loads until *flag >= e (no fence needed afterwards); false on timeout
+__device__ inline bool wait_flag_acquire(const unsigned long long *flag, unsigned long long e)
+    {
+    if (ld_acquire_sys(flag) >= e) return true;
+    const unsigned long long t0 = now_ns();
+    unsigned int k = 0;
+    while (ld_acquire_sys(flag) < e)
+        if ((++k & 1023u) == 0 && now_ns() - t0 > DIST_TIMEOUT_NS) return false;
+    return true;
+    }
+
 // After a dist_push by a whole CTA: one thread raises the halo epoch flag on every destination.
-__device__ inline void dist_raise(DistDev *d)
+__device__ inline void dist_raise_e(const DistDev *d, unsigned long long e)
     {
     __threadfence_system();
-    const unsigned long long e = ++d->hepoch;
     for (int q = 0; q < d->world; q++)
         if (d->send_ptr[q + 1] > d->send_ptr[q]) st_sys(&d->ctrl[q]->hflag[d->rank], e);
     }
+__device__ inline void dist_raise(DistDev *d) { dist_raise_e(d, ++d->hepoch); }
 
 // Consumer side: wait until every source rank has raised the current halo epoch (one thread).
 __device__ inline void dist_wait(DistDev *d)

@@ -88,6 +88,12 @@ template <int BS> struct PkShared
     unsigned int nred;           // reductions so far (slot parity)
     unsigned long long hepoch;   // halo epoch this CTA expects next
     unsigned long long t_prev;   // time stamp of the previous phase boundary (CTA 0, thread 0)
+    int pushed;                  // a thread of this CTA stored into peer memory since the last halo barrier
+    // multi-GPU: this CTA's copy of the exchange descriptor (ranks, peer pointers, halo plan: read in every
+    // push and all-reduce, each field a dependent L2 round trip when left in global memory); `epoch` and
+    // sh.hepoch advance in every CTA alike and go back to global memory when the kernel ends
+    DistDev dd;
+    int derr;                    // a spin of this CTA timed out
     };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p)
@@ -198,11 +204,12 @@ __device__ void pk_sync(const PkArgs &a, PkShared<BS> &sh, const double (&acc)[R
             unsigned int target = 0;
             if (lane == 0)
                 {
+                if (NV > 0 && a.dist != nullptr) sh.dd.epoch++;  // the epoch of this all-reduce, in every CTA alike
                 target = ++sh.gen;
                 // release.  A barrier that raises the halo flags publishes this CTA's pushes into peer memory
                 // (plain stores by any of its threads, ordered before this point by the bar.sync above): one
                 // system-scope fence per CTA, issued when the stores have long been on their way
-                if (halo && a.dist != nullptr)
+                if (halo && a.dist != nullptr && sh.pushed)
                     __threadfence_system();
                 else
                     __threadfence();
@@ -215,32 +222,54 @@ __device__ void pk_sync(const PkArgs &a, PkShared<BS> &sh, const double (&acc)[R
                 if (a.phase_acc != nullptr && lane == 0) a.sync->t_last = now_ns();
                 if (NV > 0)
                     {
+                    // every partial of this lane is fetched before the first addition: the loads are independent
+                    // L2 round trips (a dependent loop cost 1.7 us per reduced value on 148 CTAs)
+                    constexpr int PF = 5;  // partials per lane held in registers: grids up to 160 CTAs in one go
+                    double s[NV > 0 ? NV : 1], e[NV > 0 ? NV : 1];
 #pragma unroll
                     for (int k = 0; k < NV; k++)
                         {
-                        double s = MAXOP ? -1.7976931348623157e308 : 0.0, e = 0.0;
-                        for (int i = lane; i < (int)gridDim.x; i += 32)
+                        s[k] = MAXOP ? -1.7976931348623157e308 : 0.0;
+                        e[k] = 0.0;
+                        for (int i0 = 0; i0 < (int)gridDim.x; i0 += 32 * PF)
                             {
-                            if (MAXOP)
-                                s = fmax(s, __ldcg(&a.sync->part[slot][k][i]));
-                            else
-                                dd_add(s, e, __ldcg(&a.sync->part[slot][k][i]), __ldcg(&a.sync->part[slot][RED_NV + k][i]));
+                            double vs[PF], ve[PF];
+#pragma unroll
+                            for (int u = 0; u < PF; u++)
+                                {
+                                const int i = i0 + lane + 32 * u;
+                                const bool in = i < (int)gridDim.x;
+                                vs[u] = in ? __ldcg(&a.sync->part[slot][k][i]) : (MAXOP ? -1.7976931348623157e308 : 0.0);
+                                ve[u] = (in && !MAXOP) ? __ldcg(&a.sync->part[slot][RED_NV + k][i]) : 0.0;
+                                }
+#pragma unroll
+                            for (int u = 0; u < PF; u++)
+                                {  // index order i = lane, lane + 32, ...: the same fixed order as a plain loop
+                                if (MAXOP)
+                                    s[k] = fmax(s[k], vs[u]);
+                                else
+                                    dd_add(s[k], e[k], vs[u], ve[u]);
+                                }
                             }
+                        }
+#pragma unroll
+                    for (int k = 0; k < NV; k++)
+                        {
                         if (MAXOP)
                             {
 #pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(0xffffffffu, s, o));
+                            for (int o = 16; o > 0; o >>= 1) s[k] = fmax(s[k], __shfl_xor_sync(0xffffffffu, s[k], o));
                             }
                         else
-                            warp_sum_dd(s, e);
+                            warp_sum_dd(s[k], e[k]);
                         if (lane == 0)
                             {
-                            sh.tot[k] = s;
-                            sh.tot[NV + k] = e;
+                            sh.tot[k] = s[k];
+                            sh.tot[NV + k] = e[k];
                             }
                         }
                     __syncwarp();
-                    if (a.dist != nullptr) dist_allreduce_warp(a.dist, sh.tot, NV, MAXOP);
+                    if (a.dist != nullptr) dist_allreduce_warp_e(&sh.dd, &sh.derr, sh.dd.epoch, sh.tot, NV, MAXOP);
                     }
                 if (lane == 0)
                     {
@@ -251,9 +280,10 @@ __device__ void pk_sync(const PkArgs &a, PkShared<BS> &sh, const double (&acc)[R
                         }
                     a.sync->count = 0;
                     if (a.phase_acc != nullptr) a.sync->t_ar = now_ns();
-                    if (halo && a.dist != nullptr) dist_raise(a.dist);  // fence.sys + flags on the neighbours
                     __threadfence();
-                    st_release_u32(&a.sync->gen, target);
+                    st_release_u32(&a.sync->gen, target);  // this GPU's CTAs go on ...
+                    // ... while the neighbours learn that every push of the phase is complete and fenced
+                    if (halo && a.dist != nullptr) dist_raise_e(&sh.dd, sh.hepoch);
                     }
                 }
             else if (lane == 0)
@@ -268,24 +298,30 @@ __device__ void pk_sync(const PkArgs &a, PkShared<BS> &sh, const double (&acc)[R
         if (lane == 0)
             {
             if (NV > 0) sh.nred++;
-            if (halo) sh.hepoch++;
+            if (halo)
+                {
+                sh.hepoch++;
+                sh.pushed = 0;
+                }
             }
         }
     __syncthreads();
     }
 
 // multi-GPU consumer side: one lane waits until every source rank has raised halo epoch e
-__device__ inline void pk_halo_wait(DistDev *d, unsigned long long e)
+__device__ inline void pk_halo_wait(const DistDev *d, int *err, unsigned long long e)
     {
-    if (d->error) return;
+    if (*err) return;
     DistCtrl *me = d->ctrl[d->rank];
+    // acquire loads at system scope order the pushed entries before the flag for this thread (and, through
+    // the __syncwarp that follows, for its warp); stale L1 copies of the ghost rows cannot exist: they were
+    // dropped by the fence of the last grid barrier and nobody reads a ghost row before its flag
     for (int src = 0; src < d->world; src++)
-        if (d->recv_from[src] && !wait_flag(&me->hflag[src], e))
+        if (d->recv_from[src] && !wait_flag_acquire(&me->hflag[src], e))
             {
-            d->error = 1;
+            *err = 1;
             return;
             }
-    __threadfence_system();
     }
 
 // ---- gather blocks staged in shared memory (fg_setup.hpp, Operator::lcol) --------------------------------
@@ -422,7 +458,7 @@ __device__ __forceinline__ void pk_spmv(const PkArgs &a, PkShared<BS> &sh, const
             while (b < a.op.nblock && a.op.bghost[b] == 0) b = own.next(b);
             if (b < a.op.nblock)
                 {
-                if (lane == 0) pk_halo_wait(a.dist, sh.hepoch - 1);
+                if (lane == 0) pk_halo_wait(&sh.dd, &sh.derr, sh.hepoch - 1);
                 __syncwarp();
                 pk_blocks_staged<STAGE>(a, sa, own, 2, stage, acc);
                 }
@@ -440,7 +476,7 @@ __device__ __forceinline__ void pk_spmv(const PkArgs &a, PkShared<BS> &sh, const
         while (s < a.op.nslice && a.op.sghost[s] == 0) s = own.next(s);
         if (s < a.op.nslice)
             {
-            if (lane == 0) pk_halo_wait(a.dist, sh.hepoch - 1);
+            if (lane == 0) pk_halo_wait(&sh.dd, &sh.derr, sh.hepoch - 1);
             __syncwarp();
             spmv_node3_slices<STAGE, IDX16, true>(a.op, sa, own, lane, 2, acc);
             }
@@ -482,15 +518,24 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
                                   : nullptr;
     const int gtid = blockIdx.x * BS + threadIdx.x, gthreads = gridDim.x * BS;
     const bool spec = a.dist != nullptr;  // speculative second SpMV: one all-reduce less per iteration
+    if (a.dist != nullptr)
+        {  // the exchange descriptor into shared memory, word by word
+        const unsigned int *src = reinterpret_cast<const unsigned int *>(a.dist);
+        unsigned int *dst = reinterpret_cast<unsigned int *>(&sh.dd);
+        for (int i = threadIdx.x; i < (int)(sizeof(DistDev) / sizeof(unsigned int)); i += BS) dst[i] = src[i];
+        }
+    __syncthreads();
     if (threadIdx.x == 0)
         {
+        sh.derr = a.dist != nullptr ? sh.dd.error : 0;
         sh.ks = *a.st;
         kstate_reset(&sh.ks, a.tol, a.maxiter);
         if (blockIdx.x != 0) sh.ks.hist = nullptr;  // the history is recorded once
         sh.gen = ld_acquire_u32(&a.sync->gen);
         sh.nred = 0;
-        sh.hepoch = a.dist != nullptr ? a.dist->hepoch + 1 : 1;
+        sh.hepoch = a.dist != nullptr ? sh.dd.hepoch + 1 : 1;
         sh.t_prev = 0ull;
+        sh.pushed = 0;
         }
     __syncthreads();
     pk_stamp(a, sh, PKP_START);
@@ -542,12 +587,15 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
                 return make_double2(d.x * pi.x, d.y * pi.y);
                 };
             if (a.dist != nullptr)
-                dist_push<false>(a.dist, a.dist->wtail[0], gtid, gthreads, [&](int row)
-                    {
-                    double2 pi;
-                    const double2 ph = value(row, pi);
-                    return node_w(a.op.qbasis + row, ph.x, ph.y);
-                    });
+                {
+                if (dist_push_warps(&sh.dd, sh.dd.wtail[0], BS / 32, [&](int row)
+                        {
+                        double2 pi;
+                        const double2 ph = value(row, pi);
+                        return node_w(a.op.qbasis + row, ph.x, ph.y);
+                        }))
+                    sh.pushed = 1;
+                }
             pk_for_slices<STAGED>(own, a.op, [&](const int s)
                 {
                 const int row = s * SLICE + lane;
@@ -590,12 +638,15 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
                 return make_double2(d.x * si.x, d.y * si.y);
                 };
             if (a.dist != nullptr)
-                dist_push<false>(a.dist, a.dist->wtail[1], gtid, gthreads, [&](int row)
-                    {
-                    double2 si;
-                    const double2 sh_ = value(row, si);
-                    return node_w(a.op.qbasis + row, sh_.x, sh_.y);
-                    });
+                {
+                if (dist_push_warps(&sh.dd, sh.dd.wtail[1], BS / 32, [&](int row)
+                        {
+                        double2 si;
+                        const double2 sh_ = value(row, si);
+                        return node_w(a.op.qbasis + row, sh_.x, sh_.y);
+                        }))
+                    sh.pushed = 1;
+                }
             pk_for_slices<STAGED>(own, a.op, [&](const int s)
                 {
                 const int row = s * SLICE + lane;
@@ -722,7 +773,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
         if (a.dist != nullptr)
             {  // the solution of my boundary rows goes into the neighbours' ghost tails of x
             // x of rows owned by other CTAs was written before the last grid barrier of the loop
-            dist_push<false>(a.dist, a.dist->tail, gtid, gthreads, [&](int row) { return x2[row]; });
+            if (dist_push_warps(&sh.dd, sh.dd.tail, BS / 32, [&](int row) { return x2[row]; })) sh.pushed = 1;
             pk_sync<BS, 0, false>(a, sh, acc, 1);
             pk_stamp(a, sh, PKP_HALO_X);
             }
@@ -766,7 +817,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
                 {  // ghost rows: their solution was pushed by the owners
                 if (gtid - lane < a.NODt - a.NODp)
                     {  // warp-uniform: one lane waits for the owners' flags, then plain loads see the pushes
-                    if (lane == 0) pk_halo_wait(a.dist, sh.hepoch - 1);
+                    if (lane == 0) pk_halo_wait(&sh.dd, &sh.derr, sh.hepoch - 1);
                     __syncwarp();
                     for (int row = a.NODp + gtid; row < a.NODt; row += gthreads) update_row(row, false);
                     }
@@ -786,9 +837,15 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
             }
         pk_stamp(a, sh, PKP_UPDATE);
         }
+    if (a.dist != nullptr && threadIdx.x == 0 && sh.derr) a.dist->error = 1;  // a spin timed out: the host reports it
     if (blockIdx.x == 0 && threadIdx.x == 0)
         {
         *a.st = sh.ks;
+        if (a.dist != nullptr)
+            {  // the epochs the next kernel (persistent or not) continues from
+            a.dist->epoch = sh.dd.epoch;
+            a.dist->hepoch = sh.hepoch - 1;
+            }
         if (a.h_st != nullptr)
             {  // the host is spinning on h_seq: outcome first, then the number (system-scope order)
             *a.h_st = sh.ks;

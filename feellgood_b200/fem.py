@@ -25,6 +25,12 @@ ENERGY_TERMS = ("EXCHANGE", "ANISOTROPY", "DEMAG", "ZEEMAN")   # src/fem.h:30-36
 EXCHANGE, ANISOTROPY, DEMAG, ZEEMAN = range(4)
 
 
+def round_half_away(x):
+    """std::round for the step count: round half away from zero (Python's round() rounds half to even)."""
+    import math
+    return int(math.floor(x + 0.5)) if x >= 0 else -int(math.floor(-x + 0.5))
+
+
 class TimeStepper:
     """Logic for finding a reasonable time step (src/time_integration.cpp:11-38)."""
 
@@ -214,7 +220,8 @@ class Fem:
         status = 0
         t_initial = t_prm.get_t()
         t_step = s.time_step
-        step_count = int(round((t_prm.tf - t_initial) / t_step))
+        # std::round (src/time_integration.cpp:170): halves away from zero, not Python's banker's rounding
+        step_count = round_half_away((t_prm.tf - t_initial) / t_step)
         stepper = TimeStepper(t_prm.get_dt(), t_prm.DTMIN, t_prm.DTMAX)
         stats = self.stats = Stats()
         stats.max_angle = la.max_angle()

@@ -1,7 +1,10 @@
 #!/usr/bin/env python
-"""Turns the scratch output of a gpurun profiling pass (gpurun_out/) into the tracked summaries
-under profiles/: the ncu launch list (per-kernel shares), the `--set full` metrics of the top
-kernels, and profiles/spmv_traffic.json (DRAM bytes per SpMV launch, read by bench.py)."""
+"""Turns the scratch output of a gpurun profiling pass (gpurun_out/, written by scripts/profile.sh) into
+the tracked summaries under profiles/: the ncu launch list (per-kernel shares), the `--set full` metrics of
+the top kernels, and profiles/solve_traffic.json / spmv_traffic.json (DRAM bytes per launch of the solve
+kernel / of an SpMV launch of the multi-kernel solver: bench.py's static fallback for roofline.traffic).
+
+    python scripts/summarize_profiles.py <tag> [workload]"""
 import collections
 import csv
 import json
@@ -74,12 +77,12 @@ for rep in sorted(f for f in os.listdir(OUT) if f.endswith(".ncu-rep")):
                 lines_out.append("| %s | %s | %s |" % (w, row[i], units[i]))
                 vals[w] = (row[i], units[i])
         lines_out.append("")
-        if "k_spmv" in name and "dram__bytes_read.sum" in vals:
+        if ("k_spmv" in name or "k_llg_solve" in name) and "dram__bytes_read.sum" in vals:
             rd = float(vals["dram__bytes_read.sum"][0]) * UNIT[vals["dram__bytes_read.sum"][1]]
             wr = float(vals["dram__bytes_write.sum"][0]) * UNIT[vals["dram__bytes_write.sum"][1]]
             json.dump(dict(workload=workload, kernel=name, dram_bytes_per_launch=rd + wr,
                            source="%s_summary.md (%s)" % (tag, rep)),
-                      open(os.path.join(PROF, "spmv_traffic.json"), "w"))
+                      open(os.path.join(PROF, "solve_traffic.json" if "k_llg_solve" in name else "spmv_traffic.json"), "w"))
 for f in ("bench_%s.json" % workload, "bench_tube5m.json", "pytest_gpu.log"):
     p = os.path.join(OUT, f)
     if os.path.exists(p):

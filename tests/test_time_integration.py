@@ -60,6 +60,19 @@ def test_loop_on_oracle_backend(oracle):
     oc.close()
 
 
+def test_step_count_rounds_half_away_from_zero(oracle):
+    """step_count = std::round((tf - t0) / time_step) (src/time_integration.cpp:170): tf = 2.5 time steps
+    gives 3 visible steps after the initial row (the reference and the C++ shim), not Python's round(2.5) = 2."""
+    from feellgood_b200.fem import round_half_away
+    assert [round_half_away(x) for x in (0.5, 1.5, 2.5, 3.5, 2.4999, 2.0, 0.0)] == [1, 2, 3, 4, 2, 2, 0]
+    case = cases.ellipsoid()
+    fem, t_prm, status, nt, oc = run_oracle(case, tf=2.5e-12)
+    rows = np.array(fem.evol, dtype=float)
+    assert status == 0 and rows.shape[0] == 4          # t = 0, 1, 2, 3 ps
+    assert np.array_equal(rows[:, 1], [0.0, 1e-12, 2e-12, 3e-12])
+    oc.close()
+
+
 def test_dt_too_small_aborts(oracle):
     """**ABORTED**: dt < DTMIN returns status 1 (src/time_integration.cpp:185-190)."""
     case = cases.ellipsoid()
