@@ -276,7 +276,7 @@ def measure_traffic(args, kernel_regex, timeout_s=240):
            "-k", "regex:" + kernel_regex, "-s", "3", "-c", "1", "--csv", "--log-file", out.name,
            sys.executable, os.path.abspath(__file__), "--workload", args.workload, "--scale", str(args.scale),
            "--solver", args.solver, "--steps", "2", "--warmup", "3", "--no-e2e", "--no-cpu-baseline",
-           "--traffic", "off"]
+           "--traffic", "off", "--no-named-meshes"]
     try:
         subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=timeout_s,
                        env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0")))
@@ -326,6 +326,8 @@ def main():
     ap.add_argument("--traffic", default="ncu", choices=["ncu", "static", "off"],
                     help="roofline.traffic: ncu = measure DRAM bytes of the dominant kernel with a fresh ncu "
                          "capture in a child process (adds ~1 min); static = the committed capture in profiles/")
+    ap.add_argument("--no-named-meshes", dest="named_meshes", action="store_false",
+                    help="skip the short runs of BASELINE configs 1-4 that the default 1-GPU line appends")
     ap.add_argument("--kernel-times", action="store_true",
                     help="bracket every kernel with CUDA events and print the per-class table (stderr)")
     args = ap.parse_args()
@@ -554,6 +556,43 @@ def main():
                      survey_bytes_per_step=b_survey,
                      survey_equiv_gbs=b_survey / (ms * 1e-3 / args.steps) / 1e9 / world)
 
+    # ---- the other named meshes of BASELINE.json (configs 1-4), one short run each on this GPU: throughput
+    # and whole-step roofline fraction, so that the line carries every named mesh (the headline stays config 5)
+    named = None
+    if rank == 0 and world == 1 and args.named_meshes and args.workload == "film20m" and args.scale == 1.0:
+        named = {}
+        for nm in ("tube5m", "disk1m", "sp4", "ellipsoid"):
+            try:
+                w2 = workloads.build(nm)
+                la2 = LinAlgebra(w2.settings(), w2.mesh, device=local_rank)
+                la2.set_state(w2.u)
+                la2.set_solver(args.solver)
+                tm2 = w2.timing()
+                st2 = torch.cuda.ExternalStream(la2.stream(), device=torch.device("cuda", local_rank))
+                it2 = []
+                for k in range(5):
+                    la2.step(w2.Hext, tm2, angle=angles[k])
+                    la2.evolution()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st2)
+                for k in range(40):
+                    la2.step(w2.Hext, tm2, angle=angles[(5 + k) % n_ang])
+                    la2.evolution()
+                    it2.append(la2.iter["nit"])
+                e1.record(st2)
+                torch.cuda.synchronize()
+                ms2 = e0.elapsed_time(e1) / 40
+                b2 = workloads.step_bytes(w2.mesh.NOD, w2.mesh.NT, la2.n, la2.nnz, float(np.mean(it2)),
+                                          getattr(la2, "col_bytes", 4))
+                named[nm] = dict(config=w2.config, NT=w2.mesh.NT, NOD=w2.mesh.NOD, value=1e3 / ms2, unit=UNIT,
+                                 ms_per_step=ms2, steps=40, warmup=5, mean_bicgstab_iters=float(np.mean(it2)),
+                                 step_roofline_frac=b2 / (ms2 * 1e-3) / 1e9 / peak)
+                la2.close()
+                del w2, la2
+            except Exception as e:
+                named[nm] = dict(error=str(e))
+
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -572,6 +611,7 @@ def main():
                                    % (8e-6 * la.nnz),
                                 parallelism="row-block slabs x%d" % world if world > 1 else "1 GPU"),
                     roofline=roof, step_roofline=step_roof, cpu_baseline=cb, e2e=e2e, parity=parity,
+                    named_meshes=named,
                     gpu_launches=int(launches), clocks=clk)
         emit(line)
     la.close()

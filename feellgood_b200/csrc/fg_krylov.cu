@@ -1181,6 +1181,31 @@ bool pk_plan(const Operator &op, int *bs_out, size_t *smem_out)
     return staged;
     }
 
+// Warps per CTA of a 1024-thread launch on `grid` CTAs: when a warp owns only a few slices, the incomplete
+// last round of the front (SliceIter) runs with most warps idle, i.e. latency-bound (4.1 slices per warp on
+// an 8-GPU partition of the 20 M-tet mesh: a 13 % last round cost 8 us of a 36 us product).  Fewer warps per
+// CTA make the rounds fuller: pick the count in [24, 32] whose last round is fullest.
+static int pk_warps(int nslice, int grid)
+    {
+    static const int forced = getenv("FG_PK_WARPS") ? atoi(getenv("FG_PK_WARPS")) : 0;
+    if (forced >= 1 && forced <= 32) return forced;
+    if (nslice >= 16 * grid * 32) return 32;  // many rounds: the tail does not matter
+    int best = 32;
+    double best_fill = -1.0;
+    for (int nw = 32; nw >= 24; nw--)
+        {
+        const long long W = (long long)grid * nw;
+        const long long rem = nslice % W;
+        const double fill = rem == 0 ? 1.0 : (double)rem / (double)W;
+        if (fill > best_fill + 0.02)  // prefer more warps unless the gain is real
+            {
+            best_fill = fill;
+            best = nw;
+            }
+        }
+    return best;
+    }
+
 int bicgstab_run_pk(const Operator &op, KrylovWork &w, double tol, int maxiter, const PkUpdate *upd)
     {
     if (op.kind != OP_NODE3 || !w.pk)
@@ -1244,7 +1269,9 @@ int bicgstab_run_pk(const Operator &op, KrylovWork &w, double tol, int maxiter, 
         }
     void *args[] = {&a};
     const bool prof = prof_begin(w.prof, w.stream, KC_SOLVE);
-    FG_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(bs), args, smem, w.stream));
+    // the instantiation bounds the CTA at `bs` threads; a 1024-thread unstaged launch may use fewer warps
+    const int threads = (bs == 1024 && !staged) ? 32 * pk_warps(op.nslice, grid) : bs;
+    FG_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, smem, w.stream));
     if (prof) prof_end(w.prof, w.stream);
     if (w.launches) ++*w.launches;
     if (mailbox)

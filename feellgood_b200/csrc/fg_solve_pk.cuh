@@ -135,7 +135,7 @@ template <int BS, int NV, bool MAXOP>
 __device__ void pk_sync(const PkArgs &a, PkShared<BS> &sh, const double (&acc)[RED_NV], const int halo)
     {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    constexpr int NW = BS / 32;
+    const int NW = (int)blockDim.x >> 5;  // warps really launched (<= BS / 32, see pk_plan)
     if (NV > 0)
         {
 #pragma unroll
@@ -287,10 +287,11 @@ __device__ void pk_sync(const PkArgs &a, PkShared<BS> &sh, const double (&acc)[R
                     }
                 }
             else if (lane == 0)
-                {
+                {  // the acquire load orders everything that follows (for this thread; for the rest of the CTA
+                   // through the bar.sync below) after the releasing store, and drops stale L1 lines: no
+                   // separate fence (it cost ~0.5 us per barrier and CTA)
                 while (ld_acquire_u32(&a.sync->gen) != target)
                     ;
-                __threadfence();
                 }
             __syncwarp();
             if (NV > 0 && lane < NV) sh.tot[lane] = __ldcg(&a.sync->tot[slot][lane]);
@@ -512,17 +513,20 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
     const int lane = threadIdx.x & 31;
     // Row ownership (SliceIter, fg_krylov.cu): a front of W slices per round, the last round dealt out per CTA
     // STAGED: the units are gather blocks of 8 slices, owned by thread groups of 4 warps
-    const SliceIter own = STAGED ? slices_balanced(a.op.nblock, BS / PK_GROUP, threadIdx.x / PK_GROUP)
-                                 : slices_balanced(a.op.nslice, BS / 32, threadIdx.x >> 5);
+    // BS is the LARGEST CTA of this instantiation; the launch may use fewer warps (pk_plan picks the count that
+    // fills the last round of slices best), so strides and ownership come from blockDim
+    const int nthr = (int)blockDim.x;
+    const SliceIter own = STAGED ? slices_balanced(a.op.nblock, nthr / PK_GROUP, threadIdx.x / PK_GROUP)
+                                 : slices_balanced(a.op.nslice, nthr / 32, threadIdx.x >> 5);
     double4 *const stage = STAGED ? pk_stage_smem + (size_t)(threadIdx.x / PK_GROUP) * (size_t)((a.op.stage_cap + 3) & ~3)
                                   : nullptr;
-    const int gtid = blockIdx.x * BS + threadIdx.x, gthreads = gridDim.x * BS;
+    const int gtid = blockIdx.x * nthr + threadIdx.x, gthreads = gridDim.x * nthr;
     const bool spec = a.dist != nullptr;  // speculative second SpMV: one all-reduce less per iteration
     if (a.dist != nullptr)
         {  // the exchange descriptor into shared memory, word by word
         const unsigned int *src = reinterpret_cast<const unsigned int *>(a.dist);
         unsigned int *dst = reinterpret_cast<unsigned int *>(&sh.dd);
-        for (int i = threadIdx.x; i < (int)(sizeof(DistDev) / sizeof(unsigned int)); i += BS) dst[i] = src[i];
+        for (int i = threadIdx.x; i < (int)(sizeof(DistDev) / sizeof(unsigned int)); i += nthr) dst[i] = src[i];
         }
     __syncthreads();
     if (threadIdx.x == 0)
@@ -588,7 +592,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
                 };
             if (a.dist != nullptr)
                 {
-                if (dist_push_warps(&sh.dd, sh.dd.wtail[0], BS / 32, [&](int row)
+                if (dist_push_warps(&sh.dd, sh.dd.wtail[0], nthr / 32, [&](int row)
                         {
                         double2 pi;
                         const double2 ph = value(row, pi);
@@ -639,7 +643,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
                 };
             if (a.dist != nullptr)
                 {
-                if (dist_push_warps(&sh.dd, sh.dd.wtail[1], BS / 32, [&](int row)
+                if (dist_push_warps(&sh.dd, sh.dd.wtail[1], nthr / 32, [&](int row)
                         {
                         double2 si;
                         const double2 sh_ = value(row, si);
@@ -773,7 +777,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
         if (a.dist != nullptr)
             {  // the solution of my boundary rows goes into the neighbours' ghost tails of x
             // x of rows owned by other CTAs was written before the last grid barrier of the loop
-            if (dist_push_warps(&sh.dd, sh.dd.tail, BS / 32, [&](int row) { return x2[row]; })) sh.pushed = 1;
+            if (dist_push_warps(&sh.dd, sh.dd.tail, nthr / 32, [&](int row) { return x2[row]; })) sh.pushed = 1;
             pk_sync<BS, 0, false>(a, sh, acc, 1);
             pk_stamp(a, sh, PKP_HALO_X);
             }

@@ -26,6 +26,11 @@ def test_reference_arm_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == j["value"] and "sp4" in cb["sample"]
     assert j["e2e"] == dict(value=j["value"], unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
     assert j["config"]["workload"] == "sp4"
+    # the WHOLE workload of the product arm (no tet-ratio extrapolation), the counts really done, and both
+    # CPU figures of BASELINE.md section 3 (threaded = the line's value, serial on a sample)
+    assert cb["full_workload"] is True and "the whole workload" in cb["sample"] and "186000 tets" in cb["sample"]
+    assert j["steps"] == cb["steps"] == 2 and j["warmup"] == cb["warmup"] >= 1
+    assert cb["serial"]["cores"] == 1 and 0 < cb["serial"]["value"] <= 1.5 * cb["value"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():
