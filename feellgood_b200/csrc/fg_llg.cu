@@ -86,6 +86,7 @@ struct fg_ctx
     bool use_blocks = false;     // fg_set_operator(ctx, 1): solve with the assembled 2x2 blocks (A/B checks)
     int solver_kind = 0;         // fg_set_solver: 0 persistent kernel, 1 one kernel per phase
     unsigned char *sghost = nullptr;  // multi-GPU: slices with a ghost column
+    unsigned long long *d_unit = nullptr;  // fg_set_state: max | |u|^2 - 1 | over the magnetic nodes (bits of a double)
     unsigned short *lcol = nullptr;   // gather blocks of the persistent SpMV (fg_setup.hpp)
     int *bptr = nullptr, *bhalo = nullptr;
     unsigned char *bghost = nullptr;
@@ -109,6 +110,7 @@ struct fg_ctx
     bool have_basis = false, prepared = false, space_field = false, assembled = false;
     bool commit_pending = false;  // fg_commit is lazy: the next k_basis copies NEXT -> CURRENT on its way
     bool iso_regions = true;   // no region has K or K3: the element fast path applies (k_tet_iso)
+    bool cubic_regions = false;  // a magnetic region has K3: the lean general kernel does not apply
     double v_max = 0.0;
     // profiling
     int profiling = 0;
@@ -265,6 +267,22 @@ int launch_elements(fg_ctx *c)
             else
                 CTX_LAUNCH_C(c, KC_TET, (k_tet_iso<1, false>), grid, A, c->cur, c->basis, c->sp, c->rec);
             }
+        else if (!c->cubic_regions && c->sp.idx_dir == FG_IDX_UNDEF && getenv("FG_TET_NOLEAN") == nullptr)
+            {  // uniaxial anisotropy only, no drift: the lean general kernel (k_tet_lean)
+            const int gl = grid_for(c->NTm, TET_LEAN_BLOCK);
+            const bool prof_ = prof_begin(c->kw.prof, c->stream, KC_TET);
+            if (c->h.npi_tet == 5 && c->space_field)
+                k_tet_lean<5, true><<<gl, TET_LEAN_BLOCK, 0, c->stream>>>(A, c->cur, c->sp, c->rec);
+            else if (c->h.npi_tet == 5)
+                k_tet_lean<5, false><<<gl, TET_LEAN_BLOCK, 0, c->stream>>>(A, c->cur, c->sp, c->rec);
+            else if (c->space_field)
+                k_tet_lean<1, true><<<gl, TET_LEAN_BLOCK, 0, c->stream>>>(A, c->cur, c->sp, c->rec);
+            else
+                k_tet_lean<1, false><<<gl, TET_LEAN_BLOCK, 0, c->stream>>>(A, c->cur, c->sp, c->rec);
+            if (prof_) prof_end(c->kw.prof, c->stream);
+            ++c->launches;
+            FG_CUDA(cudaGetLastError());
+            }
         else if (c->h.npi_tet == 5)
             {
             if (c->space_field)
@@ -330,7 +348,9 @@ int launch_assemble(fg_ctx *c, double dt)
         int per_sm = 1;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_node, BLOCK, 0) != cudaSuccess || per_sm < 1)
             per_sm = 1;
-        wave = per_sm * NUM_SMS;
+        int sms = NUM_SMS;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+        wave = per_sm * sms;
         }
     int grid = (c->h.nslice + BLOCK / 32 - 1) / (BLOCK / 32);
     if (grid > wave) grid = wave;
@@ -705,6 +725,7 @@ static int create_ctx(const fg_mesh *mesh, const fg_params *prm, int device, con
             R.has_K = p.K != 0;
             R.has_K3 = p.K3 != 0;
             if (p.Ms > 0 && (R.has_K || R.has_K3)) c->iso_regions = false;
+            if (p.Ms > 0 && R.has_K3) c->cubic_regions = true;
             for (int k = 0; k < 3; k++)
                 {
                 R.uk[k] = p.uk[k];
@@ -976,8 +997,7 @@ int fg_dist_connect(fg_ctx *c, const void *blobs)
         void *base = c->arena;
         if (q != c->rank)
             {
-            const bool needed = D.send_ptr[q + 1] > D.send_ptr[q] || true;  // mailboxes: every peer
-            if (needed && !c->peer_base[q])
+            if (!c->peer_base[q])  // every peer is mapped: the all-reduce mailboxes go to all of them
                 FG_CUDA(cudaIpcOpenMemHandle(&c->peer_base[q], B[q].handle, cudaIpcMemLazyEnablePeerAccess));
             base = c->peer_base[q];
             }
@@ -1012,7 +1032,7 @@ void fg_destroy(fg_ctx *c)
                     c->tet_detJ, c->ext_field, c->tet_reg, c->reg_tet, c->rec, c->tri_ind,
                     c->tri_reg, c->tri_surf, c->tri_dMs, c->reg_tri, c->trec, c->perm, c->sptr,
                     c->scol, c->sdeg, c->iptr, c->tch_ptr, c->tch_nodes, c->tet_loc, c->tet_slot, c->itptr, c->sinct, c->sS, c->Aw, c->val, c->Sdiag, c->Dm, c->qbasis,
-                    c->scol16, c->sghost, c->lcol, c->bptr, c->bhalo, c->bghost, c->mtri_ind, c->mtri_reg, c->mtri_surf, c->mtri_nrm, c->mtri_dMs, c->extra_edges,
+                    c->scol16, c->sghost, c->d_unit, c->lcol, c->bptr, c->bhalo, c->bghost, c->mtri_ind, c->mtri_reg, c->mtri_surf, c->mtri_nrm, c->mtri_dMs, c->extra_edges,
                     c->d_scal, c->node_pos, c->corr, c->tcorr, c->src, c->cptr, c->cidx};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -1086,6 +1106,22 @@ int fg_set_state(fg_ctx *c, const double *u, const double *v, const double *phi,
         return FG_ERR_INVALID;
         }
     FG_TRY(push_fields(c, c->cur, u, v, phi, phiv, true));
+        {  // |u| = 1 on the magnetic nodes is a precondition (include/feellgood_b200.h): the matrix-free operator
+           // applies the node-diagonal block in the closed form that holds for an orthonormal triad (ep, eq, u)
+        if (!c->d_unit) FG_CUDA(cudaMalloc(&c->d_unit, sizeof(unsigned long long)));
+        FG_CUDA(cudaMemsetAsync(c->d_unit, 0, sizeof(unsigned long long), c->stream));
+        CTX_LAUNCH(c, k_check_unit, grid_for(c->NODt, BLOCK), c->NODt, c->nonmag, c->cur, c->d_unit);
+        unsigned long long bits = 0;
+        FG_CUDA(cudaMemcpyAsync(&bits, c->d_unit, sizeof bits, cudaMemcpyDeviceToHost, c->stream));
+        FG_CUDA(cudaStreamSynchronize(c->stream));
+        double dev = 0.0;
+        memcpy(&dev, &bits, sizeof dev);
+        if (!(dev <= 1e-6))
+            {
+            set_error("fg_set_state: the magnetisation of a magnetic node is not a unit vector (max | |u|^2 - 1 | = %g)", dev);
+            return FG_ERR_INVALID;
+            }
+        }
     FG_CUDA(cudaMemcpyAsync(c->next, c->cur, sizeof(NodeRec) * (size_t)c->NODt, cudaMemcpyDeviceToDevice, c->stream));
     FG_CUDA(cudaStreamSynchronize(c->stream));
     c->have_basis = c->prepared = c->assembled = false;

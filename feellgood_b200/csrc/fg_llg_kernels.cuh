@@ -159,6 +159,25 @@ __host__ __device__ __forceinline__ void node_set_basis(const double u[3], doubl
         }
     }
 
+// fg_set_state: max over the magnetic nodes of | |u|^2 - 1 | (non-negative doubles order like their bit
+// patterns, so an integer atomicMax does it; NaN compares above everything and is caught as well)
+__global__ void __launch_bounds__(BLOCK)
+k_check_unit(int NOD, const unsigned char *__restrict__ nonmag, const NodeRec *__restrict__ cur,
+             unsigned long long *out)
+    {
+    const int a = blockIdx.x * BLOCK + threadIdx.x;
+    double dev = 0.0;
+    if (a < NOD && !nonmag[a])
+        {
+        const double *u = cur[a].u;
+        dev = fabs(u[0] * u[0] + u[1] * u[1] + u[2] * u[2] - 1.0);
+        if (!(dev == dev)) dev = 1.7976931348623157e308;
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dev = fmax(dev, __shfl_xor_sync(0xffffffffu, dev, o));
+    if ((threadIdx.x & 31) == 0 && dev > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(dev));
+    }
+
 // Also writes the basis as a unit quaternion (32 B): what the Krylov kernels read (fg_common.cuh).
 // COMMIT: mesh::evolution (src/mesh.h:189-193) fused in: `src` is the NEXT record, copied to CURRENT (`dst`)
 // on the way (fg_commit is lazy), so the copy costs one 64-byte write per node instead of a pass of its own.
@@ -226,7 +245,10 @@ struct StepPrm
 // the per-element constants (grad U, Hd, Hv, the exchange products Ex) stay live: the reference's
 // per-point tables U, V, H, H_aniso (4 x 3 x NPI doubles) never exist.  Every sum keeps the
 // reference's order of accumulation.
-template <int NPI>
+// CUBIC / DRIFT = false compile the cubic-anisotropy and the recentring-drift branches out (the caller
+// guarantees that no region has K3 / that idx_dir is undefined): same arithmetic on what remains, fewer
+// live registers (the general kernel needs 254).
+template <int NPI, bool CUBIC = true, bool DRIFT = true>
 __host__ __device__ __forceinline__ void tet_core(const TetIn &T, const TetRegion &R, const StepPrm &sp,
                                          const double (&Hext)[3][NPI], double contrib[4],
                                          double BE[3][4])
@@ -278,7 +300,7 @@ __host__ __device__ __forceinline__ void tet_core(const TetIn &T, const TetRegio
 #pragma unroll
         for (int i = 0; i < 4; i++) BE[d][i] = 0.0;
 
-    const bool drift = sp.idx_dir != FG_IDX_UNDEF;
+    const bool drift = DRIFT && sp.idx_dir != FG_IDX_UNDEF;
     double dUk[3] = {0, 0, 0}, dVk[3] = {0, 0, 0};
     if (drift)  // add_drift_BE, tetra.cpp:150-169 (accumulated for all points before the fields)
         {
@@ -339,7 +361,7 @@ __host__ __device__ __forceinline__ void tet_core(const TetIn &T, const TetRegio
             for (int i = 0; i < 4; i++) su += T.u[i][d] * tet_a<NPI>(i, g);
             Ug[d] = su;
             }
-        if (R.has_K || R.has_K3)
+        if (R.has_K || (CUBIC && R.has_K3))
             {
 #pragma unroll
             for (int d = 0; d < 3; d++)
@@ -362,7 +384,7 @@ __host__ __device__ __forceinline__ void tet_core(const TetIn &T, const TetRegio
             const double s = Ug[0] * R.uk[0] + Ug[1] * R.uk[1] + Ug[2] * R.uk[2];
             uH += R.Kbis * (s * s);
             }
-        if (R.has_K3)  // calc_aniso_cub, tetra.cpp:183-208 (uk_v.cwiseProduct(ex) kept literally)
+        if (CUBIC && R.has_K3)  // calc_aniso_cub, tetra.cpp:183-208 (uk_v.cwiseProduct(ex) kept literally)
             {
             const double uu[3] = {dot3(R.ex, Ug), dot3(R.ey, Ug), dot3(R.ez, Ug)};
             const double uv[3] = {dot3(R.ex, Vg), dot3(R.ey, Vg), dot3(R.ez, Vg)};
@@ -476,6 +498,37 @@ k_tet(const TetArrays A, const NodeRec *__restrict__ cur, const Basis *__restric
             // the record goes where the node's row will stream it from (its incidence slot); the
             // projection Lp = Perm P BE (tetra.cpp:306) is applied once per NODE by the assembly,
             // to the sum of the BE of its tetrahedra (P depends on the node only)
+            if (sl[i] < 0) continue;
+            st256(rec + sl[i], make_double4(contrib[i], BE[0][i], BE[1][i], BE[2][i]));
+            }
+        }
+    }
+
+// The same element for contexts without cubic anisotropy and without recentring drift (every uniaxial
+// material, e.g. the reference's ci-tests/full_test.py): those branches compiled out, the region read where
+// it is needed instead of copied into 46 registers, CTAs of 128 threads, three per SM (<= 168 registers: 12
+// resident warps per SM instead of 8).
+constexpr int TET_LEAN_BLOCK = 128;
+template <int NPI, bool SPACE>
+__global__ void __launch_bounds__(TET_LEAN_BLOCK, 3)
+k_tet_lean(const TetArrays A, const NodeRec *__restrict__ cur, const StepPrm sp, double4 *__restrict__ rec)
+    {
+    const int stride = gridDim.x * TET_LEAN_BLOCK;
+    for (int tm = blockIdx.x * TET_LEAN_BLOCK + threadIdx.x; tm < A.NTm; tm += stride)
+        {
+        TetIn T;
+        int4 ind;
+        tet_load<NPI>(A, tm, cur, ind, T);
+        double Hext[3][NPI];
+        tet_field<NPI>(A, tm, sp, SPACE, Hext);
+        const TetRegion &R = A.regions[__ldg(A.reg + tm)];
+        double contrib[4], BE[3][4];
+        tet_core<NPI, false, false>(T, R, sp, Hext, contrib, BE);
+        const int4 s4 = __ldcs(A.slot + tm);
+        const int sl[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            {
             if (sl[i] < 0) continue;
             st256(rec + sl[i], make_double4(contrib[i], BE[0][i], BE[1][i], BE[2][i]));
             }

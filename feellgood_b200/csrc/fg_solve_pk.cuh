@@ -94,6 +94,7 @@ template <int BS> struct PkShared
     // sh.hepoch advance in every CTA alike and go back to global memory when the kernel ends
     DistDev dd;
     int derr;                    // a spin of this CTA timed out
+    int last;                    // this CTA arrived last at the open barrier (thread 0 tells its team)
     };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p)
@@ -157,52 +158,48 @@ __device__ void pk_sync(const PkArgs &a, PkShared<BS> &sh, const double (&acc)[R
             }
         }
     __syncthreads();  // every thread's phase work (and its partial) is done
-    if (wid == 0)
+    // Warp k < NV handles value k (the CTA partial and, in the last arriving CTA, the sum over the CTAs: the
+    // values are summed side by side, not one after the other); warp 0 does the barrier itself.
+    constexpr int NVW = NV > 0 ? NV : 1;
+    auto team_sync = []()
+        {
+        if (NVW > 1)
+            asm volatile("bar.sync 15, %0;" ::"n"(32 * NVW) : "memory");
+        else
+            __syncwarp();
+        };
+    if (wid < NVW)
         {
         const bool solo = gridDim.x == 1 && a.dist == nullptr;
         const unsigned int slot = sh.nred & 1u;
-        // CTA partial, fixed tree
-        double ps[NV > 0 ? NV : 1], pe[NV > 0 ? NV : 1];
+        const int k = wid;  // this warp's value
         if (NV > 0)
-            {
-#pragma unroll
-            for (int k = 0; k < NV; k++)
+            {  // CTA partial, fixed tree
+            double s = lane < NW ? sh.red_s[k][lane] : 0.0, e = lane < NW ? sh.red_e[k][lane] : 0.0;
+            if (MAXOP)
                 {
-                double s = lane < NW ? sh.red_s[k][lane] : 0.0, e = lane < NW ? sh.red_e[k][lane] : 0.0;
-                if (MAXOP)
-                    {
-                    if (lane >= NW) s = -1.7976931348623157e308;
+                if (lane >= NW) s = -1.7976931348623157e308;
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(0xffffffffu, s, o));
-                    }
-                else
-                    warp_sum_dd(s, e);
-                ps[k] = s;
-                pe[k] = e;
+                for (int o = 16; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(0xffffffffu, s, o));
                 }
-            }
-        if (solo)
-            {
-            if (NV > 0 && lane == 0)
-                {
-#pragma unroll
-                for (int k = 0; k < NV; k++) sh.tot[k] = MAXOP ? ps[k] : ps[k] + pe[k];
-                }
-            }
-        else
-            {
-            if (NV > 0 && lane == 0)
-                {
-#pragma unroll
-                for (int k = 0; k < NV; k++)
-                    {
-                    a.sync->part[slot][k][blockIdx.x] = ps[k];
-                    if (!MAXOP) a.sync->part[slot][RED_NV + k][blockIdx.x] = pe[k];
-                    }
-                }
-            unsigned int last = 0;
-            unsigned int target = 0;
+            else
+                warp_sum_dd(s, e);
             if (lane == 0)
+                {
+                if (solo)
+                    sh.tot[k] = MAXOP ? s : s + e;
+                else
+                    {
+                    a.sync->part[slot][k][blockIdx.x] = s;
+                    if (!MAXOP) a.sync->part[slot][RED_NV + k][blockIdx.x] = e;
+                    }
+                }
+            }
+        if (!solo)
+            {
+            team_sync();  // every value's partial is written before thread 0 publishes them
+            unsigned int target = 0;
+            if (wid == 0 && lane == 0)
                 {
                 if (NV > 0 && a.dist != nullptr) sh.dd.epoch++;  // the epoch of this all-reduce, in every CTA alike
                 target = ++sh.gen;
@@ -213,90 +210,86 @@ __device__ void pk_sync(const PkArgs &a, PkShared<BS> &sh, const double (&acc)[R
                     __threadfence_system();
                 else
                     __threadfence();
-                last = atomicAdd(&a.sync->count, 1u) == gridDim.x - 1 ? 1u : 0u;
-                }
-            last = __shfl_sync(0xffffffffu, last, 0);
-            if (last)
-                {  // the whole warp: every CTA's partial is in
-                __threadfence();
-                if (a.phase_acc != nullptr && lane == 0) a.sync->t_last = now_ns();
-                if (NV > 0)
+                const unsigned int last = atomicAdd(&a.sync->count, 1u) == gridDim.x - 1 ? 1u : 0u;
+                if (last)
                     {
-                    // every partial of this lane is fetched before the first addition: the loads are independent
-                    // L2 round trips (a dependent loop cost 1.7 us per reduced value on 148 CTAs)
-                    constexpr int PF = 5;  // partials per lane held in registers: grids up to 160 CTAs in one go
-                    double s[NV > 0 ? NV : 1], e[NV > 0 ? NV : 1];
+                    __threadfence();  // acquire: every CTA's partial is in
+                    if (a.phase_acc != nullptr) a.sync->t_last = now_ns();
+                    }
+                sh.last = (int)last;
+                }
+            team_sync();
+            const bool last = sh.last != 0;
+            if (last && NV > 0)
+                {  // value k over the CTAs, in index order; every partial of this lane is fetched before the
+                   // first addition (independent L2 round trips)
+                constexpr int PF = 5;  // partials per lane held in registers: grids up to 160 CTAs in one go
+                double s = MAXOP ? -1.7976931348623157e308 : 0.0, e = 0.0;
+                for (int i0 = 0; i0 < (int)gridDim.x; i0 += 32 * PF)
+                    {
+                    double vs[PF], ve[PF];
 #pragma unroll
-                    for (int k = 0; k < NV; k++)
+                    for (int u = 0; u < PF; u++)
                         {
-                        s[k] = MAXOP ? -1.7976931348623157e308 : 0.0;
-                        e[k] = 0.0;
-                        for (int i0 = 0; i0 < (int)gridDim.x; i0 += 32 * PF)
-                            {
-                            double vs[PF], ve[PF];
-#pragma unroll
-                            for (int u = 0; u < PF; u++)
-                                {
-                                const int i = i0 + lane + 32 * u;
-                                const bool in = i < (int)gridDim.x;
-                                vs[u] = in ? __ldcg(&a.sync->part[slot][k][i]) : (MAXOP ? -1.7976931348623157e308 : 0.0);
-                                ve[u] = (in && !MAXOP) ? __ldcg(&a.sync->part[slot][RED_NV + k][i]) : 0.0;
-                                }
-#pragma unroll
-                            for (int u = 0; u < PF; u++)
-                                {  // index order i = lane, lane + 32, ...: the same fixed order as a plain loop
-                                if (MAXOP)
-                                    s[k] = fmax(s[k], vs[u]);
-                                else
-                                    dd_add(s[k], e[k], vs[u], ve[u]);
-                                }
-                            }
+                        const int i = i0 + lane + 32 * u;
+                        const bool in = i < (int)gridDim.x;
+                        vs[u] = in ? __ldcg(&a.sync->part[slot][k][i]) : (MAXOP ? -1.7976931348623157e308 : 0.0);
+                        ve[u] = (in && !MAXOP) ? __ldcg(&a.sync->part[slot][RED_NV + k][i]) : 0.0;
                         }
 #pragma unroll
-                    for (int k = 0; k < NV; k++)
+                    for (int u = 0; u < PF; u++)
                         {
                         if (MAXOP)
-                            {
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) s[k] = fmax(s[k], __shfl_xor_sync(0xffffffffu, s[k], o));
-                            }
+                            s = fmax(s, vs[u]);
                         else
-                            warp_sum_dd(s[k], e[k]);
-                        if (lane == 0)
-                            {
-                            sh.tot[k] = s[k];
-                            sh.tot[NV + k] = e[k];
-                            }
+                            dd_add(s, e, vs[u], ve[u]);
                         }
-                    __syncwarp();
-                    if (a.dist != nullptr) dist_allreduce_warp_e(&sh.dd, &sh.derr, sh.dd.epoch, sh.tot, NV, MAXOP);
                     }
+                if (MAXOP)
+                    {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(0xffffffffu, s, o));
+                    }
+                else
+                    warp_sum_dd(s, e);
                 if (lane == 0)
                     {
-                    if (NV > 0)
-                        {
-#pragma unroll
-                        for (int k = 0; k < NV; k++) a.sync->tot[slot][k] = MAXOP ? sh.tot[k] : sh.tot[k] + sh.tot[NV + k];
-                        }
-                    a.sync->count = 0;
-                    if (a.phase_acc != nullptr) a.sync->t_ar = now_ns();
-                    __threadfence();
-                    st_release_u32(&a.sync->gen, target);  // this GPU's CTAs go on ...
-                    // ... while the neighbours learn that every push of the phase is complete and fenced
-                    if (halo && a.dist != nullptr) dist_raise_e(&sh.dd, sh.hepoch);
+                    sh.tot[k] = s;
+                    sh.tot[NV + k] = e;
                     }
                 }
-            else if (lane == 0)
-                {  // the acquire load orders everything that follows (for this thread; for the rest of the CTA
-                   // through the bar.sync below) after the releasing store, and drops stale L1 lines: no
-                   // separate fence (it cost ~0.5 us per barrier and CTA)
-                while (ld_acquire_u32(&a.sync->gen) != target)
-                    ;
+            if (last) team_sync();  // all NV sums are in sh.tot (uniform: every team warp read the same sh.last)
+            if (wid == 0)
+                {
+                if (last)
+                    {
+                    if (NV > 0 && a.dist != nullptr) dist_allreduce_warp_e(&sh.dd, &sh.derr, sh.dd.epoch, sh.tot, NV, MAXOP);
+                    if (lane == 0)
+                        {
+                        if (NV > 0)
+                            {
+#pragma unroll
+                            for (int q = 0; q < NV; q++) a.sync->tot[slot][q] = MAXOP ? sh.tot[q] : sh.tot[q] + sh.tot[NV + q];
+                            }
+                        a.sync->count = 0;
+                        if (a.phase_acc != nullptr) a.sync->t_ar = now_ns();
+                        __threadfence();
+                        st_release_u32(&a.sync->gen, target);  // this GPU's CTAs go on ...
+                        // ... while the neighbours learn that every push of the phase is complete and fenced
+                        if (halo && a.dist != nullptr) dist_raise_e(&sh.dd, sh.hepoch);
+                        }
+                    }
+                else if (lane == 0)
+                    {  // the acquire load orders everything that follows (for this thread; for the rest of the
+                       // CTA through the bar.sync below) after the releasing store, and drops stale L1 lines
+                    while (ld_acquire_u32(&a.sync->gen) != target)
+                        ;
+                    }
+                __syncwarp();
+                if (NV > 0 && lane < NV) sh.tot[lane] = __ldcg(&a.sync->tot[slot][lane]);
                 }
-            __syncwarp();
-            if (NV > 0 && lane < NV) sh.tot[lane] = __ldcg(&a.sync->tot[slot][lane]);
             }
-        if (lane == 0)
+        if (wid == 0 && lane == 0)
             {
             if (NV > 0) sh.nred++;
             if (halo)

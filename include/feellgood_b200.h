@@ -120,7 +120,10 @@ int fg_get_sizes(const fg_ctx *ctx, long long out[10]);
 int fg_get_layout(const fg_ctx *ctx, long long out[4]);
 
 /* ---- node state (Nodes::Node::d[CURRENT|NEXT], src/node.h:47-70) ---- */
-/* mesh::init_distrib + Fem ctor: set CURRENT u, v, phi, phiv and copy to NEXT; NULL = zeros */
+/* mesh::init_distrib + Fem ctor: set CURRENT u, v, phi, phiv and copy to NEXT; NULL = zeros.
+ * Precondition: |u| = 1 on every magnetic node, as mesh::init_distrib normalises it (src/mesh.cpp) and
+ * Node::make_evol keeps it (src/node.h:116-122); the matrix-free operator relies on the triad (ep, eq, u) of
+ * Node::setBasis being orthonormal.  A state that violates it (beyond 1e-6) is rejected with FG_ERR_INVALID. */
 int fg_set_state(fg_ctx *ctx, const double *u, const double *v, const double *phi,
                  const double *phiv);
 /* d[NEXT].v only (what buildInitGuess reads, src/linear_algebra.cpp:13-24) */

@@ -84,6 +84,26 @@ template <int NPI> static int run(int ncase, std::mt19937 &gen)
             for (int g = 0; g < NPI; g++) Hext[d][g] = sp.Hext[d];
         double contrib[4], BE[3][4];
         tet_core<NPI>(T, R, sp, Hext, contrib, BE);
+        if (!drift)
+            {  // the lean instantiation (cubic anisotropy and drift compiled out: k_tet_lean) on a material
+               // without cubic anisotropy is the general core bit for bit
+            TetRegion Ru = R;
+            Ru.has_K3 = 0;
+            Ru.K3 = Ru.K3bis = 0.0;
+            double cg[4], Bg[3][4], cl[4], Bl[3][4];
+            tet_core<NPI>(T, Ru, sp, Hext, cg, Bg);
+            tet_core<NPI, false, false>(T, Ru, sp, Hext, cl, Bl);
+            for (int i = 0; i < 4; i++)
+                {
+                bool same = cg[i] == cl[i];
+                for (int d = 0; d < 3; d++) same = same && Bg[d][i] == Bl[d][i];
+                if (!same)
+                    {
+                    std::fprintf(stderr, "LEAN CORE DIFFERS case %d node %d\n", it, i);
+                    fails++;
+                    }
+                }
+            }
         if (!aniso)
             {
             TetIsoIn Ti;

@@ -332,4 +332,16 @@ def test_error_paths(gpu_lib):
     with pytest.raises(capi.FgError) as e:
         la.solve(FixedTiming(case))                         # solve before prepareElements
     assert e.value.code == -4
+    # |u| = 1 on the magnetic nodes is a documented precondition of fg_set_state: violations are rejected
+    import numpy as np
+    bad_u = case.u.copy()
+    mag = np.unique(case.mesh.tet_ind[np.array([case.tet_regions[r].get("Ms", 795774.7) > 0 for r in case.mesh.tet_reg])])
+    bad_u[mag[3]] *= 1.01
+    with pytest.raises(capi.FgError) as e:
+        la.set_state(bad_u)
+    assert e.value.code == -1 and "unit vector" in str(e.value)
+    bad_u[mag[3]] = np.nan
+    with pytest.raises(capi.FgError):
+        la.set_state(bad_u)
+    la.set_state(case.u)                                    # and the context is still usable
     la.close()
