@@ -323,6 +323,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--solver", default="persistent", choices=["persistent", "multi"],
                     help="persistent: one cooperative kernel per solve (default); multi: one kernel per phase")
+    ap.add_argument("--partition", default="slab", choices=["slab", "rcb"],
+                    help="N > 1: contiguous row blocks of the reference's node order (default) or a geometric "
+                         "k-way partition (recursive coordinate bisection)")
     ap.add_argument("--traffic", default="ncu", choices=["ncu", "static", "off"],
                     help="roofline.traffic: ncu = measure DRAM bytes of the dominant kernel with a fresh ncu "
                          "capture in a child process (adds ~1 min); static = the committed capture in profiles/")
@@ -377,7 +380,8 @@ def main():
     w = workloads.build(args.workload, scale=args.scale)
     if world > 1:
         from feellgood_b200.dist import DistLinAlgebra
-        la = DistLinAlgebra(w.settings(), w.mesh, rank=rank, world=world, device=local_rank)
+        la = DistLinAlgebra(w.settings(), w.mesh, rank=rank, world=world, device=local_rank,
+                            partition=args.partition)
     else:
         la = LinAlgebra(w.settings(), w.mesh, device=local_rank)
     la.set_state(w.u)
@@ -609,7 +613,8 @@ def main():
                                 mean_bicgstab_iters=mean_it, failed_steps=nfail,
                                 l2="inputs exceed L2 (matrix %.0f MB >> 126 MB), no flush"
                                    % (8e-6 * la.nnz),
-                                parallelism="row-block slabs x%d" % world if world > 1 else "1 GPU"),
+                                parallelism=("%s x%d" % ("row-block slabs" if args.partition == "slab" else "rcb boxes", world))
+                                if world > 1 else "1 GPU"),
                     roofline=roof, step_roofline=step_roof, cpu_baseline=cb, e2e=e2e, parity=parity,
                     named_meshes=named,
                     gpu_launches=int(launches), clocks=clk)

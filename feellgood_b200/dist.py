@@ -47,44 +47,80 @@ class LocalProblem:
 
 
 class Partition:
-    def __init__(self, mesh, world, align=32):
-        """Owner ranges [cuts[r], cuts[r+1]) balanced by 1 + (tets incident to the node), which is
-        proportional to the matrix blocks of the row; cuts are aligned to the SELL slice height."""
-        self.mesh, self.world = mesh, int(world)
+    def __init__(self, mesh, world, align=32, method="slab"):
+        """Who owns which node.
+
+        method="slab" (default): owner ranges [cuts[r], cuts[r+1]) over the reference's sorted node order
+        (contiguous row blocks = slabs along the longest axis, at most two neighbours per rank), balanced
+        by 1 + (tets incident to the node), which is proportional to the matrix blocks of the row; cuts are
+        aligned to the SELL slice height.
+        method="rcb": recursive coordinate bisection of the node cloud (the METIS-style k-way alternative of
+        SURVEY.md section 8e, geometric because METIS itself is not available): the set is split along the
+        longest axis of its bounding box into two parts whose weights follow the number of ranks on each
+        side, recursively -- compact boxes instead of slabs, i.e. a smaller halo for bodies that are not
+        plate- or rod-shaped, at the price of more than two neighbours per rank."""
+        self.mesh, self.world, self.method = mesh, int(world), method
         NOD = mesh.NOD
         w = 1.0 + np.bincount(mesh.tet_ind.ravel(), minlength=NOD)
-        cum = np.cumsum(w)
-        cuts = [0]
-        for k in range(1, self.world):
-            c = int(np.searchsorted(cum, cum[-1] * k / self.world))
-            c = min(NOD, max(cuts[-1], (c + align // 2) // align * align))
-            cuts.append(c)
-        cuts.append(NOD)
-        self.cuts = np.asarray(cuts, dtype=np.int64)
+        if method == "slab":
+            cum = np.cumsum(w)
+            cuts = [0]
+            for k in range(1, self.world):
+                c = int(np.searchsorted(cum, cum[-1] * k / self.world))
+                c = min(NOD, max(cuts[-1], (c + align // 2) // align * align))
+                cuts.append(c)
+            cuts.append(NOD)
+            self.cuts = np.asarray(cuts, dtype=np.int64)
+            self.owner = (np.searchsorted(self.cuts, np.arange(NOD), side="right") - 1).astype(np.int32)
+        elif method == "rcb":
+            self.cuts = None
+            self.owner = np.zeros(NOD, dtype=np.int32)
+            self._rcb(np.arange(NOD), 0, self.world, w)
+        else:
+            raise ValueError("unknown partition method %r" % method)
+        self._owned = [np.flatnonzero(self.owner == r).astype(np.int64) for r in range(self.world)]
         self._ghosts = {}
 
+    def _rcb(self, ids, r0, nr, w):
+        if nr == 1 or ids.size == 0:
+            self.owner[ids] = r0
+            return
+        p = self.mesh.node_p[ids]
+        ax = int(np.argmax(p.max(axis=0) - p.min(axis=0)))
+        order = np.lexsort((ids, p[:, ax]))                 # ties broken by node number: deterministic
+        ids = ids[order]
+        nl = nr // 2
+        cum = np.cumsum(w[ids])
+        k = int(np.searchsorted(cum, cum[-1] * nl / nr))
+        k = min(max(k, 1), ids.size - 1) if ids.size > 1 else 0
+        self._rcb(ids[:k], r0, nl, w)
+        self._rcb(ids[k:], r0 + nl, nr - nl, w)
+
     def owner_of(self, nodes):
-        return np.searchsorted(self.cuts, nodes, side="right") - 1
+        return self.owner[np.asarray(nodes, dtype=np.int64)]
+
+    def owned(self, rank):
+        """Global ids (ascending) of the nodes a rank owns."""
+        return self._owned[rank]
 
     def _local_tets(self, rank):
-        lo, hi = self.cuts[rank], self.cuts[rank + 1]
-        t = self.mesh.tet_ind
-        return ((t >= lo) & (t < hi)).any(axis=1)
+        return (self.owner[self.mesh.tet_ind] == rank).any(axis=1)
 
     def ghosts(self, rank):
-        """Global ids (sorted) of the ghost nodes of a rank."""
+        """Global ids of the ghost nodes of a rank, grouped by owner (ascending rank), ascending inside a
+        group: every owner's segment of the ghost tail is contiguous (a slab partition: plain ascending)."""
         if rank not in self._ghosts:
-            lo, hi = self.cuts[rank], self.cuts[rank + 1]
             used = np.unique(self.mesh.tet_ind[self._local_tets(rank)])
-            self._ghosts[rank] = used[(used < lo) | (used >= hi)].astype(np.int64)
+            gh = used[self.owner[used] != rank].astype(np.int64)
+            self._ghosts[rank] = gh[np.lexsort((gh, self.owner[gh]))]
         return self._ghosts[rank]
 
     def local(self, rank):
         m = self.mesh
-        lo, hi = int(self.cuts[rank]), int(self.cuts[rank + 1])
-        n_owned = hi - lo
+        own = self.owned(rank)
+        n_owned = int(own.size)
         gh = self.ghosts(rank)
-        l2g = np.concatenate([np.arange(lo, hi, dtype=np.int64), gh])
+        l2g = np.concatenate([own, gh])
         g2l = np.full(m.NOD, -1, dtype=np.int64)
         g2l[l2g] = np.arange(l2g.size)
         tmask = self._local_tets(rank)
@@ -99,21 +135,23 @@ class Partition:
         lm = meshgen.Mesh(node_p=np.ascontiguousarray(m.node_p[l2g]), tet_ind=np.ascontiguousarray(ltet),
                           tet_reg=np.ascontiguousarray(m.tet_reg[tmask]), tri_ind=np.ascontiguousarray(ltri),
                           tri_reg=np.ascontiguousarray(ltreg), tri_dMs=np.ascontiguousarray(ldms))
-        # halo plan: my owned nodes that are ghosts of q, in q's ghost order (sorted global id)
+        # halo plan: my owned nodes that are ghosts of q, in the order q stores them (its segment of owner
+        # `rank`, ascending global id), and where that segment starts in q's ghost tail
         send_ptr, send_nodes, send_dst = [0], [], []
         recv_from = np.zeros(self.world, dtype=np.int32)
-        own = self.owner_of(gh) if gh.size else np.zeros(0, dtype=np.int64)
+        gown = self.owner[gh] if gh.size else np.zeros(0, dtype=np.int32)
         for q in range(self.world):
             if q == rank:
                 send_ptr.append(send_ptr[-1])
                 send_dst.append(0)
                 continue
             gq = self.ghosts(q)
-            a, b = np.searchsorted(gq, lo), np.searchsorted(gq, hi)
-            send_nodes.append(gq[a:b] - lo)
-            send_ptr.append(send_ptr[-1] + int(b - a))
-            send_dst.append(int(a))
-            recv_from[q] = int(np.any(own == q))
+            oq = self.owner[gq] if gq.size else np.zeros(0, dtype=np.int32)
+            a, b = int(np.searchsorted(oq, rank, side="left")), int(np.searchsorted(oq, rank, side="right"))
+            send_nodes.append(g2l[gq[a:b]])
+            send_ptr.append(send_ptr[-1] + (b - a))
+            send_dst.append(a)
+            recv_from[q] = int(np.any(gown == q))
         send_nodes = np.concatenate(send_nodes) if send_nodes else np.zeros(0, dtype=np.int64)
         return LocalProblem(rank, self.world, lm, n_owned, l2g, send_ptr, send_nodes, send_dst, recv_from)
 
@@ -123,8 +161,8 @@ class DistLinAlgebra(LinAlgebra):
     builds it identically); state setters take global arrays and keep the local part, getters
     return local arrays (`l2g` maps them back; `gather_state` assembles the global array)."""
 
-    def __init__(self, settings, mesh, rank, world, device=0, connect=True):
-        self.part = Partition(mesh, world)
+    def __init__(self, settings, mesh, rank, world, device=0, connect=True, partition="slab"):
+        self.part = Partition(mesh, world, method=partition)
         self.lp = lp = self.part.local(rank)
         self.rank, self.world = rank, world
         self.l2g, self.NOD_global = lp.l2g, mesh.NOD
@@ -174,5 +212,8 @@ class DistLinAlgebra(LinAlgebra):
         import torch.distributed as dist
         loc = self.get_state(step, what)[0 if what == "u" else 1][:self.n_owned]
         parts = [None] * self.world
-        dist.all_gather_object(parts, loc)
-        return np.concatenate(parts, axis=0)
+        dist.all_gather_object(parts, (self.l2g[:self.n_owned], loc))
+        out = np.empty((self.NOD_global, 3))
+        for ids, vals in parts:
+            out[ids] = vals
+        return out

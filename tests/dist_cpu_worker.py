@@ -36,7 +36,17 @@ def main():
     x = rng.standard_normal(n)
     y_ref = K @ x
 
-    P = Partition(case.mesh, world)
+    for method in ("slab", "rcb"):
+        run_partition(case, method, rank, world, x, y_ref, rp, col, val)
+    dist.barrier()
+    if rank == 0:
+        print("DIST_CPU_OK world=%d" % world)
+    dist.destroy_process_group()
+    oc.close()
+
+
+def run_partition(case, method, rank, world, x, y_ref, rp, col, val):
+    P = Partition(case.mesh, world, method=method)
     lp = P.local(rank)
     nl, no = lp.mesh.NOD, lp.n_owned
     # local vector: owned entries known, ghost tail filled by the neighbours' pushes
@@ -82,10 +92,6 @@ def main():
         tot += float(p)
     assert abs(tot - float(y_ref @ y_ref)) <= 1e-12 * float(y_ref @ y_ref)
     dist.barrier()
-    if rank == 0:
-        print("DIST_CPU_OK world=%d" % world)
-    dist.destroy_process_group()
-    oc.close()
 
 
 if __name__ == "__main__":

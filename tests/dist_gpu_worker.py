@@ -23,9 +23,9 @@ def settings_of(case):
                     MAXITER=case.maxiter, npi_tet=case.npi, npi_tri=case.npi_tri)
 
 
-def run_case(case, rank, world, dev, nsteps=4):
+def run_case(case, rank, world, dev, nsteps=4, partition="slab"):
     s = settings_of(case)
-    dla = DistLinAlgebra(s, case.mesh, rank, world, device=dev)
+    dla = DistLinAlgebra(s, case.mesh, rank, world, device=dev, partition=partition)
     dla.set_state(case.u, case.v, case.phi, case.phiv)
     ref = None
     if rank == 0:
@@ -65,6 +65,8 @@ def main():
     torch.cuda.set_device(dev)
     run_case(cases.small_cuboid(nx=16, ny=6, nz=3), rank, world, dev)
     run_case(cases.film(48, 16, 2), rank, world, dev)
+    # the geometric k-way (METIS-style) partition: boxes, possibly more than two neighbours per rank
+    run_case(cases.small_cuboid(nx=12, ny=10, nz=8), rank, world, dev, nsteps=3, partition="rcb")
     e = cases.ellipsoid()
     if world <= 2:
         run_case(e, rank, world, dev, nsteps=2)

@@ -13,19 +13,23 @@ import cases
 from feellgood_b200.dist import Partition
 
 
-def _plans(mesh, world):
-    P = Partition(mesh, world)
+def _plans(mesh, world, method="slab"):
+    P = Partition(mesh, world, method=method)
     return P, [P.local(r) for r in range(world)]
 
 
+@pytest.mark.parametrize("method", ["slab", "rcb"])
 @pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
-def test_partition_invariants(world):
+def test_partition_invariants(world, method):
     case = cases.small_cuboid(nx=12, ny=5, nz=3)
     mesh = case.mesh
-    P, lps = _plans(mesh, world)
-    assert P.cuts[0] == 0 and P.cuts[-1] == mesh.NOD and np.all(np.diff(P.cuts) >= 0)
+    P, lps = _plans(mesh, world, method)
+    if method == "slab":
+        assert P.cuts[0] == 0 and P.cuts[-1] == mesh.NOD and np.all(np.diff(P.cuts) >= 0)
     owned = np.concatenate([lp.l2g[:lp.n_owned] for lp in lps])
-    assert np.array_equal(owned, np.arange(mesh.NOD))            # every node owned exactly once
+    assert np.array_equal(np.sort(owned), np.arange(mesh.NOD))   # every node owned exactly once
+    if method == "slab":
+        assert np.array_equal(owned, np.arange(mesh.NOD))        # ... in contiguous blocks
     tets_seen = np.zeros(mesh.NT, dtype=int)
     for lp in lps:
         # local meshes are consistent renumberings of global tets, all touching an owned node
@@ -34,11 +38,15 @@ def test_partition_invariants(world):
         key = {tuple(t) for t in mesh.tet_ind.tolist()}
         assert all(tuple(t) in key for t in gt.tolist())
         assert np.array_equal(lp.mesh.node_p, mesh.node_p[lp.l2g])
-        # ghosts are exactly the non-owned nodes of those tets, sorted by global id
+        # ghosts are exactly the non-owned nodes of those tets, grouped by owner, ascending inside a group
+        # (a slab partition: plain ascending global id)
         gh = lp.l2g[lp.n_owned:]
-        assert np.all(np.diff(gh) > 0)
+        key2 = P.owner_of(gh).astype(np.int64) * mesh.NOD + gh
+        assert np.all(np.diff(key2) > 0)
+        if method == "slab":
+            assert np.all(np.diff(gh) > 0)
         assert set(gh.tolist()) == set(np.unique(gt).tolist()) - set(lp.l2g[:lp.n_owned].tolist())
-        mask = ((mesh.tet_ind >= P.cuts[lp.rank]) & (mesh.tet_ind < P.cuts[lp.rank + 1])).any(axis=1)
+        mask = (P.owner[mesh.tet_ind] == lp.rank).any(axis=1)
         tets_seen += mask
         assert lp.mesh.NT == mask.sum()
         # triangles: all nodes local, at least one owned
@@ -69,6 +77,22 @@ def test_balance_and_slab_neighbours():
         nb = {q for q in range(4) if lp.send_ptr[q + 1] > lp.send_ptr[q]}
         assert nb <= {lp.rank - 1, lp.rank + 1}
         assert np.all(P.cuts[1:-1] % 32 == 0)
+
+
+def test_rcb_is_compact_and_balanced():
+    """On a cube-shaped body the geometric k-way partition has a smaller halo than slabs, with balanced
+    weights; on a film both are balanced."""
+    from feellgood_b200 import meshgen
+    m = meshgen.cuboid([0, 0, 0], [16.0, 16.0, 16.0], 16, 16, 16, scale=1e-9, with_surface=False)
+    meshgen.sort_nodes(m)
+    ghosts = {}
+    for method in ("slab", "rcb"):
+        P, lps = _plans(m, 8, method)
+        w = 1.0 + np.bincount(m.tet_ind.ravel(), minlength=m.NOD)
+        loads = np.array([w[lp.l2g[:lp.n_owned]].sum() for lp in lps])
+        assert loads.max() <= 1.15 * loads.mean(), (method, loads)
+        ghosts[method] = sum(lp.n_ghost for lp in lps)
+    assert ghosts["rcb"] < 0.75 * ghosts["slab"], ghosts
 
 
 def test_gloo_world2_halo_and_allreduce(tmp_path):
