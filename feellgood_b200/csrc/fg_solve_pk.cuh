@@ -105,6 +105,15 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p)
     }
 __device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v)
     { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// arrival at the grid barrier: one acquire-release atomic (fence.acq_rel + ATOMG; `__threadfence()` would be
+// the heavier sequentially-consistent MEMBAR.SC on top of it)
+__device__ __forceinline__ unsigned int atom_add_acq_rel_u32(unsigned int *p, unsigned int v)
+    {
+    unsigned int old;
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+    }
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 
 template <int BS> __device__ __forceinline__ void pk_stamp(const PkArgs &a, PkShared<BS> &sh, int id)
     {
@@ -203,19 +212,13 @@ __device__ void pk_sync(const PkArgs &a, PkShared<BS> &sh, const double (&acc)[R
                 {
                 if (NV > 0 && a.dist != nullptr) sh.dd.epoch++;  // the epoch of this all-reduce, in every CTA alike
                 target = ++sh.gen;
-                // release.  A barrier that raises the halo flags publishes this CTA's pushes into peer memory
-                // (plain stores by any of its threads, ordered before this point by the bar.sync above): one
-                // system-scope fence per CTA, issued when the stores have long been on their way
-                if (halo && a.dist != nullptr && sh.pushed)
-                    __threadfence_system();
-                else
-                    __threadfence();
-                const unsigned int last = atomicAdd(&a.sync->count, 1u) == gridDim.x - 1 ? 1u : 0u;
-                if (last)
-                    {
-                    __threadfence();  // acquire: every CTA's partial is in
-                    if (a.phase_acc != nullptr) a.sync->t_last = now_ns();
-                    }
+                // release + acquire in one atomic.  A barrier that raises the halo flags also publishes this
+                // CTA's pushes into peer memory (plain stores by any of its threads, ordered before this point
+                // by the bar.sync above): one system-scope fence per pushing CTA, issued when the stores have
+                // long been on their way
+                if (halo && a.dist != nullptr && sh.pushed) fence_acq_rel_sys();
+                const unsigned int last = atom_add_acq_rel_u32(&a.sync->count, 1u) == gridDim.x - 1 ? 1u : 0u;
+                if (last && a.phase_acc != nullptr) a.sync->t_last = now_ns();
                 sh.last = (int)last;
                 }
             team_sync();
@@ -273,8 +276,7 @@ __device__ void pk_sync(const PkArgs &a, PkShared<BS> &sh, const double (&acc)[R
                             }
                         a.sync->count = 0;
                         if (a.phase_acc != nullptr) a.sync->t_ar = now_ns();
-                        __threadfence();
-                        st_release_u32(&a.sync->gen, target);  // this GPU's CTAs go on ...
+                        st_release_u32(&a.sync->gen, target);  // (release store) this GPU's CTAs go on ...
                         // ... while the neighbours learn that every push of the phase is complete and fenced
                         if (halo && a.dist != nullptr) dist_raise_e(&sh.dd, sh.hepoch);
                         }
