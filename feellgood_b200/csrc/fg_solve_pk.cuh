@@ -169,7 +169,9 @@ __device__ void pk_sync(const PkArgs &a, PkShared<BS> &sh, const double (&acc)[R
     __syncthreads();  // every thread's phase work (and its partial) is done
     // Warp k < NV handles value k (the CTA partial and, in the last arriving CTA, the sum over the CTAs: the
     // values are summed side by side, not one after the other); warp 0 does the barrier itself.
-    constexpr int NVW = NV > 0 ? NV : 1;
+    // (a team of one warp synchronising with __syncwarp measured 3 us slower per reduction than two warps on a
+    // named barrier -- r02n/r02o -- so a single value still gets a team of two)
+    constexpr int NVW = NV > 1 ? NV : (NV == 1 ? 2 : 1);
     auto team_sync = []()
         {
         if (NVW > 1)
@@ -182,7 +184,7 @@ __device__ void pk_sync(const PkArgs &a, PkShared<BS> &sh, const double (&acc)[R
         const bool solo = gridDim.x == 1 && a.dist == nullptr;
         const unsigned int slot = sh.nred & 1u;
         const int k = wid;  // this warp's value
-        if (NV > 0)
+        if (NV > 0 && k < NV)
             {  // CTA partial, fixed tree
             double s = lane < NW ? sh.red_s[k][lane] : 0.0, e = lane < NW ? sh.red_e[k][lane] : 0.0;
             if (MAXOP)
@@ -223,7 +225,7 @@ __device__ void pk_sync(const PkArgs &a, PkShared<BS> &sh, const double (&acc)[R
                 }
             team_sync();
             const bool last = sh.last != 0;
-            if (last && NV > 0)
+            if (last && NV > 0 && k < NV)
                 {  // value k over the CTAs, in index order; every partial of this lane is fetched before the
                    // first addition (independent L2 round trips)
                 constexpr int PF = 5;  // partials per lane held in registers: grids up to 160 CTAs in one go
