@@ -30,7 +30,7 @@ SYMBOLS = [
     "fg_matrix_create", "fg_matrix_destroy", "fg_matrix_set_values", "fg_matrix_mult", "fg_bicg",
     "fg_bicg_dir", "fg_cg", "fg_cg_dir", "fg_kernel_launches", "fg_stream", "fg_set_profiling",
     "fg_get_phase_times", "fg_get_krylov_state", "fg_get_krylov_history", "fg_set_operator", "fg_get_spmv_times", "fg_get_kernel_times", "fg_energy", "fg_energy_space", "fg_avg", "fg_max_angle", "fg_calc_charges", "fg_demag_direct", "fg_bench_spmv", "fg_host_plan", "fg_dist_create", "fg_dist_export", "fg_dist_connect", "fg_get_layout",
-    "fg_set_solver", "fg_get_solve_times", "fg_get_precond",
+    "fg_set_solver", "fg_get_solve_times", "fg_get_precond", "fg_get_records",
 ]
 
 

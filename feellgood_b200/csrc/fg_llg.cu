@@ -214,9 +214,9 @@ int launch_elements(fg_ctx *c)
         const int grid = grid_for(c->NTm, BLOCK);
         // A/B (FG_TET_STAGE=1): node records of a chunk of tetrahedra staged in shared memory (k_tet_st).  Measured
         // slower than the free-running gather kernels on the 20 M-tet film (r02g: 1.51 against 1.35 ms isotropic,
-        // 2.92 against 2.10 ms with anisotropy): the element kernel is co-limited by DRAM (0.87 ms), FP64
-        // (~0.8 ms) and L1 (0.88 ms), and the barriers of a staged chunk loop overlap the three worse than 16
-        // independent warps do.  Off by default.
+        // 2.92 against 2.10 ms with anisotropy): the element kernel is co-limited by DRAM (0.87 ms of 1.34), the
+        // L1 pipe (0.88 ms) and FP64 issue (38 % busy), and the barriers of a staged chunk loop overlap the three
+        // worse than 16 independent warps do.  Off by default.
         static const bool tet_stage = getenv("FG_TET_STAGE") != nullptr && atoi(getenv("FG_TET_STAGE")) != 0;
         const bool iso = use_iso(c);
         const size_t st_smem = 2 * (size_t)c->tch_cap * tet_stage_doubles(iso) * sizeof(double);
@@ -1707,6 +1707,37 @@ int fg_get_elements(fg_ctx *c, int first, int count, double *Kp, double *Lp)
         {
         memcpy(Kp + 64 * (size_t)where[q], &hK[64 * (size_t)q], sizeof(double) * 64);
         memcpy(Lp + 8 * (size_t)where[q], &hL[8 * (size_t)q], sizeof(double) * 8);
+        }
+    return FG_OK;
+    }
+
+int fg_get_records(fg_ctx *c, int first, int count, double *rec_out)
+    {
+    FG_TRY(check_ctx(c));
+    FG_TRY(flush_commit(c));
+    if (first < 0 || count < 0 || first + count > c->h.NT || !rec_out)
+        {
+        set_error("fg_get_records: bad range [%d,%d) of %d", first, first + count, c->h.NT);
+        return FG_ERR_INVALID;
+        }
+    if (!c->prepared && !c->assembled)
+        {
+        set_error("fg_get_records: no prepareElements since the last state change");
+        return FG_ERR_STATE;
+        }
+    memset(rec_out, 0, sizeof(double) * 16 * (size_t)count);
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    for (int t = first; t < first + count; t++)
+        {
+        const int tm = c->h.tet_to_mag[t];
+        if (tm < 0) continue;
+        int4 sl;
+        FG_CUDA(cudaMemcpy(&sl, c->tet_slot + tm, sizeof(int4), cudaMemcpyDeviceToHost));
+        const int slot[4] = {sl.x, sl.y, sl.z, sl.w};
+        for (int i = 0; i < 4; i++)
+            if (slot[i] >= 0)
+                FG_CUDA(cudaMemcpy(rec_out + 16 * (size_t)(t - first) + 4 * i, c->rec + slot[i], sizeof(double4),
+                                   cudaMemcpyDeviceToHost));
         }
     return FG_OK;
     }

@@ -310,6 +310,13 @@ class LinAlgebra:
         check(self._L.fg_get_elements(self._h, C.c_int(first), C.c_int(count), dp(Kp), dp(Lp)))
         return Kp, Lp
 
+    def records(self, first=0, count=None):
+        """(count, 4, 4) production element records {contrib, BE(3)} per local node (fg_get_records)."""
+        count = self.NT - first if count is None else count
+        out = np.zeros((count, 4, 4))
+        check(self._L.fg_get_records(self._h, C.c_int(first), C.c_int(count), dp(out)))
+        return out
+
     def tri_elements(self, first=0, count=None):
         count = self.NF - first if count is None else count
         Lp = np.empty((max(count, 1), 6))

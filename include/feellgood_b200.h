@@ -188,6 +188,12 @@ int fg_get_basis(fg_ctx *ctx, double *ep, double *eq);              /* NOD x 3 e
 /* element<N,NPI>::Kp / Lp (src/element.h:62,65) of tets [first, first+count): count x 64, x 8 */
 int fg_get_elements(fg_ctx *ctx, int first, int count, double *Kp, double *Lp);
 int fg_get_tri_elements(fg_ctx *ctx, int first, int count, double *Lp); /* count x 6 */
+/* What the PRODUCTION element kernels (k_tet_iso / k_tet_lean / k_tet) wrote for tets [first, first+count) by
+ * the last prepareElements: per local node {sum_g a_i w_g alpha_eff(g), BE(x,y,z)} (count x 4 x 4; zeros for
+ * non-magnetic tets and for nodes without a row on this device).  With the node bases they give Lp
+ * (src/tetra.cpp:306) and the state-dependent diagonal of Kp (src/tetra.cpp:108-131); fg_get_elements
+ * recomputes Kp/Lp with a separate tap kernel, this one reads the records the assembly consumes. */
+int fg_get_records(fg_ctx *ctx, int first, int count, double *rec);
 /* solver<2>::K shape (src/solver.h:75-104): rowptr n+1, col nnz */
 int fg_get_csr_pattern(const fg_ctx *ctx, int *rowptr, int *col);
 /* K values (nnz), L_rhs (n) and the initial guess Xw (n) as LinAlgebra::solve builds them

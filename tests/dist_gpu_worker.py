@@ -66,7 +66,7 @@ def main():
     run_case(cases.small_cuboid(nx=16, ny=6, nz=3), rank, world, dev)
     run_case(cases.film(48, 16, 2), rank, world, dev)
     # the geometric k-way (METIS-style) partition: boxes, possibly more than two neighbours per rank
-    run_case(cases.small_cuboid(nx=12, ny=10, nz=8), rank, world, dev, nsteps=3, partition="rcb")
+    run_case(cases.film(20, 16, 8), rank, world, dev, nsteps=3, partition="rcb")
     e = cases.ellipsoid()
     if world <= 2:
         run_case(e, rank, world, dev, nsteps=2)

@@ -90,6 +90,39 @@ def test_element_matrices(prepared):
     assert worstL < TOL_ELEM, worstL
 
 
+def test_production_records(prepared):
+    """The records the PRODUCTION element kernels wrote (k_tet_iso / k_tet_lean / k_tet, not the tap kernel
+    of test_element_matrices), against the oracle's element: Lp = Perm P vec(BE) (src/tetra.cpp:306) from the
+    stored BE and the node bases, and the state-dependent diagonal of E, E_aa = c (da_a . da_a) + contrib_a
+    (src/tetra.cpp:108-131), read off Kp[(eq_a),(eq_a)]."""
+    case, oc, la, t = prepared
+    from feellgood_b200.linear_algebra import GAMMA0, MU0
+    rec = la.records()
+    ep, eq = la.basis()
+    ind, da, w = la.tet_tables()
+    n_mag = 0
+    for k in range(oc.NT):
+        Ko, Lo = oc.element(k)
+        if not np.any(Ko):
+            assert not np.any(rec[k])
+            continue
+        n_mag += 1
+        nd = ind[k]
+        be = rec[k, :, 1:4]
+        Lp = np.concatenate([np.einsum("id,id->i", eq[nd], be), np.einsum("id,id->i", ep[nd], be)])
+        assert rel_max(Lp, Lo) < TOL_ELEM, k
+        prm = case.tet_regions[case.mesh.tet_reg[k]]
+        Abis = 2.0 * prm.get("A", 1e-11) / (MU0 * prm.get("Ms", 795774.7))
+        c = t.prefactor * (0.5 * t.get_dt() * GAMMA0) * Abis * w[k].sum()
+        Ko = Ko.reshape(8, 8)
+        for a in range(4):
+            # row 2a of the node pair = the eq-tested equation = row a of Kp (Perm), column 4 + a = unknown vq of a
+            E_aa = Ko[a, 4 + a]
+            contrib = E_aa - c * np.dot(da[k, a], da[k, a])
+            assert abs(rec[k, a, 0] - contrib) <= 1e-10 * abs(E_aa), (k, a)
+    assert n_mag > 0
+
+
 def test_tri_vectors(prepared):
     case, oc, la, _ = prepared
     Lp = la.tri_elements()
