@@ -137,6 +137,8 @@ struct Operator
     const int *col;     // OP_CSR col | OP_SELL2 / OP_NODE3 scol
     const short *col16; // OP_NODE3, optional: scol as 16-bit offsets from the lane's own row (2 B instead of
                         // 4 B per stored pair); NULL when an offset of the mesh does not fit
+    int col16_partial;  // 1: col16 is valid only in the slices WITHOUT ghost columns (sghost == 0); the others
+                        // read `col` (persistent kernel on a partition, where the ghost rows are out of reach)
     const double *val;  // OP_SELL2: 2x2 blocks | OP_NODE3: S (one double per stored node pair)
     int nslice;         // OP_SELL2 / OP_NODE3
     // OP_NODE3

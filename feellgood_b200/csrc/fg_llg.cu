@@ -76,6 +76,7 @@ struct fg_ctx
     std::vector<TriRegion> h_reg_tri;
     // pattern and per-mesh constants
     short *scol16 = nullptr;  // scol as 16-bit offsets from the row (NULL when one does not fit)
+    short *scol16_ng = nullptr;  // multi-GPU: the same, valid in the slices without ghost columns only
     int *perm = nullptr, *sptr = nullptr, *scol = nullptr, *sdeg = nullptr, *iptr = nullptr,
         *itptr = nullptr, *sinct = nullptr;
     double *sS = nullptr, *Aw = nullptr, *Sdiag = nullptr;
@@ -426,7 +427,13 @@ int run_solve(fg_ctx *c, double dt, fg_step_result *out)
         upd.dt = c->sp.dt;
         upd.NODp = c->NODp;
         upd.NODt = c->NODt;
-        FG_TRY(bicgstab_run_pk(c->op, c->kw, c->tol, c->maxiter, &upd));
+        Operator opk = c->op;
+        if (!opk.col16 && c->scol16_ng)
+            {  // 16-bit offsets in the slices without ghost columns, 32-bit columns in the others
+            opk.col16 = c->scol16_ng;
+            opk.col16_partial = 1;
+            }
+        FG_TRY(bicgstab_run_pk(opk, c->kw, c->tol, c->maxiter, &upd));
         }
     else
         FG_TRY(bicgstab_run(c->use_blocks ? c->op_K : c->op, c->kw, c->tol, c->maxiter, post_update, c));
@@ -770,35 +777,10 @@ static int create_ctx(const fg_mesh *mesh, const fg_params *prm, int device, con
         }
     CK(dev_upload(&c->sptr, h.sptr, s));
     CK(dev_upload(&c->scol, h.scol, s));
-        {  // 16-bit column offsets for the matrix-free SpMV (2 B instead of 4 B per stored pair) when every
-           // neighbour of every row lies within +-32767 device rows (single-GPU meshes in the reference's
-           // sorted node order; ghost columns of a partitioned mesh usually do not)
-        const size_t ne = h.scol.size();
-        bool fits = getenv("FG_NO_COL16") == nullptr;
-        std::vector<short> c16;
-        if (fits) c16.resize(ne);
-        if (fits)
-            {
-            int bad = 0;
-#pragma omp parallel for schedule(static) reduction(+ : bad)
-            for (int sl = 0; sl < h.nslice; sl++)
-                for (int j = h.sptr[sl]; j < h.sptr[sl + 1]; j++)
-                    for (int l = 0; l < SLICE; l++)
-                        {
-                        const size_t pos = (size_t)j * SLICE + l;
-                        const int d = h.scol[pos] - (sl * SLICE + l);
-                        if (d < -32767 || d > 32767)
-                            bad++;
-                        else
-                            c16[pos] = (short)d;
-                        }
-            fits = bad == 0;
-            }
-        if (fits && ne > 0) CK(dev_upload(&c->scol16, c16, s));
-        }
+    std::vector<unsigned char> sg;  // multi-GPU: slices that gather a ghost entry
     if (dd)
-        {  // slices that gather a ghost entry: they wait for the halo, the others do not (fg_solve_pk.cuh)
-        std::vector<unsigned char> sg((size_t)h.nslice, 0);
+        {  // they wait for the halo, the others do not (fg_solve_pk.cuh)
+        sg.assign((size_t)h.nslice, 0);
 #pragma omp parallel for schedule(static)
         for (int sl = 0; sl < h.nslice; sl++)
             {
@@ -808,6 +790,40 @@ static int create_ctx(const fg_mesh *mesh, const fg_params *prm, int device, con
             sg[(size_t)sl] = g;
             }
         CK(dev_upload(&c->sghost, sg, s));
+        }
+        {  // 16-bit column offsets for the matrix-free SpMV (2 B instead of 4 B per stored pair) when every
+           // neighbour of every row lies within +-32767 device rows (single-GPU meshes in the reference's
+           // sorted node order).  On a partition the ghost rows sit behind the owned rows, out of reach for the
+           // rows at the start of a slab: there the offsets are used for the slices WITHOUT ghost columns and
+           // the few slices with ghost columns (processed in a pass of their own anyway) read the 32-bit
+           // columns (scol16_ng, persistent kernel only).
+        const size_t ne = h.scol.size();
+        const bool want = getenv("FG_NO_COL16") == nullptr;
+        std::vector<short> c16;
+        if (want) c16.assign(ne, 0);
+        long long bad_all = 0, bad_ng = 0;
+        if (want)
+            {
+#pragma omp parallel for schedule(static) reduction(+ : bad_all, bad_ng)
+            for (int sl = 0; sl < h.nslice; sl++)
+                for (int j = h.sptr[sl]; j < h.sptr[sl + 1]; j++)
+                    for (int l = 0; l < SLICE; l++)
+                        {
+                        const size_t pos = (size_t)j * SLICE + l;
+                        const int d = h.scol[pos] - (sl * SLICE + l);
+                        if (d < -32767 || d > 32767)
+                            {
+                            bad_all++;
+                            if (sg.empty() || !sg[(size_t)sl]) bad_ng++;
+                            }
+                        else
+                            c16[pos] = (short)d;
+                        }
+            }
+        if (want && ne > 0 && bad_all == 0)
+            CK(dev_upload(&c->scol16, c16, s));
+        else if (want && ne > 0 && dd && bad_ng == 0)
+            CK(dev_upload(&c->scol16_ng, c16, s));
         }
     if (h.stage_cap > 0)
         {
@@ -1032,7 +1048,7 @@ void fg_destroy(fg_ctx *c)
                     c->tet_detJ, c->ext_field, c->tet_reg, c->reg_tet, c->rec, c->tri_ind,
                     c->tri_reg, c->tri_surf, c->tri_dMs, c->reg_tri, c->trec, c->perm, c->sptr,
                     c->scol, c->sdeg, c->iptr, c->tch_ptr, c->tch_nodes, c->tet_loc, c->tet_slot, c->itptr, c->sinct, c->sS, c->Aw, c->val, c->Sdiag, c->Dm, c->qbasis,
-                    c->scol16, c->sghost, c->d_unit, c->lcol, c->bptr, c->bhalo, c->bghost, c->mtri_ind, c->mtri_reg, c->mtri_surf, c->mtri_nrm, c->mtri_dMs, c->extra_edges,
+                    c->scol16, c->scol16_ng, c->sghost, c->d_unit, c->lcol, c->bptr, c->bhalo, c->bghost, c->mtri_ind, c->mtri_reg, c->mtri_surf, c->mtri_nrm, c->mtri_dMs, c->extra_edges,
                     c->d_scal, c->node_pos, c->corr, c->tcorr, c->src, c->cptr, c->cidx};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -1089,7 +1105,7 @@ int fg_get_layout(const fg_ctx *c, long long out[4])
         return FG_ERR_INVALID;
         }
     // the persistent solver addresses staged images with 16-bit local indices whatever the global distance
-    out[0] = (c->solver_kind == 0 && pk_plan(c->op, nullptr, nullptr)) || c->scol16 ? 2 : 4;
+    out[0] = (c->solver_kind == 0 && (pk_plan(c->op, nullptr, nullptr) || c->scol16_ng)) || c->scol16 ? 2 : 4;
     out[1] = c->nblk;
     out[2] = c->iso_regions ? 1 : 0;
     out[3] = c->NODp;

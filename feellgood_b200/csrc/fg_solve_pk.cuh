@@ -465,18 +465,24 @@ __device__ __forceinline__ void pk_spmv(const PkArgs &a, PkShared<BS> &sh, const
             pk_blocks_staged<STAGE>(a, sa, own, 0, stage, acc);
         return;
         }
-    if (a.dist != nullptr && a.op.sghost != nullptr && wait_halo)
-        {
+    if (a.dist != nullptr && a.op.sghost != nullptr)
+        {  // a partition: slices without ghost columns first (16-bit offsets when they fit), then -- after the
+           // halo flags of the phase, if there is a halo to wait for -- the slices with ghost columns, whose
+           // far columns need the 32-bit indices unless every offset of the mesh fits
         spmv_node3_slices<STAGE, IDX16, true>(a.op, sa, own, lane, 1, acc);
-        // the slices with ghost columns: wait for the neighbours' pushes of this phase (per warp: only
-        // warps that own such a slice wait)
         int s = own.begin();
         while (s < a.op.nslice && a.op.sghost[s] == 0) s = own.next(s);
         if (s < a.op.nslice)
-            {
-            if (lane == 0) pk_halo_wait(&sh.dd, &sh.derr, sh.hepoch - 1);
-            __syncwarp();
-            spmv_node3_slices<STAGE, IDX16, true>(a.op, sa, own, lane, 2, acc);
+            {  // per warp: only warps that own such a slice wait
+            if (wait_halo)
+                {
+                if (lane == 0) pk_halo_wait(&sh.dd, &sh.derr, sh.hepoch - 1);
+                __syncwarp();
+                }
+            if (IDX16 && a.op.col16_partial)
+                spmv_node3_slices<STAGE, false, true>(a.op, sa, own, lane, 2, acc);
+            else
+                spmv_node3_slices<STAGE, IDX16, true>(a.op, sa, own, lane, 2, acc);
             }
         }
     else
