@@ -469,10 +469,8 @@ __device__ __forceinline__ void pk_spmv(const PkArgs &a, PkShared<BS> &sh, const
         {  // a partition: slices without ghost columns first (16-bit offsets when they fit), then -- after the
            // halo flags of the phase, if there is a halo to wait for -- the slices with ghost columns, whose
            // far columns need the 32-bit indices unless every offset of the mesh fits
-        spmv_node3_slices<STAGE, IDX16, true>(a.op, sa, own, lane, 1, acc);
-        int s = own.begin();
-        while (s < a.op.nslice && a.op.sghost[s] == 0) s = own.next(s);
-        if (s < a.op.nslice)
+        const bool has_ghost = spmv_node3_slices<STAGE, IDX16, true>(a.op, sa, own, lane, 1, acc);
+        if (has_ghost)
             {  // per warp: only warps that own such a slice wait
             if (wait_halo)
                 {
