@@ -176,7 +176,8 @@ def test_solve_and_update(prepared):
     x_g = la.solution()
     r = rhs_o - oracle_spmv(rp, col, val_o, x_g)
     assert np.linalg.norm(r) <= 1.01 * case.tol * np.linalg.norm(rhs_o)
-    assert np.linalg.norm(x_g - x_o) <= 1e-4 * np.linalg.norm(x_o)
+    # observed ~1e-9 (equal iteration counts); 5*TOL leaves room for a one-iteration difference only
+    assert np.linalg.norm(x_g - x_o) <= 5.0 * case.tol * np.linalg.norm(x_o)
     u_o, v_o, _, _ = oc.get_state(1)
     u_g, v_g, phi_g, phiv_g = la.get_state(1)
     # the node update is exact given x (src/node.h:116-122): |du| <= dt*gamma0*|dx| per node, and x
@@ -185,8 +186,8 @@ def test_solve_and_update(prepared):
     dx = np.max(np.hypot(x_g[0::2] - x_o[0::2], x_g[1::2] - x_o[1::2]))
     assert np.max(np.abs(u_g - u_o)) <= 1.01 * case.dt * GAMMA0 * dx + 1e-14
     assert np.max(np.abs(u_g - u_o)) < 1e-6
-    assert rel_max(v_g, v_o) < 1e-4
-    assert abs(la.get_v_max() - oc.v_max()) <= 1e-4 * oc.v_max()
+    assert rel_max(v_g, v_o) < 2e-5
+    assert abs(la.get_v_max() - oc.v_max()) <= 2e-5 * oc.v_max()
     assert np.array_equal(phi_g, case.phi) and np.array_equal(phiv_g, case.phiv)
     mag, _ = oc.masks()
     assert np.max(np.abs(np.linalg.norm(u_g[mag], axis=1) - 1)) < 1e-15
