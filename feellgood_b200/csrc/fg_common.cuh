@@ -332,7 +332,7 @@ int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, pos
 // The same solve (OP_NODE3 only) as ONE persistent cooperative kernel, fused with the node update when
 // upd != NULL (fg_solve_pk.cuh); one host synchronisation per solve.
 int bicgstab_run_pk(const Operator &op, KrylovWork &w, double tol, int maxiter, const PkUpdate *upd);
-bool pk_plan(const Operator &op, int *bs_out, size_t *smem_out);
+bool pk_plan(const Operator &op, int *bs_out, size_t *smem_out, bool *head_out = nullptr);
 // Jacobi-preconditioned CG, reference src/algebra/cg.h:15-58,68-121 (same conventions)
 int cg_run(const Operator &op, KrylovWork &w, double tol, int maxiter);
 // D = 1/diag(A) for a plain CSR operator (src/algebra/sparseMat.h:174-183), then masked

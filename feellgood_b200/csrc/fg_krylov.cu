@@ -282,9 +282,49 @@ __device__ __forceinline__ SliceIter slices_balanced(int n, int per_cta, int id)
 // The ghost flag of a slice travels with its extent, fetched one slice ahead: deciding on a flag loaded in
 // the same turn would stall the (in-order) warp for an L2 round trip per slice -- measured as 12 % of the
 // product on a 2-GPU partition.
-template <int STAGE, bool IDX16, bool COH>
+// The head of a warp's first slice: extent, ghost flag, and the column indices and values of the first batch
+// of stored pairs.  The matrix is constant during a solve and so is the ownership of slices, so the
+// persistent kernel fetches it once (HEAD variant, where registers allow: k_llg_solve) and every product
+// starts with its gathers instead of behind two dependent loads (extent -> indices).  That is most of what
+// a product costs when a warp owns a single slice.
+constexpr int SPMV_U = 8;  // stored pairs per batch
+struct SpmvHead
+    {
+    int s;  // the slice, or -1
+    int p0, p1;
+    unsigned char g;
+    int cn[SPMV_U];
+    double sv[SPMV_U];
+    };
+template <bool IDX16>
+__device__ __forceinline__ void spmv_head(const Operator &op, const SliceIter it, const int lane, SpmvHead &h)
+    {
+    typedef typename std::conditional<IDX16, short, int>::type idx_t;
+    const idx_t *colbase = IDX16 ? reinterpret_cast<const idx_t *>(op.col16) : reinterpret_cast<const idx_t *>(op.col);
+    h.s = it.begin();
+    if (h.s >= op.nslice)
+        {
+        h.s = -1;
+        return;
+        }
+    h.p0 = __ldg(op.ptr + h.s);
+    h.p1 = __ldg(op.ptr + h.s + 1);
+    h.g = op.sghost != nullptr ? __ldg(op.sghost + h.s) : 0;
+    const idx_t *cp = colbase + (size_t)h.p0 * SLICE + lane;
+    const double *sp = op.val + (size_t)h.p0 * SLICE + lane;
+#pragma unroll
+    for (int u = 0; u < SPMV_U; u++)
+        {
+        const bool in = h.p0 + u < h.p1;
+        h.cn[u] = in ? (int)__ldcs(cp + u * SLICE) : 0;
+        h.sv[u] = in ? __ldcs(sp + u * SLICE) : 0.0;
+        }
+    }
+
+template <int STAGE, bool IDX16, bool COH, bool HEAD>
 __device__ __forceinline__ bool spmv_node3_slices(const Operator &op, const SpmvArgs &a, const SliceIter it,
-                                                  const int lane, const int pass, double (&acc)[RED_NV])
+                                                  const int lane, const int pass, double (&acc)[RED_NV],
+                                                  const SpmvHead &head)
     {
     const int s_end = op.nslice;
     typedef typename std::conditional<IDX16, short, int>::type idx_t;
@@ -294,7 +334,19 @@ __device__ __forceinline__ bool spmv_node3_slices(const Operator &op, const Spmv
     int s = it.begin();
     int p0 = 0, p1 = 0;
     unsigned char g = 0;
-    if (s < s_end)
+    constexpr int U = SPMV_U;
+    int cn[U];
+    bool have_cn = false;  // cn holds the first batch of slice s (from the head fetched before the barrier)
+    if (HEAD && head.s == s)
+        {
+        p0 = head.p0;
+        p1 = head.p1;
+        g = head.g;
+#pragma unroll
+        for (int u = 0; u < U; u++) cn[u] = head.cn[u];
+        have_cn = true;
+        }
+    else if (s < s_end)
         {
         p0 = __ldg(op.ptr + s);
         p1 = __ldg(op.ptr + s + 1);
@@ -318,6 +370,7 @@ __device__ __forceinline__ bool spmv_node3_slices(const Operator &op, const Spmv
             p0 = q0;
             p1 = q1;
             g = gn;
+            have_cn = false;
             continue;
             }
         const int row = s * SLICE + lane;
@@ -337,10 +390,13 @@ __device__ __forceinline__ bool spmv_node3_slices(const Operator &op, const Spmv
             {  // batches of U pairs; the column indices of the next batch are fetched while this batch
                // gathers, so the index -> gather dependency is paid once per slice, not once per batch
                // (measured 291 us against 317 us for the plain unrolled loop, film20m)
-            constexpr int U = 8;
-            int cn[U];
+            const bool from_head = HEAD && have_cn;
+            if (!have_cn)
+                {
 #pragma unroll
-            for (int u = 0; u < U; u++) cn[u] = p0 + u < p1 ? (int)__ldcs(cp + u * SLICE) : 0;
+                for (int u = 0; u < U; u++) cn[u] = p0 + u < p1 ? (int)__ldcs(cp + u * SLICE) : 0;
+                }
+            have_cn = false;
             for (int j = p0; j < p1; j += U)
                 {
                 int c[U];
@@ -349,7 +405,10 @@ __device__ __forceinline__ bool spmv_node3_slices(const Operator &op, const Spmv
                 for (int u = 0; u < U; u++)
                     {
                     c[u] = cbase + cn[u];
-                    Sv[u] = j + u < p1 ? __ldcs(sp + u * SLICE) : 0.0;
+                    if (HEAD && from_head && j == p0)
+                        Sv[u] = head.sv[u];
+                    else
+                        Sv[u] = j + u < p1 ? __ldcs(sp + u * SLICE) : 0.0;
                     }
                 cp += U * SLICE;
                 sp += U * SLICE;
@@ -391,6 +450,15 @@ __device__ __forceinline__ bool spmv_node3_slices(const Operator &op, const Spmv
         g = gn;
         }
     return other;
+    }
+
+template <int STAGE, bool IDX16, bool COH>
+__device__ __forceinline__ bool spmv_node3_slices(const Operator &op, const SpmvArgs &a, const SliceIter it,
+                                                  const int lane, const int pass, double (&acc)[RED_NV])
+    {
+    SpmvHead none;
+    none.s = -1;
+    return spmv_node3_slices<STAGE, IDX16, COH, false>(op, a, it, lane, pass, acc, none);
     }
 
 template <int STAGE, bool IDX16, bool COH>
@@ -1165,25 +1233,37 @@ int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, pos
 // BiCGStab as one persistent cooperative kernel (fg_solve_pk.cuh)
 // ------------------------------------------------------------------------------------------
 // the instantiation for a block size, column width and staging mode
-static const void *pk_kernel(int bs, bool i16, bool staged)
+static const void *pk_kernel(int bs, bool i16, bool staged, bool head)
     {
     if (staged)
         return bs == 1024 ? (const void *)k_llg_solve<1024, true, true> : (const void *)k_llg_solve<256, true, true>;
     if (bs == 1024) return i16 ? (const void *)k_llg_solve<1024, true, false> : (const void *)k_llg_solve<1024, false, false>;
+    if (bs == 512)
+        return i16 ? (const void *)k_llg_solve<512, true, false, true> : (const void *)k_llg_solve<512, false, false, true>;
     return i16 ? (const void *)k_llg_solve<256, true, false> : (const void *)k_llg_solve<256, false, false>;
     }
 
 // Launch shape of the persistent kernel for an operator: CTA size, and whether the gathered images are
 // staged in shared memory (returns true) with `smem` bytes of dynamic shared memory per CTA.
-bool pk_plan(const Operator &op, int *bs_out, size_t *smem_out)
+bool pk_plan(const Operator &op, int *bs_out, size_t *smem_out, bool *head_out)
     {
     int dev = 0, sms = NUM_SMS;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // CTA size: 1024 threads (one CTA per SM, 148 arrivals per barrier) once every warp of such a grid has a
-    // slice of its own; 256 threads below that, so that small meshes still spread over all SMs
+    // slice of its own; 256 threads below that, so that small meshes still spread over all SMs.  When 16
+    // warps per SM own at most a slice each: the 512-thread variant that keeps the head of that slice in
+    // registers (k_llg_solve<.., HEAD>), one CTA per SM (sp4, 1483 slices: 7.9 / 7.1 us per product
+    // against 8.9 / 7.5, +3.4 % steps/s, r02z).  Not for a mesh that fits one 256-thread CTA, which has no
+    // grid barrier at all (ellipsoid, 6 slices: the same variant with 256 threads measured 3.0 us per
+    // product against 2.4).  FG_PK_BLOCK=512 forces the variant on any mesh (film20m: 16 warps per SM
+    // with 128 registers are 33 % slower per product than 32 with 64).
     static const int forced = getenv("FG_PK_BLOCK") ? atoi(getenv("FG_PK_BLOCK")) : 0;
-    int bs = op.nslice >= sms * 32 ? 1024 : 256;
-    if (forced == 256 || forced == 1024) bs = forced;
+    static const bool no_head = getenv("FG_PK_NOHEAD") != nullptr && atoi(getenv("FG_PK_NOHEAD")) != 0;
+    int bs = op.nslice >= sms * 32 ? 1024 : ((op.nslice > 8 && op.nslice <= sms * 16) ? 512 : 256);
+    if (forced == 256 || forced == 512 || forced == 1024) bs = forced;
+    const bool head = !no_head && bs == 512;
+    if (bs == 512 && !head) bs = 256;  // 512 threads exist only as the HEAD variant
+    if (head_out) *head_out = head;
     // gathered images staged in shared memory when the mesh has gather blocks, a buffer per thread group fits,
     // and there are enough blocks to keep every group of a full grid busy (a group walks 8 slices per block:
     // below that size one slice per warp through L1 has the shorter critical path)
@@ -1191,7 +1271,7 @@ bool pk_plan(const Operator &op, int *bs_out, size_t *smem_out)
     const int cap = (op.stage_cap + 3) & ~3;
     size_t smem = (size_t)(bs / 128) * (size_t)cap * sizeof(double4);
     const int need = min_blocks >= 0 ? min_blocks : sms * 8;
-    const bool staged = op.lcol != nullptr && op.stage_cap > 0 && smem <= (size_t)200 * 1024 && op.nblock >= need;
+    const bool staged = !head && op.lcol != nullptr && op.stage_cap > 0 && smem <= (size_t)200 * 1024 && op.nblock >= need;
     if (bs_out) *bs_out = bs;
     if (smem_out) *smem_out = staged ? smem : 0;
     return staged;
@@ -1231,11 +1311,12 @@ int bicgstab_run_pk(const Operator &op, KrylovWork &w, double tol, int maxiter, 
         }
     int bs = 0;
     size_t smem = 0;
-    const bool staged = pk_plan(op, &bs, &smem);
+    bool head = false;
+    const bool staged = pk_plan(op, &bs, &smem, &head);
     const bool i16 = op.col16 != nullptr;
     int dev = 0, sms = NUM_SMS;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const void *fn = pk_kernel(bs, i16, staged);
+    const void *fn = pk_kernel(bs, i16, staged, head);
     if (staged && smem > 48 * 1024)
         FG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;

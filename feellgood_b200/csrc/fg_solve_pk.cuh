@@ -464,9 +464,10 @@ __device__ __forceinline__ void pk_blocks_staged(const PkArgs &a, const SpmvArgs
         }
     }
 
-template <int STAGE, bool IDX16, bool STAGED, int BS>
+template <int STAGE, bool IDX16, bool STAGED, int BS, bool HEAD>
 __device__ __forceinline__ void pk_spmv(const PkArgs &a, PkShared<BS> &sh, const SpmvArgs &sa, const SliceIter own,
-                                        const int lane, const bool wait_halo, double4 *stage, double (&acc)[RED_NV])
+                                        const int lane, const bool wait_halo, double4 *stage, double (&acc)[RED_NV],
+                                        const SpmvHead &head)
     {
     if (STAGED)
         {
@@ -492,7 +493,7 @@ __device__ __forceinline__ void pk_spmv(const PkArgs &a, PkShared<BS> &sh, const
         {  // a partition: slices without ghost columns first (16-bit offsets when they fit), then -- after the
            // halo flags of the phase, if there is a halo to wait for -- the slices with ghost columns, whose
            // far columns need the 32-bit indices unless every offset of the mesh fits
-        const bool has_ghost = spmv_node3_slices<STAGE, IDX16, true>(a.op, sa, own, lane, 1, acc);
+        const bool has_ghost = spmv_node3_slices<STAGE, IDX16, true, HEAD>(a.op, sa, own, lane, 1, acc, head);
         if (has_ghost)
             {  // per warp: only warps that own such a slice wait
             if (wait_halo)
@@ -507,7 +508,7 @@ __device__ __forceinline__ void pk_spmv(const PkArgs &a, PkShared<BS> &sh, const
             }
         }
     else
-        spmv_node3_slices<STAGE, IDX16, true>(a.op, sa, own, lane, 0, acc);
+        spmv_node3_slices<STAGE, IDX16, true, HEAD>(a.op, sa, own, lane, 0, acc, head);
     }
 
 // every slice this warp owns: plain slices, or slices w and 7 - w of the group's gather blocks
@@ -530,8 +531,12 @@ __device__ __forceinline__ void pk_for_slices(const SliceIter &own, const Operat
 
 extern __shared__ double4 pk_stage_smem[];  // STAGED: one staging buffer of stage_cap images per thread group
 
-template <int BS, bool IDX16, bool STAGED>
-__global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(const PkArgs a)
+// HEAD: the head of each warp's first slice (extent, first batch of column indices and values: spmv_head) is
+// fetched once and kept in registers for the whole solve.  27 registers that the 64 of a full SM of threads do
+// not have (ptxas spilled ~600 bytes per thread all over the kernel), so this is the variant of meshes small
+// enough for 16 warps per SM to own a slice each: one CTA of 512 threads per SM, up to 128 registers.
+template <int BS, bool IDX16, bool STAGED, bool HEAD = false>
+__global__ void __launch_bounds__(BS, (BS == 1024 || HEAD) ? 1 : (1024 / BS)) k_llg_solve(const PkArgs a)
     {
     __shared__ PkShared<BS> sh;
     const int lane = threadIdx.x & 31;
@@ -581,7 +586,10 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
     sa.y = a.r;
     sa.a0 = a.b;
     sa.o0 = a.rt;
-    pk_spmv<ST_BICG_SETUP, IDX16, STAGED, BS>(a, sh, sa, own, lane, false, stage, acc);
+    SpmvHead head;
+    head.s = -1;
+    if (HEAD && !STAGED) spmv_head<IDX16>(a.op, own, lane, head);  // constant for the whole solve
+    pk_spmv<ST_BICG_SETUP, IDX16, STAGED, BS, HEAD>(a, sh, sa, own, lane, false, stage, acc, head);
     pk_sync<BS, 2, false>(a, sh, acc, 0);
     if (threadIdx.x == 0)
         {
@@ -645,7 +653,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
         sa.y = a.v;
         sa.a0 = a.rt;
         sa.o0 = nullptr;
-        pk_spmv<ST_BICG_V, IDX16, STAGED, BS>(a, sh, sa, own, lane, true, stage, acc);
+        pk_spmv<ST_BICG_V, IDX16, STAGED, BS, HEAD>(a, sh, sa, own, lane, true, stage, acc, head);
         pk_sync<BS, 1, false>(a, sh, acc, 0);
         if (threadIdx.x == 0)
             {
@@ -706,7 +714,7 @@ __global__ void __launch_bounds__(BS, BS == 1024 ? 1 : (1024 / BS)) k_llg_solve(
             sa.x = nullptr;
             sa.y = a.t;
             sa.a0 = a.s;
-            pk_spmv<ST_BICG_T, IDX16, STAGED, BS>(a, sh, sa, own, lane, true, stage, acc);
+            pk_spmv<ST_BICG_T, IDX16, STAGED, BS, HEAD>(a, sh, sa, own, lane, true, stage, acc, head);
             if (spec)
                 {
                 acc[2] = ss_acc;

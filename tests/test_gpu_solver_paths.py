@@ -33,8 +33,13 @@ def _steps(la, case, n, seed=300):
 
 CASES = {"small_cuboid": lambda: cases.small_cuboid(), "small_cuboid_npi1": lambda: cases.small_cuboid(npi=1),
          "film": lambda: cases.film(40, 24, 2), "ellipsoid": lambda: cases.ellipsoid(),
-         # more slices than one 256-thread CTA has warps x 148: the grid-wide barriers really synchronise CTAs
-         "film_wide": lambda: cases.film(160, 120, 2)}
+         # many CTAs: the grid-wide barriers really synchronise.  The launch shapes of the persistent kernel
+         # (fg_krylov.cu pk_plan): one 256-thread CTA up to 8 slices (ellipsoid, the cuboids); 512 threads
+         # with the head of each product held in registers up to 148 x 16 slices (film: 97 slices,
+         # film_wide: 1827); 256 threads up to 148 x 32 (film_256: 3034 slices); 1024 threads beyond
+         # (film_1024: 6049 slices, and tests/test_gpu_fullsize.py)
+         "film_wide": lambda: cases.film(160, 120, 2), "film_256": lambda: cases.film(200, 160, 2),
+         "film_1024": lambda: cases.film(320, 200, 2)}
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
