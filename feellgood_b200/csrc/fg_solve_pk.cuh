@@ -46,7 +46,10 @@ struct PkSync  // one per context, device memory, zeroed at creation
     unsigned int gen;    // generation of the last released barrier
     unsigned int pad1[31];
     unsigned long long t_last, t_ar;          // profiling: when the last CTA arrived / the cross-GPU part ended
-    double tot[2][RED_NV];                    // totals of the last two reductions (slot = parity)
+    // totals of the last two reductions (slot = parity), as self-validating 8-byte words {half of the double,
+    // generation}: a CTA that sees the generation in a word has the data with it, so the totals need no
+    // second round trip after the release of the barrier (two words per value)
+    unsigned long long tot_ll[2][2 * RED_NV];
     double part[2][2 * RED_NV][PK_MAX_GRID];  // CTA partials (values, then compensations)
     };
 
@@ -108,6 +111,17 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p)
     }
 __device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v)
     { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p)
+    {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+    }
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v)
+    { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ void st_relaxed_u32(unsigned int *p, unsigned int v)
+    { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 // arrival at the grid barrier: one acquire-release atomic (fence.acq_rel + ATOMG; `__threadfence()` would be
 // the heavier sequentially-consistent MEMBAR.SC on top of it)
 __device__ __forceinline__ unsigned int atom_add_acq_rel_u32(unsigned int *p, unsigned int v)
@@ -269,31 +283,55 @@ __device__ void pk_sync(const PkArgs &a, PkShared<BS> &sh, const double (&acc)[R
             if (last) team_sync();  // all NV sums are in sh.tot (uniform: every team warp read the same sh.last)
             if (wid == 0)
                 {
+                const unsigned int tgt = __shfl_sync(0xffffffffu, target, 0);
                 if (last)
                     {
                     if (NV > 0 && a.dist != nullptr) dist_allreduce_warp_e(&sh.dd, &sh.derr, sh.dd.epoch, sh.tot, NV, MAXOP);
                     if (lane == 0)
                         {
-                        if (NV > 0)
-                            {
-#pragma unroll
-                            for (int q = 0; q < NV; q++) a.sync->tot[slot][q] = MAXOP ? sh.tot[q] : sh.tot[q] + sh.tot[NV + q];
-                            }
                         a.sync->count = 0;
                         if (a.phase_acc != nullptr) a.sync->t_ar = now_ns();
-                        st_release_u32(&a.sync->gen, target);  // (release store) this GPU's CTAs go on ...
+                        if (NV > 0)
+                            {  // release pattern: one fence, then the words the other CTAs spin on
+                            fence_acq_rel_gpu();
+#pragma unroll
+                            for (int q = 0; q < NV; q++)
+                                {
+                                const double tq = MAXOP ? sh.tot[q] : sh.tot[q] + sh.tot[NV + q];
+                                const unsigned long long bits = (unsigned long long)__double_as_longlong(tq);
+                                const unsigned long long flag = (unsigned long long)tgt << 32;
+                                st_relaxed_u64(&a.sync->tot_ll[slot][2 * q], flag | (bits & 0xffffffffull));
+                                st_relaxed_u64(&a.sync->tot_ll[slot][2 * q + 1], flag | (bits >> 32));
+                                sh.tot[q] = tq;
+                                }
+                            st_relaxed_u32(&a.sync->gen, tgt);  // kept current: the next launch starts from it
+                            }
+                        else
+                            st_release_u32(&a.sync->gen, tgt);  // (release store) this GPU's CTAs go on ...
                         // ... while the neighbours learn that every push of the phase is complete and fenced
                         if (halo && a.dist != nullptr) dist_raise_e(&sh.dd, sh.hepoch);
                         }
                     }
+                else if (NV > 0)
+                    {  // lanes 0 .. 2 NV - 1 each wait for their word of the totals: the acquire load orders
+                       // everything that follows after the releasing fence (for these threads; for the rest
+                       // of the CTA through the bar.sync below) and drops stale L1 lines
+                    unsigned long long wv = 0ull;
+                    if (lane < 2 * NV)
+                        do
+                            wv = ld_acquire_u64(&a.sync->tot_ll[slot][lane]);
+                        while ((unsigned int)(wv >> 32) != tgt);
+                    const unsigned int half = (unsigned int)wv;
+                    const unsigned int lo = __shfl_sync(0xffffffffu, half, (2 * lane) & 31);
+                    const unsigned int hi = __shfl_sync(0xffffffffu, half, (2 * lane + 1) & 31);
+                    if (lane < NV) sh.tot[lane] = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+                    }
                 else if (lane == 0)
-                    {  // the acquire load orders everything that follows (for this thread; for the rest of the
-                       // CTA through the bar.sync below) after the releasing store, and drops stale L1 lines
-                    while (ld_acquire_u32(&a.sync->gen) != target)
+                    {
+                    while (ld_acquire_u32(&a.sync->gen) != tgt)
                         ;
                     }
                 __syncwarp();
-                if (NV > 0 && lane < NV) sh.tot[lane] = __ldcg(&a.sync->tot[slot][lane]);
                 }
             }
         if (wid == 0 && lane == 0)
