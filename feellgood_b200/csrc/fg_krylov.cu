@@ -1277,28 +1277,22 @@ bool pk_plan(const Operator &op, int *bs_out, size_t *smem_out, bool *head_out)
     return staged;
     }
 
-// Warps per CTA of a 1024-thread launch on `grid` CTAs: when a warp owns only a few slices, the incomplete
-// last round of the front (SliceIter) runs with most warps idle, i.e. latency-bound (4.1 slices per warp on
-// an 8-GPU partition of the 20 M-tet mesh: a 13 % last round cost 8 us of a 36 us product).  Fewer warps per
-// CTA make the rounds fuller: pick the count in [24, 32] whose last round is fullest.
+// Warps per CTA of a 1024-thread launch on `grid` CTAs.  A product takes one round of the slice front per
+// slice of the busiest warp, and a round costs about the same with 24 warps per SM as with 32 (latency, not
+// issue slots: 6.7 us against 7.3 us on a 4-GPU partition of the 20 M-tet mesh), so: the fewest rounds first
+// -- ceil(slices / warps of the grid) -- and among the counts in [24, 32] that reach it the smallest one,
+// which leaves the last round fullest (8-GPU partition, 4.1 slices per warp at 32: 27 warps make the fifth
+// round 90 % full, -1.7 us per product).  (Round 2 first picked the fullest last round outright: 24 warps
+// and 11 rounds instead of 30 and 9 on the interior ranks at N = 4, 73 us per product against 66.)
 static int pk_warps(int nslice, int grid)
     {
     static const int forced = getenv("FG_PK_WARPS") ? atoi(getenv("FG_PK_WARPS")) : 0;
     if (forced >= 1 && forced <= 32) return forced;
     if (nslice >= 16 * grid * 32) return 32;  // many rounds: the tail does not matter
+    auto rounds = [&](int nw) { return (nslice + grid * nw - 1) / (grid * nw); };
     int best = 32;
-    double best_fill = -1.0;
-    for (int nw = 32; nw >= 24; nw--)
-        {
-        const long long W = (long long)grid * nw;
-        const long long rem = nslice % W;
-        const double fill = rem == 0 ? 1.0 : (double)rem / (double)W;
-        if (fill > best_fill + 0.02)  // prefer more warps unless the gain is real
-            {
-            best_fill = fill;
-            best = nw;
-            }
-        }
+    for (int nw = 31; nw >= 24; nw--)
+        if (rounds(nw) <= rounds(best)) best = nw;
     return best;
     }
 
