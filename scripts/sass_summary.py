@@ -14,7 +14,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "feellgood_b200", "libfeellgood_b200.so")
-WANT = ["k_llg_solveILi1024ELb1ELb0", "k_llg_solveILi256ELb1ELb0", "k_tet_isoILi5ELb1", "k_assemble_node",
+WANT = ["k_llg_solveILi1024ELb1ELb0", "k_llg_solveILi512ELb1ELb0ELb1", "k_llg_solveILi256ELb1ELb0", "k_tet_isoILi5ELb1", "k_assemble_node",
         "k_basisILb1", "k_spmv_node3ILi2ELb1ELb0"]
 txt = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
 funcs, cur = {}, None
