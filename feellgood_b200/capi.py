@@ -30,7 +30,7 @@ SYMBOLS = [
     "fg_matrix_create", "fg_matrix_destroy", "fg_matrix_set_values", "fg_matrix_mult", "fg_bicg",
     "fg_bicg_dir", "fg_cg", "fg_cg_dir", "fg_kernel_launches", "fg_stream", "fg_set_profiling",
     "fg_get_phase_times", "fg_get_krylov_state", "fg_get_krylov_history", "fg_set_operator", "fg_get_spmv_times", "fg_get_kernel_times", "fg_energy", "fg_energy_space", "fg_avg", "fg_max_angle", "fg_calc_charges", "fg_demag_direct", "fg_bench_spmv", "fg_host_plan", "fg_dist_create", "fg_dist_export", "fg_dist_connect", "fg_get_layout",
-    "fg_set_solver", "fg_get_solve_times", "fg_get_precond", "fg_get_records",
+    "fg_set_solver", "fg_get_solve_times", "fg_get_precond", "fg_get_records", "fg_solver_launch_shape",
 ]
 
 
@@ -123,6 +123,14 @@ def lib():
 def check(rc):
     if rc != FG_OK:
         raise FgError(rc, lib().fg_last_error().decode())
+
+
+def solver_launch_shape(nslice, n_sm=0):
+    """Launch shape of the persistent solve kernel for `nslice` SELL slices on `n_sm` SMs (0: 148), computed
+    on the host: dict(block, warps, grid, head)  (fg_solver_launch_shape)."""
+    out = (C.c_int * 4)()
+    check(lib().fg_solver_launch_shape(int(nslice), int(n_sm), out))
+    return dict(block=out[0], warps=out[1], grid=out[2], head=bool(out[3]))
 
 
 def dp(a):

@@ -333,6 +333,7 @@ int bicgstab_run(const Operator &op, KrylovWork &w, double tol, int maxiter, pos
 // upd != NULL (fg_solve_pk.cuh); one host synchronisation per solve.
 int bicgstab_run_pk(const Operator &op, KrylovWork &w, double tol, int maxiter, const PkUpdate *upd);
 bool pk_plan(const Operator &op, int *bs_out, size_t *smem_out, bool *head_out = nullptr);
+void pk_launch_shape(int nslice, int sms, int out[4]);
 // Jacobi-preconditioned CG, reference src/algebra/cg.h:15-58,68-121 (same conventions)
 int cg_run(const Operator &op, KrylovWork &w, double tol, int maxiter);
 // D = 1/diag(A) for a plain CSR operator (src/algebra/sparseMat.h:174-183), then masked

@@ -1245,10 +1245,8 @@ static const void *pk_kernel(int bs, bool i16, bool staged, bool head)
 
 // Launch shape of the persistent kernel for an operator: CTA size, and whether the gathered images are
 // staged in shared memory (returns true) with `smem` bytes of dynamic shared memory per CTA.
-bool pk_plan(const Operator &op, int *bs_out, size_t *smem_out, bool *head_out)
+static bool pk_plan_sms(const Operator &op, int sms, int *bs_out, size_t *smem_out, bool *head_out)
     {
-    int dev = 0, sms = NUM_SMS;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // CTA size: 1024 threads (one CTA per SM, 148 arrivals per barrier) once every warp of such a grid has a
     // slice of its own; 256 threads below that, so that small meshes still spread over all SMs.  When 16
     // warps per SM own at most a slice each: the 512-thread variant that keeps the head of that slice in
@@ -1276,6 +1274,12 @@ bool pk_plan(const Operator &op, int *bs_out, size_t *smem_out, bool *head_out)
     if (smem_out) *smem_out = staged ? smem : 0;
     return staged;
     }
+bool pk_plan(const Operator &op, int *bs_out, size_t *smem_out, bool *head_out)
+    {
+    int dev = 0, sms = NUM_SMS;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return pk_plan_sms(op, sms, bs_out, smem_out, head_out);
+    }
 
 // Warps per CTA of a 1024-thread launch on `grid` CTAs.  A product takes one round of the slice front per
 // slice of the busiest warp, and a round costs about the same with 24 warps per SM as with 32 (latency, not
@@ -1294,6 +1298,28 @@ static int pk_warps(int nslice, int grid)
     for (int nw = 31; nw >= 24; nw--)
         if (rounds(nw) <= rounds(best)) best = nw;
     return best;
+    }
+
+// What bicgstab_run_pk launches for an unstaged operator of `nslice` slices on a device with `sms` SMs,
+// computed without a device (fg_solver_launch_shape; the residency per SM follows the launch bounds of
+// k_llg_solve): out = {CTA size of the instantiation, warps per CTA launched, CTAs, 1 = HEAD variant}.
+void pk_launch_shape(int nslice, int sms, int out[4])
+    {
+    Operator op = {};
+    op.nslice = nslice;
+    int bs = 0;
+    bool head = false;
+    pk_plan_sms(op, sms, &bs, nullptr, &head);
+    const int per_sm = (bs == 1024 || head) ? 1 : 1024 / bs;
+    int wave = per_sm * sms;
+    if (wave > PK_MAX_GRID) wave = PK_MAX_GRID;
+    int grid = (nslice + bs / 32 - 1) / (bs / 32);
+    if (grid > wave) grid = wave;
+    if (grid < 1) grid = 1;
+    out[0] = bs;
+    out[1] = bs == 1024 ? pk_warps(nslice, grid) : bs / 32;
+    out[2] = grid;
+    out[3] = head ? 1 : 0;
     }
 
 int bicgstab_run_pk(const Operator &op, KrylovWork &w, double tol, int maxiter, const PkUpdate *upd)

@@ -1112,6 +1112,17 @@ int fg_get_layout(const fg_ctx *c, long long out[4])
     return FG_OK;
     }
 
+int fg_solver_launch_shape(int nslice, int n_sm, int out[4])
+    {
+    if (nslice < 1 || !out)
+        {
+        set_error("fg_solver_launch_shape: nslice >= 1 and out are required");
+        return FG_ERR_INVALID;
+        }
+    pk_launch_shape(nslice, n_sm > 0 ? n_sm : NUM_SMS, out);
+    return FG_OK;
+    }
+
 int fg_set_state(fg_ctx *c, const double *u, const double *v, const double *phi, const double *phiv)
     {
     FG_TRY(check_ctx(c));

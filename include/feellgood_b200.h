@@ -118,6 +118,11 @@ int fg_get_sizes(const fg_ctx *ctx, long long out[10]);
  * out[1] = stored node pairs including SELL padding, out[2] = 1 when the element fast path
  * (no anisotropy in any region) is available, out[3] = padded node rows */
 int fg_get_layout(const fg_ctx *ctx, long long out[4]);
+/* launch shape of the persistent solve kernel (fg_set_solver 0) for a mesh of `nslice` SELL slices (32 node
+ * rows each) on a device with `n_sm` SMs (<= 0: 148), computed on the host, no device needed (no reference
+ * counterpart; tests pin the heuristics with it): out = {threads per CTA of the kernel variant, warps per CTA
+ * actually launched, CTAs, 1 when the variant keeps the head of each warp's first slice in registers} */
+int fg_solver_launch_shape(int nslice, int n_sm, int out[4]);
 
 /* ---- node state (Nodes::Node::d[CURRENT|NEXT], src/node.h:47-70) ---- */
 /* mesh::init_distrib + Fem ctor: set CURRENT u, v, phi, phiv and copy to NEXT; NULL = zeros.

@@ -133,3 +133,44 @@ def test_algorithmic_byte_model():
         + 2 * (2 * (12 * nnz + 20 * n) + 144 * n) + 136 * 1000)
     b0 = workloads.step_bytes(1000, 6000, n, nnz, 0)
     assert workloads.step_bytes(1000, 6000, n, nnz, 10) - b0 == 10 * workloads.iter_bytes(n, nnz)
+
+
+def test_persistent_kernel_launch_shape():
+    """Launch shape of the persistent solve kernel (fg_krylov.cu pk_plan / pk_warps through
+    fg_solver_launch_shape, no device needed): the variant per mesh size, and the warp count of a
+    1024-thread launch -- fewest rounds of the slice front first, then the fullest last round.  The
+    interior and end ranks of the 4-GPU partition of the 20 M-tet mesh (39 035 / 39 091 slices) must get
+    the same shape: the first heuristic gave them 24 warps / 11 rounds against 30 / 9."""
+    from feellgood_b200 import capi
+    S = 148
+    shape = lambda n: capi.solver_launch_shape(n, S)
+    # variants: one 256-thread CTA up to 8 slices; 512 threads + register-held heads up to 16 warps per SM;
+    # 256 threads (4 CTAs per SM) below one slice per warp of a full 1024-thread grid; 1024 threads beyond
+    assert shape(6) == dict(block=256, warps=8, grid=1, head=False)
+    assert shape(8)["grid"] == 1 and not shape(8)["head"]
+    assert shape(9) == dict(block=512, warps=16, grid=1, head=True)
+    assert shape(1483) == dict(block=512, warps=16, grid=93, head=True)          # sp4
+    assert shape(S * 16) == dict(block=512, warps=16, grid=S, head=True)
+    assert shape(S * 16 + 1) == dict(block=256, warps=8, grid=297, head=False)
+    assert shape(S * 32 - 1) == dict(block=256, warps=8, grid=4 * S, head=False)
+    assert shape(S * 32) == dict(block=1024, warps=32, grid=S, head=False)
+    assert shape(156252) == dict(block=1024, warps=32, grid=S, head=False)       # film20m
+    assert shape(78126)["warps"] == 32                                           # its 2-GPU partition
+    assert shape(39035) == shape(39091) == dict(block=1024, warps=30, grid=S, head=False)   # 4 GPUs
+    assert shape(19517) == shape(19574) == dict(block=1024, warps=27, grid=S, head=False)   # 8 GPUs
+    rounds = lambda n, nw: -(-n // (S * nw))
+    for n in list(range(S * 32, S * 32 * 16, 997)) + [S * 32 * 16 - 1]:
+        s = shape(n)
+        assert s["block"] == 1024 and s["grid"] == S and 24 <= s["warps"] <= 32
+        best = min(rounds(n, nw) for nw in range(24, 33))
+        assert rounds(n, s["warps"]) == best == rounds(n, 32), n       # never more rounds than 32 warps
+        assert s["warps"] == min(nw for nw in range(24, 33) if rounds(n, nw) == best), n
+    # every slice has a warp: warps of the grid x rounds covers the mesh; small meshes get one slice per warp
+    for n in (1, 5, 33, 500, 2368, 2369, 4000, 4735):
+        s = shape(n)
+        assert s["grid"] * s["warps"] >= n or s["block"] == 256 and s["grid"] == 4 * S
+    # another SM count (the shape follows the device, not a constant)
+    assert capi.solver_launch_shape(132 * 32, 132) == dict(block=1024, warps=32, grid=132, head=False)
+    import pytest
+    with pytest.raises(capi.FgError):
+        capi.solver_launch_shape(0)
