@@ -116,6 +116,11 @@ def lib():
         L.fg_destroy.argtypes = [C.c_void_p]
         L.fg_matrix_destroy.restype = None
         L.fg_matrix_destroy.argtypes = [C.c_void_p]
+        # the per-step calls: with argtypes ctypes converts Python numbers itself, which costs a fraction of
+        # building c_double objects per call (the host path of a step is GPU idle time on small meshes)
+        L.fg_step.argtypes = [C.c_void_p, C.c_double, c_double_p, C.c_double, C.c_double, C.c_int, C.c_double,
+                              C.POINTER(StepResult)]
+        L.fg_commit.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 

@@ -136,6 +136,7 @@ class LinAlgebra:
         h = C.c_void_p()
         check(create(L, C.byref(cm), C.byref(cp), C.c_int(device), C.byref(h)))
         self._h = h
+        self._step_args = None
         out = (C.c_longlong * 10)()
         check(L.fg_get_sizes(h, out))
         (_, self.NT, self.NF, self.n_magTet, self.n_magTri, self.E, self.E_mag, self.n, self.nnz,
@@ -281,12 +282,14 @@ class LinAlgebra:
         if angle is None:
             angle = M_2_PI * mt19937_uniform01(_c_rand())
         self.last_angle = angle
-        H = f64(Hext)
-        r = capi.StepResult()
-        check(self._L.fg_step(self._h, C.c_double(angle), dp(H), C.c_double(t_prm.get_dt()),
-                              C.c_double(t_prm.prefactor), C.c_int(self.idx_dir),
-                              C.c_double(self.DW_vz), C.byref(r)))
-        return self._store(r)
+        sc = self._step_args
+        if sc is None:  # argument buffers of the per-step call, marshalled once (5 us per step otherwise)
+            r = capi.StepResult()
+            sc = self._step_args = ((C.c_double * 3)(), r, C.pointer(r))
+        H = sc[0]
+        H[0], H[1], H[2] = Hext
+        check(self._L.fg_step(self._h, angle, H, t_prm.get_dt(), t_prm.prefactor, self.idx_dir, self.DW_vz, sc[2]))
+        return self._store(sc[1])
 
     def get_v_max(self):
         return self.v_max
