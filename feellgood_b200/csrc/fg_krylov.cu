@@ -18,6 +18,7 @@
 #include "fg_common.cuh"
 #include "fg_reduce.cuh"
 #include "fg_krylov_state.cuh"
+#include "fg_slice_iter.cuh"
 
 namespace fg
 {
@@ -232,51 +233,9 @@ template <bool COH> __device__ __forceinline__ double4 ld_image(const double4 *p
     return ld256_nc(p);
     }
 
-// Which slices a warp owns.  Regular rounds: slice g + k W for k = 0 .. (W = warps of the grid, g = this
-// warp's index in the grid), so that at any moment the whole grid works on one contiguous front of W slices
-// (the gathered images of a front are shared through L2 and, inside a CTA, through L1).  The last,
-// incomplete round is dealt out per CTA instead (`tail`: at most one extra slice per warp), so that every SM
-// ends with the same number of slices to one, whatever the ratio of slices to warps (it is ~4 per warp on
-// the 8-GPU partition of the 20 M-tet mesh, where a round-robin tail left 17 SMs with 25 % more work).
-struct SliceIter
-    {
-    int first;     // g, or INT_MAX when the warp has no regular slice
-    int W;         // stride of the regular rounds
-    int main_end;  // regular slices are below this index
-    int tail;      // the warp's slice of the last round, or INT_MAX
-    __device__ __forceinline__ int begin() const { return first < main_end ? first : tail; }
-    __device__ __forceinline__ int next(int s) const
-        {
-        if (s >= main_end) return INT_MAX;  // s was the tail slice
-        const int n = s + W;
-        return n < main_end ? n : tail;
-        }
-    };
-// plain grid-stride ownership (stand-alone kernels)
-__device__ __forceinline__ SliceIter slices_strided(int g, int W, int nslice)
-    {
-    SliceIter it;
-    it.first = g;
-    it.W = W;
-    it.main_end = nslice;
-    it.tail = INT_MAX;
-    return it;
-    }
-// front + per-CTA tail (persistent kernel): n units (slices or gather blocks) dealt to `per_cta` owners per
-// CTA (warps or thread groups), this owner being number `id` of its CTA
+// Row ownership (SliceIter, slices_strided, slices_balanced_at): fg_slice_iter.cuh
 __device__ __forceinline__ SliceIter slices_balanced(int n, int per_cta, int id)
-    {
-    const int W = gridDim.x * per_cta;
-    const int q = n / W, rem = n - q * W;
-    SliceIter it;
-    it.first = blockIdx.x * per_cta + id;
-    it.W = W;
-    it.main_end = q * W;
-    const int t0 = it.main_end + (int)(((long long)rem * blockIdx.x) / gridDim.x);
-    const int t1 = it.main_end + (int)(((long long)rem * (blockIdx.x + 1)) / gridDim.x);
-    it.tail = t0 + id < t1 ? t0 + id : INT_MAX;
-    return it;
-    }
+    { return slices_balanced_at(n, per_cta, id, (int)blockIdx.x, (int)gridDim.x); }
 
 // Returns true when the warp met a slice that belongs to the other pass (pass 1: a slice with ghost columns).
 // The ghost flag of a slice travels with its extent, fetched one slice ahead: deciding on a flag loaded in

@@ -187,3 +187,13 @@ def test_device_cg_state_machine_against_reference(oracle, tmp_path):
     x, info = _emulate(exe, rp, col, val, np.zeros(n), np.zeros(n), none, 1e-10, 50, mode="cg")
     xo, io = oracle.cg(rp, col, val, np.zeros(n), np.zeros(n), tol=1e-10, maxiter=50)
     assert info["status"] == io["status"] and info["nit"] == io["nit"] == 0
+
+
+def test_slice_ownership_of_the_persistent_kernel(tmp_path):
+    """SliceIter / slices_balanced_at (csrc/fg_slice_iter.cuh, the code the kernels call) enumerated on the
+    CPU: every slice owned once, fronts of W slices, the last round dealt out per CTA to within one slice."""
+    exe = str(tmp_path / "slice_iter_test")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-I", CSRC, "-o", exe,
+                           os.path.join(cases.ROOT, "tests", "cpp", "slice_iter_test.cpp")])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "SLICE_ITER_OK" in r.stdout, r.stdout + r.stderr[-2000:]
